@@ -1,0 +1,221 @@
+"""Generate tests/golden/*.npz by running the REAL reference (imported from /root/reference).
+
+Run in the build container only (the reference does not exist on the GPU box):
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+Every fixture stores the seeded inputs together with what the unmodified reference code
+returned, so tests can replay them against (a) the oracle restatement and (b) the CUDA path.
+Nothing here is imported by the product.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+from torch import nn
+
+REF = os.environ.get("SM3_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from src.models import resnet as ref_resnet          # noqa: E402  (reference)
+from src.models import simclr as ref_simclr          # noqa: E402  (reference)
+from src.models.evaluator import KNNOnlineEvaluator  # noqa: E402  (reference)
+from tiny_encoder import tiny                        # noqa: E402
+
+SEED = 3407  # the reference's default seed (src/utils/misc.py:193)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def ref_infonce(p1, p2, T, dtype):
+    """Unbound SimCLRSkinV3._cal_logits (self unused, simclr.py:290-322) + stock CE + backward."""
+    a = p1.to(dtype).clone().requires_grad_(True)
+    b = p2.to(dtype).clone().requires_grad_(True)
+    logits, labels = ref_simclr.SimCLRSkinV3._cal_logits(None, a, b, nn.Identity(), nn.Identity(), T)
+    loss = nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    return logits, labels, loss, a.grad, b.grad
+
+
+def gen_infonce(name, n, d, T, correlated, store_logits):
+    g = torch.Generator().manual_seed(SEED + n + d)
+    p1 = torch.randn(n, d, generator=g)
+    p2 = p1 + 0.5 * torch.randn(n, d, generator=g) if correlated else torch.randn(n, d, generator=g)
+    out = {"p1": _np(p1), "p2": _np(p2), "temperature": np.float64(T), "n": n, "d": d}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        logits, labels, loss, g1, g2 = ref_infonce(p1, p2, T, dt)
+        out[f"loss_{tag}"] = _np(loss)
+        if store_logits:
+            out[f"dp1_{tag}"] = _np(g1)
+            out[f"dp2_{tag}"] = _np(g2)
+        elif tag == "f64":      # big case: keep a strided subset of gradient rows (fixture size)
+            out["grad_rows"] = np.arange(0, n, 5)
+            out["dp1_rows_f64"] = _np(g1)[::5]
+            out["dp2_rows_f64"] = _np(g2)[::5]
+            out["dp1_sum_f64"] = _np(g1).sum(0); out["dp2_sum_f64"] = _np(g2).sum(0)
+            out["dp_abs_sum_f64"] = np.float64(_np(g1.abs().sum() + g2.abs().sum()))
+        if store_logits:
+            out[f"logits_{tag}"] = _np(logits)
+        else:
+            out[f"logits_row0_{tag}"] = _np(logits[0])
+            out[f"logits_col0_{tag}"] = _np(logits[:, 0])
+        assert int(labels.abs().sum()) == 0 and labels.dtype == torch.long
+        # retrieval contract: top-1 / top-5 non-self neighbour of every row (reference sim matrix)
+        if tag == "f64":
+            z = torch.nn.functional.normalize(torch.cat([p1, p2]).to(dt), dim=1)
+            sim = z @ z.T
+            sim.fill_diagonal_(-float("inf"))
+            out["top5_idx"] = _np(sim.topk(5, dim=1).indices)
+            out["top5_val"] = _np(sim.topk(5, dim=1).values)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", out["loss_f64"])
+
+
+def gen_edge_cases():
+    """Zero row (eps clamp path), duplicated rows, n=1 (no negatives), n=2."""
+    out = {}
+    g = torch.Generator().manual_seed(SEED)
+    cases = {}
+    p1 = torch.randn(5, 8, generator=g); p2 = torch.randn(5, 8, generator=g)
+    p1[2] = 0.0                                   # F.normalize eps clamp -> z = 0
+    cases["zero_row"] = (p1, p2)
+    p1 = torch.randn(4, 8, generator=g); p2 = p1.clone()      # z_{i+N} == z_i
+    cases["dup_rows"] = (p1, p2)
+    cases["n1"] = (torch.randn(1, 8, generator=g), torch.randn(1, 8, generator=g))
+    cases["n2"] = (torch.randn(2, 8, generator=g), torch.randn(2, 8, generator=g))
+    cases["ragged_n3_d5"] = (torch.randn(3, 5, generator=g), torch.randn(3, 5, generator=g))
+    for k, (a, b) in cases.items():
+        for T in (0.1, 0.5):
+            logits, labels, loss, g1, g2 = ref_infonce(a, b, T, torch.float64)
+            key = f"{k}_T{T}"
+            out[key + "_p1"] = _np(a); out[key + "_p2"] = _np(b)
+            out[key + "_logits"] = _np(logits); out[key + "_loss"] = _np(loss)
+            out[key + "_dp1"] = _np(g1); out[key + "_dp2"] = _np(g2)
+    out["case_names"] = np.array(sorted(cases.keys()))
+    np.savez_compressed(os.path.join(OUT, "infonce_edge.npz"), **out)
+    print("edge cases", list(cases))
+
+
+def gen_heads():
+    """8-head CE exactly as the reference scripts write it (they are loops in scripts, not
+    functions, so the loops are replayed literally with the reference's criterion objects)."""
+    num_classes = [5, 3, 2, 3, 3, 3, 3, 2]           # tools/mlc_eval.py:63
+    g = torch.Generator().manual_seed(SEED)
+    B = 37
+    out = {"num_classes": np.array(num_classes)}
+    logits = [torch.randn(B, c, generator=g, dtype=torch.float64).requires_grad_(True) for c in num_classes]
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in num_classes], dim=1)
+    # --- tools/mlc_eval.py:157-162: weighted sum / num_labels ---
+    label_weights = [1.0, 0.5, 2.0, 1.0, 1.0, 0.25, 1.0, 3.0]
+    criterion = nn.CrossEntropyLoss()                # tools/mlc_eval.py:420 region (plain CE)
+    loss = 0.0
+    for i in range(8):
+        loss += label_weights[i] * criterion(logits[i], labels[:, i])
+    loss = loss / 8
+    loss.backward()
+    out["eval_logits"] = np.concatenate([_np(x) for x in logits], axis=1)
+    out["eval_labels"] = _np(labels)
+    out["eval_weights"] = np.array(label_weights)
+    out["eval_loss"] = _np(loss)
+    out["eval_grad"] = np.concatenate([_np(x.grad) for x in logits], axis=1)
+    # --- tools/mlc_train.py:255-261,381: pred / T, ignore_index=-100, / len(assignments) ---
+    T = 0.1
+    preds = [torch.randn(B, c, generator=g, dtype=torch.float64).requires_grad_(True) for c in num_classes]
+    assign = labels.clone()
+    assign[::5, 3] = -100
+    assign[1::7, 0] = -100
+    criterion = nn.CrossEntropyLoss(ignore_index=-100)   # tools/mlc_train.py:381
+    loss = 0
+    for i, pred in enumerate(preds):
+        scores = pred / T
+        loss += criterion(scores, assign[:, i])
+    loss = loss / 8
+    loss.backward()
+    out["dc_logits"] = np.concatenate([_np(x) for x in preds], axis=1)
+    out["dc_labels"] = _np(assign)
+    out["dc_temperature"] = np.float64(T)
+    out["dc_loss"] = _np(loss)
+    out["dc_grad"] = np.concatenate([_np(x.grad) for x in preds], axis=1)
+    np.savez_compressed(os.path.join(OUT, "heads.npz"), **out)
+    print("heads eval loss", out["eval_loss"], "dc loss", out["dc_loss"])
+
+
+def gen_knn():
+    g = torch.Generator().manual_seed(SEED)
+    B, NB, D, C, K = 9, 300, 32, 5, 20
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=g, dtype=torch.float64), dim=1)
+    bank = torch.nn.functional.normalize(torch.randn(NB, D, generator=g, dtype=torch.float64), dim=1)
+    tb = torch.randint(0, C, (NB,), generator=g)
+    ev = KNNOnlineEvaluator(None, None, C, k=K, temperature=0.07)
+    pred = ev.predict(q, bank, tb)                    # evaluator.py:43-83
+    sim = q @ bank.T
+    w, idx = sim.topk(k=K, dim=-1)                    # evaluator.py:61-63
+    np.savez_compressed(os.path.join(OUT, "knn.npz"), query=_np(q), bank=_np(bank), bank_labels=_np(tb),
+                        k=K, num_classes=C, temperature=0.07, pred_labels=_np(pred),
+                        topk_idx=_np(idx), topk_val=_np(w))
+    print("knn pred[:,0]", _np(pred[:, 0]))
+
+
+def gen_model():
+    """Full reference wrappers (SimCLR / SimCLRSkinV3 / SimCLRSkinV32) with the tiny encoder."""
+    ref_resnet.__dict__["tiny"] = tiny
+    out = {}
+    N, PD, T = 6, 8, 0.1
+    g = torch.Generator().manual_seed(SEED)
+    imgs = [torch.randn(N, 3, 16, 16, generator=g, dtype=torch.float64) for _ in range(4)]
+    out["imgs"] = np.stack([_np(x) for x in imgs])
+    for cls_name in ("SimCLRSkinV3", "SimCLRSkinV32"):
+        torch.manual_seed(SEED)
+        model = getattr(ref_simclr, cls_name)("tiny", weights=None, proj_dim=PD, temperature=T).double()
+        model.train()
+        sd = {k: _np(v) for k, v in model.state_dict().items()}
+        for k, v in sd.items():
+            out[f"{cls_name}/sd/{k}"] = v
+        out[f"{cls_name}/sd_keys"] = np.array(list(sd.keys()))
+        criterion = nn.CrossEntropyLoss()
+        for style, wts in ((0, (0.5, 0.5)), (1, (0.5, 0.5)), (2, (0.25,) * 4)):
+            model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+            model.zero_grad(set_to_none=True)
+            outputs = model([imgs[0], imgs[1]], [imgs[2], imgs[3]], style)
+            # loss combination of tools/backbone_train.py:98-121
+            cross = sum(w * criterion(*outputs[2][k]) for k, w in enumerate(wts))
+            derm = criterion(*outputs[0]); clinic = criterion(*outputs[1])
+            loss = derm + clinic + cross
+            loss.backward()
+            pre = f"{cls_name}/style{style}/"
+            out[pre + "derm_loss"] = _np(derm); out[pre + "clinic_loss"] = _np(clinic)
+            out[pre + "cross_losses"] = np.array([float(criterion(*o)) for o in outputs[2]])
+            out[pre + "loss"] = _np(loss)
+            out[pre + "logits_shape"] = np.array(outputs[0][0].shape)
+            for k, p in model.named_parameters():
+                out[pre + "grad/" + k] = _np(p.grad) if p.grad is not None else np.zeros(0)
+    out["N"] = N; out["proj_dim"] = PD; out["temperature"] = T
+    np.savez_compressed(os.path.join(OUT, "model_tiny.npz"), **out)
+    print("model goldens written")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen_infonce("infonce_n4_d8_T05", 4, 8, 0.5, False, True)
+    gen_infonce("infonce_n64_d128_T01", 64, 128, 0.1, False, True)        # BASELINE config 1
+    gen_infonce("infonce_n48_d128_T01_corr", 48, 128, 0.1, True, True)    # run.sh scale: 96/2 GPUs
+    gen_infonce("infonce_n200_d64_T02_corr", 200, 64, 0.2, True, False)   # ragged vs 128-row tiles
+    gen_infonce("infonce_n512_d256_T01", 512, 256, 0.1, False, False)     # config-4 width
+    gen_edge_cases()
+    gen_heads()
+    gen_knn()
+    gen_model()
+
+
+if __name__ == "__main__":
+    main()

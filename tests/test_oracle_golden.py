@@ -1,0 +1,198 @@
+"""Pins oracle/ (the CPU restatement) to outputs of the REAL reference stored in tests/golden/.
+
+CPU only.  These goldens were produced by oracle/make_golden.py importing /root/reference.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port, sm3_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FULL = ["infonce_n4_d8_T05", "infonce_n64_d128_T01", "infonce_n48_d128_T01_corr"]
+BIG = ["infonce_n200_d64_T02_corr", "infonce_n512_d256_T01"]
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_literal_logits_match_reference(name):
+    g = load(name)
+    logits, labels = O.infonce_logits(g["p1"], g["p2"], float(g["temperature"]))
+    assert logits.shape == g["logits_f64"].shape
+    np.testing.assert_allclose(logits, g["logits_f64"], rtol=0, atol=1e-12)
+    assert labels.dtype == np.int64 and not labels.any()
+    assert abs(O.cross_entropy_col0(logits) - float(g["loss_f64"])) < 1e-12
+
+
+@pytest.mark.parametrize("name", FULL + BIG)
+def test_closed_form_loss_and_grads(name):
+    g = load(name)
+    T = float(g["temperature"])
+    loss, dp1, dp2 = O.infonce_closed_form(g["p1"], g["p2"], T, chunk=96)
+    assert abs(loss - float(g["loss_f64"])) < 1e-12 * max(1.0, abs(loss))
+    if "dp1_f64" in g:
+        np.testing.assert_allclose(dp1, g["dp1_f64"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(dp2, g["dp2_f64"], rtol=0, atol=1e-14)
+    else:
+        r = g["grad_rows"]
+        np.testing.assert_allclose(dp1[r], g["dp1_rows_f64"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(dp2[r], g["dp2_rows_f64"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(dp1.sum(0), g["dp1_sum_f64"], rtol=0, atol=1e-12)
+        assert abs(np.abs(dp1).sum() + np.abs(dp2).sum() - float(g["dp_abs_sum_f64"])) < 1e-10
+
+
+@pytest.mark.parametrize("name", FULL + BIG)
+def test_sufficient_statistics_equal_reference_ce(name):
+    """CE([pos, lse_neg], 0) == CE(reference logits [M, M-1], 0); column 0 == reference positives."""
+    g = load(name)
+    T = float(g["temperature"])
+    n = int(g["n"])
+    z, _ = O.normalize(np.concatenate([g["p1"], g["p2"]]).astype(np.float64))
+    pos, lse_neg = O.infonce_stats(z, n, T, chunk=100)
+    assert abs(O.stats_to_loss(pos, lse_neg) - float(g["loss_f64"])) < 1e-12 * max(1, float(g["loss_f64"]))
+    col0 = g["logits_f64"][:, 0] if "logits_f64" in g else g["logits_col0_f64"]
+    np.testing.assert_allclose(pos, col0, rtol=0, atol=1e-12)
+    # negatives in ascending column order (row 0: columns 1..M-1 without n)
+    row0 = g["logits_f64"][0] if "logits_f64" in g else g["logits_row0_f64"]
+    s0 = (z[0] @ z.T) / T
+    expect = np.concatenate([[s0[n]], np.delete(s0, [0, n])])
+    np.testing.assert_allclose(row0, expect, rtol=0, atol=1e-12)
+
+
+def test_stats_backward_matches_autograd_through_ce():
+    g = load("infonce_n48_d128_T01_corr")
+    T, n = float(g["temperature"]), int(g["n"])
+    p = np.concatenate([g["p1"], g["p2"]]).astype(np.float64)
+    z, inv = O.normalize(p)
+    pos, lse_neg = O.infonce_stats(z, n, T)
+    # upstream grads the stock CE hands back for logits [pos, lse_neg], target 0, mean reduction
+    m = 2 * n
+    sig = 1.0 / (1.0 + np.exp(pos - lse_neg))          # softmax prob of column 1
+    g_lse, g_pos = sig / m, -sig / m
+    dz = O.stats_backward(z, n, T, g_pos, g_lse)
+    dp = O.normalize_bwd(dz, z, inv)
+    np.testing.assert_allclose(dp[:n], g["dp1_f64"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(dp[n:], g["dp2_f64"], rtol=0, atol=1e-14)
+
+
+def test_edge_cases():
+    g = load("infonce_edge")
+    for case in g["case_names"]:
+        for T in (0.1, 0.5):
+            k = f"{case}_T{T}"
+            p1, p2 = g[k + "_p1"], g[k + "_p2"]
+            logits, _ = O.infonce_logits(p1, p2, T)
+            np.testing.assert_allclose(logits, g[k + "_logits"], rtol=0, atol=1e-12)
+            loss, dp1, dp2 = O.infonce_closed_form(p1, p2, T)
+            assert abs(loss - float(g[k + "_loss"])) < 1e-12, k
+            # the zero row hits F.normalize's eps clamp: its gradient is dz / 1e-12 (~1e12), so rtol
+            np.testing.assert_allclose(dp1, g[k + "_dp1"], rtol=1e-12, atol=1e-12, err_msg=k)
+            np.testing.assert_allclose(dp2, g[k + "_dp2"], rtol=1e-12, atol=1e-12, err_msg=k)
+
+
+def test_analytic_known_answers():
+    """SURVEY 8c KATs: identical rows / orthonormal rows -> log(M-1); duplicated pairs."""
+    n, d, T = 8, 32, 0.1
+    m = 2 * n
+    same = np.ones((n, d))
+    loss, _, _ = O.infonce_closed_form(same, same, T)
+    assert abs(loss - np.log(m - 1)) < 1e-12
+    eye = np.eye(m, d)
+    loss, _, _ = O.infonce_closed_form(eye[:n], eye[n:], T)
+    assert abs(loss - np.log(m - 1)) < 1e-12
+    e = np.eye(n, d)
+    loss, _, _ = O.infonce_closed_form(e, e, T)
+    assert abs(loss - (np.log(np.exp(1 / T) + m - 2) - 1 / T)) < 1e-12
+
+
+def test_sharded_rows_reproduce_global(tmp_path):
+    """W-rank row-block sharding with global column order [all f1 ; all f2]."""
+    g = load("infonce_n64_d128_T01")
+    T, n = float(g["temperature"]), int(g["n"])
+    z, _ = O.normalize(np.concatenate([g["p1"], g["p2"]]).astype(np.float64))
+    W = 4
+    nl = n // W
+    losses = []
+    for r in range(W):
+        rows = O.global_row_index(nl, r * nl, n)
+        pos, lse = O.infonce_stats(z, n, T, rows=rows)
+        losses.append(O.stats_to_loss(pos, lse))
+    assert abs(np.mean(losses) - float(g["loss_f64"])) < 1e-12
+
+
+def test_heads_match_reference_loops():
+    g = load("heads")
+    loss, grad = O.multihead_ce(g["eval_logits"], g["eval_labels"], g["eval_weights"])
+    assert abs(loss - float(g["eval_loss"])) < 1e-12
+    np.testing.assert_allclose(grad, g["eval_grad"], rtol=0, atol=1e-14)
+    loss, grad = O.multihead_ce(g["dc_logits"], g["dc_labels"], None, 1.0 / float(g["dc_temperature"]), -100)
+    assert abs(loss - float(g["dc_loss"])) < 1e-11
+    np.testing.assert_allclose(grad, g["dc_grad"], rtol=0, atol=1e-13)
+
+
+def test_bce_matches_torch():
+    """H2 has no reference counterpart (parity unpinned): oracle == torch BCE-with-logits."""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(33, 24)) * 3
+    t = (rng.random((33, 24)) < 0.3).astype(np.float64)
+    xt = torch.tensor(x, requires_grad=True)
+    l = torch.nn.functional.binary_cross_entropy_with_logits(xt, torch.tensor(t))
+    l.backward()
+    loss, dx = O.bce_with_logits(x, t)
+    assert abs(loss - l.item()) < 1e-12
+    np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=0, atol=1e-14)
+    pw = rng.random(24) * 3 + 0.5
+    xt = torch.tensor(x, requires_grad=True)
+    l = torch.nn.functional.binary_cross_entropy_with_logits(xt, torch.tensor(t), pos_weight=torch.tensor(pw))
+    l.backward()
+    loss, dx = O.bce_with_logits(x, t, pw)
+    assert abs(loss - l.item()) < 1e-12
+    np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=0, atol=1e-14)
+
+
+def test_knn_matches_reference_evaluator():
+    g = load("knn")
+    val, idx = O.knn_topk(g["query"], g["bank"], int(g["k"]))
+    assert (idx == g["topk_idx"]).all()
+    np.testing.assert_allclose(val, g["topk_val"], rtol=0, atol=1e-14)
+    pred, _ = O.knn_predict(g["query"], g["bank"], g["bank_labels"], int(g["num_classes"]), int(g["k"]),
+                            float(g["temperature"]))
+    assert (pred == g["pred_labels"]).all()
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_torch_port_matches_reference(name):
+    """oracle/ref_port.py (the CPU baseline bench.py times) == the real reference, fp32 and fp64."""
+    g = load(name)
+    T = float(g["temperature"])
+    for tag, dt, tol in (("f32", torch.float32, 2e-6), ("f64", torch.float64, 1e-13)):
+        p1 = torch.from_numpy(g["p1"]).to(dt)
+        p2 = torch.from_numpy(g["p2"]).to(dt)
+        logits, target = ref_port.port_cal_logits(p1, p2, T)
+        np.testing.assert_allclose(logits.numpy(), g[f"logits_{tag}"], rtol=0, atol=tol * 10)
+        loss, d1, d2 = ref_port.port_infonce_step(p1, p2, T)
+        assert abs(loss.item() - float(g[f"loss_{tag}"])) <= tol * max(1, abs(loss.item()))
+        np.testing.assert_allclose(d1.numpy(), g[f"dp1_{tag}"], rtol=0, atol=tol)
+    # the row-block sample (used for shapes the reference cannot hold) sums to the full step
+    p1 = torch.from_numpy(g["p1"]).double(); p2 = torch.from_numpy(g["p2"]).double()
+    m = 2 * p1.shape[0]
+    tot, a1 = 0.0, 0
+    blk = max(1, m // 4)
+    for s in range(0, m, blk):
+        l, d1, _ = ref_port.port_infonce_step_rowblock(p1, p2, T, s, min(blk, m - s))
+        tot += l.item(); a1 = a1 + d1
+    assert abs(tot - float(g["loss_f64"])) < 1e-12
+    np.testing.assert_allclose(a1.numpy(), g["dp1_f64"], rtol=0, atol=1e-13)
+
+
+def test_torch_port_heads():
+    g = load("heads")
+    nc = list(g["num_classes"])
+    outs = list(torch.split(torch.from_numpy(g["eval_logits"]), nc, dim=1))
+    l = ref_port.port_multihead_ce(outs, torch.from_numpy(g["eval_labels"]), g["eval_weights"])
+    assert abs(l.item() - float(g["eval_loss"])) < 1e-12
