@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- contrastive pairs/sec (fwd+bwd) of the fused cross-modal InfoNCE hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one pass of the hot path over one synthetic batch: normalise -> fused similarity + InfoNCE
+statistics -> CE on the statistics -> fused backward -> normalise-backward (gradients w.r.t. both projector
+outputs).  Workloads (BASELINE.json):
+  cfg4 (default): global batch N=32768 pairs, D=256, bf16, T=0.1, one cross-modal term -- the configuration the
+        north_star target ("global batch 32768 x dim 256") is quoted on; it fits one GPU because the [M,M] logits
+        are never materialised.  With N>1 ranks the SAME global batch is row-sharded (strong scaling), negatives
+        all-gathered over NCCL.
+  cfg2: N=4096 pairs, D=128, bf16 (configs[1]); also always reported inside the cfg4 line under "cfg2".
+Rank 0 prints ONE JSON line.  `value` = device-timed whole-job throughput with inputs resident in HBM;
+`e2e` = the same metric through the host-buffer C-ABI / public API with H2D + D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "cfg4": dict(n=32768, d=256, T=0.1, name="cfg4: fused cross-modal InfoNCE fwd+bwd, global batch 32768 x dim 256, bf16"),
+    "cfg2": dict(n=4096, d=128, T=0.1, name="cfg2: fused cross-modal InfoNCE fwd+bwd, batch 4096 x dim 128, bf16"),
+}
+SEED = 3407
+KERNELS_PER_STEP = 7   # l2norm_fwd, infonce_fwd, finalize, loss, bwd_prep, infonce_bwd, l2norm_bwd
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops"]), tflops_sustained=float(p.get("bf16_tflops_sustained", 0)),
+                    hbm=float(p["hbm_gbs"]), source="MEASURED_PEAKS.json (of measured)")
+    except Exception:
+        return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback (of fallback)")
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (pynvml; nvidia-smi as a fallback)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            mask = get(h)
+            for bit, name in names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            time.sleep(0.02)
+
+    def __enter__(self):
+        def run():
+            try:
+                self._loop_nvml()
+            except Exception as e:  # pragma: no cover
+                self.reasons.add(f"sampler_error:{type(e).__name__}")
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        busy = s[len(s) // 2:] if s else []
+        return {"sm_mhz": (statistics.median(busy) if busy else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    if n_gpus != world and rank == 0:
+        print(f"[bench] note: --gpus {n_gpus} but WORLD_SIZE={world}; using {world} rank(s)", file=sys.stderr)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x: float, world: int) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def synth(n_global, d, rank, world, device):
+    """p1, p2 ~ N(0,1) (the projector ends in an affine-free BatchNorm, simclr.py:26), bf16, this rank's pairs."""
+    n_local = n_global // world
+    g = torch.Generator(device="cpu").manual_seed(SEED + rank)
+    p1 = torch.randn(n_local, d, generator=g).bfloat16()
+    p2 = torch.randn(n_local, d, generator=g).bfloat16()
+    return p1, p2
+
+
+def time_device(sm3, p1, p2, T, group, world, steps, warmup, flush):
+    """K steps of the public op on HBM-resident inputs; per-stage CUDA events on the launching stream."""
+    from skin_sm3_b200 import functional as F3
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda().requires_grad_(True)
+    marks = []
+
+    def mark(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()                      # torch's current stream == the stream the kernels launch on
+        marks.append((name, ev))
+
+    def step():
+        a.grad = b.grad = None
+        loss = sm3.fused_infonce(a, b, T, precision="bf16", group=group)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    barrier(world)
+    per_step, stage_ms, loss = [], {}, None
+    F3._PROFILE = mark
+    try:
+        for _ in range(steps):
+            if flush is not None:
+                flush.add_(1.0)          # > L2 (126 MB) write between timed iterations; not timed
+            marks.clear()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = step()
+            e1.record()
+            e1.synchronize()
+            per_step.append(e0.elapsed_time(e1))
+            for (n0, ev0), (n1, ev1) in zip(marks[:-1], marks[1:]):
+                stage_ms.setdefault(n1, []).append(ev0.elapsed_time(ev1))
+    finally:
+        F3._PROFILE = None
+    barrier(world)
+    total_ms = max_over_ranks(sum(per_step), world)
+    stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+    return total_ms, stage_avg, float(loss.item())
+
+
+def time_e2e(sm3, p1, p2, T, group, world, steps, warmup):
+    """Same metric end to end: pinned host buffers -> H2D -> fused fwd+bwd -> D2H of loss and both gradients."""
+    n_local, d = p1.shape
+    hp1, hp2 = p1.pin_memory(), p2.pin_memory()
+    if world == 1:
+        host = sm3.HostInfoNCE(n_local, d, torch.bfloat16, sm3.ALGO_AUTO)     # the C-ABI host entry point
+        fn = lambda: host(hp1, hp2, T)                                         # noqa: E731  (synchronises inside)
+        h2d, d2h = host.h2d_bytes, host.d2h_bytes
+    else:
+        og1 = torch.empty_like(hp1).pin_memory(); og2 = torch.empty_like(hp2).pin_memory()
+        ol = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def fn():
+            a = hp1.cuda(non_blocking=True).requires_grad_(True)
+            b = hp2.cuda(non_blocking=True).requires_grad_(True)
+            loss = sm3.fused_infonce(a, b, T, precision="bf16", group=group)
+            loss.backward()
+            ol.copy_(loss.detach().reshape(1), non_blocking=True)
+            og1.copy_(a.grad, non_blocking=True); og2.copy_(b.grad, non_blocking=True)
+            torch.cuda.synchronize()
+        h2d = 2 * n_local * d * 2
+        d2h = 4 + h2d
+    for _ in range(warmup):
+        fn()
+    barrier(world)
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record(); e1.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier(world)
+    ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms), world)
+    return ms, h2d, d2h
+
+
+def cpu_reference(n, d, T, budget_s=20.0, max_reps=8):
+    """The reference's materialising CPU path (oracle/ref_port.py, an op-for-op torch port pinned to the real
+    reference by tests/test_oracle_golden.py) on the host cores.  Bounded sample -> pairs/s."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(SEED)
+    p1 = torch.randn(n, d, generator=g)
+    p2 = torch.randn(n, d, generator=g)
+    m = 2 * n
+    full = m * m * 4 * 8 < 24e9                    # ~8 live [M,M] fp32 temporaries must fit comfortably
+    if full:
+        fn = lambda: ref_port.port_infonce_step(p1, p2, T)           # noqa: E731
+        scale, sample = 1.0, f"full step N={n} D={d} fp32 (reference op sequence, {cores} threads)"
+    else:
+        rows = 512
+        fn = lambda: ref_port.port_infonce_step_rowblock(p1, p2, T, 1024, rows)   # noqa: E731
+        scale = m / rows
+        sample = (f"row block of {rows}/{m} logits rows x all {m} columns of N={n} D={d} fp32 "
+                  f"(full [M,M] step needs ~{m * m * 4 * 6 / 1e9:.0f} GB); time scaled x{scale:.0f}")
+    fn()
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_reps and (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times) * scale
+    return dict(value=n / t, unit="pairs/s", cores=cores, kind="port", sample=sample, ms_per_step=t * 1e3,
+                reps=len(times))
+
+
+def heads_probe(sm3, pk):
+    """Multi-label head losses (K4 8-head CE, K5 BCE): latency at the reference size and HBM GB/s at a
+    bandwidth-sized batch."""
+    out = {}
+    for name, B in (("b512", 512), ("b4M", 1 << 22)):
+        x = torch.randn(B, 24, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        y = torch.stack([torch.randint(0, c, (B,), device="cuda") for c in sm3.NUM_CLASSES], 1)
+        t = torch.nn.functional.one_hot(y[:, 0], 24).to(torch.bfloat16)
+        for op, fn, nbytes in (("ce8", lambda: sm3.multihead_ce(x, y), B * 24 * 4 + B * 64 + 4),
+                               ("bce", lambda: sm3.bce_with_logits(x, t), B * 24 * 6)):
+            for _ in range(3):
+                fn()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out[f"{op}_{name}"] = {"us": round(ms * 1e3, 2), "GB/s": round(nbytes / ms / 1e6, 1),
+                                   "frac_hbm": round(nbytes / ms / 1e6 / pk["hbm"], 3)}
+    return out
+
+
+def run_ours(args):
+    import skin_sm3_b200 as sm3
+    world, rank, local = dist_setup(args.gpus)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        group = dist.group.WORLD
+    wl = WORKLOADS[args.workload]
+    n, d, T = wl["n"], wl["d"], wl["T"]
+    assert n % world == 0
+    pk = peaks()
+    p1, p2 = synth(n, d, rank, world, "cuda")
+    flush = torch.zeros(64 * 1024 * 1024, device="cuda")            # 256 MB > 126 MB L2
+    with ClockSampler(local) as clk:
+        total_ms, stages, loss = time_device(sm3, p1, p2, T, group, world, args.steps, args.warmup, flush)
+    e2e_ms, h2d, d2h = time_e2e(sm3, p1, p2, T, group, world, args.steps, args.warmup)
+    ms_step = total_ms / args.steps
+    m_cols, m_rows = 2 * n, 2 * n // world
+    flops_bwd = 4.0 * m_rows * m_cols * d
+    flops_fwd = 2.0 * m_rows * m_cols * d
+    line = {
+        "metric": "contrastive pairs/sec (fwd+bwd)", "value": n / (ms_step * 1e-3), "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["name"], "global_pairs": n, "rows_per_rank": m_rows, "dim": d, "temperature": T,
+                   "terms": 1, "sharding": f"row-block x{world}, all-gathered negatives" if world > 1 else "single GPU",
+                   "l2": "256 MB flush write between timed steps (inputs are L2-sized by design)"},
+        "loss": loss,
+        "e2e": {"value": n / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "api": "sm3_infonce_host (C ABI, pinned host buffers)" if world == 1 else
+                       "skin_sm3_b200.fused_infonce(group=WORLD) + pinned H2D/D2H"},
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "stages_ms": {k: round(v, 4) for k, v in stages.items()},
+        "clocks": clk.summary(),
+    }
+    t_bwd = stages.get("stats_bwd")
+    t_fwd = stages.get("stats_fwd")
+    if t_bwd:
+        ach = flops_bwd / (t_bwd * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "infonce_tc_bwd_kernel (K3; includes its 1-block prep kernel)",
+                            "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                            "traffic": None, "peak_source": pk["source"] + ", burst bf16",
+                            "flops_per_launch": flops_bwd}
+    if t_fwd:
+        ach = flops_fwd / (t_fwd * 1e-3) / 1e12
+        line["roofline_fwd"] = {"bound": "tensor", "kernel": "infonce_tc_fwd_kernel (K2; includes the finalize kernel)",
+                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
+    line["step_tc_frac"] = (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12 / pk["tflops"]
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_reference(n, d, T)
+        if args.workload != "cfg2":     # configs[1] rides along in the same line
+            w2 = WORKLOADS["cfg2"]
+            q1, q2 = synth(w2["n"], w2["d"], 0, 1, "cuda")
+            ms2, st2, _ = time_device(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup, flush)
+            e2, _, _ = time_e2e(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup)
+            f2 = 6.0 * (2 * w2["n"]) ** 2 * w2["d"]
+            line["cfg2"] = {"workload": w2["name"], "value": w2["n"] / (ms2 / args.steps * 1e-3), "unit": "pairs/s",
+                            "ms_per_step": ms2 / args.steps, "e2e_value": w2["n"] / (e2 / args.steps * 1e-3),
+                            "step_tc_frac": f2 / (ms2 / args.steps * 1e-3) / 1e12 / pk["tflops"],
+                            "stages_ms": {k: round(v, 4) for k, v in st2.items()},
+                            "cpu_baseline": cpu_reference(w2["n"], w2["d"], w2["T"], budget_s=12.0, max_reps=4)}
+        try:
+            line["heads"] = heads_probe(sm3, pk)
+        except Exception as e:   # the head probe must never take the headline down
+            line["heads"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (op-for-op port in oracle/ref_port.py;
+    the Python reference itself cannot travel to the GPU box) on all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    n, d, T = wl["n"], wl["d"], wl["T"]
+    reps = max(1, args.steps)
+    r = cpu_reference(n, d, T, budget_s=60.0, max_reps=min(reps, 8))
+    line = {
+        "impl": "reference", "metric": "contrastive pairs/sec (fwd+bwd)", "value": r["value"], "unit": "pairs/s",
+        "n_gpus": world, "steps": r["reps"], "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "global_pairs": n, "dim": d, "temperature": T, "terms": 1,
+                   "device": "host CPU"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+/*
+ * sm3_b200.h -- C ABI of the B200-native SM3 contrastive hot path (libsm3_b200.so).
+ *
+ * Drop-in boundary for the reference's loss path.  The reference (Dylan-H-Wang/skin-sm3) is pure
+ * Python/PyTorch; the entry points below are what its modules bind to through ctypes (see
+ * INTEGRATION.md for the binding stub).  Each function cites the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless the name ends in _host;
+ *   - tensors are contiguous row-major; rows 16-byte aligned for the vectorised paths
+ *     (unaligned / ragged shapes take a scalar path inside the same kernels, never the CPU);
+ *   - the caller owns every buffer including the workspace (size from the *_workspace_bytes query);
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises the device;
+ *   - return 0 on success, a negative SM3_ERR_* otherwise; text via sm3_last_error() (thread local);
+ *   - no C++ exceptions cross this boundary; functions are re-entrant (autograd calls backward from
+ *     a worker thread).
+ */
+#ifndef SM3_B200_H_
+#define SM3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SM3_ABI_VERSION 1
+
+/* dtype codes */
+#define SM3_F32 0
+#define SM3_F16 1
+#define SM3_BF16 2
+
+/* error codes */
+#define SM3_OK 0
+#define SM3_ERR_SHAPE (-1)     /* bad shape / alignment / null pointer            */
+#define SM3_ERR_DTYPE (-2)     /* unsupported dtype or embedding width for `algo` */
+#define SM3_ERR_CUDA (-3)      /* CUDA runtime / driver error (see last_error)    */
+#define SM3_ERR_WORKSPACE (-4) /* workspace too small                             */
+
+/* algorithm selector for the similarity kernels */
+#define SM3_ALGO_AUTO 0
+#define SM3_ALGO_SIMT 1 /* fp32 FMA path: exact-fp32 parity, any D <= 256, any dtype      */
+#define SM3_ALGO_TC 2   /* TMA + tcgen05/TMEM path: bf16 rows, D in {64,128,192,256}      */
+
+int sm3_version(void);
+const char* sm3_last_error(void);
+/* 1 if the current device is sm_100 class (tcgen05 path usable), 0 if not, <0 on error */
+int sm3_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  row L2 normalisation      replaces F.normalize(features, dim=1)
+ *                               src/models/simclr.py:62 (SimCLR.forward), :138 (V2), :294 (V3/V32)
+ * rows [0,rows_a) come from p_a, rows [rows_a, rows_a+rows_b) from p_b (the reference's
+ * torch.cat([proj1(f1), proj2(f2)]) simclr.py:293 without the copy); p_b may be NULL.
+ *   z[r]        = p[r] / max(||p[r]||_2, eps)         (stored as z_dtype)
+ *   inv_norm[r] = 1 / max(||p[r]||_2, eps)            (fp32)
+ * ---------------------------------------------------------------------------------------------- */
+int sm3_l2norm_fwd(const void* p_a, int64_t rows_a, const void* p_b, int64_t rows_b, int D, int p_dtype,
+                   void* z, int z_dtype, float* inv_norm, float eps, void* stream);
+
+/* backward of the above (autograd of simclr.py:294):
+ *   dz = scale * sum_{k<n_partials} dz_partials[k]      (fp32 [rows, D] each, partial stride = rows*D)
+ *   dp[r] = inv_norm[r] * (dz[r] - z[r] * <z[r], dz[r]>)     (rows on the eps clamp: inv_norm*dz)   */
+int sm3_l2norm_bwd(const float* dz_partials, int n_partials, float scale, const void* z, int z_dtype,
+                   const float* inv_norm, float eps, void* dp_a, int64_t rows_a, void* dp_b, int64_t rows_b,
+                   int D, int dp_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  fused similarity + InfoNCE statistics (never materialises the [M,M] logits)
+ *     replaces  matmul(features, features.T) -> mask/gather/cat -> /T      simclr.py:296-320
+ *     (= :64-88, :140-164) and the log-softmax half of nn.CrossEntropyLoss  backbone_train.py:531
+ *
+ * Row-block form (single GPU: n_local == n_global, pair_offset == 0, z_rows == z_cols):
+ *   z_cols : [2*n_global, D]  all normalised rows in the reference's order [all first views ; all second]
+ *   z_rows : [2*n_local , D]  this rank's rows  [first halves ; second halves]; local row l has global
+ *            index  g(l) = pair_offset + l            (l <  n_local)
+ *                          n_global + pair_offset + l - n_local   (l >= n_local)
+ * Outputs, one per local row i (global index g):
+ *   pos[i]     = <z_g, z_pos(g)> * inv_T,       pos(g) = (g + n_global) mod 2*n_global
+ *   neg_sum[i] = sum_{j not in {g, pos(g)}} exp((<z_g, z_j> - 1) * inv_T)        (shifted sum)
+ *   lse_neg[i] = inv_T + log(neg_sum[i])
+ * so that stock CE on logits [pos, lse_neg] with target 0 equals the reference's CE on [M, M-1].
+ * ---------------------------------------------------------------------------------------------- */
+size_t sm3_infonce_workspace_bytes(int n_local, int n_global, int D, int dtype, int algo, int backward);
+
+int sm3_infonce_fwd(const void* z_rows, const void* z_cols, int n_local, int pair_offset, int n_global, int D,
+                    int dtype, float inv_T, float* pos, float* lse_neg, float* neg_sum, void* workspace,
+                    size_t workspace_bytes, int algo, void* stream);
+
+/* K3  backward: d/dz_rows of  sum_i (g_pos_i * pos_i + g_lse_i * lse_neg_i)  over ALL global rows,
+ *     restricted to this rank's rows (S symmetric => row-local, no column reduce-scatter):
+ *       a_j   = g_lse_j / neg_sum_j
+ *       H_ij  = exp((s_ij - 1) inv_T) (a_i + a_j)   j not in {i, pos(i)} ;  H_{i,pos(i)} = g_pos_i + g_pos_pos(i)
+ *       dz_i  = inv_T * sum_j H_ij z_j
+ *     replaces the autograd backward of simclr.py:300-320 + CE (two GEMMs + index_put scatter).
+ *     *_rows arrays have 2*n_local entries, *_cols arrays 2*n_global (identical pointers on one GPU).
+ *     Output: dz_partials fp32 [n_partials, 2*n_local, D] inside the workspace; the call returns
+ *     n_partials (>=1) -- feed it to sm3_l2norm_bwd.  Negative return = error.                       */
+int sm3_infonce_bwd(const void* z_rows, const void* z_cols, int n_local, int pair_offset, int n_global, int D,
+                    int dtype, float inv_T, const float* g_pos_rows, const float* g_lse_rows,
+                    const float* neg_sum_rows, const float* g_pos_cols, const float* g_lse_cols,
+                    const float* neg_sum_cols, void* workspace, size_t workspace_bytes, int algo, void* stream);
+
+/* loss half of nn.CrossEntropyLoss()(logits, 0) on the sufficient statistics, fused with its own
+ * gradient (tools/backbone_train.py:101-121):
+ *   loss   = scale * sum_i softplus(lse_neg_i - pos_i)             (scale = weight / M_global)
+ *   g_lse_i = scale * sigmoid(lse_neg_i - pos_i) ;  g_pos_i = -g_lse_i
+ * `loss` is a device scalar; accumulate != 0 adds into it (several terms into one loss).           */
+int sm3_infonce_loss(const float* pos, const float* lse_neg, int64_t rows, float scale, float* loss,
+                     int accumulate, float* g_pos, float* g_lse, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  multi-head softmax cross-entropy, forward + backward in one launch
+ *     replaces the 8-head loops  tools/mlc_eval.py:159-162,235-238  tools/backbone_eval.py:102-105
+ *     tools/backbone_train.py:178-181  and  tools/mlc_train.py:255-261 (pred / T, ignore_index :381)
+ *   logits : [B, sum(class_counts)]   heads concatenated along dim 1 (n = 5,3,2,3,3,3,3,2 -> 24)
+ *   labels : [B, H] int64
+ *   loss   = (1/H) sum_h w_h * mean_{b: label != ignore} CE(logits_h[b] * inv_T, labels[b,h])
+ *   dlogits (may be NULL) = grad_scale * d loss / d logits, same dtype as logits.
+ *   class_counts_host / weights_host are HOST arrays of length H (weights may be NULL = all 1).
+ *   use_ignore_index == 0 promises no label equals ignore_index (single pass over the data).
+ * ---------------------------------------------------------------------------------------------- */
+size_t sm3_multihead_ce_workspace_bytes(int64_t B, int H);
+int sm3_multihead_ce(const void* logits, int dtype, const int64_t* labels, int64_t B, int H,
+                     const int* class_counts_host, const float* weights_host, float inv_T,
+                     int use_ignore_index, int64_t ignore_index, float* loss, void* dlogits, float grad_scale,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* K5  BCE-with-logits (multi-hot seven-point-checklist targets), forward + backward in one launch.
+ *     north_star-named; the reference contains no BCE => parity unpinned, oracle is
+ *     torch.nn.functional.binary_cross_entropy_with_logits(reduction="mean").
+ *   x, t : [B, C] (t in t_dtype: f32/f16/bf16) ; pos_weight: device fp32 [C] or NULL.            */
+size_t sm3_bce_workspace_bytes(int64_t B, int C);
+int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_dtype, const float* pos_weight, int64_t B,
+                   int C, float* loss, void* dx, float grad_scale, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N1  similarity top-k retrieval   replaces  sim = query @ bank.T ; sim.topk(k)
+ *     src/models/evaluator.py:61-63 (KNNOnlineEvaluator.predict)
+ *   vals [Bq, k] fp32 descending, idx [Bq, k] int64; ties broken towards the lower bank index.
+ *   exclude_self_offset >= 0 masks bank column (exclude_self_offset + q) for query q (retrieval
+ *   inside one batch: the reference's "non-self neighbour" test backbone_train.py:103-105); -1 = off.
+ * ---------------------------------------------------------------------------------------------- */
+int sm3_sim_topk(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype, int k,
+                 int64_t exclude_self_offset, float* vals, int64_t* idx, void* stream);
+
+/* Host-buffer convenience entry (the "plugin call" timed end to end by bench.py): copies p1/p2 from
+ * HOST memory, runs normalise -> K2 -> loss -> K3 -> normalise-backward on `stream`, copies the loss
+ * and both gradients back to HOST memory and synchronises the stream.  All device scratch comes from
+ * `device_scratch` (size from sm3_infonce_host_scratch_bytes).  p/dp dtype = io_dtype.              */
+size_t sm3_infonce_host_scratch_bytes(int n_pairs, int D, int io_dtype, int algo);
+int sm3_infonce_host(const void* p1_host, const void* p2_host, int n_pairs, int D, int io_dtype,
+                     float temperature, float* loss_host, void* dp1_host, void* dp2_host, void* device_scratch,
+                     size_t scratch_bytes, int algo, void* stream);
+
+/* debug / bring-up: single-tile tcgen05 probe used by tests/test_umma_probe.py (not a product path).
+ *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */
+int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SM3_B200_H_ */

@@ -1,0 +1,202 @@
+// extern "C" surface of libsm3_b200.so (see include/sm3_b200.h).  Argument validation, algorithm choice
+// (tcgen05 vs fp32-FMA kernels -- both CUDA, there is no CPU path), and the host-buffer convenience entry.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sm3 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static int pick_algo(const InfoNceProblem& pb, int algo) {
+  if (algo == SM3_ALGO_AUTO) return infonce_tc_supported(pb) ? SM3_ALGO_TC : SM3_ALGO_SIMT;
+  return algo;
+}
+
+static int check_problem(const InfoNceProblem& pb) {
+  SM3_REQUIRE(pb.z_rows && pb.z_cols, SM3_ERR_SHAPE, "infonce: null embedding pointer");
+  SM3_REQUIRE(dtype_ok(pb.dtype), SM3_ERR_DTYPE, "infonce: bad dtype %d", pb.dtype);
+  SM3_REQUIRE(pb.inv_T > 0.f && pb.inv_T * 2.0f * 1.4426950f < 240.f, SM3_ERR_SHAPE,
+              "infonce: temperature %g outside the constant-shift range (need 1/T < 83)", 1.0 / pb.inv_T);
+  return SM3_OK;
+}
+
+}  // namespace sm3
+
+using namespace sm3;
+
+extern "C" int sm3_version(void) { return SM3_ABI_VERSION; }
+extern "C" const char* sm3_last_error(void) { return get_error(); }
+
+extern "C" int sm3_device_supported(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("no usable CUDA device");
+    return SM3_ERR_CUDA;
+  }
+  return prop.major == 10 ? 1 : 0;
+}
+
+extern "C" int sm3_l2norm_fwd(const void* p_a, int64_t rows_a, const void* p_b, int64_t rows_b, int D, int p_dtype,
+                              void* z, int z_dtype, float* inv_norm, float eps, void* stream) {
+  SM3_REQUIRE(p_a && z && inv_norm, SM3_ERR_SHAPE, "l2norm_fwd: null pointer");
+  SM3_REQUIRE(rows_a >= 0 && rows_b >= 0 && (rows_b == 0 || p_b), SM3_ERR_SHAPE, "l2norm_fwd: bad row counts");
+  SM3_REQUIRE(D >= 1, SM3_ERR_SHAPE, "l2norm_fwd: D=%d", D);
+  SM3_REQUIRE(dtype_ok(p_dtype) && dtype_ok(z_dtype), SM3_ERR_DTYPE, "l2norm_fwd: bad dtype");
+  SM3_REQUIRE(eps > 0.f, SM3_ERR_SHAPE, "l2norm_fwd: eps must be > 0");
+  return l2norm_fwd_launch(p_a, rows_a, p_b, rows_b, D, p_dtype, z, z_dtype, inv_norm, eps, (cudaStream_t)stream);
+}
+
+extern "C" int sm3_l2norm_bwd(const float* dz_partials, int n_partials, float scale, const void* z, int z_dtype,
+                              const float* inv_norm, float eps, void* dp_a, int64_t rows_a, void* dp_b,
+                              int64_t rows_b, int D, int dp_dtype, void* stream) {
+  SM3_REQUIRE(dz_partials && z && inv_norm && dp_a, SM3_ERR_SHAPE, "l2norm_bwd: null pointer");
+  SM3_REQUIRE(n_partials >= 1, SM3_ERR_SHAPE, "l2norm_bwd: n_partials=%d", n_partials);
+  SM3_REQUIRE(rows_a >= 0 && rows_b >= 0 && (rows_b == 0 || dp_b), SM3_ERR_SHAPE, "l2norm_bwd: bad row counts");
+  SM3_REQUIRE(dtype_ok(z_dtype) && dtype_ok(dp_dtype), SM3_ERR_DTYPE, "l2norm_bwd: bad dtype");
+  return l2norm_bwd_launch(dz_partials, n_partials, scale, z, z_dtype, inv_norm, eps, dp_a, rows_a, dp_b, rows_b, D,
+                           dp_dtype, (cudaStream_t)stream);
+}
+
+extern "C" size_t sm3_infonce_workspace_bytes(int n_local, int n_global, int D, int dtype, int algo, int backward) {
+  InfoNceProblem pb{nullptr, nullptr, n_local, 0, n_global, D, dtype, 1.0f};
+  // AUTO must cover whichever kernel the call ends up using
+  size_t a = 0, b = 0;
+  if (algo != SM3_ALGO_TC) a = infonce_simt_workspace(pb, backward);
+  if (algo != SM3_ALGO_SIMT) b = infonce_tc_workspace(pb, backward);
+  return a > b ? a : b;
+}
+
+extern "C" int sm3_infonce_fwd(const void* z_rows, const void* z_cols, int n_local, int pair_offset, int n_global,
+                               int D, int dtype, float inv_T, float* pos, float* lse_neg, float* neg_sum,
+                               void* workspace, size_t workspace_bytes, int algo, void* stream) {
+  InfoNceProblem pb{z_rows, z_cols, n_local, pair_offset, n_global, D, dtype, inv_T};
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  SM3_REQUIRE(pos && lse_neg && neg_sum && workspace, SM3_ERR_SHAPE, "infonce_fwd: null output/workspace");
+  const int a = pick_algo(pb, algo);
+  if (a == SM3_ALGO_TC) {
+    SM3_REQUIRE(infonce_tc_supported(pb), SM3_ERR_DTYPE,
+                "infonce_fwd: tcgen05 path needs bf16 rows, D in {64,128,192,256}, 16-byte aligned (got dtype=%d D=%d)",
+                dtype, D);
+    return infonce_tc_fwd(pb, pos, lse_neg, neg_sum, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  SM3_REQUIRE(a == SM3_ALGO_SIMT, SM3_ERR_SHAPE, "infonce_fwd: unknown algo %d", algo);
+  return infonce_simt_fwd(pb, pos, lse_neg, neg_sum, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sm3_infonce_bwd(const void* z_rows, const void* z_cols, int n_local, int pair_offset, int n_global,
+                               int D, int dtype, float inv_T, const float* g_pos_rows, const float* g_lse_rows,
+                               const float* neg_sum_rows, const float* g_pos_cols, const float* g_lse_cols,
+                               const float* neg_sum_cols, void* workspace, size_t workspace_bytes, int algo,
+                               void* stream) {
+  InfoNceProblem pb{z_rows, z_cols, n_local, pair_offset, n_global, D, dtype, inv_T};
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  SM3_REQUIRE(g_pos_rows && g_lse_rows && neg_sum_rows && g_pos_cols && g_lse_cols && neg_sum_cols && workspace,
+              SM3_ERR_SHAPE, "infonce_bwd: null pointer");
+  const int a = pick_algo(pb, algo);
+  if (a == SM3_ALGO_TC) {
+    SM3_REQUIRE(infonce_tc_supported(pb), SM3_ERR_DTYPE,
+                "infonce_bwd: tcgen05 path needs bf16 rows, D in {64,128,192,256}, 16-byte aligned (got dtype=%d D=%d)",
+                dtype, D);
+    return infonce_tc_bwd(pb, g_pos_rows, g_lse_rows, neg_sum_rows, g_pos_cols, g_lse_cols, neg_sum_cols, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+  }
+  SM3_REQUIRE(a == SM3_ALGO_SIMT, SM3_ERR_SHAPE, "infonce_bwd: unknown algo %d", algo);
+  return infonce_simt_bwd(pb, g_pos_rows, g_lse_rows, neg_sum_rows, g_pos_cols, g_lse_cols, neg_sum_cols, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer entry: H2D -> normalise -> K2 -> loss -> K3 -> normalise-backward -> D2H, one stream.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct HostPlan {
+  size_t p1, p2, z, inv, pos, lse, nsum, gpos, glse, loss, dp1, dp2, ws, ws_bytes, total;
+  int z_dtype, algo;
+};
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+HostPlan plan_host(int n, int D, int io_dtype, int algo) {
+  HostPlan h{};
+  const size_t m = 2 * (size_t)n;
+  InfoNceProblem probe{(const void*)256, (const void*)256, n, 0, n, D, SM3_BF16, 10.f};
+  int a = algo;
+  if (a == SM3_ALGO_AUTO) a = infonce_tc_supported(probe) ? SM3_ALGO_TC : SM3_ALGO_SIMT;
+  h.algo = a;
+  h.z_dtype = (a == SM3_ALGO_TC) ? SM3_BF16 : SM3_F32;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  h.p1 = take((size_t)n * D * dtype_size(io_dtype));
+  h.p2 = take((size_t)n * D * dtype_size(io_dtype));
+  h.z = take(m * D * dtype_size(h.z_dtype));
+  h.inv = take(m * 4); h.pos = take(m * 4); h.lse = take(m * 4); h.nsum = take(m * 4);
+  h.gpos = take(m * 4); h.glse = take(m * 4); h.loss = take(256);
+  h.dp1 = take((size_t)n * D * dtype_size(io_dtype));
+  h.dp2 = take((size_t)n * D * dtype_size(io_dtype));
+  InfoNceProblem pb{nullptr, nullptr, n, 0, n, D, h.z_dtype, 1.f};
+  const size_t w0 = (a == SM3_ALGO_TC) ? infonce_tc_workspace(pb, 0) : infonce_simt_workspace(pb, 0);
+  const size_t w1 = (a == SM3_ALGO_TC) ? infonce_tc_workspace(pb, 1) : infonce_simt_workspace(pb, 1);
+  h.ws_bytes = w0 > w1 ? w0 : w1;
+  h.ws = take(h.ws_bytes);
+  h.total = o;
+  return h;
+}
+}  // namespace
+
+extern "C" size_t sm3_infonce_host_scratch_bytes(int n_pairs, int D, int io_dtype, int algo) {
+  if (n_pairs < 1 || D < 1 || !dtype_ok(io_dtype)) return 0;
+  return plan_host(n_pairs, D, io_dtype, algo).total;
+}
+
+extern "C" int sm3_infonce_host(const void* p1_host, const void* p2_host, int n_pairs, int D, int io_dtype,
+                                float temperature, float* loss_host, void* dp1_host, void* dp2_host,
+                                void* device_scratch, size_t scratch_bytes, int algo, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(p1_host && p2_host && loss_host && device_scratch, SM3_ERR_SHAPE, "infonce_host: null pointer");
+  SM3_REQUIRE(n_pairs >= 1 && D >= 1 && dtype_ok(io_dtype), SM3_ERR_SHAPE, "infonce_host: bad shape/dtype");
+  SM3_REQUIRE(temperature > 0.f, SM3_ERR_SHAPE, "infonce_host: temperature must be > 0");
+  const HostPlan h = plan_host(n_pairs, D, io_dtype, algo);
+  SM3_REQUIRE(scratch_bytes >= h.total, SM3_ERR_WORKSPACE, "infonce_host: scratch %zu < %zu", scratch_bytes, h.total);
+  char* base = (char*)device_scratch;
+  const size_t in_bytes = (size_t)n_pairs * D * dtype_size(io_dtype);
+  const int64_t n = n_pairs, m = 2 * n;
+  const float inv_T = 1.0f / temperature;
+  SM3_CHECK_CUDA(cudaMemcpyAsync(base + h.p1, p1_host, in_bytes, cudaMemcpyHostToDevice, st));
+  SM3_CHECK_CUDA(cudaMemcpyAsync(base + h.p2, p2_host, in_bytes, cudaMemcpyHostToDevice, st));
+  int rc = sm3_l2norm_fwd(base + h.p1, n, base + h.p2, n, D, io_dtype, base + h.z, h.z_dtype, (float*)(base + h.inv),
+                          1e-12f, st);
+  if (rc) return rc;
+  rc = sm3_infonce_fwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T, (float*)(base + h.pos),
+                       (float*)(base + h.lse), (float*)(base + h.nsum), base + h.ws, h.ws_bytes, h.algo, st);
+  if (rc) return rc;
+  rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, 1.0f / (float)m, (float*)(base + h.loss), 0,
+                        (float*)(base + h.gpos), (float*)(base + h.glse), st);
+  if (rc) return rc;
+  SM3_CHECK_CUDA(cudaMemcpyAsync(loss_host, base + h.loss, 4, cudaMemcpyDeviceToHost, st));
+  if (dp1_host && dp2_host) {
+    const int np = sm3_infonce_bwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T,
+                                   (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
+                                   (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
+                                   base + h.ws, h.ws_bytes, h.algo, st);
+    if (np < 0) return np;
+    rc = sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
+                        base + h.dp1, n, base + h.dp2, n, D, io_dtype, st);
+    if (rc) return rc;
+    SM3_CHECK_CUDA(cudaMemcpyAsync(dp1_host, base + h.dp1, in_bytes, cudaMemcpyDeviceToHost, st));
+    SM3_CHECK_CUDA(cudaMemcpyAsync(dp2_host, base + h.dp2, in_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  SM3_CHECK_CUDA(cudaStreamSynchronize(st));
+  return SM3_OK;
+}

@@ -1,0 +1,171 @@
+// Shared helpers for the sm_100a kernels of libsm3_b200 (error state, dtype load/store, reductions).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sm3_b200.h"
+
+namespace sm3 {
+
+// ---- error state (thread local; no exceptions cross the C ABI) -------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SM3_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::sm3::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SM3_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define SM3_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::sm3::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+inline int dtype_size(int dt) { return dt == SM3_F32 ? 4 : 2; }
+inline bool dtype_ok(int dt) { return dt == SM3_F32 || dt == SM3_F16 || dt == SM3_BF16; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- scalar dtype conversion ------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 128-bit vector access: VecIO<T>::N elements per 16-byte transaction ---------------------------
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&o)[4]) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&o)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+};
+template <> struct VecIO<__half> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __half* p, float (&o)[8]) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+  __device__ static __forceinline__ void store(__half* p, const float (&o)[8]) {
+    uint4 v;
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+template <> struct VecIO<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&o)[8]) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (result valid in every thread)
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem32[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (lane < nw) ? smem32[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// global row index of local row l (see sm3_b200.h, K2) and its positive partner
+__device__ __forceinline__ int global_row(int l, int n_local, int pair_offset, int n_global) {
+  return l < n_local ? pair_offset + l : n_global + pair_offset + (l - n_local);
+}
+__device__ __forceinline__ int positive_of(int g, int n_global) {
+  return g < n_global ? g + n_global : g - n_global;
+}
+
+// dtype dispatch helper for host code
+#define SM3_DISPATCH_DTYPE(dt, T, ...)                       \
+  do {                                                       \
+    if ((dt) == SM3_F32) { using T = float; __VA_ARGS__; }   \
+    else if ((dt) == SM3_F16) { using T = __half; __VA_ARGS__; } \
+    else { using T = __nv_bfloat16; __VA_ARGS__; }           \
+  } while (0)
+
+// ---- kernel launch entry points implemented in the .cu files (host side) ---------------------------
+int l2norm_fwd_launch(const void* p_a, int64_t rows_a, const void* p_b, int64_t rows_b, int D, int p_dtype, void* z,
+                      int z_dtype, float* inv_norm, float eps, cudaStream_t st);
+int l2norm_bwd_launch(const float* dz_partials, int n_partials, float scale, const void* z, int z_dtype,
+                      const float* inv_norm, float eps, void* dp_a, int64_t rows_a, void* dp_b, int64_t rows_b, int D,
+                      int dp_dtype, cudaStream_t st);
+
+struct InfoNceProblem {
+  const void* z_rows;
+  const void* z_cols;
+  int n_local, pair_offset, n_global, D, dtype;
+  float inv_T;
+};
+size_t infonce_simt_workspace(const InfoNceProblem& pb, int backward);
+int infonce_simt_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+int infonce_simt_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* glse_r, const float* nsum_r,
+                     const float* gpos_c, const float* glse_c, const float* nsum_c, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+bool infonce_tc_supported(const InfoNceProblem& pb);
+size_t infonce_tc_workspace(const InfoNceProblem& pb, int backward);
+int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* glse_r, const float* nsum_r,
+                   const float* gpos_c, const float* glse_c, const float* nsum_c, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int infonce_finalize_launch(const float* partial_sums, int n_partials, int64_t rows, float inv_T, float* neg_sum,
+                            float* lse_neg, cudaStream_t st);
+int infonce_loss_launch(const float* pos, const float* lse_neg, int64_t rows, float scale, float* loss, int accumulate,
+                        float* g_pos, float* g_lse, cudaStream_t st);
+
+}  // namespace sm3

@@ -1,0 +1,387 @@
+// K4 multi-head softmax cross-entropy and K5 BCE-with-logits: forward + backward in one launch each,
+// coalesced 128-bit global access staged through shared memory, deterministic last-block reduction.
+// Also the two tiny per-row kernels that close the InfoNCE forward (partial-sum finalize, CE-on-statistics).
+//
+// K4 replaces the reference's 8-head loops: tools/mlc_eval.py:159-162, tools/backbone_eval.py:102-105,
+// tools/backbone_train.py:178-181, tools/mlc_train.py:255-261 (+ ignore_index=-100 at :381).
+// K5 has no reference counterpart; it mirrors torch's binary_cross_entropy_with_logits.
+#include "common.cuh"
+
+namespace sm3 {
+namespace {
+
+constexpr int kMaxHeads = 16;
+constexpr int kMaxClassesTotal = 64;
+constexpr int kHeadThreads = 256;
+
+struct HeadMeta {
+  int H, C;                    // heads, total classes
+  int offset[kMaxHeads + 1];   // class offset of each head
+  float weight[kMaxHeads];
+};
+
+// workspace layout (floats unless stated): [0] uint32 ticket | [16..16+H) valid counts | [64 ...) block partials
+constexpr int kWsCounts = 16;
+constexpr int kWsPartials = 64;
+
+__global__ void heads_count_kernel(const int64_t* __restrict__ labels, int64_t B, int H, int64_t ignore_index,
+                                   float* __restrict__ ws) {
+  // one block; exact integer counts of labels != ignore_index per head
+  __shared__ int cnt[kMaxHeads];
+  if (threadIdx.x < kMaxHeads) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int local[kMaxHeads];
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) local[h] = 0;
+  for (int64_t i = threadIdx.x; i < B * H; i += blockDim.x) {
+    const int h = (int)(i % H);
+    const bool v = __ldg(labels + i) != ignore_index;
+#pragma unroll
+    for (int k = 0; k < kMaxHeads; ++k) local[k] += (k == h && v) ? 1 : 0;
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    int v = local[h];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && h < H && v) atomicAdd(&cnt[h], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < H) ws[kWsCounts + threadIdx.x] = (float)cnt[threadIdx.x];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kHeadThreads)
+multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels, int64_t B, HeadMeta meta,
+                    float inv_T, int use_ignore, int64_t ignore_index, float* __restrict__ loss_out,
+                    T* __restrict__ dlogits, float grad_scale, float* __restrict__ ws) {
+  extern __shared__ float smem[];
+  const int C = meta.C, H = meta.H;
+  const int ldx = C + 1;                      // +1 float: conflict-free row-per-thread access
+  float* xs = smem;                           // [kHeadThreads][C+1]
+  int* ys = reinterpret_cast<int*>(smem + kHeadThreads * ldx);  // [kHeadThreads][H+1]
+  float* red = reinterpret_cast<float*>(ys + kHeadThreads * (H + 1));  // [8 warps][H]
+  __shared__ bool is_last;
+
+  const int64_t row0 = (int64_t)blockIdx.x * kHeadThreads;
+  const int rows_here = (int)min((int64_t)kHeadThreads, B - row0);
+  const int tid = threadIdx.x;
+
+  // ---- coalesced stage-in ----
+  const int64_t n_el = (int64_t)rows_here * C;
+  const T* src = logits + row0 * C;
+  constexpr int V = VecIO<T>::N;
+  const bool vec_ok = (((uintptr_t)src & 15u) == 0);
+  const int64_t n_vec = vec_ok ? n_el / V : 0;
+  for (int64_t v = tid; v < n_vec; v += kHeadThreads) {
+    float t[V];
+    VecIO<T>::load(src + v * V, t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int e = (int)(v * V) + i;
+      xs[(e / C) * ldx + (e % C)] = t[i];
+    }
+  }
+  for (int64_t e = n_vec * V + tid; e < n_el; e += kHeadThreads) xs[(e / C) * ldx + (e % C)] = to_f32(src[e]);
+  const int64_t* lsrc = labels + row0 * H;
+  for (int e = tid; e < rows_here * H; e += kHeadThreads) {
+    const int64_t y = __ldg(lsrc + e);
+    const int h = e % H;
+    const int nc = meta.offset[h + 1] - meta.offset[h];
+    int yi;
+    if (use_ignore && y == ignore_index) yi = -1;
+    else yi = (y >= 0 && y < nc) ? (int)y : -2;   // -2: out of range -> contributes NaN like a device assert would
+    ys[(e / H) * (H + 1) + h] = yi;
+  }
+  __syncthreads();
+
+  // ---- one row per thread ----
+  float head_loss[kMaxHeads];
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) head_loss[h] = 0.f;
+  if (tid < rows_here) {
+    float* x = xs + tid * ldx;
+    const int* y = ys + tid * (H + 1);
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+      if (h < H) {
+        const int o = meta.offset[h], nc = meta.offset[h + 1] - o;
+        float mx = -INFINITY;
+        for (int c = 0; c < nc; ++c) mx = fmaxf(mx, x[o + c] * inv_T);
+        float se = 0.f;
+        for (int c = 0; c < nc; ++c) se += __expf(x[o + c] * inv_T - mx);
+        const float lse = mx + __logf(se);
+        const int yy = y[h];
+        const bool valid = yy >= 0;
+        float cnt = use_ignore ? ws[kWsCounts + h] : (float)B;
+        const float gs = (valid && cnt > 0.f) ? grad_scale * meta.weight[h] * inv_T / (cnt * (float)H) : 0.f;
+        if (valid) head_loss[h] = lse - x[o + yy] * inv_T;
+        if (yy == -2) head_loss[h] = NAN;
+        const float inv_se = 1.0f / se;
+        for (int c = 0; c < nc; ++c) {
+          const float p = __expf(x[o + c] * inv_T - mx) * inv_se;
+          x[o + c] = (p - (c == yy ? 1.f : 0.f)) * gs;
+        }
+      }
+    }
+  }
+
+  // ---- block reduction of the per-head loss sums ----
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    if (h < H) {
+      const float v = warp_sum(head_loss[h]);
+      if (lane == 0) red[warp * H + h] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < H) {
+    float s = 0.f;
+    for (int w = 0; w < kHeadThreads / 32; ++w) s += red[w * H + tid];
+    ws[kWsPartials + (int64_t)blockIdx.x * H + tid] = s;
+  }
+
+  // ---- coalesced stage-out of the gradient ----
+  if (dlogits != nullptr) {
+    T* dst = dlogits + row0 * C;
+    const bool vo = (((uintptr_t)dst & 15u) == 0);
+    const int64_t nv = vo ? n_el / V : 0;
+    for (int64_t v = tid; v < nv; v += kHeadThreads) {
+      float t[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int e = (int)(v * V) + i;
+        t[i] = xs[(e / C) * ldx + (e % C)];
+      }
+      VecIO<T>::store(dst + v * V, t);
+    }
+    for (int64_t e = nv * V + tid; e < n_el; e += kHeadThreads) dst[e] = from_f32<T>(xs[(e / C) * ldx + (e % C)]);
+  }
+
+  // ---- last block folds the partials in a fixed order (deterministic) ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float total = 0.f;
+    if (tid < H) {
+      float s = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ws + kWsPartials + (int64_t)b * H + tid);
+      const float cnt = use_ignore ? ws[kWsCounts + tid] : (float)B;
+      total = meta.weight[tid] * (s / cnt) / (float)H;   // cnt == 0 -> NaN, as torch's mean over nothing
+    }
+    if (tid < 32) {
+      total = warp_sum(total);    // H <= 16 < 32: every head lives in warp 0
+      if (tid == 0) { *loss_out = total; *reinterpret_cast<unsigned*>(ws) = 0u; }
+    }
+  }
+}
+
+// ---------------- K5: BCE with logits ----------------
+constexpr int kBceThreads = 256;
+
+template <typename TX, typename TT>
+__global__ void __launch_bounds__(kBceThreads)
+bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __restrict__ pos_weight, int64_t n,
+           int C, float inv_n, float* __restrict__ loss_out, TX* __restrict__ dx, float grad_scale,
+           float* __restrict__ ws, int vec_ok) {
+  __shared__ float red[32];
+  __shared__ bool is_last;
+  float acc = 0.f;
+  auto elem = [&](float xv, float tv, int64_t idx) -> float {
+    const float sp = fmaxf(-xv, 0.f) + log1pf(__expf(-fabsf(xv)));   // softplus(-x)
+    const float sig = 1.0f / (1.0f + __expf(-xv));
+    float lw = 1.f;
+    if (pos_weight != nullptr) lw = 1.f + (__ldg(pos_weight + (idx % C)) - 1.f) * tv;
+    acc += (1.f - tv) * xv + lw * sp;
+    return ((1.f - tv) - lw * (1.f - sig)) * inv_n * grad_scale;
+  };
+  const int64_t stride = (int64_t)gridDim.x * kBceThreads;
+  const int64_t gid = (int64_t)blockIdx.x * kBceThreads + threadIdx.x;
+  const int64_t n8 = vec_ok ? n / 8 : 0;
+  for (int64_t v = gid; v < n8; v += stride) {
+    float xv[8], tv[8], g[8];
+    if constexpr (sizeof(TX) == 4) {
+      float a[4], b[4];
+      VecIO<float>::load((const float*)x + v * 8, a); VecIO<float>::load((const float*)x + v * 8 + 4, b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xv[i] = a[i]; xv[4 + i] = b[i]; }
+    } else { VecIO<TX>::load(x + v * 8, xv); }
+    if constexpr (sizeof(TT) == 4) {
+      float a[4], b[4];
+      VecIO<float>::load((const float*)t + v * 8, a); VecIO<float>::load((const float*)t + v * 8 + 4, b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { tv[i] = a[i]; tv[4 + i] = b[i]; }
+    } else { VecIO<TT>::load(t + v * 8, tv); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = elem(xv[i], tv[i], v * 8 + i);
+    if (dx != nullptr) {
+      if constexpr (sizeof(TX) == 4) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = g[i]; b[i] = g[4 + i]; }
+        VecIO<float>::store((float*)dx + v * 8, a); VecIO<float>::store((float*)dx + v * 8 + 4, b);
+      } else { VecIO<TX>::store(dx + v * 8, g); }
+    }
+  }
+  for (int64_t e = n8 * 8 + gid; e < n; e += stride) {
+    const float g = elem(to_f32(x[e]), to_f32(t[e]), e);
+    if (dx != nullptr) dx[e] = from_f32<TX>(g);
+  }
+  const float bs = block_sum(acc, red);
+  if (threadIdx.x == 0) ws[kWsPartials + blockIdx.x] = bs;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kBceThreads) s += __ldcg(ws + kWsPartials + b);
+    s = block_sum(s, red);   // fixed tree for a fixed grid => deterministic
+    if (threadIdx.x == 0) { *loss_out = s * inv_n; *reinterpret_cast<unsigned*>(ws) = 0u; }
+  }
+}
+
+// ---------------- InfoNCE tail kernels ----------------
+__global__ void infonce_finalize_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, float inv_T,
+                                        float* __restrict__ neg_sum, float* __restrict__ lse_neg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  float s = 0.f;
+  for (int k = 0; k < n_partials; ++k) s += partial[(int64_t)k * rows + i];
+  neg_sum[i] = s;
+  lse_neg[i] = inv_T + logf(s);     // s == 0 (no negatives, N == 1) -> -inf, CE([pos,-inf],0) = 0
+}
+
+__global__ void __launch_bounds__(1024)
+infonce_loss_kernel(const float* __restrict__ pos, const float* __restrict__ lse_neg, int64_t rows, float scale,
+                    float* __restrict__ loss, int accumulate, float* __restrict__ g_pos, float* __restrict__ g_lse) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) {
+    const float x = lse_neg[i] - pos[i];
+    const float sp = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));   // log(e^pos + e^lse) - pos
+    const float sig = 1.0f / (1.0f + expf(-x));
+    acc += sp;
+    if (g_lse != nullptr) g_lse[i] = scale * sig;
+    if (g_pos != nullptr) g_pos[i] = -scale * sig;
+  }
+  const float s = block_sum(acc, red);
+  if (threadIdx.x == 0) *loss = (accumulate ? *loss : 0.f) + s * scale;
+}
+
+}  // namespace
+
+int infonce_finalize_launch(const float* partial_sums, int n_partials, int64_t rows, float inv_T, float* neg_sum,
+                            float* lse_neg, cudaStream_t st) {
+  if (rows == 0) return SM3_OK;
+  infonce_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(partial_sums, n_partials, rows, inv_T,
+                                                                           neg_sum, lse_neg);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+int infonce_loss_launch(const float* pos, const float* lse_neg, int64_t rows, float scale, float* loss, int accumulate,
+                        float* g_pos, float* g_lse, cudaStream_t st) {
+  infonce_loss_kernel<<<1, 1024, 0, st>>>(pos, lse_neg, rows, scale, loss, accumulate, g_pos, g_lse);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+}  // namespace sm3
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace sm3;
+
+extern "C" size_t sm3_multihead_ce_workspace_bytes(int64_t B, int H) {
+  const int64_t blocks = (B + kHeadThreads - 1) / kHeadThreads;
+  return (size_t)(kWsPartials + blocks * (H > 0 ? H : 1)) * sizeof(float);
+}
+
+extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* labels, int64_t B, int H,
+                                const int* class_counts_host, const float* weights_host, float inv_T,
+                                int use_ignore_index, int64_t ignore_index, float* loss, void* dlogits,
+                                float grad_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(logits && labels && loss && workspace && class_counts_host, SM3_ERR_SHAPE, "multihead_ce: null pointer");
+  SM3_REQUIRE(dtype_ok(dtype), SM3_ERR_DTYPE, "multihead_ce: bad dtype %d", dtype);
+  SM3_REQUIRE(H >= 1 && H <= kMaxHeads, SM3_ERR_SHAPE, "multihead_ce: H=%d not in [1,%d]", H, kMaxHeads);
+  SM3_REQUIRE(B >= 1, SM3_ERR_SHAPE, "multihead_ce: empty batch");
+  HeadMeta meta;
+  meta.H = H;
+  meta.offset[0] = 0;
+  for (int h = 0; h < H; ++h) {
+    SM3_REQUIRE(class_counts_host[h] >= 1, SM3_ERR_SHAPE, "multihead_ce: head %d has %d classes", h, class_counts_host[h]);
+    meta.offset[h + 1] = meta.offset[h] + class_counts_host[h];
+    meta.weight[h] = weights_host ? weights_host[h] : 1.0f;
+  }
+  meta.C = meta.offset[H];
+  SM3_REQUIRE(meta.C <= kMaxClassesTotal, SM3_ERR_SHAPE, "multihead_ce: %d total classes > %d", meta.C, kMaxClassesTotal);
+  SM3_REQUIRE(workspace_bytes >= sm3_multihead_ce_workspace_bytes(B, H), SM3_ERR_WORKSPACE, "multihead_ce: workspace too small");
+  float* ws = (float*)workspace;
+  SM3_CHECK_CUDA(cudaMemsetAsync(ws, 0, kWsPartials * sizeof(float), st));
+  if (use_ignore_index) {
+    heads_count_kernel<<<1, 1024, 0, st>>>(labels, B, H, ignore_index, ws);
+    SM3_CHECK_CUDA(cudaGetLastError());
+  }
+  const unsigned grid = (unsigned)((B + kHeadThreads - 1) / kHeadThreads);
+  const size_t smem = (size_t)kHeadThreads * (meta.C + 1) * 4 + (size_t)kHeadThreads * (H + 1) * 4 + (kHeadThreads / 32) * H * 4;
+  SM3_DISPATCH_DTYPE(dtype, T, {
+    SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    multihead_ce_kernel<T><<<grid, kHeadThreads, smem, st>>>((const T*)logits, labels, B, meta, inv_T, use_ignore_index,
+                                                             ignore_index, loss, (T*)dlogits, grad_scale, ws);
+  });
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+static unsigned bce_grid(int64_t n) {
+  const int64_t want = (n / 8 + kBceThreads - 1) / kBceThreads + 1;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+extern "C" size_t sm3_bce_workspace_bytes(int64_t B, int C) {
+  (void)B; (void)C;
+  return (size_t)(kWsPartials + 148 * 8 * 2) * sizeof(float);
+}
+
+extern "C" int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_dtype, const float* pos_weight,
+                              int64_t B, int C, float* loss, void* dx, float grad_scale, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(x && t && loss && workspace, SM3_ERR_SHAPE, "bce: null pointer");
+  SM3_REQUIRE(dtype_ok(x_dtype) && dtype_ok(t_dtype), SM3_ERR_DTYPE, "bce: bad dtype");
+  SM3_REQUIRE(B >= 1 && C >= 1, SM3_ERR_SHAPE, "bce: empty input");
+  const int64_t n = B * (int64_t)C;
+  const unsigned grid = bce_grid(n);
+  SM3_REQUIRE(workspace_bytes >= (size_t)(kWsPartials + grid) * sizeof(float), SM3_ERR_WORKSPACE, "bce: workspace too small");
+  float* ws = (float*)workspace;
+  SM3_CHECK_CUDA(cudaMemsetAsync(ws, 0, 16, st));
+  const int vec_ok = aligned16(x) && aligned16(t) && (dx == nullptr || aligned16(dx));
+  const float inv_n = 1.0f / (float)n;
+  SM3_DISPATCH_DTYPE(x_dtype, TX, SM3_DISPATCH_DTYPE(t_dtype, TT, {
+    bce_kernel<TX, TT><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n, loss, (TX*)dx,
+                                                    grad_scale, ws, vec_ok);
+  }));
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+extern "C" int sm3_infonce_loss(const float* pos, const float* lse_neg, int64_t rows, float scale, float* loss,
+                                int accumulate, float* g_pos, float* g_lse, void* stream) {
+  SM3_REQUIRE(pos && lse_neg && loss, SM3_ERR_SHAPE, "infonce_loss: null pointer");
+  return infonce_loss_launch(pos, lse_neg, rows, scale, loss, accumulate, g_pos, g_lse, (cudaStream_t)stream);
+}

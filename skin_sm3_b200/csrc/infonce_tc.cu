@@ -1,0 +1,770 @@
+// K2/K3 on the 5th-generation tensor cores: flash-style fused similarity + InfoNCE for bf16 embeddings.
+//
+//   forward  : S-tile = Zr (128 x D, resident in TMEM) * Zc^T (128 x D tile, TMA -> smem, SWIZZLE_128B)
+//              accumulated in TMEM, read back with tcgen05.ld by 8 softmax warps (one thread = one row, no
+//              shuffles), exp2 with the constant shift 1/T (|s| <= 1 for unit rows), running row sums.
+//   backward : per 128 x 64 tile   S = Zr Zc^T (tcgen05, A from TMEM)  ->  H = exp(.)(a_i + a_j) as bf16
+//              written back into the S columns of TMEM  ->  dZ (128 x D, TMEM) += H * Zc, the SAME smem tile
+//              re-read as an MN-major B operand.  Row-local thanks to the symmetry of S (see sm3_b200.h).
+//   Nothing of size [M, M] is ever written; HBM traffic is ~ M*D*2 bytes per row-block pass (L2 resident).
+//
+// Replaces: matmul + mask/gather/cat + /T of src/models/simclr.py:296-320 (= :64-88, :140-164), the CE of
+// tools/backbone_train.py:531 and the autograd backward of both.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer + TMEM owner,
+// warps 2..9 = softmax/epilogue (warp_id % 4 selects the TMEM lane quadrant, the pair of warps sharing a
+// quadrant split the tile's columns).  Pipelines: smem full/empty (TMA <-> MMA), TMEM S full/empty
+// (MMA <-> softmax), and in the backward H-ready (softmax -> MMA).
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace sm3 {
+namespace {
+
+using namespace ptx;
+
+constexpr int kThreadsTC = 320;
+constexpr int kBM = 128;
+constexpr float kLog2eTC = 1.4426950408889634f;
+
+struct TcParams {
+  int n_local, pair_offset, n_global, D;
+  int m_rows, m_cols;
+  float inv_T, c2;
+  int tiles_per_split, col_tiles;
+  const __nv_bfloat16* z_rows;
+  float* pos;
+  float* partial;      // fwd: [splits][m_rows]
+  const float *gpos_r, *glse_r, *nsum_r, *gpos_c;
+  const float* acol;   // bwd: a_j = g_lse_j / neg_sum_j, zero padded to a multiple of 64
+  float* dz_partial;   // bwd: [splits][m_rows][D]
+};
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// row-major bf16 matrix [rows, cols]; box = 64 columns (128 B, one swizzle row) x box_rows rows
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SM3_REQUIRE(fn != nullptr, SM3_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SM3_REQUIRE(r == CUDA_SUCCESS, SM3_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u",
+              (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return SM3_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bring-up probe: one 128 x n x k MMA chain, every operand source/layout combination the real kernels use
+// ------------------------------------------------------------------------------------------------
+template <bool A_TMEM, bool B_MN>
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __nv_bfloat16* __restrict__ a_global, float* __restrict__ c, int n, int k) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sA = base;                        // k/64 panels of [128 x 128 B]
+  const uint32_t sB = base + 4 * 16384;            // K-major: k/64 panels [n x 128 B]; MN-major: n/64 panels [k x 128 B]
+  const uint32_t bars = sB + 4 * 32768;
+  const uint32_t bar_full = bars, bar_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_d = tmem, tmem_a = tmem + 256;
+
+  if (threadIdx.x == 0) {
+    const uint32_t a_bytes = A_TMEM ? 0u : (uint32_t)(128 * k * 2);
+    mbar_expect_tx(bar_full, a_bytes + (uint32_t)(n * k * 2));
+    if (!A_TMEM)
+      for (int pnl = 0; pnl < k / 64; ++pnl) tma_load_2d(sA + pnl * 16384, &tmap_a, bar_full, pnl * 64, 0);
+    if (!B_MN)
+      for (int pnl = 0; pnl < k / 64; ++pnl) tma_load_2d(sB + pnl * (n * 128), &tmap_b, bar_full, pnl * 64, 0);
+    else
+      for (int pnl = 0; pnl < n / 64; ++pnl) tma_load_2d(sB + pnl * (k * 128), &tmap_b, bar_full, pnl * 64, 0);
+  }
+  if (A_TMEM) {
+    // thread = row; 32 words (64 bf16) per tcgen05.st; element k at column k/2, even k in the low half
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a_global + (size_t)threadIdx.x * k);
+    for (int ch = 0; ch < k / 64; ++ch) {
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = src[ch * 32 + i];
+      tmem_st_x32(tmem_a + ((uint32_t)(warp * 32) << 16) + ch * 32, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_full, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, n, 0, B_MN ? 1 : 0);
+    for (int ks = 0; ks < k / 16; ++ks) {
+      uint64_t bdesc;
+      if (!B_MN) bdesc = make_smem_desc(sB + (ks >> 2) * (n * 128) + (ks & 3) * 32, 16, 1024);
+      else bdesc = make_smem_desc(sB + ks * 2048, (uint32_t)(k * 128), 1024);
+      if (A_TMEM) {
+        umma_ts(tmem_d, tmem_a + ks * 8, bdesc, idesc, ks > 0);
+      } else {
+        const uint64_t adesc = make_smem_desc(sA + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+        umma_ss(tmem_d, adesc, bdesc, idesc, ks > 0);
+      }
+    }
+    umma_commit(bar_done);
+  }
+  __syncwarp();
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  for (int ch = 0; ch < n / 32; ++ch) {
+    uint32_t r[32];
+    tmem_ld_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + ch * 32, r);
+    tmem_ld_wait(r);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) c[(size_t)threadIdx.x * n + ch * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+  (void)lane;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int DP> struct FwdCfg {
+  static constexpr int BN = 128;
+  static constexpr uint32_t PANEL = BN * 128;          // 16 KB: 128 rows x 64 bf16
+  static constexpr uint32_t STAGE = DP * PANEL;
+  static constexpr int NSTAGE = DP == 4 ? 3 : 4;       // 192 KB / 192 KB / 128 KB / 64 KB
+  static constexpr int NS = 3;                         // TMEM S stages at columns 128, 256, 384 (A at [0, 32*DP))
+  static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 512 /*xsum*/;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
+  using C = FwdCfg<DP>;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE, NS = C::NS;
+  constexpr int D = 64 * DP;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sB = base;
+  const uint32_t bars = sB + NSTAGE * C::STAGE;
+  auto bar_full = [&](int i) { return bars + 8u * i; };
+  auto bar_empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
+  auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
+  auto bar_sempty = [&](int i) { return bars + 8u * (2 * NSTAGE + NS + i); };
+  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 2 * NS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 2 * NS + 1));
+  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * kBM;
+  const int split = blockIdx.y;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
+  const int n_tiles = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_sempty(i), 8); }
+    mbar_init(bar_aready, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      prefetch_tensormap(&tmap_cols);
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+        mbar_wait(bar_empty(s), ph ^ 1u);
+        mbar_expect_tx(bar_full(s), C::STAGE);
+        const int row = (t_begin + it) * BN;
+#pragma unroll
+        for (int pnl = 0; pnl < DP; ++pnl)
+          tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      mbar_wait(bar_aready, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % NSTAGE, as = it % NS;
+        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u, aph = (uint32_t)(it / NS) & 1u;
+        mbar_wait(bar_sempty(as), aph ^ 1u);
+        mbar_wait(bar_full(s), ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + 128u + (uint32_t)as * 128u;
+#pragma unroll
+        for (int ks = 0; ks < 4 * DP; ++ks) {
+          const uint64_t bdesc = make_smem_desc(sB + s * C::STAGE + (ks >> 2) * C::PANEL + (ks & 3) * 32, 16, 1024);
+          umma_ts(d_tmem, tmem + ks * 8, bdesc, idesc, ks > 0);
+        }
+        umma_commit(bar_empty(s));
+        umma_commit(bar_sfull(as));
+      }
+    }
+  } else {
+    // =========================== softmax warps ===========================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may touch
+    const int half = (warp - 2) >> 2;    // which 64 of the tile's 128 columns
+    const int row_in_tile = q * 32 + lane;
+    const int l = r0 + row_in_tile;
+    const bool valid = l < p.m_rows;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+
+    // ---- stage this CTA's 128 rows into TMEM as the A operand (packed bf16 pairs) ----
+#pragma unroll
+    for (int ch = 0; ch < DP; ++ch) {
+      if ((ch & 1) == half) {
+        uint32_t r[32];
+        if (valid) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)l * D + ch * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 v = __ldg(src + i);
+            r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        tmem_st_x32(tmem + lane_addr + ch * 32, r);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_aready);
+
+    const int g = valid ? global_row(l, p.n_local, p.pair_offset, p.n_global) : -1;
+    const int pj = valid ? positive_of(g, p.n_global) : -1;
+    const float c2 = p.c2;
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+    float posval = 0.f;
+    bool found = false;
+
+    for (int it = 0; it < n_tiles; ++it) {
+      const int as = it % NS;
+      const uint32_t aph = (uint32_t)(it / NS) & 1u;
+      mbar_wait(bar_sfull(as), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem + lane_addr + 128u + (uint32_t)as * 128u + (uint32_t)half * 64u;
+      uint32_t v0[32], v1[32];
+      tmem_ld_x32(taddr, v0);
+      tmem_ld_x32(taddr + 32, v1);
+      tmem_ld_wait(v0);
+      tmem_ld_wait(v1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sempty(as));      // S stage is in registers: hand it back to the MMA warp
+
+      const int cb = (t_begin + it) * BN + half * 64;
+      const bool need = (cb + 64 > p.m_cols) ||
+                        (valid && ((unsigned)(g - cb) < 64u || (unsigned)(pj - cb) < 64u));
+      if (!__any_sync(0xffffffffu, need)) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          sum0 += ex2(fmaf(__uint_as_float(v0[i]), c2, -c2));
+          sum1 += ex2(fmaf(__uint_as_float(v0[i + 1]), c2, -c2));
+          sum2 += ex2(fmaf(__uint_as_float(v0[i + 2]), c2, -c2));
+          sum3 += ex2(fmaf(__uint_as_float(v0[i + 3]), c2, -c2));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          sum0 += ex2(fmaf(__uint_as_float(v1[i]), c2, -c2));
+          sum1 += ex2(fmaf(__uint_as_float(v1[i + 1]), c2, -c2));
+          sum2 += ex2(fmaf(__uint_as_float(v1[i + 2]), c2, -c2));
+          sum3 += ex2(fmaf(__uint_as_float(v1[i + 3]), c2, -c2));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float s = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
+          const int col = cb + i;
+          const bool is_pos = (col == pj);
+          if (is_pos) { posval = s * p.inv_T; found = true; }
+          if (col < p.m_cols && col != g && !is_pos) sum0 += ex2(fmaf(s, c2, -c2));
+        }
+      }
+    }
+    float total = (sum0 + sum1) + (sum2 + sum3);
+    if (found) p.pos[l] = posval;
+    if (half == 1) xsum[row_in_tile] = total;
+    named_bar_sync(1, 256);
+    if (half == 0 && valid) p.partial[(size_t)split * p.m_rows + l] = total + xsum[row_in_tile];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int DP> struct BwdCfg {
+  static constexpr int BN = 64;
+  static constexpr uint32_t PANEL = BN * 128;          // 8 KB: 64 rows x 64 bf16
+  static constexpr uint32_t STAGE = DP * PANEL;        // <= 32 KB
+  static constexpr int NSTAGE = 4;
+  static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 + 256;
+  // TMEM columns: A [0, 32*DP) | S/H stage 0 [128,192) | stage 1 [192,256) | dZ [256, 256 + 64*DP)
+};
+
+__global__ void tc_bwd_prep_kernel(const float* __restrict__ glse, const float* __restrict__ nsum, int m_cols,
+                                   int m_pad, float* __restrict__ acol) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m_pad) return;
+  float a = 0.f;
+  if (j < m_cols) { const float s = nsum[j]; a = s > 0.f ? glse[j] / s : 0.f; }
+  acol[j] = a;
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
+  using C = BwdCfg<DP>;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
+  constexpr int D = 64 * DP;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sB = base;
+  const uint32_t bars = sB + NSTAGE * C::STAGE;
+  auto bar_full = [&](int i) { return bars + 8u * i; };
+  auto bar_empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
+  auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
+  auto bar_hfull = [&](int i) { return bars + 8u * (2 * NSTAGE + 2 + i); };
+  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 4);
+  const uint32_t bar_dzfull = bars + 8u * (2 * NSTAGE + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 6));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * kBM;
+  const int split = blockIdx.y;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
+  const int n_tiles = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_hfull(i), 8); }
+    mbar_init(bar_aready, 8);
+    mbar_init(bar_dzfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t kColS = 128, kColDZ = 256;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      prefetch_tensormap(&tmap_cols);
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+        mbar_wait(bar_empty(s), ph ^ 1u);
+        mbar_expect_tx(bar_full(s), C::STAGE);
+        const int row = (t_begin + it) * BN;
+#pragma unroll
+        for (int pnl = 0; pnl < DP; ++pnl)
+          tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);     // S  = Zr  * Zc^T   (B K-major)
+      constexpr uint32_t idesc_z = make_idesc_bf16(128, D, 0, 1);      // dZ += H  * Zc     (B MN-major)
+      auto issue_s = [&](int it) {
+        const int s = it % NSTAGE, as = it & 1;
+        mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + kColS + (uint32_t)as * 64u;
+#pragma unroll
+        for (int ks = 0; ks < 4 * DP; ++ks) {
+          const uint64_t bdesc = make_smem_desc(sB + s * C::STAGE + (ks >> 2) * C::PANEL + (ks & 3) * 32, 16, 1024);
+          umma_ts(d_tmem, tmem + ks * 8, bdesc, idesc_s, ks > 0);
+        }
+        umma_commit(bar_sfull(as));
+      };
+      mbar_wait(bar_aready, 0);
+      tc_fence_after();
+      if (n_tiles > 0) issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % NSTAGE, as = it & 1;
+        mbar_wait(bar_hfull(as), (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t h_tmem = tmem + kColS + (uint32_t)as * 64u;
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks) {
+          // H k-columns [0,32) live at TMEM cols +0..15, k-columns [32,64) at +32..47 (written by the two warp halves)
+          const uint32_t a_tmem = h_tmem + (ks < 2 ? ks * 8 : 32 + (ks - 2) * 8);
+          const uint64_t bdesc = make_smem_desc(sB + s * C::STAGE + ks * 2048, C::PANEL, 1024);
+          umma_ts(tmem + kColDZ, a_tmem, bdesc, idesc_z, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty(s));
+        if (it + 2 < n_tiles) issue_s(it + 2);   // in-order tensor pipe: overwrites S/H stage `as` only after dZ(it)
+      }
+      umma_commit(bar_dzfull);
+    }
+  } else {
+    // =========================== softmax / epilogue warps ===========================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;    // which 32 of the tile's 64 columns
+    const int row_in_tile = q * 32 + lane;
+    const int l = r0 + row_in_tile;
+    const bool valid = l < p.m_rows;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+
+#pragma unroll
+    for (int ch = 0; ch < DP; ++ch) {
+      if ((ch & 1) == half) {
+        uint32_t r[32];
+        if (valid) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)l * D + ch * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 v = __ldg(src + i);
+            r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        tmem_st_x32(tmem + lane_addr + ch * 32, r);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_aready);
+
+    const int g = valid ? global_row(l, p.n_local, p.pair_offset, p.n_global) : -1;
+    const int pj = valid ? positive_of(g, p.n_global) : -1;
+    float a_i = 0.f, gp_i = 0.f;
+    if (valid) {
+      const float s = p.nsum_r[l];
+      a_i = s > 0.f ? p.glse_r[l] / s : 0.f;
+      gp_i = p.gpos_r[l];
+    }
+    const float c2 = p.c2;
+
+    for (int it = 0; it < n_tiles; ++it) {
+      const int as = it & 1;
+      mbar_wait(bar_sfull(as), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)as * 64u + (uint32_t)half * 32u;
+      uint32_t v[32];
+      tmem_ld_x32(taddr, v);
+      tmem_ld_wait(v);
+      const int cb = (t_begin + it) * BN + half * 32;
+      const bool need = (cb + 32 > p.m_cols) ||
+                        (valid && ((unsigned)(g - cb) < 32u || (unsigned)(pj - cb) < 32u));
+      uint32_t h[16];
+      const float4* ap = reinterpret_cast<const float4*>(p.acol + cb);
+      if (!__any_sync(0xffffffffu, need)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 aj = __ldg(ap + i);
+          const float e0 = ex2(fmaf(__uint_as_float(v[4 * i]), c2, -c2)) * (a_i + aj.x);
+          const float e1 = ex2(fmaf(__uint_as_float(v[4 * i + 1]), c2, -c2)) * (a_i + aj.y);
+          const float e2 = ex2(fmaf(__uint_as_float(v[4 * i + 2]), c2, -c2)) * (a_i + aj.z);
+          const float e3 = ex2(fmaf(__uint_as_float(v[4 * i + 3]), c2, -c2)) * (a_i + aj.w);
+          h[2 * i] = pack_bf16x2(e0, e1);
+          h[2 * i + 1] = pack_bf16x2(e2, e3);
+        }
+      } else {
+        float hv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = cb + i;
+          const float s = __uint_as_float(v[i]);
+          float x = 0.f;
+          if (valid && col < p.m_cols && col != g) {
+            if (col == pj) x = gp_i + p.gpos_c[col];
+            else x = ex2(fmaf(s, c2, -c2)) * (a_i + p.acol[col]);
+          }
+          hv[i] = x;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
+      }
+      tmem_st_x16(taddr, h);          // H overwrites this thread's own (already consumed) S columns
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hfull(as));
+    }
+
+    // ---- epilogue: dZ (TMEM fp32) * 1/T -> global partial ----
+    mbar_wait(bar_dzfull, 0);
+    tc_fence_after();
+    float* dst = p.dz_partial + ((size_t)split * p.m_rows + (valid ? l : 0)) * D;
+#pragma unroll
+    for (int ch = 0; ch < 2 * DP; ++ch) {
+      if ((ch & 1) == half) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem + lane_addr + kColDZ + ch * 32, v);
+        tmem_ld_wait(v);
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(dst + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] = make_float4(__uint_as_float(v[4 * i]) * p.inv_T, __uint_as_float(v[4 * i + 1]) * p.inv_T,
+                               __uint_as_float(v[4 * i + 2]) * p.inv_T, __uint_as_float(v[4 * i + 3]) * p.inv_T);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// column splits: minimise  waves(row_tiles * s) * (tiles_per_split + setup)  on this many SMs
+int tc_pick_splits(int row_tiles, int col_tiles, int setup_tiles, int max_splits) {
+  const int sms = num_sms();
+  int best = 1;
+  double best_cost = 1e30;
+  const int smax = col_tiles < max_splits ? col_tiles : max_splits;
+  for (int s = 1; s <= smax; ++s) {
+    const int tps = (col_tiles + s - 1) / s;
+    const int real = (col_tiles + tps - 1) / tps;
+    if (real != s) continue;
+    const long ctas = (long)row_tiles * s;
+    const long waves = (ctas + sms - 1) / sms;
+    const double cost = (double)waves * (tps + setup_tiles) + 0.01 * s;
+    if (cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+struct TcPlan {
+  int row_tiles, col_tiles, splits, tiles_per_split;
+};
+TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
+  TcPlan pl;
+  const int m_rows = 2 * pb.n_local, m_cols = 2 * pb.n_global;
+  const int bn = bwd ? 64 : 128;
+  pl.row_tiles = (m_rows + kBM - 1) / kBM;
+  pl.col_tiles = (m_cols + bn - 1) / bn;
+  int max_splits = 32;
+  if (bwd) {   // bound the fp32 partial-gradient workspace to ~1 GiB
+    const size_t per = (size_t)m_rows * pb.D * 4;
+    const size_t cap = ((size_t)1 << 30) / (per ? per : 1);
+    if ((size_t)max_splits > cap) max_splits = cap < 1 ? 1 : (int)cap;
+  }
+  pl.splits = tc_pick_splits(pl.row_tiles, pl.col_tiles, bwd ? 6 : 4, max_splits);
+  pl.tiles_per_split = (pl.col_tiles + pl.splits - 1) / pl.splits;
+  return pl;
+}
+
+void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p) {
+  p.n_local = pb.n_local; p.pair_offset = pb.pair_offset; p.n_global = pb.n_global; p.D = pb.D;
+  p.m_rows = 2 * pb.n_local; p.m_cols = 2 * pb.n_global;
+  p.inv_T = pb.inv_T; p.c2 = pb.inv_T * kLog2eTC;
+  p.tiles_per_split = pl.tiles_per_split; p.col_tiles = pl.col_tiles;
+  p.z_rows = (const __nv_bfloat16*)pb.z_rows;
+}
+
+template <int DP>
+int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)FwdCfg<DP>::SMEM));
+  infonce_tc_fwd_kernel<DP><<<dim3(pl.row_tiles, pl.splits), kThreadsTC, FwdCfg<DP>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+template <int DP>
+int launch_bwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BwdCfg<DP>::SMEM));
+  infonce_tc_bwd_kernel<DP><<<dim3(pl.row_tiles, pl.splits), kThreadsTC, BwdCfg<DP>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+size_t bwd_acol_offset(const InfoNceProblem& pb, const TcPlan& pl) {
+  const size_t dz = (size_t)pl.splits * 2 * pb.n_local * pb.D * sizeof(float);
+  return (dz + 255) & ~(size_t)255;
+}
+
+}  // namespace
+
+bool infonce_tc_supported(const InfoNceProblem& pb) {
+  static int sm100 = -1;
+  if (sm100 < 0) sm100 = sm3_device_supported() == 1 ? 1 : 0;
+  return sm100 == 1 && pb.dtype == SM3_BF16 && pb.D % 64 == 0 && pb.D >= 64 && pb.D <= 256 && aligned16(pb.z_rows) &&
+         aligned16(pb.z_cols);
+}
+
+size_t infonce_tc_workspace(const InfoNceProblem& pb, int backward) {
+  if (pb.D % 64 != 0 || pb.D < 64 || pb.D > 256) return 0;
+  const TcPlan pl = tc_plan(pb, backward != 0);
+  if (!backward) return (size_t)pl.splits * 2 * pb.n_local * sizeof(float) + 256;
+  const size_t m_pad = ((size_t)2 * pb.n_global + 63) / 64 * 64 + 64;
+  return bwd_acol_offset(pb, pl) + m_pad * sizeof(float) + 256;
+}
+
+int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  SM3_REQUIRE(pb.n_local >= 1 && pb.n_global >= pb.n_local && pb.pair_offset >= 0 &&
+                  pb.pair_offset + pb.n_local <= pb.n_global && pb.n_global <= (1 << 29),
+              SM3_ERR_SHAPE, "infonce: bad row block (n_local=%d offset=%d n_global=%d)", pb.n_local, pb.pair_offset,
+              pb.n_global);
+  SM3_REQUIRE(ws_bytes >= infonce_tc_workspace(pb, 0), SM3_ERR_WORKSPACE, "infonce(tc) fwd: workspace too small");
+  const TcPlan pl = tc_plan(pb, false);
+  TcParams p{};
+  fill_params(pb, pl, p);
+  p.pos = pos;
+  p.partial = (float*)ws;
+  CUtensorMap tmap;
+  int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 128);
+  if (rc) return rc;
+  switch (pb.D / 64) {
+    case 1: rc = launch_fwd<1>(tmap, p, pl, st); break;
+    case 2: rc = launch_fwd<2>(tmap, p, pl, st); break;
+    case 3: rc = launch_fwd<3>(tmap, p, pl, st); break;
+    default: rc = launch_fwd<4>(tmap, p, pl, st); break;
+  }
+  if (rc) return rc;
+  return infonce_finalize_launch(p.partial, pl.splits, p.m_rows, pb.inv_T, neg_sum, lse_neg, st);
+}
+
+int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* glse_r, const float* nsum_r,
+                   const float* gpos_c, const float* glse_c, const float* nsum_c, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  SM3_REQUIRE(pb.n_local >= 1 && pb.n_global >= pb.n_local && pb.pair_offset >= 0 &&
+                  pb.pair_offset + pb.n_local <= pb.n_global && pb.n_global <= (1 << 29),
+              SM3_ERR_SHAPE, "infonce: bad row block (n_local=%d offset=%d n_global=%d)", pb.n_local, pb.pair_offset,
+              pb.n_global);
+  SM3_REQUIRE(ws_bytes >= infonce_tc_workspace(pb, 1), SM3_ERR_WORKSPACE, "infonce(tc) bwd: workspace too small");
+  const TcPlan pl = tc_plan(pb, true);
+  TcParams p{};
+  fill_params(pb, pl, p);
+  p.gpos_r = gpos_r; p.glse_r = glse_r; p.nsum_r = nsum_r; p.gpos_c = gpos_c;
+  p.dz_partial = (float*)ws;
+  float* acol = (float*)((char*)ws + bwd_acol_offset(pb, pl));
+  p.acol = acol;
+  const int m_pad = (p.m_cols + 63) / 64 * 64 + 64;
+  tc_bwd_prep_kernel<<<(m_pad + 255) / 256, 256, 0, st>>>(glse_c, nsum_c, p.m_cols, m_pad, acol);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  CUtensorMap tmap;
+  int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 64);
+  if (rc) return rc;
+  switch (pb.D / 64) {
+    case 1: rc = launch_bwd<1>(tmap, p, pl, st); break;
+    case 2: rc = launch_bwd<2>(tmap, p, pl, st); break;
+    case 3: rc = launch_bwd<3>(tmap, p, pl, st); break;
+    default: rc = launch_bwd<4>(tmap, p, pl, st); break;
+  }
+  if (rc) return rc;
+  return pl.splits;
+}
+
+}  // namespace sm3
+
+// ---------------------------------------------------------------------------------------------------
+// debug probe (C ABI).  variant bit0: A operand from TMEM (else smem/TMA); bit1: B given as [k, n]
+// row-major and consumed MN-major (C = A*B), else B given as [n, k] row-major, K-major (C = A*B^T).
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,
+                                    void* stream) {
+  using namespace sm3;
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(a_bf16 && b_bf16 && c, SM3_ERR_SHAPE, "probe: null pointer");
+  SM3_REQUIRE(n >= 32 && n <= 256 && n % 32 == 0 && k >= 64 && k <= 256 && k % 64 == 0, SM3_ERR_SHAPE,
+              "probe: need n in [32,256] %%32, k in [64,256] %%64");
+  const bool a_tmem = variant & 1, b_mn = variant & 2;
+  SM3_REQUIRE(!b_mn || n % 64 == 0, SM3_ERR_SHAPE, "probe: MN-major B needs n %% 64 == 0");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, a_bf16, 128, (uint64_t)k, 128);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_bf16(&tb, b_bf16, (uint64_t)n, (uint64_t)k, (uint32_t)n);
+  else rc = make_tmap_bf16(&tb, b_bf16, (uint64_t)k, (uint64_t)n, (uint32_t)k);
+  if (rc) return rc;
+  const int smem = 4 * 16384 + 4 * 32768 + 1024 + 64;
+  const __nv_bfloat16* ag = (const __nv_bfloat16*)a_bf16;
+#define SM3_PROBE(AT, BM)                                                                                           \
+  do {                                                                                                              \
+    SM3_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel<AT, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    umma_probe_kernel<AT, BM><<<1, 128, smem, st>>>(ta, tb, ag, c, n, k);                                           \
+  } while (0)
+  if (a_tmem && b_mn) SM3_PROBE(true, true);
+  else if (a_tmem) SM3_PROBE(true, false);
+  else if (b_mn) SM3_PROBE(false, true);
+  else SM3_PROBE(false, false);
+#undef SM3_PROBE
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}

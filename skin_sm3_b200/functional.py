@@ -1,0 +1,432 @@
+"""torch.autograd.Function drop-ins for the SM3 contrastive hot path, backed by libsm3_b200.so.
+
+Reference being replaced (paths relative to the reference checkout):
+  * ``l2_normalize``            F.normalize(x, dim=1)                      src/models/simclr.py:62,138,294
+  * ``cal_logits``              SimCLRSkinV3._cal_logits after projectors  src/models/simclr.py:293-322
+                                (= SimCLR.forward :61-88, SimCLRSkinV2._cal_logits :137-166)
+  * ``fused_infonce``           the above + nn.CrossEntropyLoss + backward tools/backbone_train.py:101-125,531
+  * ``multihead_ce``            the 8-head CE loops                        tools/mlc_eval.py:159-162,
+                                                                           tools/mlc_train.py:255-261
+  * ``bce_with_logits``         north_star's multi-hot head loss (no reference counterpart)
+
+``cal_logits`` returns *sufficient-statistics logits* ``[M, 2] = [pos/T, log sum_neg exp(s/T)]`` with
+all-zero labels: the training script's own ``nn.CrossEntropyLoss()(logits, labels)`` then yields exactly
+the reference loss, and autograd hands (g_pos, g_lse) back to the fused backward kernel.  The ``[M, M-1]``
+logits matrix of the reference never exists.
+
+Everything here requires CUDA tensors and the built extension; there is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, check, dtype_code, lib, ptr, require_cuda, stream_ptr
+
+NUM_CLASSES = (5, 3, 2, 3, 3, 3, 3, 2)   # DIAG + seven-point checklist (tools/mlc_eval.py:63)
+_EPS = 1e-12                             # F.normalize default
+
+
+# bench.py installs a callable(name) here that records a CUDA event on the current stream after each stage
+_PROFILE = None
+
+
+def _mark(name: str) -> None:
+    if _PROFILE is not None:
+        _PROFILE(name)
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _autocast_on() -> bool:
+    try:
+        return torch.is_autocast_enabled("cuda")
+    except TypeError:  # older signature
+        return torch.is_autocast_enabled()
+
+
+def pick_precision(p: torch.Tensor, precision: str = "auto"):
+    """-> (z dtype, algo).  'bf16': bf16 rows on the tcgen05 kernels (D % 64 == 0, D <= 256; other widths use
+    the FMA kernels on bf16 rows).  'fp32': fp32 rows on the FMA kernels (reference-exact fp32 parity).
+    'auto': fp32 inputs outside autocast -> 'fp32', everything else -> 'bf16'."""
+    if precision == "auto":
+        precision = "fp32" if (p.dtype == torch.float32 and not _autocast_on()) else "bf16"
+    if precision == "fp32":
+        return torch.float32, ALGO_SIMT
+    if precision != "bf16":
+        raise ValueError(f"precision must be 'auto', 'bf16' or 'fp32', got {precision!r}")
+    d = p.shape[-1]
+    return torch.bfloat16, (ALGO_TC if (d % 64 == 0 and 64 <= d <= 256) else ALGO_SIMT)
+
+
+# ======================================================================================================
+# raw (non-autograd) wrappers around the C ABI
+# ======================================================================================================
+class core:
+    """Thin typed wrappers; every method launches on the current stream of the tensors' device."""
+
+    @staticmethod
+    def normalize_pair(p1: torch.Tensor, p2: Optional[torch.Tensor], z_dtype: torch.dtype, eps: float = _EPS):
+        dev = require_cuda(p1, p2)
+        p1 = _contig(p1)
+        n1, d = p1.shape
+        n2 = 0
+        if p2 is not None:
+            p2 = _contig(p2)
+            if p2.shape[1] != d or p2.dtype != p1.dtype:
+                raise ValueError("p1 / p2 must agree in width and dtype")
+            n2 = p2.shape[0]
+        z = torch.empty((n1 + n2, d), dtype=z_dtype, device=dev)
+        inv = torch.empty(n1 + n2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().sm3_l2norm_fwd(ptr(p1), n1, ptr(p2), n2, d, dtype_code(p1), ptr(z), dtype_code(z), ptr(inv),
+                                       eps, stream_ptr()), "sm3_l2norm_fwd")
+        return z, inv
+
+    @staticmethod
+    def normalize_bwd(dz_partials: torch.Tensor, n_partials: int, scale: float, z: torch.Tensor, inv: torch.Tensor,
+                      n1: int, n2: int, out_dtype: torch.dtype, eps: float = _EPS):
+        dev = require_cuda(dz_partials, z, inv)
+        d = z.shape[1]
+        dp1 = torch.empty((n1, d), dtype=out_dtype, device=dev)
+        dp2 = torch.empty((n2, d), dtype=out_dtype, device=dev) if n2 else None
+        with torch.cuda.device(dev):
+            check(lib().sm3_l2norm_bwd(ptr(dz_partials), n_partials, scale, ptr(z), dtype_code(z), ptr(inv), eps,
+                                       ptr(dp1), n1, ptr(dp2), n2, d, dtype_code(dp1), stream_ptr()),
+                  "sm3_l2norm_bwd")
+        return dp1, dp2
+
+    @staticmethod
+    def workspace(n_local: int, n_global: int, d: int, z: torch.Tensor, algo: int, backward: bool) -> torch.Tensor:
+        nbytes = lib().sm3_infonce_workspace_bytes(n_local, n_global, d, dtype_code(z), algo, int(backward))
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=z.device)
+
+    @staticmethod
+    def stats_fwd(z_rows: torch.Tensor, z_cols: torch.Tensor, n_local: int, pair_offset: int, n_global: int,
+                  temperature: float, algo: int = ALGO_AUTO):
+        dev = require_cuda(z_rows, z_cols)
+        d = z_rows.shape[1]
+        m = 2 * n_local
+        assert z_rows.shape[0] == m and z_cols.shape[0] == 2 * n_global and z_cols.shape[1] == d
+        assert z_rows.is_contiguous() and z_cols.is_contiguous() and z_rows.dtype == z_cols.dtype
+        out = torch.empty((3, m), dtype=torch.float32, device=dev)   # pos, lse_neg, neg_sum
+        ws = core.workspace(n_local, n_global, d, z_rows, algo, False)
+        with torch.cuda.device(dev):
+            check(lib().sm3_infonce_fwd(ptr(z_rows), ptr(z_cols), n_local, pair_offset, n_global, d,
+                                        dtype_code(z_rows), 1.0 / temperature, ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                        ptr(ws), ws.numel(), algo, stream_ptr()), "sm3_infonce_fwd")
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def stats_bwd(z_rows, z_cols, n_local, pair_offset, n_global, temperature, g_pos_r, g_lse_r, nsum_r,
+                  g_pos_c, g_lse_c, nsum_c, algo: int = ALGO_AUTO):
+        """-> (fp32 partial-gradient workspace, n_partials); feed to normalize_bwd / sum_partials."""
+        dev = require_cuda(z_rows, z_cols)
+        d = z_rows.shape[1]
+        for t in (g_pos_r, g_lse_r, nsum_r, g_pos_c, g_lse_c, nsum_c):
+            assert t.dtype == torch.float32 and t.is_contiguous()
+        ws = core.workspace(n_local, n_global, d, z_rows, algo, True)
+        with torch.cuda.device(dev):
+            npart = check(lib().sm3_infonce_bwd(ptr(z_rows), ptr(z_cols), n_local, pair_offset, n_global, d,
+                                                dtype_code(z_rows), 1.0 / temperature, ptr(g_pos_r), ptr(g_lse_r),
+                                                ptr(nsum_r), ptr(g_pos_c), ptr(g_lse_c), ptr(nsum_c), ptr(ws),
+                                                ws.numel(), algo, stream_ptr()), "sm3_infonce_bwd")
+        return ws, npart
+
+    @staticmethod
+    def sum_partials(ws: torch.Tensor, n_partials: int, m: int, d: int) -> torch.Tensor:
+        v = ws[: n_partials * m * d * 4].view(torch.float32).view(n_partials, m, d)
+        return v[0] if n_partials == 1 else v.sum(0)
+
+    @staticmethod
+    def loss(pos, lse_neg, scale: float, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+             want_grads: bool = True):
+        dev = require_cuda(pos, lse_neg)
+        m = pos.numel()
+        if out is None:
+            out = torch.empty((), dtype=torch.float32, device=dev)
+        g = torch.empty((2, m), dtype=torch.float32, device=dev) if want_grads else None
+        with torch.cuda.device(dev):
+            check(lib().sm3_infonce_loss(ptr(pos), ptr(lse_neg), m, scale, ptr(out), int(accumulate),
+                                         ptr(g[0]) if want_grads else None, ptr(g[1]) if want_grads else None,
+                                         stream_ptr()), "sm3_infonce_loss")
+        return out, (g[0] if want_grads else None), (g[1] if want_grads else None)
+
+
+# ======================================================================================================
+# cross-rank plumbing (row-block sharding): global order = [all first views ; all second views]
+# ======================================================================================================
+def gather_global_order(t_local: torch.Tensor, group=None) -> torch.Tensor:
+    """t_local: [2*n_local, ...] = [first halves ; second halves] of this rank.  Returns [2*n_global, ...]
+    with rank r's first halves at [r*n_local, (r+1)*n_local) and its second halves n_global further on.
+    Equal n_local on every rank (DistributedSampler drops/pads, reference src/utils/misc.py:400)."""
+    w = dist.get_world_size(group)
+    m = t_local.shape[0]
+    n_local = m // 2
+    out = torch.empty((2 * n_local * w,) + tuple(t_local.shape[1:]), dtype=t_local.dtype, device=t_local.device)
+    first, second = out[: n_local * w], out[n_local * w:]
+    t_local = _contig(t_local)
+    dist.all_gather_into_tensor(first, t_local[:n_local], group=group)
+    dist.all_gather_into_tensor(second, t_local[n_local:], group=group)
+    return out
+
+
+def _group_info(group):
+    if group is None or not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+# ======================================================================================================
+# autograd Functions
+# ======================================================================================================
+class _L2Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, eps, out_dtype):
+        z, inv = core.normalize_pair(p, None, out_dtype or p.dtype, eps)
+        ctx.save_for_backward(z, inv)
+        ctx.eps, ctx.p_dtype = eps, p.dtype
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        z, inv = ctx.saved_tensors
+        dz32 = _contig(dz.float())
+        dp, _ = core.normalize_bwd(dz32, 1, 1.0, z, inv, z.shape[0], 0, ctx.p_dtype, ctx.eps)
+        return dp, None, None
+
+
+def l2_normalize(p: torch.Tensor, eps: float = _EPS, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Row-wise ``F.normalize(p, dim=1, eps)`` (2-D input)."""
+    if p.dim() != 2:
+        raise ValueError("l2_normalize expects a 2-D tensor [rows, D]")
+    return _L2Normalize.apply(p, eps, out_dtype)
+
+
+class _InfoNCELogits(torch.autograd.Function):
+    """normalise -> (all-gather) -> K2 statistics;  backward = (all-gather of 3 floats/row) -> K3 -> normalise-bwd."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, temperature, z_dtype, algo, group):
+        w, rank = _group_info(group)
+        n_local = p1.shape[0]
+        z, inv = core.normalize_pair(p1, p2, z_dtype)
+        z_cols = gather_global_order(z, group) if w > 1 else z
+        n_global = n_local * w
+        pos, lse, nsum = core.stats_fwd(z, z_cols, n_local, rank * n_local, n_global, temperature, algo)
+        ctx.save_for_backward(z, inv, z_cols, nsum)
+        ctx.meta = (temperature, algo, group, w, rank, n_local, p1.dtype)
+        return torch.stack((pos, lse), dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, inv, z_cols, nsum = ctx.saved_tensors
+        temperature, algo, group, w, rank, n_local, p_dtype = ctx.meta
+        g = g.float()
+        g_pos, g_lse = _contig(g[:, 0]), _contig(g[:, 1])
+        if w > 1:
+            packed = gather_global_order(torch.stack((g_pos, g_lse, nsum), dim=1), group)
+            gp_c, gl_c, ns_c = (_contig(packed[:, k]) for k in range(3))
+        else:
+            gp_c, gl_c, ns_c = g_pos, g_lse, nsum
+        ws, npart = core.stats_bwd(z, z_cols, n_local, rank * n_local, n_local * w, temperature, g_pos, g_lse, nsum,
+                                   gp_c, gl_c, ns_c, algo)
+        dp1, dp2 = core.normalize_bwd(ws, npart, 1.0, z, inv, n_local, n_local, p_dtype)
+        return dp1, dp2, None, None, None, None
+
+
+def cal_logits(p1: torch.Tensor, p2: torch.Tensor, temperature: float, precision: str = "auto", group=None):
+    """Drop-in for the body of ``_cal_logits`` after the projectors (simclr.py:293-322).
+
+    p1, p2: projector outputs ``[N, D]`` (first / second halves of the reference's ``torch.cat``).
+    Returns ``(logits[2N, 2] fp32, labels[2N] int64 zeros)`` such that ``nn.CrossEntropyLoss()(logits, labels)``
+    equals the reference's loss on its ``[2N, 2N-1]`` logits, with identical gradients into p1 / p2.
+    With ``group`` (torch.distributed process group) the negatives are all-gathered across ranks; each rank
+    returns the logits of its own 2N rows (mean over ranks of the per-rank CE == global-batch loss).
+    """
+    if p1.dim() != 2 or p1.shape != p2.shape:
+        raise ValueError("cal_logits expects two [N, D] tensors of identical shape")
+    require_cuda(p1, p2)
+    if temperature <= 0:
+        raise ValueError("temperature must be > 0")
+    z_dtype, algo = pick_precision(p1, precision)
+    logits = _InfoNCELogits.apply(p1, p2, float(temperature), z_dtype, algo, group)
+    labels = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)
+    return logits, labels
+
+
+class _FusedInfoNCE(torch.autograd.Function):
+    """Scalar loss with the backward computed eagerly in forward (one pass: fwd + bwd kernels back to back)."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, temperature, z_dtype, algo, group, weight):
+        w, rank = _group_info(group)
+        n_local = p1.shape[0]
+        n_global = n_local * w
+        _mark("start")
+        z, inv = core.normalize_pair(p1, p2, z_dtype)
+        _mark("normalize")
+        z_cols = gather_global_order(z, group) if w > 1 else z
+        _mark("gather_z")
+        pos, lse, nsum = core.stats_fwd(z, z_cols, n_local, rank * n_local, n_global, temperature, algo)
+        _mark("stats_fwd")
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        loss, g_pos, g_lse = core.loss(pos, lse, weight / (2 * n_local), want_grads=need_grad)
+        _mark("loss")
+        if need_grad:
+            if w > 1:
+                packed = gather_global_order(torch.stack((g_pos, g_lse, nsum), dim=1), group)
+                gp_c, gl_c, ns_c = (_contig(packed[:, k]) for k in range(3))
+            else:
+                gp_c, gl_c, ns_c = g_pos, g_lse, nsum
+            _mark("gather_stats")
+            ws, npart = core.stats_bwd(z, z_cols, n_local, rank * n_local, n_global, temperature, g_pos, g_lse, nsum,
+                                       gp_c, gl_c, ns_c, algo)
+            _mark("stats_bwd")
+            dp1, dp2 = core.normalize_bwd(ws, npart, 1.0, z, inv, n_local, n_local, p1.dtype)
+            _mark("normalize_bwd")
+            ctx.save_for_backward(dp1, dp2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dp1, dp2 = ctx.saved_tensors
+        return dp1 * g.to(dp1.dtype), dp2 * g.to(dp2.dtype), None, None, None, None, None
+
+
+def fused_infonce(p1: torch.Tensor, p2: torch.Tensor, temperature: float, precision: str = "auto", group=None,
+                  weight: float = 1.0) -> torch.Tensor:
+    """``weight * CrossEntropy(_cal_logits(p1, p2, T))`` as one fused op (fp32 scalar).
+
+    Per-rank normalisation follows the reference / DDP convention: mean over this rank's 2N rows."""
+    if p1.dim() != 2 or p1.shape != p2.shape:
+        raise ValueError("fused_infonce expects two [N, D] tensors of identical shape")
+    require_cuda(p1, p2)
+    if temperature <= 0:
+        raise ValueError("temperature must be > 0")
+    z_dtype, algo = pick_precision(p1, precision)
+    return _FusedInfoNCE.apply(p1, p2, float(temperature), z_dtype, algo, group, float(weight))
+
+
+# ------------------------------------------------------------------------------------------------------
+# heads
+# ------------------------------------------------------------------------------------------------------
+class _MultiHeadCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, class_counts, weights, inv_t, ignore_index, use_ignore):
+        import ctypes as C
+        dev = require_cuda(logits, labels)
+        logits = _contig(logits)
+        labels = _contig(labels.to(torch.int64))
+        b, c_total = logits.shape
+        h = len(class_counts)
+        if sum(class_counts) != c_total or labels.shape != (b, h):
+            raise ValueError(f"logits [B,{c_total}] / labels {tuple(labels.shape)} do not match heads {class_counts}")
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dlogits = torch.empty_like(logits) if need_grad else None
+        nbytes = lib().sm3_multihead_ce_workspace_bytes(b, h)
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        cc = (C.c_int * h)(*class_counts)
+        wt = (C.c_float * h)(*weights) if weights is not None else None
+        with torch.cuda.device(dev):
+            check(lib().sm3_multihead_ce(ptr(logits), dtype_code(logits), ptr(labels), b, h, cc, wt, inv_t,
+                                         int(use_ignore), ignore_index, ptr(loss), ptr(dlogits), 1.0, ptr(ws),
+                                         ws.numel(), stream_ptr()), "sm3_multihead_ce")
+        if need_grad:
+            ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g.to(dlogits.dtype), None, None, None, None, None, None
+
+
+def multihead_ce(outputs, labels: torch.Tensor, weights: Optional[Sequence[float]] = None, temperature: float = 1.0,
+                 ignore_index: Optional[int] = None, class_counts: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """``sum_h w_h * CE(outputs[h] / T, labels[:, h]) / H`` in one launch (forward + backward).
+
+    outputs: list of H tensors ``[B, n_h]`` (the reference heads' return value) or one ``[B, sum n_h]`` tensor.
+    ignore_index=None promises there are no ignored labels (mlc_eval form); an int enables the
+    DeepCluster form of tools/mlc_train.py:381 (``ignore_index=-100``)."""
+    if isinstance(outputs, (list, tuple)):
+        class_counts = [int(o.shape[1]) for o in outputs]
+        logits = torch.cat(list(outputs), dim=1)
+    else:
+        logits = outputs
+        class_counts = list(class_counts if class_counts is not None else NUM_CLASSES)
+    w = None if weights is None else [float(x) for x in weights]
+    return _MultiHeadCE.apply(logits, labels, tuple(class_counts), w, 1.0 / float(temperature),
+                              -100 if ignore_index is None else int(ignore_index), ignore_index is not None)
+
+
+class _BCEWithLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, t, pos_weight):
+        dev = require_cuda(x, t, pos_weight)
+        x = _contig(x)
+        t = _contig(t)
+        if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            t = t.to(torch.float32)
+        if x.shape != t.shape or x.dim() != 2:
+            raise ValueError("bce_with_logits expects logits and targets of identical shape [B, C]")
+        b, c = x.shape
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x) if need_grad else None
+        pw = None if pos_weight is None else _contig(pos_weight.float())
+        ws = torch.empty(int(lib().sm3_bce_workspace_bytes(b, c)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().sm3_bce_logits(ptr(x), dtype_code(x), ptr(t), dtype_code(t), ptr(pw), b, c, ptr(loss), ptr(dx),
+                                       1.0, ptr(ws), ws.numel(), stream_ptr()), "sm3_bce_logits")
+        if need_grad:
+            ctx.save_for_backward(dx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g.to(dx.dtype), None, None
+
+
+def bce_with_logits(x: torch.Tensor, target: torch.Tensor, pos_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mean-reduced ``binary_cross_entropy_with_logits`` over multi-hot targets, forward + backward in one launch."""
+    return _BCEWithLogits.apply(x, target, pos_weight)
+
+
+# ------------------------------------------------------------------------------------------------------
+# host-buffer entry (the call bench.py times end to end)
+# ------------------------------------------------------------------------------------------------------
+class HostInfoNCE:
+    """Pinned-host-buffer front end of ``sm3_infonce_host``: H2D copy, fused fwd+bwd, D2H of loss and grads."""
+
+    def __init__(self, n_pairs: int, d: int, dtype: torch.dtype = torch.bfloat16, algo: int = ALGO_AUTO,
+                 device: Optional[torch.device] = None):
+        self.n, self.d, self.dtype, self.algo = n_pairs, d, dtype, algo
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        code = _lib._DTYPES[dtype]
+        with torch.cuda.device(self.device):
+            nbytes = lib().sm3_infonce_host_scratch_bytes(n_pairs, d, code, algo)
+        if nbytes == 0:
+            raise ValueError("bad shape for HostInfoNCE")
+        self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        self.dp1 = torch.empty((n_pairs, d), dtype=dtype).pin_memory()
+        self.dp2 = torch.empty((n_pairs, d), dtype=dtype).pin_memory()
+        self.h2d_bytes = 2 * n_pairs * d * self.dp1.element_size()
+        self.d2h_bytes = 4 + self.h2d_bytes
+
+    def __call__(self, p1_host: torch.Tensor, p2_host: torch.Tensor, temperature: float):
+        assert not p1_host.is_cuda and p1_host.dtype == self.dtype and tuple(p1_host.shape) == (self.n, self.d)
+        with torch.cuda.device(self.device):
+            check(lib().sm3_infonce_host(p1_host.data_ptr(), p2_host.data_ptr(), self.n, self.d,
+                                         _lib._DTYPES[self.dtype], temperature, self.loss.data_ptr(),
+                                         self.dp1.data_ptr(), self.dp2.data_ptr(), ptr(self.scratch),
+                                         self.scratch.numel(), self.algo, stream_ptr()), "sm3_infonce_host")
+        return self.loss, self.dp1, self.dp2

@@ -1,0 +1,353 @@
+"""Parity tests proper: the CUDA path (through the C ABI / autograd drop-ins) against the golden fixtures
+produced by the real reference and against the CPU oracle on seeded inputs.  Run with ``-m gpu`` on a B200.
+
+Tolerances (BASELINE.json north_star): fp32 loss 1e-5 relative, gradients 1e-4 relative;
+bf16 loss and gradients 2e-2 relative.  "relative" for a gradient tensor = max|delta| / max|reference|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import sm3_oracle as O  # noqa: E402  (checker only)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FULL = ["infonce_n4_d8_T05", "infonce_n64_d128_T01", "infonce_n48_d128_T01_corr"]
+BIG = ["infonce_n200_d64_T02_corr", "infonce_n512_d256_T01"]
+LOSS_TOL = {"fp32": 1e-5, "bf16": 2e-2}
+GRAD_TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def sm3():
+    import skin_sm3_b200 as m
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert m.lib().sm3_device_supported() == 1, "not an sm_100 device"
+    return m
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+def cuda(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)
+
+
+def relerr(a, ref):
+    a = np.asarray(a, np.float64); ref = np.asarray(ref, np.float64)
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def run_term(sm3, p1, p2, T, precision):
+    a = p1.clone().requires_grad_(True)
+    b = p2.clone().requires_grad_(True)
+    logits, labels = sm3.cal_logits(a, b, T, precision=precision)
+    assert logits.shape == (2 * p1.shape[0], 2) and logits.dtype == torch.float32
+    assert labels.dtype == torch.long and int(labels.abs().sum()) == 0
+    loss = F.cross_entropy(logits, labels)          # the script's own nn.CrossEntropyLoss()
+    loss.backward()
+    return loss.item(), a.grad.float().cpu().numpy(), b.grad.float().cpu().numpy(), logits.detach()
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(7, 8), (33, 5), (64, 128), (130, 256), (9, 512), (5, 1030)])
+def test_l2norm_forward_backward(sm3, dtype, shape):
+    g = torch.Generator().manual_seed(1)
+    p = torch.randn(*shape, generator=g).to(dtype)
+    p[1] = 0                                            # eps-clamp row
+    pc = p.cuda().requires_grad_(True)
+    z = sm3.l2_normalize(pc)
+    w = torch.randn(*shape, generator=g).cuda()
+    (z.float() * w).sum().backward()
+    ref_p = p.double().requires_grad_(True)
+    ref = F.normalize(ref_p, dim=1)
+    (ref * w.cpu().double()).sum().backward()
+    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    assert relerr(z.float().cpu(), ref.detach()) < tol
+    gref = ref_p.grad.numpy()
+    keep = np.ones(shape[0], bool); keep[1] = False      # clamped row: gradient is w / eps (1e12 scale)
+    assert relerr(pc.grad.float().cpu().numpy()[keep], gref[keep]) < (2e-5 if dtype == torch.float32 else 2e-2)
+    assert relerr(pc.grad.float().cpu().numpy()[1], gref[1]) < 1e-2
+    assert not z[1].any()
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 / K3 against the reference-generated goldens
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", FULL + BIG)
+def test_infonce_matches_reference_golden(sm3, name, precision):
+    g = load(name)
+    T, n = float(g["temperature"]), int(g["n"])
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    p1, p2 = cuda(g["p1"], dt), cuda(g["p2"], dt)
+    loss, d1, d2, logits = run_term(sm3, p1, p2, T, precision)
+    if precision == "fp32":
+        ref_loss = float(g["loss_f64"])
+        ref1 = g["dp1_f64"] if "dp1_f64" in g else None
+    else:   # oracle evaluated on the bf16-rounded inputs the kernel actually saw
+        ref_loss, r1, r2 = O.infonce_closed_form(p1.float().cpu().numpy(), p2.float().cpu().numpy(), T)
+        ref1 = r1
+    assert abs(loss - ref_loss) <= LOSS_TOL[precision] * max(abs(ref_loss), 1e-3), (loss, ref_loss)
+    if precision == "fp32":
+        if ref1 is not None:
+            assert relerr(d1, g["dp1_f64"]) < GRAD_TOL[precision]
+            assert relerr(d2, g["dp2_f64"]) < GRAD_TOL[precision]
+            col0 = g["logits_f64"][:, 0]
+        else:
+            r = g["grad_rows"]
+            assert relerr(d1[r], g["dp1_rows_f64"]) < GRAD_TOL[precision]
+            assert relerr(d2[r], g["dp2_rows_f64"]) < GRAD_TOL[precision]
+            assert relerr(d1.sum(0), g["dp1_sum_f64"]) < 1e-3
+            col0 = g["logits_col0_f64"]
+        # column 0 of our logits == the reference's positives column
+        assert relerr(logits[:, 0].cpu().numpy(), col0) < 1e-5
+    else:
+        assert relerr(d1, ref1) < GRAD_TOL[precision]
+        assert relerr(d2, r2) < GRAD_TOL[precision]
+
+
+def test_infonce_edge_cases_fp32(sm3):
+    g = load("infonce_edge")
+    for case in g["case_names"]:
+        for T in (0.1, 0.5):
+            k = f"{case}_T{T}"
+            loss, d1, d2, _ = run_term(sm3, cuda(g[k + "_p1"]), cuda(g[k + "_p2"]), T, "fp32")
+            ref = float(g[k + "_loss"])
+            assert abs(loss - ref) <= 1e-5 * max(abs(ref), 1.0), (k, loss, ref)
+            assert np.isfinite(d1).all() and np.isfinite(d2).all(), k
+            assert relerr(d1, g[k + "_dp1"]) < 1e-4, k
+            assert relerr(d2, g[k + "_dp2"]) < 1e-4, k
+
+
+@pytest.mark.parametrize("n,d,T", [(1024, 128, 0.1), (1000, 64, 0.5), (333, 192, 0.2), (1536, 256, 0.1),
+                                   (64, 256, 0.1), (129, 128, 0.07)])
+def test_tensor_core_path_vs_oracle(sm3, n, d, T):
+    """tcgen05 kernels (bf16 rows) vs the fp64 closed form on the same bf16-rounded inputs; ragged tile edges."""
+    g = torch.Generator().manual_seed(n + d)
+    p1 = torch.randn(n, d, generator=g).bfloat16()
+    p2 = (p1.float() + 0.5 * torch.randn(n, d, generator=g)).bfloat16()
+    loss, d1, d2, logits = run_term(sm3, p1.cuda(), p2.cuda(), T, "bf16")
+    ref_loss, r1, r2 = O.infonce_closed_form(p1.float().numpy(), p2.float().numpy(), T)
+    assert abs(loss - ref_loss) <= 2e-2 * max(abs(ref_loss), 1e-3), (loss, ref_loss)
+    assert relerr(d1, r1) < 2e-2 and relerr(d2, r2) < 2e-2
+    # retrieval contract: the positive is found exactly where the reference finds it (argmax agreement)
+    z, _ = O.normalize(np.concatenate([p1.float().numpy(), p2.float().numpy()]))
+    pos_ref, lse_ref = O.infonce_stats(z, n, T)
+    assert relerr(logits[:, 0].cpu().numpy(), pos_ref) < 2e-2
+    assert np.abs(logits[:, 1].cpu().numpy() - lse_ref).max() < 2e-2
+
+
+def test_tensor_core_and_fma_kernels_agree_on_identical_rows(sm3):
+    """Same bf16 rows through both CUDA kernels: differences are accumulation-order only."""
+    n, d, T = 700, 128, 0.1
+    g = torch.Generator().manual_seed(7)
+    p = torch.randn(2 * n, d, generator=g).cuda()
+    z, _ = sm3.core.normalize_pair(p, None, torch.bfloat16)
+    a = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
+    b = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_SIMT)
+    for x, y in zip(a, b):
+        assert relerr(x.cpu(), y.cpu()) < 1e-4
+    gp = torch.randn(2 * n, generator=g).cuda() * 1e-3
+    gl = torch.rand(2 * n, generator=g).cuda() * 1e-3
+    outs = []
+    for algo in (sm3.ALGO_TC, sm3.ALGO_SIMT):
+        ws, k = sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, b[2], gp, gl, b[2], algo)
+        outs.append(sm3.core.sum_partials(ws, k, 2 * n, d).clone())
+    assert relerr(outs[0].cpu(), outs[1].cpu()) < 1.5e-2     # H is rounded to bf16 on the tensor-core path
+
+
+def test_row_block_sharding_reproduces_single_block(sm3):
+    """W-rank emulation on one GPU: per-rank row blocks with global column order == one-block result."""
+    n, d, T, W = 512, 128, 0.1, 4
+    g = torch.Generator().manual_seed(11)
+    p = torch.randn(2 * n, d, generator=g).cuda()
+    for z_dtype, algo in ((torch.bfloat16, sm3.ALGO_TC), (torch.float32, sm3.ALGO_SIMT)):
+        z, _ = sm3.core.normalize_pair(p, None, z_dtype)
+        pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, algo)
+        gp = torch.randn(2 * n, generator=g).cuda() * 1e-3
+        gl = torch.rand(2 * n, generator=g).cuda() * 1e-3
+        ws, k = sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, algo)
+        dz = sm3.core.sum_partials(ws, k, 2 * n, d).clone()
+        nl = n // W
+        for r in range(W):
+            rows = torch.from_numpy(O.global_row_index(nl, r * nl, n)).cuda()
+            zr = z[rows].contiguous()
+            ps, ls, ns = sm3.core.stats_fwd(zr, z, nl, r * nl, n, T, algo)
+            assert relerr(ps.cpu(), pos[rows].cpu()) < 1e-5 and relerr(ns.cpu(), nsum[rows].cpu()) < 1e-5
+            assert relerr(ls.cpu(), lse[rows].cpu()) < 1e-5
+            ws, k = sm3.core.stats_bwd(zr, z, nl, r * nl, n, T, gp[rows].contiguous(), gl[rows].contiguous(),
+                                       nsum[rows].contiguous(), gp, gl, nsum, algo)
+            dzr = sm3.core.sum_partials(ws, k, 2 * nl, d)
+            assert relerr(dzr.cpu(), dz[rows].cpu()) < 1e-4
+
+
+def test_fused_scalar_loss_and_grad_scaling(sm3):
+    """fused_infonce == CE(cal_logits) incl. an upstream scale (GradScaler x loss weight, backbone_train.py:101-125)."""
+    g = load("infonce_n64_d128_T01")
+    T = float(g["temperature"])
+    p1 = cuda(g["p1"]).requires_grad_(True); p2 = cuda(g["p2"]).requires_grad_(True)
+    loss = sm3.fused_infonce(p1, p2, T, precision="fp32")
+    (loss * 65536.0 * 0.5).backward()
+    assert abs(loss.item() - float(g["loss_f64"])) < 1e-5 * float(g["loss_f64"])
+    assert relerr(p1.grad.cpu().numpy() / 32768.0, g["dp1_f64"]) < 1e-4
+    assert relerr(p2.grad.cpu().numpy() / 32768.0, g["dp2_f64"]) < 1e-4
+
+
+def test_host_buffer_entry(sm3):
+    g = load("infonce_n64_d128_T01")
+    T, n, d = float(g["temperature"]), int(g["n"]), int(g["d"])
+    for dt, algo, tl, tg in ((torch.float32, sm3.ALGO_SIMT, 1e-5, 1e-4), (torch.bfloat16, sm3.ALGO_TC, 2e-2, 2e-2)):
+        h = sm3.HostInfoNCE(n, d, dt, algo)
+        p1 = torch.from_numpy(g["p1"]).to(dt).pin_memory(); p2 = torch.from_numpy(g["p2"]).to(dt).pin_memory()
+        loss, d1, d2 = h(p1, p2, T)
+        ref_loss, r1, r2 = O.infonce_closed_form(p1.float().numpy(), p2.float().numpy(), T)
+        assert abs(loss.item() - ref_loss) < tl * ref_loss
+        assert relerr(d1.float().numpy(), r1) < tg and relerr(d2.float().numpy(), r2) < tg
+
+
+def test_known_answers_at_full_size(sm3):
+    """Size-independent properties at BASELINE config-4 scale (N=32768, D=256, M=65536 rows)."""
+    n, d, T = 32768, 256, 0.1
+    m = 2 * n
+    # (i) all rows identical -> every similarity is 1 -> loss = log(M-1)
+    p = torch.ones(n, d, device="cuda", dtype=torch.bfloat16)
+    loss = sm3.fused_infonce(p, p, T, precision="bf16")
+    assert abs(loss.item() - np.log(m - 1)) < 1e-3
+    # (ii) z_{i+N} = z_i = e_{i mod D}: positives 1, D-fold duplicates among the negatives
+    idx = torch.arange(n, device="cuda") % d
+    e = torch.zeros(n, d, device="cuda", dtype=torch.bfloat16)
+    e[torch.arange(n, device="cuda"), idx] = 1
+    loss = sm3.fused_infonce(e, e, T, precision="bf16")
+    same = m // d - 2                    # negatives identical to the row, rest orthogonal
+    expect = np.log(np.exp(1 / T) * (1 + same) + (m - 2 - same)) - 1 / T
+    assert abs(loss.item() - expect) < 1e-3 * expect
+    # (iii) random rows: gradient of every row is orthogonal to the row itself (normalise backward)
+    g = torch.Generator(device="cuda").manual_seed(3407)
+    p1 = torch.randn(n, d, generator=g, device="cuda").bfloat16().requires_grad_(True)
+    p2 = torch.randn(n, d, generator=g, device="cuda").bfloat16().requires_grad_(True)
+    loss = sm3.fused_infonce(p1, p2, T, precision="bf16")
+    loss.backward()
+    assert abs(loss.item() - np.log(m - 1)) < 0.2 * np.log(m - 1)
+    dots = (p1.grad.float() * p1.float()).sum(1).abs().max().item()
+    scale = (p1.grad.float().norm(dim=1) * p1.float().norm(dim=1)).max().item()
+    assert dots < 3e-2 * scale
+    # (iv) tensor-core path == FMA path on a 256-row block of the same problem
+    z, _ = sm3.core.normalize_pair(p1.detach(), p2.detach(), torch.bfloat16)
+    nl = 128
+    rows = torch.from_numpy(O.global_row_index(nl, 5 * nl, n)).cuda()
+    zr = z[rows].contiguous()
+    a = sm3.core.stats_fwd(zr, z, nl, 5 * nl, n, T, sm3.ALGO_TC)
+    b = sm3.core.stats_fwd(zr, z, nl, 5 * nl, n, T, sm3.ALGO_SIMT)
+    for x, y in zip(a, b):
+        assert relerr(x.cpu(), y.cpu()) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# heads
+# ---------------------------------------------------------------------------------------------------
+def test_multihead_ce_matches_reference_loops(sm3):
+    g = load("heads")
+    nc = [int(c) for c in g["num_classes"]]
+    x = cuda(g["eval_logits"]).requires_grad_(True)
+    loss = sm3.multihead_ce(list(torch.split(x, nc, dim=1)), cuda(g["eval_labels"], torch.long),
+                            weights=list(g["eval_weights"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["eval_loss"])) < 1e-5 * float(g["eval_loss"])
+    assert relerr(x.grad.cpu().numpy(), g["eval_grad"]) < 1e-4
+    x = cuda(g["dc_logits"]).requires_grad_(True)
+    loss = sm3.multihead_ce(x, cuda(g["dc_labels"], torch.long), temperature=float(g["dc_temperature"]),
+                            ignore_index=-100, class_counts=nc)
+    loss.backward()
+    assert abs(loss.item() - float(g["dc_loss"])) < 1e-5 * float(g["dc_loss"])
+    assert relerr(x.grad.cpu().numpy(), g["dc_grad"]) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B", [1, 64, 257, 4096, 100003])
+def test_multihead_ce_vs_oracle(sm3, dtype, B):
+    rng = np.random.default_rng(B)
+    nc = list(sm3.NUM_CLASSES)
+    x = torch.from_numpy(rng.normal(size=(B, 24)).astype(np.float32) * 2).to(dtype)
+    y = np.stack([rng.integers(0, c, B) for c in nc], axis=1)
+    y[rng.random((B, 8)) < 0.1] = -100
+    if (y[:, 0] == -100).all():
+        y[0, :] = 0
+    w = [1, 2, 0.5, 1, 1, 3, 1, 0.25]
+    xc = x.cuda().requires_grad_(True)
+    loss = sm3.multihead_ce(xc, torch.from_numpy(y).cuda(), weights=w, temperature=0.5, ignore_index=-100)
+    loss.backward()
+    ref, gref = O.multihead_ce(x.float().numpy(), y, w, 2.0, -100, nc)
+    if np.isnan(ref):
+        assert np.isnan(loss.item())
+        return
+    assert abs(loss.item() - ref) < 2e-5 * abs(ref)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert relerr(xc.grad.float().cpu().numpy(), gref) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1, 24), (37, 24), (512, 24), (1001, 5), (65536, 24)])
+def test_bce_with_logits_vs_torch_oracle(sm3, dtype, shape):
+    rng = np.random.default_rng(shape[0])
+    x = torch.from_numpy(rng.normal(size=shape).astype(np.float32) * 3).to(dtype)
+    t = torch.from_numpy((rng.random(shape) < 0.3).astype(np.float32))
+    pw = torch.from_numpy(rng.random(shape[1]).astype(np.float32) * 3 + 0.5)
+    for pos_weight in (None, pw):
+        xc = x.cuda().requires_grad_(True)
+        loss = sm3.bce_with_logits(xc, t.cuda(), None if pos_weight is None else pos_weight.cuda())
+        loss.backward()
+        ref, gref = O.bce_with_logits(x.float().numpy(), t.numpy(), None if pos_weight is None else pw.numpy())
+        assert abs(loss.item() - ref) < 1e-5 * abs(ref)
+        assert relerr(xc.grad.float().cpu().numpy(), gref) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# drop-in module against the real reference wrappers (tiny encoder golden)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cls_name", ["SimCLRSkinV3", "SimCLRSkinV32"])
+def test_dropin_model_matches_reference(sm3, cls_name):
+    from skin_sm3_b200 import dropin
+    dropin.install()
+    from src.models import resnet as my_resnet
+    from src.models import simclr as mine
+    from tiny_encoder import tiny
+    my_resnet.__dict__["tiny"] = tiny
+    g = load("model_tiny")
+    N, PD, T = int(g["N"]), int(g["proj_dim"]), float(g["temperature"])
+    model = getattr(mine, cls_name)("tiny", weights=None, proj_dim=PD, temperature=T)
+    keys = [str(k) for k in g[f"{cls_name}/sd_keys"]]
+    assert list(model.state_dict().keys()) == keys
+    sd = {k: torch.from_numpy(g[f"{cls_name}/sd/{k}"]) for k in keys}
+    imgs = [cuda(g["imgs"][i]) for i in range(4)]
+    crit = torch.nn.CrossEntropyLoss().cuda()          # tools/backbone_train.py:531
+    for style, wts in ((0, (0.5, 0.5)), (1, (0.5, 0.5)), (2, (0.25,) * 4)):
+        model.load_state_dict(sd)
+        model = model.float().cuda().train()
+        model.zero_grad(set_to_none=True)
+        out = model([imgs[0], imgs[1]], [imgs[2], imgs[3]], style)
+        assert len(out) == 3 and len(out[2]) == len(wts)
+        cross = sum(w * crit(*out[2][k]) for k, w in enumerate(wts))
+        derm, clinic = crit(*out[0]), crit(*out[1])
+        loss = derm + clinic + cross                     # tools/backbone_train.py:98-121
+        loss.backward()
+        pre = f"{cls_name}/style{style}/"
+        assert abs(derm.item() - float(g[pre + "derm_loss"])) < 1e-4 * abs(float(g[pre + "derm_loss"]))
+        assert abs(clinic.item() - float(g[pre + "clinic_loss"])) < 1e-4 * abs(float(g[pre + "clinic_loss"]))
+        got = np.array([crit(*o).item() for o in out[2]])
+        assert np.abs(got - g[pre + "cross_losses"]).max() < 1e-4 * np.abs(g[pre + "cross_losses"]).max()
+        assert abs(loss.item() - float(g[pre + "loss"])) < 1e-4 * abs(float(g[pre + "loss"]))
+        for k, p in model.named_parameters():
+            ref = g[pre + "grad/" + k]
+            if ref.size == 0:
+                assert p.grad is None or not p.grad.any()
+                continue
+            assert relerr(p.grad.cpu().numpy(), ref) < 2e-3, (style, k)
