@@ -326,7 +326,7 @@ def run_ours(args):
         line["roofline_fwd"] = {"bound": "tensor", "kernel": "infonce_tc_fwd_kernel (K2; includes the finalize kernel)",
                                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
     line["step_tc_frac"] = (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12 / pk["tflops"]
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_extras:
         line["cpu_baseline"] = cpu_reference(n, d, T)
         if args.workload != "cfg2":     # configs[1] rides along in the same line
             w2 = WORKLOADS["cfg2"]
@@ -381,6 +381,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / cfg2 / heads (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -71,11 +71,12 @@ def test_l2norm_forward_backward(sm3, dtype, shape):
     ref = F.normalize(ref_p, dim=1)
     (ref * w.cpu().double()).sum().backward()
     tol = 1e-6 if dtype == torch.float32 else 8e-3
-    assert relerr(z.float().cpu(), ref.detach()) < tol
+    assert relerr(z.detach().float().cpu(), ref.detach()) < tol
     gref = ref_p.grad.numpy()
     keep = np.ones(shape[0], bool); keep[1] = False      # clamped row: gradient is w / eps (1e12 scale)
     assert relerr(pc.grad.float().cpu().numpy()[keep], gref[keep]) < (2e-5 if dtype == torch.float32 else 2e-2)
-    assert relerr(pc.grad.float().cpu().numpy()[1], gref[1]) < 1e-2
+    if dtype != torch.float16:                           # w / 1e-12 overflows fp16, in the reference too
+        assert relerr(pc.grad.float().cpu().numpy()[1], gref[1]) < 1e-2
     assert not z[1].any()
 
 
