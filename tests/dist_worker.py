@@ -1,0 +1,123 @@
+"""Worker for the multi-rank tests (launched by torchrun / mp.spawn).  backend=nccl: real kernels on GPUs;
+backend=gloo: the host-side sharding logic on CPU with the oracle standing in for the kernels."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import sm3_oracle as O  # noqa: E402  (checker / stand-in, tests only)
+
+
+class OracleCore:
+    """CPU stand-in for skin_sm3_b200.functional.core with identical signatures (gloo tests only)."""
+
+    @staticmethod
+    def normalize_pair(p1, p2, z_dtype, eps=1e-12):
+        p = torch.cat([p1, p2]) if p2 is not None else p1
+        z, inv = O.normalize(p.double().numpy(), eps)
+        return torch.from_numpy(z), torch.from_numpy(inv).float()
+
+    @staticmethod
+    def stats_fwd(z_rows, z_cols, n_local, pair_offset, n_global, temperature, algo=0):
+        rows = O.global_row_index(n_local, pair_offset, n_global)
+        zc = z_cols.double().numpy()
+        assert np.allclose(zc[rows], z_rows.double().numpy()), "row block is not where the global order says"
+        pos, lse = O.infonce_stats(zc, n_global, temperature, rows=rows)
+        nsum = np.exp(lse - 1.0 / temperature)
+        return (torch.from_numpy(pos).float(), torch.from_numpy(lse).float(), torch.from_numpy(nsum).float())
+
+    @staticmethod
+    def stats_bwd(z_rows, z_cols, n_local, pair_offset, n_global, temperature, gp_r, gl_r, ns_r, gp_c, gl_c, ns_c,
+                  algo=0):
+        rows = O.global_row_index(n_local, pair_offset, n_global)
+        assert torch.allclose(gp_c[rows], gp_r) and torch.allclose(gl_c[rows], gl_r) and torch.allclose(ns_c[rows], ns_r)
+        dz = O.stats_backward(z_cols.double().numpy(), n_global, temperature, gp_c.double().numpy(),
+                              gl_c.double().numpy())
+        return torch.from_numpy(dz[rows].copy()), 1
+
+    @staticmethod
+    def loss(pos, lse_neg, scale, out=None, accumulate=False, want_grads=True):
+        x = (lse_neg - pos).double()
+        sig = torch.sigmoid(x)
+        val = (torch.nn.functional.softplus(x).sum() * scale).float()
+        return val, (-scale * sig).float(), (scale * sig).float()
+
+    @staticmethod
+    def normalize_bwd(dz, n_partials, scale, z, inv, n1, n2, out_dtype, eps=1e-12):
+        dp = O.normalize_bwd(dz.double().numpy() * scale, z.double().numpy(), inv.double().numpy())
+        dp = torch.from_numpy(dp).to(out_dtype)
+        return dp[:n1], dp[n1:]
+
+
+def main():
+    backend = sys.argv[1]
+    out_path = sys.argv[2] if len(sys.argv) > 2 else None
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl")
+        dev = "cuda"
+    else:
+        dist.init_process_group("gloo")
+        dev = "cpu"
+    import skin_sm3_b200 as sm3
+    from skin_sm3_b200 import functional as F3
+    if backend == "gloo":
+        F3.core = OracleCore
+        F3.require_cuda = lambda *t: torch.device("cpu")
+    results = {}
+    cases = [(64 * world, 128, 0.1, "bf16"), (48 * world, 128, 0.5, "fp32")] if backend == "nccl" else \
+            [(6 * world, 16, 0.1, "fp32"), (5 * world, 8, 0.5, "fp32")]
+    for n_global, d, T, precision in cases:
+        g = torch.Generator().manual_seed(1234 + n_global)
+        P1 = torch.randn(n_global, d, generator=g)
+        P2 = P1 + 0.5 * torch.randn(n_global, d, generator=g)
+        dt = torch.bfloat16 if precision == "bf16" else (torch.float32 if backend == "nccl" else torch.float64)
+        P1, P2 = P1.to(dt), P2.to(dt)
+        nl = n_global // world
+        sl = slice(rank * nl, (rank + 1) * nl)
+        # ---- gather order ----
+        local = torch.cat([P1[sl], P2[sl]]).to(dev)
+        full = sm3.gather_global_order(local, dist.group.WORLD)
+        assert torch.equal(full.cpu(), torch.cat([P1, P2])), "gather_global_order != [all first ; all second]"
+        # ---- sharded logits + the script's CE + backward; DDP averages gradients over ranks ----
+        a = P1[sl].to(dev).requires_grad_(True)
+        b = P2[sl].to(dev).requires_grad_(True)
+        logits, labels = sm3.cal_logits(a, b, T, precision=precision, group=dist.group.WORLD)
+        loss = torch.nn.functional.cross_entropy(logits.float(), labels)
+        loss.backward()
+        lt = loss.detach().clone().float()
+        dist.all_reduce(lt)
+        loss_global = lt.item() / world
+        ref_loss, r1, r2 = O.infonce_closed_form(P1.double().numpy(), P2.double().numpy(), T)
+        ltol, gtol = (2e-2, 2e-2) if precision == "bf16" else ((1e-5, 1e-4) if backend == "nccl" else (1e-6, 1e-5))   # stand-in returns fp32 stats like the kernels
+        assert abs(loss_global - ref_loss) <= ltol * abs(ref_loss), (loss_global, ref_loss)
+        # d(global mean loss)/dp = (1/W) * sum over ranks of d(L_r)/dp ; our backward already sums over ranks
+        g1 = a.grad.double().cpu().numpy() / world
+        g2 = b.grad.double().cpu().numpy() / world
+        e1 = np.abs(g1 - r1[sl]).max() / np.abs(r1).max()
+        e2 = np.abs(g2 - r2[sl]).max() / np.abs(r2).max()
+        assert e1 <= gtol and e2 <= gtol, (e1, e2)
+        # ---- fused scalar form ----
+        a2 = P1[sl].to(dev).requires_grad_(True)
+        b2 = P2[sl].to(dev).requires_grad_(True)
+        l2 = sm3.fused_infonce(a2, b2, T, precision=precision, group=dist.group.WORLD)
+        l2.backward()
+        assert abs(l2.item() - loss.item()) <= 1e-5 * abs(loss.item()) + 1e-7
+        e3 = (a2.grad.double() - a.grad.double()).abs().max().item() / a.grad.double().abs().max().item()
+        assert e3 <= 1e-5, e3
+        results[f"{n_global}x{d}"] = (loss_global, ref_loss, float(e1), float(e2))
+    if rank == 0 and out_path:
+        with open(out_path, "w") as f:
+            f.write(repr(results))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
