@@ -50,48 +50,54 @@ __global__ void heads_count_kernel(const int64_t* __restrict__ labels, int64_t B
   if (threadIdx.x < H) ws[kWsCounts + threadIdx.x] = (float)cnt[threadIdx.x];
 }
 
-template <typename T>
+// kFixed == true: the SM3 head layout (5,3,2,3,3,3,3,2 -> 24 logits, 8 heads) is a compile-time constant, so
+// every index computation in the staging loops is a shift/multiply and the per-row softmaxes unroll into
+// registers.  kFixed == false: arbitrary layout from `meta` (same algorithm, runtime bounds).
+template <typename T, bool kFixed>
 __global__ void __launch_bounds__(kHeadThreads)
 multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels, int64_t B, HeadMeta meta,
                     float inv_T, int use_ignore, int64_t ignore_index, float* __restrict__ loss_out,
                     T* __restrict__ dlogits, float grad_scale, float* __restrict__ ws) {
   extern __shared__ float smem[];
-  const int C = meta.C, H = meta.H;
+  const int C = kFixed ? 24 : meta.C;
+  const int H = kFixed ? 8 : meta.H;
   const int ldx = C + 1;                      // +1 float: conflict-free row-per-thread access
   float* xs = smem;                           // [kHeadThreads][C+1]
   int* ys = reinterpret_cast<int*>(smem + kHeadThreads * ldx);  // [kHeadThreads][H+1]
   float* red = reinterpret_cast<float*>(ys + kHeadThreads * (H + 1));  // [8 warps][H]
   __shared__ bool is_last;
+  constexpr int kOff[9] = {0, 5, 8, 10, 13, 16, 19, 22, 24};
 
   const int64_t row0 = (int64_t)blockIdx.x * kHeadThreads;
   const int rows_here = (int)min((int64_t)kHeadThreads, B - row0);
   const int tid = threadIdx.x;
 
   // ---- coalesced stage-in ----
-  const int64_t n_el = (int64_t)rows_here * C;
+  const int n_el = rows_here * C;
   const T* src = logits + row0 * C;
   constexpr int V = VecIO<T>::N;
   const bool vec_ok = (((uintptr_t)src & 15u) == 0);
-  const int64_t n_vec = vec_ok ? n_el / V : 0;
-  for (int64_t v = tid; v < n_vec; v += kHeadThreads) {
+  const int n_vec = vec_ok ? n_el / V : 0;
+  for (int v = tid; v < n_vec; v += kHeadThreads) {
     float t[V];
-    VecIO<T>::load(src + v * V, t);
+    VecIO<T>::load(src + (size_t)v * V, t);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const int e = (int)(v * V) + i;
-      xs[(e / C) * ldx + (e % C)] = t[i];
+      const int e = v * V + i;
+      const int r = e / C;
+      xs[r * ldx + (e - r * C)] = t[i];
     }
   }
-  for (int64_t e = n_vec * V + tid; e < n_el; e += kHeadThreads) xs[(e / C) * ldx + (e % C)] = to_f32(src[e]);
+  for (int e = n_vec * V + tid; e < n_el; e += kHeadThreads) { const int r = e / C; xs[r * ldx + (e - r * C)] = to_f32(src[e]); }
   const int64_t* lsrc = labels + row0 * H;
   for (int e = tid; e < rows_here * H; e += kHeadThreads) {
     const int64_t y = __ldg(lsrc + e);
-    const int h = e % H;
-    const int nc = meta.offset[h + 1] - meta.offset[h];
+    const int r = e / H, h = e - r * H;
+    const int nc = kFixed ? (kOff[h + 1] - kOff[h]) : (meta.offset[h + 1] - meta.offset[h]);
     int yi;
     if (use_ignore && y == ignore_index) yi = -1;
-    else yi = (y >= 0 && y < nc) ? (int)y : -2;   // -2: out of range -> contributes NaN like a device assert would
-    ys[(e / H) * (H + 1) + h] = yi;
+    else yi = (y >= 0 && y < nc) ? (int)y : -2;   // -2: out of range -> NaN loss (torch would device-assert)
+    ys[r * (H + 1) + h] = yi;
   }
   __syncthreads();
 
@@ -102,9 +108,35 @@ multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ la
   if (tid < rows_here) {
     float* x = xs + tid * ldx;
     const int* y = ys + tid * (H + 1);
+    if constexpr (kFixed) {
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) {
-      if (h < H) {
+      for (int h = 0; h < 8; ++h) {
+        constexpr int kMaxNc = 5;
+        const int o = kOff[h], nc = kOff[h + 1] - kOff[h];
+        float v[kMaxNc];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kMaxNc; ++c) if (c < nc) { v[c] = x[o + c] * inv_T; mx = fmaxf(mx, v[c]); }
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxNc; ++c) if (c < nc) { v[c] = __expf(v[c] - mx); se += v[c]; }
+        const int yy = y[h];
+        const bool valid = yy >= 0;
+        const float cnt = use_ignore ? ws[kWsCounts + h] : (float)B;
+        const float gs = (valid && cnt > 0.f) ? grad_scale * meta.weight[h] * inv_T / (cnt * 8.0f) : 0.f;
+        const float inv_se = __frcp_rn(se);
+        float xy = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxNc; ++c) if (c < nc) {
+          if (c == yy) xy = x[o + c] * inv_T;
+          x[o + c] = (v[c] * inv_se - (c == yy ? 1.f : 0.f)) * gs;
+        }
+        if (valid) head_loss[h] = mx + __logf(se) - xy;
+        if (yy == -2) head_loss[h] = NAN;
+      }
+    } else {
+#pragma unroll 1
+      for (int h = 0; h < H; ++h) {
         const int o = meta.offset[h], nc = meta.offset[h + 1] - o;
         float mx = -INFINITY;
         for (int c = 0; c < nc; ++c) mx = fmaxf(mx, x[o + c] * inv_T);
@@ -113,15 +145,18 @@ multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ la
         const float lse = mx + __logf(se);
         const int yy = y[h];
         const bool valid = yy >= 0;
-        float cnt = use_ignore ? ws[kWsCounts + h] : (float)B;
+        const float cnt = use_ignore ? ws[kWsCounts + h] : (float)B;
         const float gs = (valid && cnt > 0.f) ? grad_scale * meta.weight[h] * inv_T / (cnt * (float)H) : 0.f;
-        if (valid) head_loss[h] = lse - x[o + yy] * inv_T;
-        if (yy == -2) head_loss[h] = NAN;
+        float hl = 0.f;
+        if (valid) hl = lse - x[o + yy] * inv_T;
+        if (yy == -2) hl = NAN;
         const float inv_se = 1.0f / se;
         for (int c = 0; c < nc; ++c) {
           const float p = __expf(x[o + c] * inv_T - mx) * inv_se;
           x[o + c] = (p - (c == yy ? 1.f : 0.f)) * gs;
         }
+#pragma unroll
+        for (int k = 0; k < kMaxHeads; ++k) if (k == h) head_loss[k] = hl;
       }
     }
   }
@@ -146,17 +181,18 @@ multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ la
   if (dlogits != nullptr) {
     T* dst = dlogits + row0 * C;
     const bool vo = (((uintptr_t)dst & 15u) == 0);
-    const int64_t nv = vo ? n_el / V : 0;
-    for (int64_t v = tid; v < nv; v += kHeadThreads) {
+    const int nv = vo ? n_el / V : 0;
+    for (int v = tid; v < nv; v += kHeadThreads) {
       float t[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const int e = (int)(v * V) + i;
-        t[i] = xs[(e / C) * ldx + (e % C)];
+        const int e = v * V + i;
+        const int r = e / C;
+        t[i] = xs[r * ldx + (e - r * C)];
       }
-      VecIO<T>::store(dst + v * V, t);
+      VecIO<T>::store(dst + (size_t)v * V, t);
     }
-    for (int64_t e = nv * V + tid; e < n_el; e += kHeadThreads) dst[e] = from_f32<T>(xs[(e / C) * ldx + (e % C)]);
+    for (int e = nv * V + tid; e < n_el; e += kHeadThreads) { const int r = e / C; dst[e] = from_f32<T>(xs[r * ldx + (e - r * C)]); }
   }
 
   // ---- last block folds the partials in a fixed order (deterministic) ----
@@ -169,14 +205,23 @@ multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ la
   __syncthreads();
   if (is_last) {
     __threadfence();
-    float total = 0.f;
-    if (tid < H) {
-      float s = 0.f;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ws + kWsPartials + (int64_t)b * H + tid);
-      const float cnt = use_ignore ? ws[kWsCounts + tid] : (float)B;
-      total = meta.weight[tid] * (s / cnt) / (float)H;   // cnt == 0 -> NaN, as torch's mean over nothing
-    }
+    // 16 groups x 16 head lanes: group g sums blocks g, g+16, ... for head (tid & 15); groups are then folded in a
+    // fixed order => deterministic for a fixed grid, and parallel enough for 10^4 blocks.
+    __shared__ float fold[16][17];
+    const int hh = tid & 15, grp = tid >> 4;
+    float s = 0.f;
+    if (hh < H)
+      for (unsigned b = grp; b < gridDim.x; b += 16) s += __ldcg(ws + kWsPartials + (int64_t)b * H + hh);
+    fold[grp][hh] = s;
+    __syncthreads();
     if (tid < 32) {
+      float total = 0.f;
+      if (tid < H) {
+        float t = 0.f;
+        for (int g2 = 0; g2 < 16; ++g2) t += fold[g2][tid];
+        const float cnt = use_ignore ? ws[kWsCounts + tid] : (float)B;
+        total = meta.weight[tid] * (t / cnt) / (float)H;   // cnt == 0 -> NaN, as torch's mean over nothing
+      }
       total = warp_sum(total);    // H <= 16 < 32: every head lives in warp 0
       if (tid == 0) { *loss_out = total; *reinterpret_cast<unsigned*>(ws) = 0u; }
     }
@@ -195,8 +240,10 @@ bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __re
   __shared__ bool is_last;
   float acc = 0.f;
   auto elem = [&](float xv, float tv, int64_t idx) -> float {
-    const float sp = fmaxf(-xv, 0.f) + log1pf(__expf(-fabsf(xv)));   // softplus(-x)
-    const float sig = 1.0f / (1.0f + __expf(-xv));
+    const float e = __expf(-fabsf(xv));                               // one exp feeds softplus and sigmoid
+    const float r = __frcp_rn(1.0f + e);
+    const float sp = fmaxf(-xv, 0.f) + __logf(1.0f + e);              // softplus(-x)
+    const float sig = xv >= 0.f ? r : e * r;
     float lw = 1.f;
     if (pos_weight != nullptr) lw = 1.f + (__ldg(pos_weight + (idx % C)) - 1.f) * tv;
     acc += (1.f - tv) * xv + lw * sp;
@@ -263,18 +310,45 @@ __global__ void infonce_finalize_kernel(const float* __restrict__ partial, int n
   lse_neg[i] = inv_T + logf(s);     // s == 0 (no negatives, N == 1) -> -inf, CE([pos,-inf],0) = 0
 }
 
+__device__ __forceinline__ float ce_stat_term(float pos, float lse, float scale, float& g) {
+  const float x = lse - pos;
+  const float e = __expf(-fabsf(x));
+  const float r = __frcp_rn(1.0f + e);
+  g = scale * (x >= 0.f ? r : e * r);                      // scale * sigmoid(x)
+  return fmaxf(x, 0.f) + log1pf(e);                        // log(e^pos + e^lse) - pos
+}
+
 __global__ void __launch_bounds__(1024)
 infonce_loss_kernel(const float* __restrict__ pos, const float* __restrict__ lse_neg, int64_t rows, float scale,
                     float* __restrict__ loss, int accumulate, float* __restrict__ g_pos, float* __restrict__ g_lse) {
   __shared__ float red[32];
   float acc = 0.f;
-  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) {
-    const float x = lse_neg[i] - pos[i];
-    const float sp = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));   // log(e^pos + e^lse) - pos
-    const float sig = 1.0f / (1.0f + expf(-x));
-    acc += sp;
-    if (g_lse != nullptr) g_lse[i] = scale * sig;
-    if (g_pos != nullptr) g_pos[i] = -scale * sig;
+  const bool vec = ((((uintptr_t)pos | (uintptr_t)lse_neg | (uintptr_t)g_pos | (uintptr_t)g_lse) & 15u) == 0);
+  const int64_t n4 = vec ? rows / 4 : 0;
+  for (int64_t i = threadIdx.x; i < n4; i += 2 * blockDim.x) {
+    const int64_t j = i + blockDim.x;
+    const bool two = j < n4;
+    const float4 p0 = reinterpret_cast<const float4*>(pos)[i];
+    const float4 l0 = reinterpret_cast<const float4*>(lse_neg)[i];
+    float4 p1 = p0, l1 = l0;
+    if (two) { p1 = reinterpret_cast<const float4*>(pos)[j]; l1 = reinterpret_cast<const float4*>(lse_neg)[j]; }
+    float4 g0, g1;
+    acc += ce_stat_term(p0.x, l0.x, scale, g0.x) + ce_stat_term(p0.y, l0.y, scale, g0.y) +
+           ce_stat_term(p0.z, l0.z, scale, g0.z) + ce_stat_term(p0.w, l0.w, scale, g0.w);
+    if (g_lse) reinterpret_cast<float4*>(g_lse)[i] = g0;
+    if (g_pos) reinterpret_cast<float4*>(g_pos)[i] = make_float4(-g0.x, -g0.y, -g0.z, -g0.w);
+    if (two) {
+      acc += ce_stat_term(p1.x, l1.x, scale, g1.x) + ce_stat_term(p1.y, l1.y, scale, g1.y) +
+             ce_stat_term(p1.z, l1.z, scale, g1.z) + ce_stat_term(p1.w, l1.w, scale, g1.w);
+      if (g_lse) reinterpret_cast<float4*>(g_lse)[j] = g1;
+      if (g_pos) reinterpret_cast<float4*>(g_pos)[j] = make_float4(-g1.x, -g1.y, -g1.z, -g1.w);
+    }
+  }
+  for (int64_t i = n4 * 4 + threadIdx.x; i < rows; i += blockDim.x) {
+    float g;
+    acc += ce_stat_term(pos[i], lse_neg[i], scale, g);
+    if (g_lse) g_lse[i] = g;
+    if (g_pos) g_pos[i] = -g;
   }
   const float s = block_sum(acc, red);
   if (threadIdx.x == 0) *loss = (accumulate ? *loss : 0.f) + s * scale;
@@ -338,10 +412,19 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
   }
   const unsigned grid = (unsigned)((B + kHeadThreads - 1) / kHeadThreads);
   const size_t smem = (size_t)kHeadThreads * (meta.C + 1) * 4 + (size_t)kHeadThreads * (H + 1) * 4 + (kHeadThreads / 32) * H * 4;
+  static const int kSm3Layout[8] = {5, 3, 2, 3, 3, 3, 3, 2};
+  bool fixed = (H == 8);
+  for (int h = 0; fixed && h < 8; ++h) fixed = (class_counts_host[h] == kSm3Layout[h]);
   SM3_DISPATCH_DTYPE(dtype, T, {
-    SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    multihead_ce_kernel<T><<<grid, kHeadThreads, smem, st>>>((const T*)logits, labels, B, meta, inv_T, use_ignore_index,
-                                                             ignore_index, loss, (T*)dlogits, grad_scale, ws);
+    if (fixed) {
+      SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      multihead_ce_kernel<T, true><<<grid, kHeadThreads, smem, st>>>((const T*)logits, labels, B, meta, inv_T,
+          use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
+    } else {
+      SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      multihead_ce_kernel<T, false><<<grid, kHeadThreads, smem, st>>>((const T*)logits, labels, B, meta, inv_T,
+          use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
+    }
   });
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;

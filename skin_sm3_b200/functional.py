@@ -401,6 +401,39 @@ def bce_with_logits(x: torch.Tensor, target: torch.Tensor, pos_weight: Optional[
 
 
 # ------------------------------------------------------------------------------------------------------
+# retrieval (N1)
+# ------------------------------------------------------------------------------------------------------
+def sim_topk(query: torch.Tensor, bank: torch.Tensor, k: int, exclude_self_offset: int = -1):
+    """``(query @ bank.T).topk(k, dim=-1)`` without materialising the similarity matrix
+    (reference src/models/evaluator.py:61-63).  Returns (values fp32 [B,k] descending, indices int64 [B,k]);
+    ties resolve to the lower bank index.  ``exclude_self_offset >= 0`` masks bank row (offset + q) for query q
+    (in-batch retrieval of the non-self neighbour, tools/backbone_train.py:103-105)."""
+    dev = require_cuda(query, bank)
+    if query.dim() != 2 or bank.dim() != 2 or query.shape[1] != bank.shape[1] or query.dtype != bank.dtype:
+        raise ValueError("sim_topk expects query [B, D] and bank [N, D] of the same dtype")
+    query, bank = _contig(query), _contig(bank)
+    b, d = query.shape
+    vals = torch.empty((b, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((b, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().sm3_sim_topk(ptr(query), ptr(bank), b, bank.shape[0], d, dtype_code(query), int(k),
+                                 int(exclude_self_offset), ptr(vals), ptr(idx), stream_ptr()), "sm3_sim_topk")
+    return vals, idx
+
+
+def knn_predict(query: torch.Tensor, bank: torch.Tensor, bank_labels: torch.Tensor, num_classes: int, k: int = 200,
+                temperature: float = 0.07) -> torch.Tensor:
+    """Weighted k-NN vote of KNNOnlineEvaluator.predict (reference src/models/evaluator.py:43-83): class ids per
+    query sorted by descending score.  The top-k search is the fused kernel; the k-way vote is a [B, k] scatter."""
+    w, idx = sim_topk(query, bank, k)
+    labels = bank_labels.to(idx.device)[idx]                                   # [B, k]
+    w = (w / temperature).exp()
+    scores = torch.zeros((query.shape[0], num_classes), dtype=torch.float32, device=idx.device)
+    scores.scatter_add_(1, labels, w)
+    return scores.argsort(dim=-1, descending=True)
+
+
+# ------------------------------------------------------------------------------------------------------
 # host-buffer entry (the call bench.py times end to end)
 # ------------------------------------------------------------------------------------------------------
 class HostInfoNCE:

@@ -352,3 +352,52 @@ def test_dropin_model_matches_reference(sm3, cls_name):
                 assert p.grad is None or not p.grad.any()
                 continue
             assert relerr(p.grad.cpu().numpy(), ref) < 2e-3, (style, k)
+
+
+# ---------------------------------------------------------------------------------------------------
+# N1 retrieval
+# ---------------------------------------------------------------------------------------------------
+def test_knn_topk_matches_reference_evaluator(sm3):
+    g = load("knn")
+    q, bank = cuda(g["query"]), cuda(g["bank"])
+    k = int(g["k"])
+    vals, idx = sm3.sim_topk(q, bank, k)
+    assert (idx.cpu().numpy() == g["topk_idx"]).all()            # exact index agreement with torch.topk of the reference
+    assert relerr(vals.cpu().numpy(), g["topk_val"]) < 1e-6
+    pred = sm3.knn_predict(q, bank, cuda(g["bank_labels"], torch.long), int(g["num_classes"]), k,
+                           float(g["temperature"]))
+    assert (pred.cpu().numpy() == g["pred_labels"]).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("bq,nb,d,k", [(5, 7, 12, 3), (64, 1500, 128, 200), (257, 4096, 256, 50), (33, 1025, 64, 256)])
+def test_sim_topk_vs_oracle(sm3, dtype, bq, nb, d, k):
+    rng = np.random.default_rng(bq + nb)
+    q = torch.from_numpy(rng.normal(size=(bq, d)).astype(np.float32)).to(dtype)
+    bank = torch.from_numpy(rng.normal(size=(nb, d)).astype(np.float32)).to(dtype)
+    bank[3] = bank[1]                                             # exact tie -> lower index first
+    vals, idx = sm3.sim_topk(q.cuda(), bank.cuda(), k)
+    rv, ri = O.knn_topk(q.float().numpy(), bank.float().numpy(), k)
+    v, i = vals.cpu().numpy(), idx.cpu().numpy()
+    assert relerr(v, rv) < 1e-5
+    sim = q.double().numpy() @ bank.double().numpy().T
+    for r in range(bq):
+        if (i[r] == ri[r]).all():
+            continue
+        # any disagreement must be a near-tie in fp32 accumulation order
+        bad = np.nonzero(i[r] != ri[r])[0]
+        assert np.abs(sim[r, i[r][bad]] - sim[r, ri[r][bad]]).max() < 1e-4 * np.abs(sim[r]).max(), (r, bad)
+    both = np.sort(i, axis=1)
+    assert (both[:, 1:] != both[:, :-1]).all()                    # no duplicates
+
+
+def test_in_batch_retrieval_top1_is_the_positive(sm3):
+    """golden: top-5 non-self neighbours of every row from the reference similarity matrix (argmax agreement)."""
+    g = load("infonce_n48_d128_T01_corr")
+    p = np.concatenate([g["p1"], g["p2"]])
+    z, _ = sm3.core.normalize_pair(cuda(p), None, torch.float32)
+    vals, idx = sm3.sim_topk(z, z, 5, exclude_self_offset=0)
+    assert (idx.cpu().numpy() == g["top5_idx"]).all()
+    assert relerr(vals.cpu().numpy(), g["top5_val"]) < 1e-5
+    n = int(g["n"])
+    assert (idx[:, 0].cpu().numpy() == (np.arange(2 * n) + n) % (2 * n)).all()   # correlated pairs: positive is top-1
