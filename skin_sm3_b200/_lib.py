@@ -13,7 +13,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsm3_b200.so")
+LIB_PATH = os.environ.get("SM3_LIB_PATH") or os.path.join(_HERE, "lib", "libsm3_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 F32, F16, BF16 = 0, 1, 2

@@ -15,6 +15,8 @@
 // warps 2..9 = softmax/epilogue (warp_id % 4 selects the TMEM lane quadrant, the pair of warps sharing a
 // quadrant split the tile's columns).  Pipelines: smem full/empty (TMA <-> MMA), TMEM S full/empty
 // (MMA <-> softmax), and in the backward H-ready (softmax -> MMA).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -25,9 +27,21 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kThreadsTC = 320;
 constexpr int kBM = 128;
 constexpr float kLog2eTC = 1.4426950408889634f;
+
+// Optional pipeline trace (build with -DSM3_TRACE: `make TRACE=1` -> lib/libsm3_b200_trace.so).  CTA (0,0) stamps
+// clock64() at the hand-off points of the first tiles; tools/trace_tc.py prints the timeline.  Compiled out otherwise.
+#ifdef SM3_TRACE
+constexpr int kTraceTiles = 512, kTraceKinds = 8;
+__device__ long long g_trace[kTraceTiles * kTraceKinds];
+#define SM3_TR(kind, it)                                                                 \
+  do {                                                                                   \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (it) < kTraceTiles) g_trace[(it) * kTraceKinds + (kind)] = clock64(); \
+  } while (0)
+#else
+#define SM3_TR(kind, it) do { } while (0)
+#endif
 
 struct TcParams {
   int n_local, pair_offset, n_global, D;
@@ -177,11 +191,11 @@ template <int DP> struct FwdCfg {
   static constexpr uint32_t STAGE = DP * PANEL;
   static constexpr int NSTAGE = DP == 4 ? 3 : 4;       // 192 KB / 192 KB / 128 KB / 64 KB
   static constexpr int NS = 3;                         // TMEM S stages at columns 128, 256, 384 (A at [0, 32*DP))
-  static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 512 /*xsum*/;
+  static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 3 * 512 /*xsum*/;
 };
 
-template <int DP>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+template <int DP, int NG>
+__global__ void __launch_bounds__(64 + 256 * NG, 1)
 infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
   using C = FwdCfg<DP>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE, NS = C::NS;
@@ -198,7 +212,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   auto bar_sempty = [&](int i) { return bars + 8u * (2 * NSTAGE + NS + i); };
   const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 2 * NS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 2 * NS + 1));
-  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);
+  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);   // [2*NG - 1][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * kBM;
@@ -210,7 +224,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
     for (int i = 0; i < NS; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_sempty(i), 8); }
-    mbar_init(bar_aready, 8);
+    mbar_init(bar_aready, 8 * NG);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -223,46 +237,53 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      prefetch_tensormap(&tmap_cols);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % NSTAGE;
-        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
-        mbar_wait(bar_empty(s), ph ^ 1u);
+    // =========================== TMA producer (warp-uniform loop, one elected lane issues) ===========
+    if (elect_one()) prefetch_tensormap(&tmap_cols);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE;
+      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      mbar_wait(bar_empty(s), ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
         const int row = (t_begin + it) * BN;
 #pragma unroll
         for (int pnl = 0; pnl < DP; ++pnl)
           tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      mbar_wait(bar_aready, 0);
+    // =========================== MMA issuer (warp-uniform loop, one elected lane issues) ============
+    mbar_wait(bar_aready, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE, as = it % NS;
+      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u, aph = (uint32_t)(it / NS) & 1u;
+      mbar_wait(bar_sempty(as), aph ^ 1u);
+      mbar_wait(bar_full(s), ph);
       tc_fence_after();
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % NSTAGE, as = it % NS;
-        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u, aph = (uint32_t)(it / NS) & 1u;
-        mbar_wait(bar_sempty(as), aph ^ 1u);
-        mbar_wait(bar_full(s), ph);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem + 128u + (uint32_t)as * 128u;
+      const uint32_t d_tmem = tmem + 128u + (uint32_t)as * 128u;
+      const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4 * DP; ++ks) {
-          const uint64_t bdesc = make_smem_desc(sB + s * C::STAGE + (ks >> 2) * C::PANEL + (ks & 3) * 32, 16, 1024);
-          umma_ts(d_tmem, tmem + ks * 8, bdesc, idesc, ks > 0);
-        }
+        for (int ks = 0; ks < 4 * DP; ++ks)
+          umma_ts(d_tmem, tmem + ks * 8, desc64(lo0 + (((ks >> 2) * C::PANEL + (ks & 3) * 32) >> 4), dhi), idesc,
+                  ks > 0);
         umma_commit(bar_empty(s));
         umma_commit(bar_sfull(as));
       }
+      __syncwarp();
     }
   } else {
     // =========================== softmax warps ===========================
-    const int q = warp & 3;              // TMEM lane quadrant this warp may touch
-    const int half = (warp - 2) >> 2;    // which 64 of the tile's 128 columns
+    // NG groups of 8 warps; group g owns the tiles with it % NG == g, so consecutive tiles are processed by
+    // different warps of the same SM sub-partition and their TMEM-load / barrier latencies overlap.
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may touch
+    const int grp = (warp - 2) >> 3;           // softmax group
+    const int half = ((warp - 2) >> 2) & 1;    // which 64 of the tile's 128 columns
+    const int combo = grp * 2 + half;
     const int row_in_tile = q * 32 + lane;
     const int l = r0 + row_in_tile;
     const bool valid = l < p.m_rows;
@@ -271,7 +292,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     // ---- stage this CTA's 128 rows into TMEM as the A operand (packed bf16 pairs) ----
 #pragma unroll
     for (int ch = 0; ch < DP; ++ch) {
-      if ((ch & 1) == half) {
+      if ((ch % (2 * NG)) == combo) {
         uint32_t r[32];
         if (valid) {
           const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)l * D + ch * 64);
@@ -299,7 +320,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     float posval = 0.f;
     bool found = false;
 
-    for (int it = 0; it < n_tiles; ++it) {
+    for (int it = grp; it < n_tiles; it += NG) {
       const int as = it % NS;
       const uint32_t aph = (uint32_t)(it / NS) & 1u;
       mbar_wait(bar_sfull(as), aph);
@@ -345,9 +366,13 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     }
     float total = (sum0 + sum1) + (sum2 + sum3);
     if (found) p.pos[l] = posval;
-    if (half == 1) xsum[row_in_tile] = total;
-    named_bar_sync(1, 256);
-    if (half == 0 && valid) p.partial[(size_t)split * p.m_rows + l] = total + xsum[row_in_tile];
+    if (combo != 0) xsum[(combo - 1) * 128 + row_in_tile] = total;
+    named_bar_sync(1, 256 * NG);
+    if (combo == 0 && valid) {
+#pragma unroll
+      for (int c = 0; c < 2 * NG - 1; ++c) total += xsum[c * 128 + row_in_tile];
+      p.partial[(size_t)split * p.m_rows + l] = total;
+    }
   }
 
   tc_fence_before();
@@ -376,8 +401,8 @@ __global__ void tc_bwd_prep_kernel(const float* __restrict__ glse, const float* 
   acol[j] = a;
 }
 
-template <int DP>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+template <int DP, int NG>
+__global__ void __launch_bounds__(64 + 256 * NG, 1)
 infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
   using C = BwdCfg<DP>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
@@ -406,7 +431,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_hfull(i), 8); }
-    mbar_init(bar_aready, 8);
+    mbar_init(bar_aready, 8 * NG);
     mbar_init(bar_dzfull, 1);
     fence_barrier_init();
   }
@@ -421,62 +446,74 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   constexpr uint32_t kColS = 128, kColDZ = 256;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      prefetch_tensormap(&tmap_cols);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % NSTAGE;
-        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
-        mbar_wait(bar_empty(s), ph ^ 1u);
+    // =========================== TMA producer (warp-uniform loop, one elected lane issues) ===========
+    if (elect_one()) prefetch_tensormap(&tmap_cols);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE;
+      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      mbar_wait(bar_empty(s), ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
         const int row = (t_begin + it) * BN;
 #pragma unroll
         for (int pnl = 0; pnl < DP; ++pnl)
           tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);     // S  = Zr  * Zc^T   (B K-major)
-      constexpr uint32_t idesc_z = make_idesc_bf16(128, D, 0, 1);      // dZ += H  * Zc     (B MN-major)
-      auto issue_s = [&](int it) {
-        const int s = it % NSTAGE, as = it & 1;
-        mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem + kColS + (uint32_t)as * 64u;
-#pragma unroll
-        for (int ks = 0; ks < 4 * DP; ++ks) {
-          const uint64_t bdesc = make_smem_desc(sB + s * C::STAGE + (ks >> 2) * C::PANEL + (ks & 3) * 32, 16, 1024);
-          umma_ts(d_tmem, tmem + ks * 8, bdesc, idesc_s, ks > 0);
-        }
-        umma_commit(bar_sfull(as));
-      };
-      mbar_wait(bar_aready, 0);
+    // =========================== MMA issuer (warp-uniform loop, one elected lane issues) ============
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);     // S  = Zr  * Zc^T   (B K-major)
+    constexpr uint32_t idesc_z = make_idesc_bf16(128, D, 0, 1);      // dZ += H  * Zc     (B MN-major)
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    auto issue_s = [&](int it) {
+      const int s = it % NSTAGE, as = it & 1;
+      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u);
       tc_fence_after();
-      if (n_tiles > 0) issue_s(0);
-      if (n_tiles > 1) issue_s(1);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % NSTAGE, as = it & 1;
-        mbar_wait(bar_hfull(as), (uint32_t)(it >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t h_tmem = tmem + kColS + (uint32_t)as * 64u;
+      const uint32_t d_tmem = tmem + kColS + (uint32_t)as * 64u;
+      const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4 * DP; ++ks)
+          umma_ts(d_tmem, tmem + ks * 8, desc64(lo0 + (((ks >> 2) * C::PANEL + (ks & 3) * 32) >> 4), dhi), idesc_s,
+                  ks > 0);
+        umma_commit(bar_sfull(as));
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar_aready, 0);
+    tc_fence_after();
+    if (n_tiles > 0) issue_s(0);
+    if (n_tiles > 1) issue_s(1);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE, as = it & 1;
+      mbar_wait(bar_hfull(as), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      SM3_TR(0, it);
+      const uint32_t h_tmem = tmem + kColS + (uint32_t)as * 64u;
+      const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, C::PANEL);   // MN-major: LBO = panel stride
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BN / 16; ++ks) {
           // H k-columns [0,32) live at TMEM cols +0..15, k-columns [32,64) at +32..47 (written by the two warp halves)
           const uint32_t a_tmem = h_tmem + (ks < 2 ? ks * 8 : 32 + (ks - 2) * 8);
-          const uint64_t bdesc = make_smem_desc(sB + s * C::STAGE + ks * 2048, C::PANEL, 1024);
-          umma_ts(tmem + kColDZ, a_tmem, bdesc, idesc_z, (it > 0 || ks > 0) ? 1u : 0u);
+          umma_ts(tmem + kColDZ, a_tmem, desc64(lo0 + ks * (2048 >> 4), dhi), idesc_z, (it > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(bar_empty(s));
-        if (it + 2 < n_tiles) issue_s(it + 2);   // in-order tensor pipe: overwrites S/H stage `as` only after dZ(it)
       }
-      umma_commit(bar_dzfull);
+      __syncwarp();
+      SM3_TR(1, it);
+      if (it + 2 < n_tiles) issue_s(it + 2);   // in-order tensor pipe: overwrites S/H stage `as` only after dZ(it)
+      SM3_TR(2, it);
     }
+    if (elect_one()) umma_commit(bar_dzfull);
+    __syncwarp();
   } else {
     // =========================== softmax / epilogue warps ===========================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;    // which 32 of the tile's 64 columns
+    const int grp = (warp - 2) >> 3;           // softmax group: owns tiles with it % NG == grp
+    const int half = ((warp - 2) >> 2) & 1;    // which 32 of the tile's 64 columns
+    const int combo = grp * 2 + half;
     const int row_in_tile = q * 32 + lane;
     const int l = r0 + row_in_tile;
     const bool valid = l < p.m_rows;
@@ -484,7 +521,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
 
 #pragma unroll
     for (int ch = 0; ch < DP; ++ch) {
-      if ((ch & 1) == half) {
+      if ((ch % (2 * NG)) == combo) {
         uint32_t r[32];
         if (valid) {
           const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)l * D + ch * 64);
@@ -515,14 +552,16 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     }
     const float c2 = p.c2;
 
-    for (int it = 0; it < n_tiles; ++it) {
+    for (int it = grp; it < n_tiles; it += NG) {
       const int as = it & 1;
       mbar_wait(bar_sfull(as), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
+      if (warp == 2 && lane == 0) SM3_TR(3, it);
       const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)as * 64u + (uint32_t)half * 32u;
       uint32_t v[32];
       tmem_ld_x32(taddr, v);
       tmem_ld_wait(v);
+      if (warp == 2 && lane == 0) SM3_TR(4, it);
       const int cb = (t_begin + it) * BN + half * 32;
       const bool need = (cb + 32 > p.m_cols) ||
                         (valid && ((unsigned)(g - cb) < 32u || (unsigned)(pj - cb) < 32u));
@@ -555,11 +594,13 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
 #pragma unroll
         for (int i = 0; i < 16; ++i) h[i] = pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
       }
+      if (warp == 2 && lane == 0) SM3_TR(5, it);
       tmem_st_x16(taddr, h);          // H overwrites this thread's own (already consumed) S columns
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfull(as));
+      if (warp == 2 && lane == 0) SM3_TR(6, it);
     }
 
     // ---- epilogue: dZ (TMEM fp32) * 1/T -> global partial ----
@@ -568,7 +609,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     float* dst = p.dz_partial + ((size_t)split * p.m_rows + (valid ? l : 0)) * D;
 #pragma unroll
     for (int ch = 0; ch < 2 * DP; ++ch) {
-      if ((ch & 1) == half) {
+      if ((ch % (2 * NG)) == combo) {
         uint32_t v[32];
         tmem_ld_x32(tmem + lane_addr + kColDZ + ch * 32, v);
         tmem_ld_wait(v);
@@ -637,21 +678,41 @@ void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p) {
   p.z_rows = (const __nv_bfloat16*)pb.z_rows;
 }
 
+// number of softmax warp groups (8 warps each): tuning knob, SM3_TC_GROUPS=1|2.  Measured on B200 (cfg4): one group
+// is faster in the forward (1.93 vs 2.57 ms: with 3 TMEM S stages two tiles in flight starve the MMA warp of a free
+// stage) and equal in the backward, so 1 is the default.
+int tc_groups() {
+  static int g = 0;
+  if (g == 0) {
+    const char* e = getenv("SM3_TC_GROUPS");
+    g = (e && e[0] == '2') ? 2 : 1;
+  }
+  return g;
+}
+
+template <int DP, int NG>
+int launch_fwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd_kernel<DP, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)FwdCfg<DP>::SMEM));
+  infonce_tc_fwd_kernel<DP, NG><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, FwdCfg<DP>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
 template <int DP>
 int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)FwdCfg<DP>::SMEM));
-  infonce_tc_fwd_kernel<DP><<<dim3(pl.row_tiles, pl.splits), kThreadsTC, FwdCfg<DP>::SMEM, st>>>(tmap, p);
+  return tc_groups() == 1 ? launch_fwd_ng<DP, 1>(tmap, p, pl, st) : launch_fwd_ng<DP, 2>(tmap, p, pl, st);
+}
+template <int DP, int NG>
+int launch_bwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BwdCfg<DP>::SMEM));
+  infonce_tc_bwd_kernel<DP, NG><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, BwdCfg<DP>::SMEM, st>>>(tmap, p);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
 template <int DP>
 int launch_bwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BwdCfg<DP>::SMEM));
-  infonce_tc_bwd_kernel<DP><<<dim3(pl.row_tiles, pl.splits), kThreadsTC, BwdCfg<DP>::SMEM, st>>>(tmap, p);
-  SM3_CHECK_CUDA(cudaGetLastError());
-  return SM3_OK;
+  return tc_groups() == 1 ? launch_bwd_ng<DP, 1>(tmap, p, pl, st) : launch_bwd_ng<DP, 2>(tmap, p, pl, st);
 }
 
 size_t bwd_acol_offset(const InfoNceProblem& pb, const TcPlan& pl) {
@@ -733,6 +794,15 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
 }
 
 }  // namespace sm3
+
+#ifdef SM3_TRACE
+extern "C" int sm3_debug_read_trace(long long* host, int n) {
+  using namespace sm3;
+  const int cap = kTraceTiles * kTraceKinds;
+  SM3_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * (n < cap ? n : cap)));
+  return SM3_OK;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // debug probe (C ABI).  variant bit0: A operand from TMEM (else smem/TMA); bit1: B given as [k, n]

@@ -123,6 +123,29 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Descriptor halves for the issue loops: the upper word is constant per operand kind, the lower word is
+// (address >> 4) | (LBO >> 4) << 16, so advancing an operand is ONE integer add on the low word.
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
+// one lane of a converged warp (the compiler keeps the guarded region's operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // instruction descriptor for kind::f16, bf16 x bf16 -> fp32, dense
 //   [4,6) D fmt (1 = f32) | [7,10) A fmt (1 = bf16) | [10,13) B fmt | 15 A major | 16 B major (1 = MN)
 //   [17,23) N >> 3 | [24,29) M >> 4
