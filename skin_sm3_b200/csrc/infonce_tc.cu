@@ -194,7 +194,8 @@ template <int DP> struct FwdCfg {
   static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 3 * 512 /*xsum*/;
 };
 
-template <int DP, int NG>
+// POLY: how many of every 8 exponentials run on the FMA pipes (ex2_fma) instead of MUFU.
+template <int DP, int NG, int POLY>
 __global__ void __launch_bounds__(64 + 256 * NG, 1)
 infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
   using C = FwdCfg<DP>;
@@ -264,6 +265,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       mbar_wait(bar_sempty(as), aph ^ 1u);
       mbar_wait(bar_full(s), ph);
       tc_fence_after();
+      SM3_TR(0, it);
       const uint32_t d_tmem = tmem + 128u + (uint32_t)as * 128u;
       const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
       if (elect_one()) {
@@ -275,6 +277,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
         umma_commit(bar_sfull(as));
       }
       __syncwarp();
+      SM3_TR(2, it);
     }
   } else {
     // =========================== softmax warps ===========================
@@ -320,49 +323,51 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     float posval = 0.f;
     bool found = false;
 
+    // (Register double-buffering of the next tile's TMEM loads was tried and is slower: it delays the release of
+    // the S stage by a whole tile of exponentials and starves the MMA warp.)
     for (int it = grp; it < n_tiles; it += NG) {
       const int as = it % NS;
-      const uint32_t aph = (uint32_t)(it / NS) & 1u;
-      mbar_wait(bar_sfull(as), aph);
+      mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u);
       tc_fence_after();
+      if (warp == 2 && lane == 0) SM3_TR(3, it);
       const uint32_t taddr = tmem + lane_addr + 128u + (uint32_t)as * 128u + (uint32_t)half * 64u;
-      uint32_t v0[32], v1[32];
-      tmem_ld_x32(taddr, v0);
-      tmem_ld_x32(taddr + 32, v1);
-      tmem_ld_wait(v0);
-      tmem_ld_wait(v1);
+      uint32_t a[32], b[32];
+      tmem_ld_x32(taddr, a);
+      tmem_ld_x32(taddr + 32, b);
+      tmem_ld_wait(a);
+      tmem_ld_wait(b);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sempty(as));      // S stage is in registers: hand it back to the MMA warp
+      if (warp == 2 && lane == 0) SM3_TR(4, it);
 
       const int cb = (t_begin + it) * BN + half * 64;
       const bool need = (cb + 64 > p.m_cols) ||
                         (valid && ((unsigned)(g - cb) < 64u || (unsigned)(pj - cb) < 64u));
       if (!__any_sync(0xffffffffu, need)) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          sum0 += ex2(fmaf(__uint_as_float(v0[i]), c2, -c2));
-          sum1 += ex2(fmaf(__uint_as_float(v0[i + 1]), c2, -c2));
-          sum2 += ex2(fmaf(__uint_as_float(v0[i + 2]), c2, -c2));
-          sum3 += ex2(fmaf(__uint_as_float(v0[i + 3]), c2, -c2));
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          sum0 += ex2(fmaf(__uint_as_float(v1[i]), c2, -c2));
-          sum1 += ex2(fmaf(__uint_as_float(v1[i + 1]), c2, -c2));
-          sum2 += ex2(fmaf(__uint_as_float(v1[i + 2]), c2, -c2));
-          sum3 += ex2(fmaf(__uint_as_float(v1[i + 3]), c2, -c2));
+        for (int i = 0; i < 64; i += 4) {
+          const uint32_t* v = i < 32 ? a : b;
+          const float x0 = fmaf(__uint_as_float(v[(i) & 31]), c2, -c2);
+          const float x1 = fmaf(__uint_as_float(v[(i + 1) & 31]), c2, -c2);
+          const float x2 = fmaf(__uint_as_float(v[(i + 2) & 31]), c2, -c2);
+          const float x3 = fmaf(__uint_as_float(v[(i + 3) & 31]), c2, -c2);
+          sum0 += ((i & 7) < POLY) ? ex2_fma(x0) : ex2(x0);
+          sum1 += (((i + 1) & 7) < POLY) ? ex2_fma(x1) : ex2(x1);
+          sum2 += (((i + 2) & 7) < POLY) ? ex2_fma(x2) : ex2(x2);
+          sum3 += (((i + 3) & 7) < POLY) ? ex2_fma(x3) : ex2(x3);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
-          const float s = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
+          const float s = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
           const int col = cb + i;
           const bool is_pos = (col == pj);
           if (is_pos) { posval = s * p.inv_T; found = true; }
           if (col < p.m_cols && col != g && !is_pos) sum0 += ex2(fmaf(s, c2, -c2));
         }
       }
+      if (warp == 2 && lane == 0) SM3_TR(5, it);
     }
     float total = (sum0 + sum1) + (sum2 + sum3);
     if (found) p.pos[l] = posval;
@@ -690,17 +695,44 @@ int tc_groups() {
   return g;
 }
 
-template <int DP, int NG>
+// exponentials per 8 evaluated on the FMA pipes (ex2_fma) instead of MUFU in the forward: tuning knob
+// SM3_TC_POLY=0..4.  Default 0: on B200 the kernel runs under the 1 kW power cap (SM clock ~1.3-1.5 GHz under this
+// load), where trading one MUFU op for ~11 FMA/ALU ops shortens the cycle count per tile (trace build: 1550 -> 1350)
+// but not the wall time; measured 1.74 / 1.78 / 1.80 ms for POLY = 0 / 2 / 3 at cfg4.
+int tc_poly() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SM3_TC_POLY");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 4) v = 0;
+  }
+  return v;
+}
+
+template <int DP, int NG, int POLY>
 int launch_fwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd_kernel<DP, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd_kernel<DP, NG, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)FwdCfg<DP>::SMEM));
-  infonce_tc_fwd_kernel<DP, NG><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, FwdCfg<DP>::SMEM, st>>>(tmap, p);
+  infonce_tc_fwd_kernel<DP, NG, POLY><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, FwdCfg<DP>::SMEM, st>>>(tmap, p);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
 template <int DP>
 int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  return tc_groups() == 1 ? launch_fwd_ng<DP, 1>(tmap, p, pl, st) : launch_fwd_ng<DP, 2>(tmap, p, pl, st);
+  if (tc_groups() == 2) {
+    switch (tc_poly()) {
+      case 0: return launch_fwd_ng<DP, 2, 0>(tmap, p, pl, st);
+      case 3: return launch_fwd_ng<DP, 2, 3>(tmap, p, pl, st);
+      default: return launch_fwd_ng<DP, 2, 2>(tmap, p, pl, st);
+    }
+  }
+  switch (tc_poly()) {
+    case 0: return launch_fwd_ng<DP, 1, 0>(tmap, p, pl, st);
+    case 1: return launch_fwd_ng<DP, 1, 1>(tmap, p, pl, st);
+    case 3: return launch_fwd_ng<DP, 1, 3>(tmap, p, pl, st);
+    case 4: return launch_fwd_ng<DP, 1, 4>(tmap, p, pl, st);
+    default: return launch_fwd_ng<DP, 1, 2>(tmap, p, pl, st);
+  }
 }
 template <int DP, int NG>
 int launch_bwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {

@@ -208,6 +208,20 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-4 polynomial for
+// 2^f (max relative error 3.1e-6), n added straight into the exponent field.  Used for a fraction of the
+// exponentials so the MUFU pipe (16/clk/SM) stops being co-critical with the tensor pipe.  Valid for x <= 0.
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits of r now hold round(x)
+  const float n = r - 12582912.0f;
+  const float f = x - n;
+  float p = fmaf(f, 0.00960039534f, 0.0559168942f);
+  p = fmaf(p, f, 0.240237191f);
+  p = fmaf(p, f, 0.693121970f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
