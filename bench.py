@@ -40,6 +40,15 @@ SEED = 3407
 KERNELS_PER_STEP = 7   # l2norm_fwd, infonce_fwd, finalize, loss, bwd_prep, infonce_bwd, l2norm_bwd
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -77,7 +86,7 @@ class ClockSampler:
             for bit, name in names.items():
                 if mask & bit:
                     self.reasons.add(name)
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def __enter__(self):
         def run():
@@ -94,10 +103,9 @@ class ClockSampler:
         self._t.join(timeout=2)
 
     def summary(self):
-        s = sorted(self.samples)
-        busy = s[len(s) // 2:] if s else []
-        return {"sm_mhz": (statistics.median(busy) if busy else None), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+        s = self.samples
+        return {"sm_mhz": (statistics.median(s) if s else None), "sm_min_mhz": (min(s) if s else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
 def dist_setup(n_gpus: int):
@@ -254,9 +262,27 @@ def cpu_reference(n, d, T, budget_s=20.0, max_reps=8):
 
 
 def heads_probe(sm3, pk):
-    """Multi-label head losses (K4 8-head CE, K5 BCE): latency at the reference size and HBM GB/s at a
-    bandwidth-sized batch."""
+    """HBM-bound kernels: multi-label head losses (K4 8-head CE, K5 BCE) -- latency at the reference size and
+    GB/s at a bandwidth-sized batch -- and K1 row normalisation fwd / bwd."""
     out = {}
+    M, D = 1 << 21, 256
+    p = torch.randn(M, D, device="cuda", dtype=torch.bfloat16)
+    z, inv = sm3.core.normalize_pair(p, None, torch.bfloat16)
+    dz = torch.randn(M, D, device="cuda", dtype=torch.float32)
+    for op, fn, nbytes in (("l2norm_fwd_2Mx256", lambda: sm3.core.normalize_pair(p, None, torch.bfloat16), M * D * 4 + 4 * M),
+                           ("l2norm_bwd_2Mx256", lambda: sm3.core.normalize_bwd(dz, 1, 1.0, z, inv, M, 0, torch.bfloat16),
+                            M * D * (4 + 2 + 2) + 4 * M)):
+        for _ in range(3):
+            fn()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record(); e1.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out[op] = {"us": round(ms * 1e3, 2), "GB/s": round(nbytes / ms / 1e6, 1),
+                   "frac_hbm": round(nbytes / ms / 1e6 / pk["hbm"], 3)}
+    del p, z, inv, dz
     for name, B in (("b512", 512), ("b4M", 1 << 22)):
         x = torch.randn(B, 24, device="cuda", dtype=torch.bfloat16, requires_grad=True)
         y = torch.stack([torch.randint(0, c, (B,), device="cuda") for c in sm3.NUM_CLASSES], 1)
@@ -275,6 +301,23 @@ def heads_probe(sm3, pk):
             out[f"{op}_{name}"] = {"us": round(ms * 1e3, 2), "GB/s": round(nbytes / ms / 1e6, 1),
                                    "frac_hbm": round(nbytes / ms / 1e6 / pk["hbm"], 3)}
     return out
+
+
+def gpu_reference_port(n, d, T, reps=5):
+    """Context only: the reference's materialising op sequence (oracle/ref_port.py) on the SAME GPU, fp32."""
+    from oracle import ref_port
+    g = torch.Generator().manual_seed(SEED)
+    p1 = torch.randn(n, d, generator=g).cuda(); p2 = torch.randn(n, d, generator=g).cuda()
+    for _ in range(2):
+        ref_port.port_infonce_step(p1, p2, T)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ref_port.port_infonce_step(p1, p2, T)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    return {"value": n / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+            "what": f"reference op sequence (port) on this GPU, fp32, N={n} D={d}; not the headline baseline"}
 
 
 def run_ours(args):
@@ -319,8 +362,10 @@ def run_ours(args):
         ach = flops_bwd / (t_bwd * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "infonce_tc_bwd_kernel (K3; includes its 1-block prep kernel)",
                             "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                            "traffic": None, "peak_source": pk["source"] + ", burst bf16",
-                            "flops_per_launch": flops_bwd}
+                            "traffic": (ncu_traffic().get("infonce_tc_bwd_kernel", {}).get("dram_bytes_per_launch")
+                                        if (args.workload == "cfg4" and world == 1) else None),
+                            "traffic_source": ncu_traffic().get("source"),
+                            "peak_source": pk["source"] + ", burst bf16", "flops_per_launch": flops_bwd}
     if t_fwd:
         ach = flops_fwd / (t_fwd * 1e-3) / 1e12
         line["roofline_fwd"] = {"bound": "tensor", "kernel": "infonce_tc_fwd_kernel (K2; includes the finalize kernel)",
@@ -339,6 +384,10 @@ def run_ours(args):
                             "step_tc_frac": f2 / (ms2 / args.steps * 1e-3) / 1e12 / pk["tflops"],
                             "stages_ms": {k: round(v, 4) for k, v in st2.items()},
                             "cpu_baseline": cpu_reference(w2["n"], w2["d"], w2["T"], budget_s=12.0, max_reps=4)}
+            try:
+                line["cfg2"]["gpu_reference_port"] = gpu_reference_port(w2["n"], w2["d"], w2["T"])
+            except Exception as e:
+                line["cfg2"]["gpu_reference_port"] = {"error": repr(e)[:200]}
         try:
             line["heads"] = heads_probe(sm3, pk)
         except Exception as e:   # the head probe must never take the headline down
@@ -377,7 +426,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")

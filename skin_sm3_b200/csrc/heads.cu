@@ -5,10 +5,16 @@
 // K4 replaces the reference's 8-head loops: tools/mlc_eval.py:159-162, tools/backbone_eval.py:102-105,
 // tools/backbone_train.py:178-181, tools/mlc_train.py:255-261 (+ ignore_index=-100 at :381).
 // K5 has no reference counterpart; it mirrors torch's binary_cross_entropy_with_logits.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sm3 {
 namespace {
+
+__device__ __forceinline__ float ex2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 constexpr int kMaxHeads = 16;
 constexpr int kMaxClassesTotal = 64;
@@ -228,10 +234,194 @@ multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ la
   }
 }
 
+// SM3 layout fast path (24 logits = 5,3,2,3,3,3,3,2; 8 int64 labels): one row per thread straight from global
+// memory.  A row is 48 B (16-bit logits) or 96 B (fp32) => 3 / 6 aligned 128-bit loads per thread, 4 for the labels,
+// all issued before first use; consecutive lanes touch consecutive rows, so every fetched sector is consumed by the
+// warp.  No shared-memory transposition, no block barriers on the data path.
+template <typename T>
+__global__ void __launch_bounds__(kHeadThreads)
+multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels, int64_t B, HeadMeta meta,
+                        float inv_T, int use_ignore, int64_t ignore_index, float* __restrict__ loss_out,
+                        T* __restrict__ dlogits, float grad_scale, float* __restrict__ ws) {
+  constexpr int C = 24, H = 8;
+  constexpr int kOff[9] = {0, 5, 8, 10, 13, 16, 19, 22, 24};
+  constexpr int V = VecIO<T>::N;            // 4 (fp32) or 8 (16-bit)
+  constexpr int NV = C / V;                 // 6 or 3 vectors per row
+  __shared__ float red[(kHeadThreads / 32) * H];
+  __shared__ float gsc[H];       // per-head gradient scale: grad_scale * w_h * inv_T / (count_h * H)
+  __shared__ bool is_last;
+  const int tid = threadIdx.x;
+  const int64_t row = (int64_t)blockIdx.x * kHeadThreads + tid;
+  if (tid < H) {
+    const float cnt = use_ignore ? ws[kWsCounts + tid] : (float)B;
+    gsc[tid] = cnt > 0.f ? grad_scale * meta.weight[tid] * inv_T / (cnt * (float)H) : 0.f;
+  }
+  __syncthreads();
+  float head_loss[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) head_loss[h] = 0.f;
+
+  // ---- warp-coalesced global access: the warp's 32 rows are one contiguous span (32*C elements, 32*H labels);
+  // lane i moves 16-byte vectors i, i+32, ... of that span, a per-warp shared-memory slab turns them into rows.
+  constexpr int kRowBytes = C * (int)sizeof(T);                 // 48 or 96
+  constexpr int kSlabX = 32 * kRowBytes;                        // logits / gradient slab per warp
+  constexpr int kSlabY = 32 * H * 4;                            // labels as int32 (ignore / out-of-range pre-decoded)
+  __shared__ __align__(16) unsigned char slab[(kHeadThreads / 32) * (kSlabX + kSlabY)];
+  const int lane_ = tid & 31, warp_ = tid >> 5;
+  unsigned char* sx = slab + warp_ * (kSlabX + kSlabY);
+  int* sy = reinterpret_cast<int*>(sx + kSlabX);
+  const int64_t wrow0 = (int64_t)blockIdx.x * kHeadThreads + warp_ * 32;
+  const int wrows = (int)max((int64_t)0, min((int64_t)32, B - wrow0));
+  {
+    const uint4* gsrc = reinterpret_cast<const uint4*>(logits + wrow0 * C);
+    const int nvec = wrows * kRowBytes / 16;
+#pragma unroll
+    for (int v = 0; v < kRowBytes / 16; ++v) {
+      const int i = lane_ + 32 * v;
+      if (i < nvec) reinterpret_cast<uint4*>(sx)[i] = __ldg(gsrc + i);
+    }
+    const longlong2* lsrc = reinterpret_cast<const longlong2*>(labels + wrow0 * H);
+    const int nl = wrows * H / 2;
+#pragma unroll
+    for (int v = 0; v < H / 2; ++v) {
+      const int i = lane_ + 32 * v;                               // label pair i = (row i / 4, heads 2*(i%4), +1)
+      if (i < nl) {
+        const longlong2 t = __ldg(lsrc + i);
+        const int h0 = (2 * i) & (H - 1);
+        int2 o;
+        // -1: ignored, -2: out of range, else the class id
+        o.x = (use_ignore && t.x == ignore_index) ? -1 : ((unsigned long long)t.x < (unsigned long long)(kOff[h0 + 1] - kOff[h0]) ? (int)t.x : -2);
+        o.y = (use_ignore && t.y == ignore_index) ? -1 : ((unsigned long long)t.y < (unsigned long long)(kOff[h0 + 2] - kOff[h0 + 1]) ? (int)t.y : -2);
+        reinterpret_cast<int2*>(sy)[i] = o;
+      }
+    }
+  }
+  __syncwarp();
+
+  if (row < B) {
+    float x[C];
+    int y[H];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float t[V];
+      const uint4 raw = reinterpret_cast<const uint4*>(sx + lane_ * kRowBytes)[v];
+      if constexpr (sizeof(T) == 4) {
+        t[0] = __uint_as_float(raw.x); t[1] = __uint_as_float(raw.y); t[2] = __uint_as_float(raw.z); t[3] = __uint_as_float(raw.w);
+      } else {
+        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            t[2 * q] = __uint_as_float(w[q] << 16); t[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+          } else {
+            const __half2 hh = *reinterpret_cast<const __half2*>(&w[q]);
+            const float2 f = __half22float2(hh);
+            t[2 * q] = f.x; t[2 * q + 1] = f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) x[v * V + i] = t[i];
+    }
+    {
+      const int4 a = reinterpret_cast<const int4*>(sy + lane_ * H)[0];
+      const int4 b = reinterpret_cast<const int4*>(sy + lane_ * H)[1];
+      y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+    }
+    const float k2 = inv_T * 1.4426950408889634f;     // logits * inv_T, in log2 units
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      constexpr int kMaxNc = 5;
+      const int o = kOff[h], nc = kOff[h + 1] - kOff[h];
+      float e[kMaxNc];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kMaxNc; ++c) if (c < nc) { e[c] = x[o + c] * k2; mx = fmaxf(mx, e[c]); }
+      const bool in_range = y[h] >= 0;
+      const bool ignored = y[h] == -1;
+      const int yy = y[h];
+      float vy = 0.f, se = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxNc; ++c) if (c < nc) {
+        vy = (c == yy) ? e[c] : vy;
+        e[c] = ex2f_approx(e[c] - mx);
+        se += e[c];
+      }
+      const float g = (in_range && !ignored) ? gsc[h] : 0.f;
+      const float rg = rcpf_approx(se) * g;
+#pragma unroll
+      for (int c = 0; c < kMaxNc; ++c) if (c < nc) x[o + c] = fmaf(e[c], rg, (c == yy) ? -g : 0.f);
+      float hl = 0.6931471805599453f * (mx + lg2f_approx(se) - vy);
+      hl = (in_range && !ignored) ? hl : 0.f;
+      head_loss[h] = (!in_range && !ignored) ? NAN : hl;      // out-of-range label: torch would device-assert
+    }
+    if (dlogits != nullptr) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float t[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) t[i] = x[v * V + i];
+        VecIO<T>::store(reinterpret_cast<T*>(sx + lane_ * kRowBytes) + v * V, t);    // row -> slab (generic st)
+      }
+    }
+  }
+  if (dlogits != nullptr) {
+    __syncwarp();
+    uint4* gdst = reinterpret_cast<uint4*>(dlogits + wrow0 * C);
+    const int nvec = wrows * kRowBytes / 16;
+#pragma unroll
+    for (int v = 0; v < kRowBytes / 16; ++v) {
+      const int i = lane_ + 32 * v;
+      if (i < nvec) gdst[i] = reinterpret_cast<const uint4*>(sx)[i];
+    }
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    const float v = warp_sum(head_loss[h]);
+    if (lane == 0) red[warp * H + h] = v;
+  }
+  __syncthreads();
+  if (tid < H) {
+    float s2 = 0.f;
+    for (int w = 0; w < kHeadThreads / 32; ++w) s2 += red[w * H + tid];
+    ws[kWsPartials + (int64_t)blockIdx.x * H + tid] = s2;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    __shared__ float fold[16][17];
+    const int hh = tid & 15, grp = tid >> 4;
+    float s2 = 0.f;
+    if (hh < H)
+      for (unsigned b = grp; b < gridDim.x; b += 16) s2 += __ldcg(ws + kWsPartials + (int64_t)b * H + hh);
+    fold[grp][hh] = s2;
+    __syncthreads();
+    if (tid < 32) {
+      float total = 0.f;
+      if (tid < H) {
+        float t = 0.f;
+        for (int g2 = 0; g2 < 16; ++g2) t += fold[g2][tid];
+        const float cnt = use_ignore ? ws[kWsCounts + tid] : (float)B;
+        total = meta.weight[tid] * (t / cnt) / (float)H;
+      }
+      total = warp_sum(total);
+      if (tid == 0) { *loss_out = total; *reinterpret_cast<unsigned*>(ws) = 0u; }
+    }
+  }
+}
+
 // ---------------- K5: BCE with logits ----------------
 constexpr int kBceThreads = 256;
 
-template <typename TX, typename TT>
+template <typename TX, typename TT, bool kHasPW>
 __global__ void __launch_bounds__(kBceThreads)
 bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __restrict__ pos_weight, int64_t n,
            int C, float inv_n, float* __restrict__ loss_out, TX* __restrict__ dx, float grad_scale,
@@ -239,42 +429,63 @@ bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __re
   __shared__ float red[32];
   __shared__ bool is_last;
   float acc = 0.f;
+  const float gscale = inv_n * grad_scale;
   auto elem = [&](float xv, float tv, int64_t idx) -> float {
-    const float e = __expf(-fabsf(xv));                               // one exp feeds softplus and sigmoid
-    const float r = __frcp_rn(1.0f + e);
-    const float sp = fmaxf(-xv, 0.f) + __logf(1.0f + e);              // softplus(-x)
-    const float sig = xv >= 0.f ? r : e * r;
-    float lw = 1.f;
-    if (pos_weight != nullptr) lw = 1.f + (__ldg(pos_weight + (idx % C)) - 1.f) * tv;
-    acc += (1.f - tv) * xv + lw * sp;
-    return ((1.f - tv) - lw * (1.f - sig)) * inv_n * grad_scale;
+    // e = exp(-|x|), r = 1/(1+e):  softplus(-x) = max(-x,0) - log(r),  sigmoid(x) = x >= 0 ? r : 1 - r
+    const float e = ex2f_approx(-1.4426950408889634f * fabsf(xv));
+    const float r = rcpf_approx(1.0f + e);
+    const float sp = fmaxf(-xv, 0.f) - 0.6931471805599453f * lg2f_approx(r);
+    const float sig = xv >= 0.f ? r : 1.0f - r;
+    if constexpr (kHasPW) {
+      const float lw = fmaf(__ldg(pos_weight + (idx % C)) - 1.f, tv, 1.f);
+      acc += fmaf(1.f - tv, xv, lw * sp);
+      return ((1.f - tv) - lw * (1.f - sig)) * gscale;
+    } else {
+      acc += fmaf(1.f - tv, xv, sp);
+      return (sig - tv) * gscale;
+    }
   };
   const int64_t stride = (int64_t)gridDim.x * kBceThreads;
   const int64_t gid = (int64_t)blockIdx.x * kBceThreads + threadIdx.x;
   const int64_t n8 = vec_ok ? n / 8 : 0;
-  for (int64_t v = gid; v < n8; v += stride) {
-    float xv[8], tv[8], g[8];
+  auto load8x = [&](int64_t v, float (&xv)[8]) {
     if constexpr (sizeof(TX) == 4) {
       float a[4], b[4];
       VecIO<float>::load((const float*)x + v * 8, a); VecIO<float>::load((const float*)x + v * 8 + 4, b);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { xv[i] = a[i]; xv[4 + i] = b[i]; }
     } else { VecIO<TX>::load(x + v * 8, xv); }
+  };
+  auto load8t = [&](int64_t v, float (&tv)[8]) {
     if constexpr (sizeof(TT) == 4) {
       float a[4], b[4];
       VecIO<float>::load((const float*)t + v * 8, a); VecIO<float>::load((const float*)t + v * 8 + 4, b);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { tv[i] = a[i]; tv[4 + i] = b[i]; }
     } else { VecIO<TT>::load(t + v * 8, tv); }
+  };
+  auto store8 = [&](int64_t v, const float (&g)[8]) {
+    if (dx == nullptr) return;
+    if constexpr (sizeof(TX) == 4) {
+      float a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = elem(xv[i], tv[i], v * 8 + i);
-    if (dx != nullptr) {
-      if constexpr (sizeof(TX) == 4) {
-        float a[4], b[4];
+      for (int i = 0; i < 4; ++i) { a[i] = g[i]; b[i] = g[4 + i]; }
+      VecIO<float>::store((float*)dx + v * 8, a); VecIO<float>::store((float*)dx + v * 8 + 4, b);
+    } else { VecIO<TX>::store(dx + v * 8, g); }
+  };
+  for (int64_t v = gid; v < n8; v += 2 * stride) {       // two independent chunks in flight per thread
+    const int64_t v2 = v + stride;
+    const bool two = v2 < n8;
+    float xa[8], ta[8], xb[8], tb[8], g[8];
+    load8x(v, xa); load8t(v, ta);
+    if (two) { load8x(v2, xb); load8t(v2, tb); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = g[i]; b[i] = g[4 + i]; }
-        VecIO<float>::store((float*)dx + v * 8, a); VecIO<float>::store((float*)dx + v * 8 + 4, b);
-      } else { VecIO<TX>::store(dx + v * 8, g); }
+    for (int i = 0; i < 8; ++i) g[i] = elem(xa[i], ta[i], v * 8 + i);
+    store8(v, g);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = elem(xb[i], tb[i], v2 * 8 + i);
+      store8(v2, g);
     }
   }
   for (int64_t e = n8 * 8 + gid; e < n; e += stride) {
@@ -416,7 +627,10 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
   bool fixed = (H == 8);
   for (int h = 0; fixed && h < 8; ++h) fixed = (class_counts_host[h] == kSm3Layout[h]);
   SM3_DISPATCH_DTYPE(dtype, T, {
-    if (fixed) {
+    if (fixed && aligned16(logits) && aligned16(labels) && (dlogits == nullptr || aligned16(dlogits))) {
+      multihead_ce_sm3_kernel<T><<<grid, kHeadThreads, 0, st>>>((const T*)logits, labels, B, meta, inv_T,
+          use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
+    } else if (fixed) {
       SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       multihead_ce_kernel<T, true><<<grid, kHeadThreads, smem, st>>>((const T*)logits, labels, B, meta, inv_T,
           use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
@@ -431,7 +645,7 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
 }
 
 static unsigned bce_grid(int64_t n) {
-  const int64_t want = (n / 8 + kBceThreads - 1) / kBceThreads + 1;
+  const int64_t want = (n / 16 + kBceThreads - 1) / kBceThreads + 1;
   const int64_t cap = (int64_t)num_sms() * 8;
   return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
@@ -456,8 +670,12 @@ extern "C" int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_d
   const int vec_ok = aligned16(x) && aligned16(t) && (dx == nullptr || aligned16(dx));
   const float inv_n = 1.0f / (float)n;
   SM3_DISPATCH_DTYPE(x_dtype, TX, SM3_DISPATCH_DTYPE(t_dtype, TT, {
-    bce_kernel<TX, TT><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n, loss, (TX*)dx,
-                                                    grad_scale, ws, vec_ok);
+    if (pos_weight != nullptr)
+      bce_kernel<TX, TT, true><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n, loss,
+                                                             (TX*)dx, grad_scale, ws, vec_ok);
+    else
+      bce_kernel<TX, TT, false><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n, loss,
+                                                              (TX*)dx, grad_scale, ws, vec_ok);
   }));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;

@@ -221,6 +221,11 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
   const int n_tiles = t_end - t_begin;
+  // Column tiles are visited in a per-CTA rotated order.  All row blocks of a wave would otherwise sweep the SAME
+  // 32-64 KB tile at the same time and serialise on the few L2 slices holding it (measured: the forward kernel was
+  // bimodal, 1.7 ms or 3.5-6 ms at cfg4, depending on whether the CTAs happened to run in lockstep).
+  const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
+  auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_tiles ? t - n_tiles : t); };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
@@ -246,7 +251,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       mbar_wait(bar_empty(s), ph ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
-        const int row = (t_begin + it) * BN;
+        const int row = tile_of(it) * BN;
 #pragma unroll
         for (int pnl = 0; pnl < DP; ++pnl)
           tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
@@ -341,7 +346,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       if (lane == 0) mbar_arrive(bar_sempty(as));      // S stage is in registers: hand it back to the MMA warp
       if (warp == 2 && lane == 0) SM3_TR(4, it);
 
-      const int cb = (t_begin + it) * BN + half * 64;
+      const int cb = tile_of(it) * BN + half * 64;
       const bool need = (cb + 64 > p.m_cols) ||
                         (valid && ((unsigned)(g - cb) < 64u || (unsigned)(pj - cb) < 64u));
       if (!__any_sync(0xffffffffu, need)) {
@@ -377,6 +382,207 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
 #pragma unroll
       for (int c = 0; c < 2 * NG - 1; ++c) total += xsum[c * 128 + row_in_tile];
       p.partial[(size_t)split * p.m_rows + l] = total;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, 256 rows per CTA: every B tile fetched from L2 feeds TWO S-MMAs (row blocks r0 and r0+128).
+// The 128-row kernel above moves 64 KB of L2 data per 128x128x256 tile; over 148 SMs that is ~6.7 KB/clk, right at
+// the chip's L2 throughput cap (~6.3 KB/clk), which is why it was slow and erratic at cfg4.  Here the traffic halves.
+// TMEM: A0 [0,128) | A1 [128,256) | S(row block 0) [256,384) | S(row block 1) [384,512); the two S stages ping-pong
+// between the MMA warp and the 8 softmax warps exactly like FA-style two-Q-tile kernels.
+// ------------------------------------------------------------------------------------------------
+template <int DP, int POLY>
+__global__ void __launch_bounds__(320, 1)
+infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
+  using C = FwdCfg<DP>;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
+  constexpr int D = 64 * DP;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sB = base;
+  const uint32_t bars = sB + NSTAGE * C::STAGE;
+  auto bar_full = [&](int i) { return bars + 8u * i; };
+  auto bar_empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
+  auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
+  auto bar_sempty = [&](int i) { return bars + 8u * (2 * NSTAGE + 2 + i); };
+  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 5));
+  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);   // [2 row blocks][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 256;
+  const int split = blockIdx.y;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
+  const int n_tiles = t_end - t_begin;
+  const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
+  auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_tiles ? t - n_tiles : t); };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_sempty(i), 8); }
+    mbar_init(bar_aready, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t kColA1 = 128, kColS = 256;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) prefetch_tensormap(&tmap_cols);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE;
+      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      mbar_wait(bar_empty(s), ph ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(bar_full(s), C::STAGE);
+        const int row = tile_of(it) * BN;
+#pragma unroll
+        for (int pnl = 0; pnl < DP; ++pnl)
+          tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    mbar_wait(bar_aready, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE;
+      const uint32_t sph = (uint32_t)it & 1u;          // each S stage is used once per tile
+      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u);
+      const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+        mbar_wait(bar_sempty(rb), sph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + kColS + (uint32_t)rb * 128u;
+        const uint32_t a_tmem = tmem + (uint32_t)rb * kColA1;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4 * DP; ++ks)
+            umma_ts(d_tmem, a_tmem + ks * 8, desc64(lo0 + (((ks >> 2) * C::PANEL + (ks & 3) * 32) >> 4), dhi), idesc,
+                    ks > 0);
+          if (rb == 1) umma_commit(bar_empty(s));
+          umma_commit(bar_sfull(rb));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== softmax warps ===========================
+    const int q = warp & 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int l[2], g[2], pj[2];
+    bool valid[2];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+      l[rb] = r0 + rb * 128 + row_in_tile;
+      valid[rb] = l[rb] < p.m_rows;
+      g[rb] = valid[rb] ? global_row(l[rb], p.n_local, p.pair_offset, p.n_global) : -1;
+      pj[rb] = valid[rb] ? positive_of(g[rb], p.n_global) : -1;
+    }
+    // ---- stage both row blocks into TMEM as A operands ----
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+      for (int ch = 0; ch < DP; ++ch) {
+        if ((ch & 1) == half) {
+          uint32_t r[32];
+          if (valid[rb]) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)l[rb] * D + ch * 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 v = __ldg(src + i);
+              r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          }
+          tmem_st_x32(tmem + lane_addr + rb * kColA1 + ch * 32, r);
+        }
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_aready);
+
+    const float c2 = p.c2;
+    float sum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float posval[2] = {0.f, 0.f};
+    bool found[2] = {false, false};
+
+    for (int it = 0; it < n_tiles; ++it) {
+      const uint32_t sph = (uint32_t)it & 1u;
+      const int cb = tile_of(it) * BN + half * 64;
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+        mbar_wait(bar_sfull(rb), sph);
+        tc_fence_after();
+        const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)rb * 128u + (uint32_t)half * 64u;
+        uint32_t a[32], b[32];
+        tmem_ld_x32(taddr, a);
+        tmem_ld_x32(taddr + 32, b);
+        tmem_ld_wait(a);
+        tmem_ld_wait(b);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sempty(rb));
+        const bool need = (cb + 64 > p.m_cols) ||
+                          (valid[rb] && ((unsigned)(g[rb] - cb) < 64u || (unsigned)(pj[rb] - cb) < 64u));
+        if (!__any_sync(0xffffffffu, need)) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const uint32_t* v = i < 32 ? a : b;
+            const float x0 = fmaf(__uint_as_float(v[(i) & 31]), c2, -c2);
+            const float x1 = fmaf(__uint_as_float(v[(i + 1) & 31]), c2, -c2);
+            const float x2 = fmaf(__uint_as_float(v[(i + 2) & 31]), c2, -c2);
+            const float x3 = fmaf(__uint_as_float(v[(i + 3) & 31]), c2, -c2);
+            sum[rb][0] += ((i & 7) < POLY) ? ex2_fma(x0) : ex2(x0);
+            sum[rb][1] += (((i + 1) & 7) < POLY) ? ex2_fma(x1) : ex2(x1);
+            sum[rb][2] += (((i + 2) & 7) < POLY) ? ex2_fma(x2) : ex2(x2);
+            sum[rb][3] += (((i + 3) & 7) < POLY) ? ex2_fma(x3) : ex2(x3);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float sv = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
+            const int col = cb + i;
+            const bool is_pos = (col == pj[rb]);
+            if (is_pos) { posval[rb] = sv * p.inv_T; found[rb] = true; }
+            if (col < p.m_cols && col != g[rb] && !is_pos) sum[rb][0] += ex2(fmaf(sv, c2, -c2));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+      if (found[rb]) p.pos[l[rb]] = posval[rb];
+      const float total = (sum[rb][0] + sum[rb][1]) + (sum[rb][2] + sum[rb][3]);
+      if (half == 1) xsum[rb * 128 + row_in_tile] = total;
+      named_bar_sync(1, 256);
+      if (half == 0 && valid[rb]) p.partial[(size_t)split * p.m_rows + l[rb]] = total + xsum[rb * 128 + row_in_tile];
     }
   }
 
@@ -432,6 +638,11 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
   const int n_tiles = t_end - t_begin;
+  // Column tiles are visited in a per-CTA rotated order.  All row blocks of a wave would otherwise sweep the SAME
+  // 32-64 KB tile at the same time and serialise on the few L2 slices holding it (measured: the forward kernel was
+  // bimodal, 1.7 ms or 3.5-6 ms at cfg4, depending on whether the CTAs happened to run in lockstep).
+  const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
+  auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_tiles ? t - n_tiles : t); };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
@@ -459,7 +670,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       mbar_wait(bar_empty(s), ph ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
-        const int row = (t_begin + it) * BN;
+        const int row = tile_of(it) * BN;
 #pragma unroll
         for (int pnl = 0; pnl < DP; ++pnl)
           tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
@@ -567,7 +778,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       tmem_ld_x32(taddr, v);
       tmem_ld_wait(v);
       if (warp == 2 && lane == 0) SM3_TR(4, it);
-      const int cb = (t_begin + it) * BN + half * 32;
+      const int cb = tile_of(it) * BN + half * 32;
       const bool need = (cb + 32 > p.m_cols) ||
                         (valid && ((unsigned)(g - cb) < 32u || (unsigned)(pj - cb) < 32u));
       uint32_t h[16];
@@ -656,13 +867,21 @@ int tc_pick_splits(int row_tiles, int col_tiles, int setup_tiles, int max_splits
 }
 
 struct TcPlan {
-  int row_tiles, col_tiles, splits, tiles_per_split;
+  int row_tiles, col_tiles, splits, tiles_per_split, bm;
 };
+// forward: 256-row CTAs (half the L2 traffic) once there are enough rows to fill the machine that way
+int tc_fwd_rows_per_cta(int m_rows, int m_cols) {
+  const char* e = getenv("SM3_TC_FWD_BM");
+  if (e) return atoi(e) == 128 ? 128 : 256;
+  const long work = (long)((m_rows + 255) / 256) * ((m_cols + 127) / 128);     // (256-row block, column tile) pairs
+  return work >= 8L * num_sms() ? 256 : 128;
+}
 TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
   TcPlan pl;
   const int m_rows = 2 * pb.n_local, m_cols = 2 * pb.n_global;
   const int bn = bwd ? 64 : 128;
-  pl.row_tiles = (m_rows + kBM - 1) / kBM;
+  pl.bm = bwd ? kBM : tc_fwd_rows_per_cta(m_rows, m_cols);
+  pl.row_tiles = (m_rows + pl.bm - 1) / pl.bm;
   pl.col_tiles = (m_cols + bn - 1) / bn;
   int max_splits = 32;
   if (bwd) {   // bound the fp32 partial-gradient workspace to ~1 GiB
@@ -670,7 +889,7 @@ TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
     const size_t cap = ((size_t)1 << 30) / (per ? per : 1);
     if ((size_t)max_splits > cap) max_splits = cap < 1 ? 1 : (int)cap;
   }
-  pl.splits = tc_pick_splits(pl.row_tiles, pl.col_tiles, bwd ? 6 : 4, max_splits);
+  pl.splits = tc_pick_splits(pl.row_tiles, pl.col_tiles, bwd ? 6 : (pl.bm == 256 ? 3 : 4), max_splits);
   pl.tiles_per_split = (pl.col_tiles + pl.splits - 1) / pl.splits;
   return pl;
 }
@@ -717,8 +936,17 @@ int launch_fwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, 
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
+template <int DP, int POLY>
+int launch_fwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd2_kernel<DP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)FwdCfg<DP>::SMEM));
+  infonce_tc_fwd2_kernel<DP, POLY><<<dim3(pl.row_tiles, pl.splits), 320, FwdCfg<DP>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
 template <int DP>
 int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  if (pl.bm == 256) return tc_poly() == 2 ? launch_fwd2<DP, 2>(tmap, p, pl, st) : launch_fwd2<DP, 0>(tmap, p, pl, st);
   if (tc_groups() == 2) {
     switch (tc_poly()) {
       case 0: return launch_fwd_ng<DP, 2, 0>(tmap, p, pl, st);

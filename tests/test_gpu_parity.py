@@ -129,10 +129,13 @@ def test_infonce_edge_cases_fp32(sm3):
             assert relerr(d2, g[k + "_dp2"]) < 1e-4, k
 
 
+@pytest.mark.parametrize("fwd_bm", ["128", "256"])
 @pytest.mark.parametrize("n,d,T", [(1024, 128, 0.1), (1000, 64, 0.5), (333, 192, 0.2), (1536, 256, 0.1),
                                    (64, 256, 0.1), (129, 128, 0.07)])
-def test_tensor_core_path_vs_oracle(sm3, n, d, T):
-    """tcgen05 kernels (bf16 rows) vs the fp64 closed form on the same bf16-rounded inputs; ragged tile edges."""
+def test_tensor_core_path_vs_oracle(sm3, monkeypatch, n, d, T, fwd_bm):
+    """tcgen05 kernels (bf16 rows) vs the fp64 closed form on the same bf16-rounded inputs; ragged tile edges.
+    fwd_bm selects the 128-row or the 256-row-per-CTA forward kernel (the latter is the default at cfg4 scale)."""
+    monkeypatch.setenv("SM3_TC_FWD_BM", fwd_bm)
     g = torch.Generator().manual_seed(n + d)
     p1 = torch.randn(n, d, generator=g).bfloat16()
     p2 = (p1.float() + 0.5 * torch.randn(n, d, generator=g)).bfloat16()
