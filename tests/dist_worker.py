@@ -110,7 +110,7 @@ def main():
         l2.backward()
         assert abs(l2.item() - loss.item()) <= 1e-5 * abs(loss.item()) + 1e-7
         e3 = (a2.grad.double() - a.grad.double()).abs().max().item() / a.grad.double().abs().max().item()
-        assert e3 <= 1e-5, e3
+        assert e3 <= (1e-2 if precision == "bf16" else 1e-5), e3   # bf16 outputs: 1-ulp flips of the rounded gradient
         results[f"{n_global}x{d}"] = (loss_global, ref_loss, float(e1), float(e2))
     if rank == 0 and out_path:
         with open(out_path, "w") as f:
