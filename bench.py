@@ -37,6 +37,7 @@ WORKLOADS = {
     "cfg2": dict(n=4096, d=128, T=0.1, name="cfg2: fused cross-modal InfoNCE fwd+bwd, batch 4096 x dim 128, bf16"),
 }
 SEED = 3407
+COMM = os.environ.get("SM3_COMM", "auto")     # multi-rank exchange: auto (peer memory if available) | peer | nccl
 KERNELS_PER_STEP = 7   # l2norm_fwd, infonce_fwd, finalize, loss, bwd_prep, infonce_bwd, l2norm_bwd
 
 
@@ -176,7 +177,7 @@ def time_device(sm3, p1, p2, T, group, world, steps, warmup, flush):
 
     def step():
         a.grad = b.grad = None
-        loss = sm3.fused_infonce(a, b, T, precision="bf16", group=group)
+        loss = sm3.fused_infonce(a, b, T, precision="bf16", group=group, comm=COMM)
         loss.backward()
         return loss
 
@@ -226,7 +227,7 @@ def time_e2e(sm3, p1, p2, T, group, world, steps, warmup):
         def fn():
             a = hp1.cuda(non_blocking=True).requires_grad_(True)
             b = hp2.cuda(non_blocking=True).requires_grad_(True)
-            loss = sm3.fused_infonce(a, b, T, precision="bf16", group=group)
+            loss = sm3.fused_infonce(a, b, T, precision="bf16", group=group, comm=COMM)
             loss.backward()
             ol.copy_(loss.detach().reshape(1), non_blocking=True)
             og1.copy_(a.grad, non_blocking=True); og2.copy_(b.grad, non_blocking=True)
@@ -357,6 +358,10 @@ def run_ours(args):
     e2e_ms, h2d, d2h = time_e2e(sm3, p1, p2, T, group, world, args.steps, args.warmup)
     ms_step = total_ms / args.steps
     m_cols, m_rows = 2 * n, 2 * n // world
+    comm_used = "none"
+    if world > 1:
+        from skin_sm3_b200 import peer as _peer
+        comm_used = "NVLink peer memory (symmetric memory)" if _peer._CACHE else "NCCL all-gather"
     flops_bwd = 4.0 * m_rows * m_cols * d
     flops_fwd = 2.0 * m_rows * m_cols * d
     line = {
@@ -364,7 +369,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "global_pairs": n, "rows_per_rank": m_rows, "dim": d, "temperature": T,
-                   "terms": 1, "sharding": f"row-block x{world}, all-gathered negatives" if world > 1 else "single GPU",
+                   "terms": 1, "sharding": (f"row-block x{world}, global negatives exchanged over " + comm_used) if world > 1 else "single GPU",
                    "l2": "256 MB flush write between timed steps (inputs are L2-sized by design)"},
         "loss": loss,
         "e2e": {"value": n / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,

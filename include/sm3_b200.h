@@ -104,6 +104,27 @@ int sm3_infonce_bwd(const void* z_rows, const void* z_cols, int n_local, int pai
                     const float* neg_sum_rows, const float* g_pos_cols, const float* g_lse_cols,
                     const float* neg_sum_cols, void* workspace, size_t workspace_bytes, int algo, void* stream);
 
+/* Same as sm3_infonce_bwd with the per-column statistics packed as float4 rows (g_pos, g_lse, neg_sum, unused) in
+ * stats_cols[2*n_global, 4] -- the layout the peer-memory exchange below produces.                              */
+int sm3_infonce_bwd_packed(const void* z_rows, const void* z_cols, int n_local, int pair_offset, int n_global, int D,
+                           int dtype, float inv_T, const float* g_pos_rows, const float* g_lse_rows,
+                           const float* neg_sum_rows, const float* stats_cols, void* workspace, size_t workspace_bytes,
+                           int algo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cross-rank exchange over NVLink peer memory (new capability; the reference has no cross-rank negatives,
+ * src/utils/misc.py:629-659 is an unused non-differentiable all_gather).  Every rank stores its 2*n_local rows
+ * into EVERY rank's copy of the global buffer at the global row index (order [all first views ; all second]);
+ * peers_host = HOST array of `world` device pointers (peer-mapped, e.g. torch symmetric memory buffer_ptrs),
+ * including this rank's own.  The caller separates these stores from the readers with a cross-rank barrier.
+ *   sm3_peer_scatter_rows : src [2*n_local, row_bytes]  ->  peer[r][2*n_global, row_bytes]   (row_bytes % 16 == 0)
+ *   sm3_peer_scatter_stats: (g_pos, g_lse, neg_sum)[2*n_local] -> peer[r][2*n_global] float4 rows
+ * ---------------------------------------------------------------------------------------------- */
+int sm3_peer_scatter_rows(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
+                          void* const* peers_host, int world, void* stream);
+int sm3_peer_scatter_stats(const float* g_pos, const float* g_lse, const float* neg_sum, int n_local, int pair_offset,
+                           int n_global, void* const* peers_host, int world, void* stream);
+
 /* loss half of nn.CrossEntropyLoss()(logits, 0) on the sufficient statistics, fused with its own
  * gradient (tools/backbone_train.py:101-121):
  *   loss   = scale * sum_i softplus(lse_neg_i - pos_i)             (scale = weight / M_global)

@@ -118,6 +118,27 @@ extern "C" int sm3_infonce_bwd(const void* z_rows, const void* z_cols, int n_loc
                           workspace_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int sm3_infonce_bwd_packed(const void* z_rows, const void* z_cols, int n_local, int pair_offset,
+                                      int n_global, int D, int dtype, float inv_T, const float* g_pos_rows,
+                                      const float* g_lse_rows, const float* neg_sum_rows, const float* stats_cols,
+                                      void* workspace, size_t workspace_bytes, int algo, void* stream) {
+  InfoNceProblem pb{z_rows, z_cols, n_local, pair_offset, n_global, D, dtype, inv_T};
+  pb.col_stride = 4;
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  SM3_REQUIRE(g_pos_rows && g_lse_rows && neg_sum_rows && stats_cols && workspace, SM3_ERR_SHAPE,
+              "infonce_bwd_packed: null pointer");
+  const int a = pick_algo(pb, algo);
+  if (a == SM3_ALGO_TC) {
+    SM3_REQUIRE(infonce_tc_supported(pb), SM3_ERR_DTYPE, "infonce_bwd_packed: tcgen05 path needs bf16 rows, D in {64,128,192,256}");
+    return infonce_tc_bwd(pb, g_pos_rows, g_lse_rows, neg_sum_rows, stats_cols, stats_cols + 1, stats_cols + 2, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+  }
+  SM3_REQUIRE(a == SM3_ALGO_SIMT, SM3_ERR_SHAPE, "infonce_bwd_packed: unknown algo %d", algo);
+  return infonce_simt_bwd(pb, g_pos_rows, g_lse_rows, neg_sum_rows, stats_cols, stats_cols + 1, stats_cols + 2, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-buffer entry: H2D -> normalise -> K2 -> loss -> K3 -> normalise-backward -> D2H, one stream.
 // ---------------------------------------------------------------------------------------------------

@@ -149,6 +149,7 @@ struct InfoNceProblem {
   const void* z_cols;
   int n_local, pair_offset, n_global, D, dtype;
   float inv_T;
+  int col_stride = 1;   // backward: element stride of the per-column statistic arrays (4 = packed float4 rows)
 };
 size_t infonce_simt_workspace(const InfoNceProblem& pb, int backward);
 int infonce_simt_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
@@ -165,6 +166,14 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
                    cudaStream_t st);
 int infonce_finalize_launch(const float* partial_sums, int n_partials, int64_t rows, float inv_T, float* neg_sum,
                             float* lse_neg, cudaStream_t st);
+struct PeerPtrs {           // destination buffers of a peer scatter (one per rank, this rank included)
+  void* p[16];
+  int world;
+};
+int peer_scatter_rows_launch(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
+                             const PeerPtrs& peers, cudaStream_t st);
+int peer_scatter_stats_launch(const float* g_pos, const float* g_lse, const float* nsum, int n_local, int pair_offset,
+                              int n_global, const PeerPtrs& peers, cudaStream_t st);
 int infonce_loss_launch(const float* pos, const float* lse_neg, int64_t rows, float scale, float* loss, int accumulate,
                         float* g_pos, float* g_lse, cudaStream_t st);
 

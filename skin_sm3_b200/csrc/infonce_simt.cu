@@ -31,6 +31,7 @@ struct SimtParams {
   float* partial;                // [splits][m_rows]
   // backward
   const float *gpos_r, *glse_r, *nsum_r, *gpos_c, *glse_c, *nsum_c;
+  int cstride;                   // element stride of the *_c arrays
   float* dz_partial;             // [splits][m_rows][D]
 };
 
@@ -99,8 +100,8 @@ infonce_simt_kernel(SimtParams p) {
     if constexpr (BWD) {
       if (tid < kTile) {
         const int j = c0 + tid;
-        ac[tid] = j < p.m_cols ? safe_coef(p.glse_c[j], p.nsum_c[j]) : 0.f;
-        gc[tid] = j < p.m_cols ? p.gpos_c[j] : 0.f;
+        ac[tid] = j < p.m_cols ? safe_coef(p.glse_c[(size_t)j * p.cstride], p.nsum_c[(size_t)j * p.cstride]) : 0.f;
+        gc[tid] = j < p.m_cols ? p.gpos_c[(size_t)j * p.cstride] : 0.f;
       }
     }
     __syncthreads();
@@ -279,7 +280,7 @@ int infonce_simt_bwd(const InfoNceProblem& pb, const float* gpos_r, const float*
   if (rc) return rc;
   SM3_REQUIRE(ws_bytes >= infonce_simt_workspace(pb, 1), SM3_ERR_WORKSPACE, "infonce(simt) bwd: workspace too small");
   p.gpos_r = gpos_r; p.glse_r = glse_r; p.nsum_r = nsum_r;
-  p.gpos_c = gpos_c; p.glse_c = glse_c; p.nsum_c = nsum_c;
+  p.gpos_c = gpos_c; p.glse_c = glse_c; p.nsum_c = nsum_c; p.cstride = pb.col_stride;
   p.dz_partial = (float*)ws;
   rc = launch<true>(p, pb.dtype, row_tiles, splits, st);
   if (rc) return rc;

@@ -52,6 +52,7 @@ struct TcParams {
   float* pos;
   float* partial;      // fwd: [splits][m_rows]
   const float *gpos_r, *glse_r, *nsum_r, *gpos_c;
+  int cstride;         // element stride of gpos_c (1, or 4 for packed peer-exchanged statistics)
   const float* acol;   // bwd: a_j = g_lse_j / neg_sum_j, zero padded to a multiple of 64
   float* dz_partial;   // bwd: [splits][m_rows][D]
 };
@@ -603,12 +604,12 @@ template <int DP> struct BwdCfg {
   // TMEM columns: A [0, 32*DP) | S/H stage 0 [128,192) | stage 1 [192,256) | dZ [256, 256 + 64*DP)
 };
 
-__global__ void tc_bwd_prep_kernel(const float* __restrict__ glse, const float* __restrict__ nsum, int m_cols,
-                                   int m_pad, float* __restrict__ acol) {
+__global__ void tc_bwd_prep_kernel(const float* __restrict__ glse, const float* __restrict__ nsum, int stride,
+                                   int m_cols, int m_pad, float* __restrict__ acol) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m_pad) return;
   float a = 0.f;
-  if (j < m_cols) { const float s = nsum[j]; a = s > 0.f ? glse[j] / s : 0.f; }
+  if (j < m_cols) { const float s = nsum[(size_t)j * stride]; a = s > 0.f ? glse[(size_t)j * stride] / s : 0.f; }
   acol[j] = a;
 }
 
@@ -802,7 +803,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
           const float s = __uint_as_float(v[i]);
           float x = 0.f;
           if (valid && col < p.m_cols && col != g) {
-            if (col == pj) x = gp_i + p.gpos_c[col];
+            if (col == pj) x = gp_i + p.gpos_c[(size_t)col * p.cstride];
             else x = ex2(fmaf(s, c2, -c2)) * (a_i + p.acol[col]);
           }
           hv[i] = x;
@@ -1033,12 +1034,12 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
   const TcPlan pl = tc_plan(pb, true);
   TcParams p{};
   fill_params(pb, pl, p);
-  p.gpos_r = gpos_r; p.glse_r = glse_r; p.nsum_r = nsum_r; p.gpos_c = gpos_c;
+  p.gpos_r = gpos_r; p.glse_r = glse_r; p.nsum_r = nsum_r; p.gpos_c = gpos_c; p.cstride = pb.col_stride;
   p.dz_partial = (float*)ws;
   float* acol = (float*)((char*)ws + bwd_acol_offset(pb, pl));
   p.acol = acol;
   const int m_pad = (p.m_cols + 63) / 64 * 64 + 64;
-  tc_bwd_prep_kernel<<<(m_pad + 255) / 256, 256, 0, st>>>(glse_c, nsum_c, p.m_cols, m_pad, acol);
+  tc_bwd_prep_kernel<<<(m_pad + 255) / 256, 256, 0, st>>>(glse_c, nsum_c, pb.col_stride, p.m_cols, m_pad, acol);
   SM3_CHECK_CUDA(cudaGetLastError());
   CUtensorMap tmap;
   int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 64);

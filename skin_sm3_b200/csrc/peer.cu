@@ -1,0 +1,96 @@
+// Peer-memory exchange for the row-sharded objective: instead of an NCCL all-gather, every rank
+// stores its rows straight into every rank's copy of the global buffer over NVLink/NVSwitch (plain st.global on
+// peer-mapped pointers obtained from torch symmetric memory).  Two payloads use it:
+//   * the normalised bf16 embedding rows  -> z_cols[2*n_global, D]      (forward)
+//   * the per-row statistics (g_pos, g_lse, neg_sum) packed as float4  -> stats[2*n_global, 4]   (backward)
+// Local row l lands at global row g(l) = pair_offset + l (l < n_local) or n_global + pair_offset + l - n_local, i.e.
+// the reference's [all first views ; all second views] order on the concatenated batch (simclr.py:293,296-297).
+// A cross-rank barrier (symmetric-memory signal pads, issued from Python on the same stream) separates the stores
+// from the kernels that read the assembled buffers.
+#include "common.cuh"
+
+namespace sm3 {
+namespace {
+
+__global__ void __launch_bounds__(256)
+peer_scatter_rows_kernel(const uint4* __restrict__ src, int n_local, int pair_offset, int n_global, int vec_per_row,
+                         PeerPtrs peers) {
+  const int64_t total = (int64_t)2 * n_local * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(i / vec_per_row);
+    const int v = (int)(i - (int64_t)l * vec_per_row);
+    const int g = global_row(l, n_local, pair_offset, n_global);
+    const uint4 val = __ldg(src + i);
+    const int64_t off = (int64_t)g * vec_per_row + v;
+#pragma unroll 4
+    for (int r = 0; r < peers.world; ++r) reinterpret_cast<uint4*>(peers.p[r])[off] = val;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+peer_scatter_stats_kernel(const float* __restrict__ g_pos, const float* __restrict__ g_lse,
+                          const float* __restrict__ nsum, int n_local, int pair_offset, int n_global, PeerPtrs peers) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= 2 * n_local) return;
+  const int g = global_row(l, n_local, pair_offset, n_global);
+  const float4 val = make_float4(g_pos[l], g_lse[l], nsum[l], 0.f);
+  for (int r = 0; r < peers.world; ++r) reinterpret_cast<float4*>(peers.p[r])[g] = val;
+}
+
+}  // namespace
+
+int peer_scatter_rows_launch(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
+                             const PeerPtrs& peers, cudaStream_t st) {
+  const int vpr = row_bytes / 16;
+  const int64_t total = (int64_t)2 * n_local * vpr;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  peer_scatter_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4*)src, n_local, pair_offset, n_global, vpr, peers);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+int peer_scatter_stats_launch(const float* g_pos, const float* g_lse, const float* nsum, int n_local, int pair_offset,
+                              int n_global, const PeerPtrs& peers, cudaStream_t st) {
+  peer_scatter_stats_kernel<<<(2 * n_local + 255) / 256, 256, 0, st>>>(g_pos, g_lse, nsum, n_local, pair_offset, n_global,
+                                                                     peers);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+}  // namespace sm3
+
+using namespace sm3;
+
+static int fill_peers(PeerPtrs& pp, void* const* peers_host, int world) {
+  SM3_REQUIRE(peers_host != nullptr && world >= 1 && world <= 16, SM3_ERR_SHAPE, "peer scatter: world=%d not in [1,16]", world);
+  pp.world = world;
+  for (int r = 0; r < world; ++r) {
+    SM3_REQUIRE(peers_host[r] != nullptr && aligned16(peers_host[r]), SM3_ERR_SHAPE, "peer scatter: bad peer pointer %d", r);
+    pp.p[r] = peers_host[r];
+  }
+  return SM3_OK;
+}
+
+extern "C" int sm3_peer_scatter_rows(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
+                                     void* const* peers_host, int world, void* stream) {
+  SM3_REQUIRE(src && aligned16(src), SM3_ERR_SHAPE, "peer_scatter_rows: bad source pointer");
+  SM3_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0, SM3_ERR_SHAPE, "peer_scatter_rows: row_bytes %d not a multiple of 16", row_bytes);
+  SM3_REQUIRE(n_local >= 1 && pair_offset >= 0 && pair_offset + n_local <= n_global, SM3_ERR_SHAPE, "peer_scatter_rows: bad row block");
+  PeerPtrs pp;
+  int rc = fill_peers(pp, peers_host, world);
+  if (rc) return rc;
+  return peer_scatter_rows_launch(src, n_local, pair_offset, n_global, row_bytes, pp, (cudaStream_t)stream);
+}
+
+extern "C" int sm3_peer_scatter_stats(const float* g_pos, const float* g_lse, const float* neg_sum, int n_local,
+                                      int pair_offset, int n_global, void* const* peers_host, int world, void* stream) {
+  SM3_REQUIRE(g_pos && g_lse && neg_sum, SM3_ERR_SHAPE, "peer_scatter_stats: null pointer");
+  SM3_REQUIRE(n_local >= 1 && pair_offset >= 0 && pair_offset + n_local <= n_global, SM3_ERR_SHAPE, "peer_scatter_stats: bad row block");
+  PeerPtrs pp;
+  int rc = fill_peers(pp, peers_host, world);
+  if (rc) return rc;
+  return peer_scatter_stats_launch(g_pos, g_lse, neg_sum, n_local, pair_offset, n_global, pp, (cudaStream_t)stream);
+}

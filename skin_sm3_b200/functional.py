@@ -139,6 +139,21 @@ class core:
         return ws, npart
 
     @staticmethod
+    def stats_bwd_packed(z_rows, z_cols, n_local, pair_offset, n_global, temperature, g_pos_r, g_lse_r, nsum_r,
+                         stats_cols, algo: int = ALGO_AUTO):
+        """As stats_bwd with the column statistics packed as float4 rows [2*n_global, 4] (peer-exchange layout)."""
+        dev = require_cuda(z_rows, z_cols, stats_cols)
+        d = z_rows.shape[1]
+        assert stats_cols.dtype == torch.float32 and stats_cols.shape == (2 * n_global, 4) and stats_cols.is_contiguous()
+        ws = core.workspace(n_local, n_global, d, z_rows, algo, True)
+        with torch.cuda.device(dev):
+            npart = check(lib().sm3_infonce_bwd_packed(ptr(z_rows), ptr(z_cols), n_local, pair_offset, n_global, d,
+                                                       dtype_code(z_rows), 1.0 / temperature, ptr(g_pos_r), ptr(g_lse_r),
+                                                       ptr(nsum_r), ptr(stats_cols), ptr(ws), ws.numel(), algo,
+                                                       stream_ptr()), "sm3_infonce_bwd_packed")
+        return ws, npart
+
+    @staticmethod
     def sum_partials(ws: torch.Tensor, n_partials: int, m: int, d: int) -> torch.Tensor:
         v = ws[: n_partials * m * d * 4].view(torch.float32).view(n_partials, m, d)
         return v[0] if n_partials == 1 else v.sum(0)
@@ -260,18 +275,40 @@ def cal_logits(p1: torch.Tensor, p2: torch.Tensor, temperature: float, precision
     return logits, labels
 
 
+def _resolve_comm(comm: str, w: int, z_dtype, n_global: int, d: int, device, group):
+    """-> PeerBuffers or None (NCCL).  'auto' uses the peer-memory exchange when symmetric memory can be set up."""
+    if w == 1 or comm == "nccl" or z_dtype != torch.bfloat16:
+        if comm == "peer" and w > 1:
+            raise RuntimeError("comm='peer' needs the bf16 tensor-core path")
+        return None
+    from . import peer
+    try:
+        return peer.get_peer_buffers(group, n_global, d, device)
+    except peer.PeerUnavailable:
+        if comm == "peer":
+            raise
+        return None
+
+
 class _FusedInfoNCE(torch.autograd.Function):
     """Scalar loss with the backward computed eagerly in forward (one pass: fwd + bwd kernels back to back)."""
 
     @staticmethod
-    def forward(ctx, p1, p2, temperature, z_dtype, algo, group, weight):
+    def forward(ctx, p1, p2, temperature, z_dtype, algo, group, weight, comm):
         w, rank = _group_info(group)
         n_local = p1.shape[0]
         n_global = n_local * w
+        pbuf = _resolve_comm(comm, w, z_dtype, n_global, p1.shape[1], p1.device, group)
+        slot = pbuf.next_slot() if pbuf is not None else 0
         _mark("start")
         z, inv = core.normalize_pair(p1, p2, z_dtype)
         _mark("normalize")
-        z_cols = gather_global_order(z, group) if w > 1 else z
+        if w == 1:
+            z_cols = z
+        elif pbuf is not None:
+            z_cols = pbuf.scatter_z(slot, z, n_local)          # NVLink peer stores + cross-rank barrier
+        else:
+            z_cols = gather_global_order(z, group)            # NCCL all-gather
         _mark("gather_z")
         pos, lse, nsum = core.stats_fwd(z, z_cols, n_local, rank * n_local, n_global, temperature, algo)
         _mark("stats_fwd")
@@ -279,38 +316,49 @@ class _FusedInfoNCE(torch.autograd.Function):
         loss, g_pos, g_lse = core.loss(pos, lse, weight / (2 * n_local), want_grads=need_grad)
         _mark("loss")
         if need_grad:
-            if w > 1:
-                packed = gather_global_order(torch.stack((g_pos, g_lse, nsum), dim=1), group)
-                gp_c, gl_c, ns_c = (_contig(packed[:, k]) for k in range(3))
+            if pbuf is not None:
+                stats = pbuf.scatter_stats(slot, g_pos, g_lse, nsum, n_local)
+                _mark("gather_stats")
+                ws, npart = core.stats_bwd_packed(z, z_cols, n_local, rank * n_local, n_global, temperature, g_pos,
+                                                  g_lse, nsum, stats, algo)
             else:
-                gp_c, gl_c, ns_c = g_pos, g_lse, nsum
-            _mark("gather_stats")
-            ws, npart = core.stats_bwd(z, z_cols, n_local, rank * n_local, n_global, temperature, g_pos, g_lse, nsum,
-                                       gp_c, gl_c, ns_c, algo)
+                if w > 1:
+                    packed = gather_global_order(torch.stack((g_pos, g_lse, nsum), dim=1), group)
+                    gp_c, gl_c, ns_c = (_contig(packed[:, k]) for k in range(3))
+                else:
+                    gp_c, gl_c, ns_c = g_pos, g_lse, nsum
+                _mark("gather_stats")
+                ws, npart = core.stats_bwd(z, z_cols, n_local, rank * n_local, n_global, temperature, g_pos, g_lse,
+                                           nsum, gp_c, gl_c, ns_c, algo)
             _mark("stats_bwd")
             dp1, dp2 = core.normalize_bwd(ws, npart, 1.0, z, inv, n_local, n_local, p1.dtype)
             _mark("normalize_bwd")
             ctx.save_for_backward(dp1, dp2)
+        ctx.comm_used = "peer" if pbuf is not None else ("nccl" if w > 1 else "none")
         return loss
 
     @staticmethod
     def backward(ctx, g):
         dp1, dp2 = ctx.saved_tensors
-        return dp1 * g.to(dp1.dtype), dp2 * g.to(dp2.dtype), None, None, None, None, None
+        return dp1 * g.to(dp1.dtype), dp2 * g.to(dp2.dtype), None, None, None, None, None, None
 
 
 def fused_infonce(p1: torch.Tensor, p2: torch.Tensor, temperature: float, precision: str = "auto", group=None,
-                  weight: float = 1.0) -> torch.Tensor:
+                  weight: float = 1.0, comm: str = "auto") -> torch.Tensor:
     """``weight * CrossEntropy(_cal_logits(p1, p2, T))`` as one fused op (fp32 scalar).
 
-    Per-rank normalisation follows the reference / DDP convention: mean over this rank's 2N rows."""
+    Per-rank normalisation follows the reference / DDP convention: mean over this rank's 2N rows.
+    ``comm`` (multi-rank only): 'peer' = NVLink peer-memory exchange (symmetric memory), 'nccl' = NCCL all-gather,
+    'auto' = peer when it can be set up, else NCCL."""
     if p1.dim() != 2 or p1.shape != p2.shape:
         raise ValueError("fused_infonce expects two [N, D] tensors of identical shape")
     require_cuda(p1, p2)
     if temperature <= 0:
         raise ValueError("temperature must be > 0")
     z_dtype, algo = pick_precision(p1, precision)
-    return _FusedInfoNCE.apply(p1, p2, float(temperature), z_dtype, algo, group, float(weight))
+    if comm not in ("auto", "peer", "nccl"):
+        raise ValueError("comm must be 'auto', 'peer' or 'nccl'")
+    return _FusedInfoNCE.apply(p1, p2, float(temperature), z_dtype, algo, group, float(weight), comm)
 
 
 # ------------------------------------------------------------------------------------------------------

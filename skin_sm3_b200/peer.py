@@ -1,0 +1,89 @@
+"""Peer-memory (NVLink / NVSwitch) exchange for the row-sharded objective: every rank stores its rows straight into
+every rank's copy of the global buffers -- no NCCL on the hot path.
+
+Buffers live in torch symmetric memory (``torch.distributed._symmetric_memory``), which hands back the peer-mapped
+device pointers and a stream-ordered cross-rank barrier (signal pads).  Two buffers per slot:
+  z_cols [2*n_global, D] bf16   normalised embeddings in the reference's [all first ; all second] order
+  stats  [2*n_global, 4] fp32   (g_pos, g_lse, neg_sum, -) per global row for the row-local symmetric backward
+Slots are double-buffered: a rank that has passed both barriers of step k+1 knows every peer finished reading the
+slot of step k, so slot (k+2) % 2 can be overwritten.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, lib, ptr, stream_ptr
+
+_CACHE: Dict[Tuple, "PeerBuffers"] = {}
+
+
+class PeerUnavailable(RuntimeError):
+    pass
+
+
+class PeerBuffers:
+    DEPTH = 2
+
+    def __init__(self, group, n_global: int, d: int, device: torch.device):
+        try:
+            import torch.distributed._symmetric_memory as symm
+        except Exception as e:  # pragma: no cover
+            raise PeerUnavailable(f"torch symmetric memory is not importable: {e!r}") from e
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 16:
+            raise PeerUnavailable("peer exchange supports up to 16 ranks")
+        self.n_global, self.d = n_global, d
+        self.z, self.zh, self.zp = [], [], []
+        self.st, self.sth, self.stp = [], [], []
+        try:
+            for _ in range(self.DEPTH):
+                z = symm.empty((2 * n_global, d), dtype=torch.bfloat16, device=device)
+                zh = symm.rendezvous(z, self.group)
+                st = symm.empty((2 * n_global, 4), dtype=torch.float32, device=device)
+                sth = symm.rendezvous(st, self.group)
+                self.z.append(z); self.zh.append(zh); self.zp.append((C.c_void_p * self.world)(*zh.buffer_ptrs))
+                self.st.append(st); self.sth.append(sth); self.stp.append((C.c_void_p * self.world)(*sth.buffer_ptrs))
+        except PeerUnavailable:
+            raise
+        except Exception as e:
+            raise PeerUnavailable(f"symmetric-memory rendezvous failed: {e!r}") from e
+        self.step = 0
+
+    def next_slot(self) -> int:
+        k = self.step % self.DEPTH
+        self.step += 1
+        return k
+
+    # ---- forward exchange: rows of the local normalised z -> every rank's z_cols[slot] ----
+    def scatter_z(self, slot: int, z_local: torch.Tensor, n_local: int) -> torch.Tensor:
+        assert z_local.dtype == torch.bfloat16 and z_local.is_contiguous() and z_local.shape == (2 * n_local, self.d)
+        with torch.cuda.device(z_local.device):
+            check(lib().sm3_peer_scatter_rows(ptr(z_local), n_local, self.rank * n_local, self.n_global, self.d * 2,
+                                              self.zp[slot], self.world, stream_ptr()), "sm3_peer_scatter_rows")
+            self.zh[slot].barrier(channel=0)
+        return self.z[slot]
+
+    # ---- backward exchange: (g_pos, g_lse, neg_sum) of the local rows -> every rank's stats[slot] ----
+    def scatter_stats(self, slot: int, g_pos, g_lse, nsum, n_local: int) -> torch.Tensor:
+        with torch.cuda.device(g_pos.device):
+            check(lib().sm3_peer_scatter_stats(ptr(g_pos), ptr(g_lse), ptr(nsum), n_local, self.rank * n_local,
+                                               self.n_global, self.stp[slot], self.world, stream_ptr()),
+                  "sm3_peer_scatter_stats")
+            self.sth[slot].barrier(channel=1)
+        return self.st[slot]
+
+
+def get_peer_buffers(group, n_global: int, d: int, device: torch.device) -> PeerBuffers:
+    g = group if group is not None else dist.group.WORLD
+    key = (id(g), n_global, d, device.index)
+    pb = _CACHE.get(key)
+    if pb is None:
+        pb = PeerBuffers(g, n_global, d, device)
+        _CACHE[key] = pb
+    return pb

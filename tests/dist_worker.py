@@ -106,11 +106,21 @@ def main():
         # ---- fused scalar form ----
         a2 = P1[sl].to(dev).requires_grad_(True)
         b2 = P2[sl].to(dev).requires_grad_(True)
-        l2 = sm3.fused_infonce(a2, b2, T, precision=precision, group=dist.group.WORLD)
+        l2 = sm3.fused_infonce(a2, b2, T, precision=precision, group=dist.group.WORLD, comm="nccl")
         l2.backward()
         assert abs(l2.item() - loss.item()) <= 1e-5 * abs(loss.item()) + 1e-7
         e3 = (a2.grad.double() - a.grad.double()).abs().max().item() / a.grad.double().abs().max().item()
         assert e3 <= (1e-2 if precision == "bf16" else 1e-5), e3   # bf16 outputs: 1-ulp flips of the rounded gradient
+        if backend == "nccl" and precision == "bf16":
+            # NVLink peer-memory exchange (symmetric memory) must give the same numbers as the NCCL path;
+            # three steps exercise the double-buffered slots.
+            for _ in range(3):
+                a3 = P1[sl].to(dev).requires_grad_(True)
+                b3 = P2[sl].to(dev).requires_grad_(True)
+                l3 = sm3.fused_infonce(a3, b3, T, precision=precision, group=dist.group.WORLD, comm="peer")
+                l3.backward()
+                assert abs(l3.item() - l2.item()) <= 1e-6 * abs(l2.item()) + 1e-7, (l3.item(), l2.item())
+                assert torch.equal(a3.grad, a2.grad) and torch.equal(b3.grad, b2.grad), "peer path != nccl path"
         results[f"{n_global}x{d}"] = (loss_global, ref_loss, float(e1), float(e2))
     if rank == 0 and out_path:
         with open(out_path, "w") as f:
