@@ -361,7 +361,10 @@ def run_ours(args):
     comm_used = "none"
     if world > 1:
         from skin_sm3_b200 import peer as _peer
-        comm_used = "NVLink peer memory (symmetric memory)" if _peer._CACHE else "NCCL all-gather"
+        comm_used = "NCCL all-gather"
+        if _peer._CACHE:
+            mc = any(b.multicast for b in _peer._CACHE.values())
+            comm_used = "NVLink peer memory (symmetric memory" + (", NVSwitch multicast stores)" if mc else ", unicast stores)")
     flops_bwd = 4.0 * m_rows * m_cols * d
     flops_fwd = 2.0 * m_rows * m_cols * d
     line = {

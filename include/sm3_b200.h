@@ -124,6 +124,12 @@ int sm3_peer_scatter_rows(const void* src, int n_local, int pair_offset, int n_g
                           void* const* peers_host, int world, void* stream);
 int sm3_peer_scatter_stats(const float* g_pos, const float* g_lse, const float* neg_sum, int n_local, int pair_offset,
                            int n_global, void* const* peers_host, int world, void* stream);
+/* NVSwitch multicast forms: multicast_dst is the multicast mapping of the same symmetric buffer (one multimem.st per
+ * 16 bytes reaches every rank, so each GPU sends its rows once instead of `world` times).                        */
+int sm3_peer_multicast_rows(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
+                            void* multicast_dst, void* stream);
+int sm3_peer_multicast_stats(const float* g_pos, const float* g_lse, const float* neg_sum, int n_local, int pair_offset,
+                             int n_global, void* multicast_dst, void* stream);
 
 /* loss half of nn.CrossEntropyLoss()(logits, 0) on the sufficient statistics, fused with its own
  * gradient (tools/backbone_train.py:101-121):

@@ -38,6 +38,8 @@ SIGNATURES = {
     "sm3_infonce_bwd_packed": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "sm3_peer_scatter_rows": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp), _i, _vp]),
     "sm3_peer_scatter_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(_vp), _i, _vp]),
+    "sm3_peer_multicast_rows": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sm3_peer_multicast_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sm3_infonce_loss": (_i, [_vp, _vp, _i64, _f, _vp, _i, _vp, _vp, _vp]),
     "sm3_multihead_ce_workspace_bytes": (_sz, [_i64, _i]),
     "sm3_multihead_ce": (_i, [_vp, _i, _vp, _i64, _i, C.POINTER(_i), C.POINTER(_f), _f, _i, _i64, _vp, _vp, _f,

@@ -27,6 +27,36 @@ peer_scatter_rows_kernel(const uint4* __restrict__ src, int n_local, int pair_of
   }
 }
 
+// NVSwitch multicast variant: ONE multimem store per 16-byte vector lands in every rank's buffer (the switch
+// replicates), so each GPU sends its rows once instead of `world` times.
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__global__ void __launch_bounds__(256)
+peer_multicast_rows_kernel(const uint4* __restrict__ src, int n_local, int pair_offset, int n_global, int vec_per_row,
+                           uint4* __restrict__ mc_dst) {
+  const int64_t total = (int64_t)2 * n_local * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(i / vec_per_row);
+    const int v = (int)(i - (int64_t)l * vec_per_row);
+    const int g = global_row(l, n_local, pair_offset, n_global);
+    multimem_st_v4(mc_dst + (int64_t)g * vec_per_row + v, __ldg(src + i));
+  }
+}
+__global__ void __launch_bounds__(256)
+peer_multicast_stats_kernel(const float* __restrict__ g_pos, const float* __restrict__ g_lse,
+                            const float* __restrict__ nsum, int n_local, int pair_offset, int n_global,
+                            uint4* __restrict__ mc_dst) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= 2 * n_local) return;
+  const int g = global_row(l, n_local, pair_offset, n_global);
+  uint4 v;
+  v.x = __float_as_uint(g_pos[l]); v.y = __float_as_uint(g_lse[l]); v.z = __float_as_uint(nsum[l]); v.w = 0u;
+  multimem_st_v4(mc_dst + g, v);
+}
+
 __global__ void __launch_bounds__(256)
 peer_scatter_stats_kernel(const float* __restrict__ g_pos, const float* __restrict__ g_lse,
                           const float* __restrict__ nsum, int n_local, int pair_offset, int n_global, PeerPtrs peers) {
@@ -63,6 +93,32 @@ int peer_scatter_stats_launch(const float* g_pos, const float* g_lse, const floa
 }  // namespace sm3
 
 using namespace sm3;
+
+extern "C" int sm3_peer_multicast_rows(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
+                                       void* multicast_dst, void* stream) {
+  SM3_REQUIRE(src && aligned16(src) && multicast_dst && aligned16(multicast_dst), SM3_ERR_SHAPE, "peer_multicast_rows: bad pointer");
+  SM3_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0, SM3_ERR_SHAPE, "peer_multicast_rows: row_bytes %d not a multiple of 16", row_bytes);
+  SM3_REQUIRE(n_local >= 1 && pair_offset >= 0 && pair_offset + n_local <= n_global, SM3_ERR_SHAPE, "peer_multicast_rows: bad row block");
+  const int vpr = row_bytes / 16;
+  const int64_t total = (int64_t)2 * n_local * vpr;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  peer_multicast_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, n_local, pair_offset,
+                                                                                n_global, vpr, (uint4*)multicast_dst);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+extern "C" int sm3_peer_multicast_stats(const float* g_pos, const float* g_lse, const float* neg_sum, int n_local,
+                                        int pair_offset, int n_global, void* multicast_dst, void* stream) {
+  SM3_REQUIRE(g_pos && g_lse && neg_sum && multicast_dst && aligned16(multicast_dst), SM3_ERR_SHAPE, "peer_multicast_stats: bad pointer");
+  SM3_REQUIRE(n_local >= 1 && pair_offset >= 0 && pair_offset + n_local <= n_global, SM3_ERR_SHAPE, "peer_multicast_stats: bad row block");
+  peer_multicast_stats_kernel<<<(2 * n_local + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      g_pos, g_lse, neg_sum, n_local, pair_offset, n_global, (uint4*)multicast_dst);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
 
 static int fill_peers(PeerPtrs& pp, void* const* peers_host, int world) {
   SM3_REQUIRE(peers_host != nullptr && world >= 1 && world <= 16, SM3_ERR_SHAPE, "peer scatter: world=%d not in [1,16]", world);
