@@ -24,14 +24,16 @@ struct HeadMeta {
   int H, C;                    // heads, total classes
   int offset[kMaxHeads + 1];   // class offset of each head
   float weight[kMaxHeads];
+  float gs[kMaxHeads];         // grad_scale * w_h * inv_T / (B * H): valid when no label can be ignored
 };
 
 // workspace layout (floats unless stated): [0] uint32 ticket | [16..16+H) valid counts | [64 ...) block partials
 constexpr int kWsCounts = 16;
+constexpr int kWsGs = 32;        // per-head gradient scales written by heads_count_kernel (ignore_index form)
 constexpr int kWsPartials = 64;
 
 __global__ void heads_count_kernel(const int64_t* __restrict__ labels, int64_t B, int H, int64_t ignore_index,
-                                   float* __restrict__ ws) {
+                                   float* __restrict__ ws, HeadMeta meta, float inv_T, float grad_scale) {
   // one block; exact integer counts of labels != ignore_index per head
   __shared__ int cnt[kMaxHeads];
   if (threadIdx.x < kMaxHeads) cnt[threadIdx.x] = 0;
@@ -53,7 +55,11 @@ __global__ void heads_count_kernel(const int64_t* __restrict__ labels, int64_t B
     if ((threadIdx.x & 31) == 0 && h < H && v) atomicAdd(&cnt[h], v);
   }
   __syncthreads();
-  if (threadIdx.x < H) ws[kWsCounts + threadIdx.x] = (float)cnt[threadIdx.x];
+  if (threadIdx.x < H) {
+    const float c = (float)cnt[threadIdx.x];
+    ws[kWsCounts + threadIdx.x] = c;
+    ws[kWsGs + threadIdx.x] = c > 0.f ? grad_scale * meta.weight[threadIdx.x] * inv_T / (c * (float)H) : 0.f;
+  }
 }
 
 // kFixed == true: the SM3 head layout (5,3,2,3,3,3,3,2 -> 24 logits, 8 heads) is a compile-time constant, so
@@ -247,133 +253,136 @@ multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict_
   constexpr int kOff[9] = {0, 5, 8, 10, 13, 16, 19, 22, 24};
   constexpr int V = VecIO<T>::N;            // 4 (fp32) or 8 (16-bit)
   constexpr int NV = C / V;                 // 6 or 3 vectors per row
-  __shared__ float red[(kHeadThreads / 32) * H];
-  __shared__ float gsc[H];       // per-head gradient scale: grad_scale * w_h * inv_T / (count_h * H)
-  __shared__ bool is_last;
-  const int tid = threadIdx.x;
-  const int64_t row = (int64_t)blockIdx.x * kHeadThreads + tid;
-  if (tid < H) {
-    const float cnt = use_ignore ? ws[kWsCounts + tid] : (float)B;
-    gsc[tid] = cnt > 0.f ? grad_scale * meta.weight[tid] * inv_T / (cnt * (float)H) : 0.f;
-  }
-  __syncthreads();
-  float head_loss[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) head_loss[h] = 0.f;
-
-  // ---- warp-coalesced global access: the warp's 32 rows are one contiguous span (32*C elements, 32*H labels);
-  // lane i moves 16-byte vectors i, i+32, ... of that span, a per-warp shared-memory slab turns them into rows.
   constexpr int kRowBytes = C * (int)sizeof(T);                 // 48 or 96
   constexpr int kSlabX = 32 * kRowBytes;                        // logits / gradient slab per warp
   constexpr int kSlabY = 32 * H * 4;                            // labels as int32 (ignore / out-of-range pre-decoded)
   __shared__ __align__(16) unsigned char slab[(kHeadThreads / 32) * (kSlabX + kSlabY)];
+  __shared__ float red[(kHeadThreads / 32) * H];
+  __shared__ bool is_last;
+  (void)grad_scale;
+  const int tid = threadIdx.x;
   const int lane_ = tid & 31, warp_ = tid >> 5;
   unsigned char* sx = slab + warp_ * (kSlabX + kSlabY);
   int* sy = reinterpret_cast<int*>(sx + kSlabX);
-  const int64_t wrow0 = (int64_t)blockIdx.x * kHeadThreads + warp_ * 32;
-  const int wrows = (int)max((int64_t)0, min((int64_t)32, B - wrow0));
-  {
-    const uint4* gsrc = reinterpret_cast<const uint4*>(logits + wrow0 * C);
-    const int nvec = wrows * kRowBytes / 16;
-#pragma unroll
-    for (int v = 0; v < kRowBytes / 16; ++v) {
-      const int i = lane_ + 32 * v;
-      if (i < nvec) reinterpret_cast<uint4*>(sx)[i] = __ldg(gsrc + i);
-    }
-    const longlong2* lsrc = reinterpret_cast<const longlong2*>(labels + wrow0 * H);
-    const int nl = wrows * H / 2;
-#pragma unroll
-    for (int v = 0; v < H / 2; ++v) {
-      const int i = lane_ + 32 * v;                               // label pair i = (row i / 4, heads 2*(i%4), +1)
-      if (i < nl) {
-        const longlong2 t = __ldg(lsrc + i);
-        const int h0 = (2 * i) & (H - 1);
-        int2 o;
-        // -1: ignored, -2: out of range, else the class id
-        o.x = (use_ignore && t.x == ignore_index) ? -1 : ((unsigned long long)t.x < (unsigned long long)(kOff[h0 + 1] - kOff[h0]) ? (int)t.x : -2);
-        o.y = (use_ignore && t.y == ignore_index) ? -1 : ((unsigned long long)t.y < (unsigned long long)(kOff[h0 + 2] - kOff[h0 + 1]) ? (int)t.y : -2);
-        reinterpret_cast<int2*>(sy)[i] = o;
-      }
-    }
-  }
-  __syncwarp();
 
-  if (row < B) {
-    float x[C];
-    int y[H];
+  // per-head gradient scales: host-computed when nothing can be ignored, else from the counting kernel (no barrier)
+  float gsc[H];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float t[V];
-      const uint4 raw = reinterpret_cast<const uint4*>(sx + lane_ * kRowBytes)[v];
-      if constexpr (sizeof(T) == 4) {
-        t[0] = __uint_as_float(raw.x); t[1] = __uint_as_float(raw.y); t[2] = __uint_as_float(raw.z); t[3] = __uint_as_float(raw.w);
-      } else {
-        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+  for (int h = 0; h < H; ++h) gsc[h] = use_ignore ? __ldg(ws + kWsGs + h) : meta.gs[h];
+  const float k2 = inv_T * 1.4426950408889634f;     // logits * inv_T, in log2 units
+
+  float head_loss[H];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-            t[2 * q] = __uint_as_float(w[q] << 16); t[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
-          } else {
-            const __half2 hh = *reinterpret_cast<const __half2*>(&w[q]);
-            const float2 f = __half22float2(hh);
-            t[2 * q] = f.x; t[2 * q + 1] = f.y;
-          }
+  for (int h = 0; h < H; ++h) head_loss[h] = 0.f;
+
+  // persistent loop over 256-row tiles: one loss reduction per CTA instead of one per tile
+  const int64_t n_tiles = (B + kHeadThreads - 1) / kHeadThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t wrow0 = tile * kHeadThreads + warp_ * 32;
+    const int64_t row = wrow0 + lane_;
+    const int wrows = (int)max((int64_t)0, min((int64_t)32, B - wrow0));
+    // ---- warp-coalesced global -> per-warp slab (the warp's 32 rows are one contiguous span) ----
+    {
+      const uint4* gsrc = reinterpret_cast<const uint4*>(logits + wrow0 * C);
+      const int nvec = wrows * kRowBytes / 16;
+#pragma unroll
+      for (int v = 0; v < kRowBytes / 16; ++v) {
+        const int i = lane_ + 32 * v;
+        if (i < nvec) reinterpret_cast<uint4*>(sx)[i] = __ldg(gsrc + i);
+      }
+      const longlong2* lsrc = reinterpret_cast<const longlong2*>(labels + wrow0 * H);
+      const int nl = wrows * H / 2;
+#pragma unroll
+      for (int v = 0; v < H / 2; ++v) {
+        const int i = lane_ + 32 * v;                               // label pair i = (row i / 4, heads 2*(i%4), +1)
+        if (i < nl) {
+          const longlong2 t = __ldg(lsrc + i);
+          const int h0 = (2 * i) & (H - 1);
+          int2 o;   // -1: ignored, -2: out of range, else the class id
+          o.x = (use_ignore && t.x == ignore_index) ? -1 : ((unsigned long long)t.x < (unsigned long long)(kOff[h0 + 1] - kOff[h0]) ? (int)t.x : -2);
+          o.y = (use_ignore && t.y == ignore_index) ? -1 : ((unsigned long long)t.y < (unsigned long long)(kOff[h0 + 2] - kOff[h0 + 1]) ? (int)t.y : -2);
+          reinterpret_cast<int2*>(sy)[i] = o;
         }
       }
-#pragma unroll
-      for (int i = 0; i < V; ++i) x[v * V + i] = t[i];
     }
-    {
-      const int4 a = reinterpret_cast<const int4*>(sy + lane_ * H)[0];
-      const int4 b = reinterpret_cast<const int4*>(sy + lane_ * H)[1];
-      y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
-    }
-    const float k2 = inv_T * 1.4426950408889634f;     // logits * inv_T, in log2 units
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      constexpr int kMaxNc = 5;
-      const int o = kOff[h], nc = kOff[h + 1] - kOff[h];
-      float e[kMaxNc];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kMaxNc; ++c) if (c < nc) { e[c] = x[o + c] * k2; mx = fmaxf(mx, e[c]); }
-      const bool in_range = y[h] >= 0;
-      const bool ignored = y[h] == -1;
-      const int yy = y[h];
-      float vy = 0.f, se = 0.f;
-#pragma unroll
-      for (int c = 0; c < kMaxNc; ++c) if (c < nc) {
-        vy = (c == yy) ? e[c] : vy;
-        e[c] = ex2f_approx(e[c] - mx);
-        se += e[c];
-      }
-      const float g = (in_range && !ignored) ? gsc[h] : 0.f;
-      const float rg = rcpf_approx(se) * g;
-#pragma unroll
-      for (int c = 0; c < kMaxNc; ++c) if (c < nc) x[o + c] = fmaf(e[c], rg, (c == yy) ? -g : 0.f);
-      float hl = 0.6931471805599453f * (mx + lg2f_approx(se) - vy);
-      hl = (in_range && !ignored) ? hl : 0.f;
-      head_loss[h] = (!in_range && !ignored) ? NAN : hl;      // out-of-range label: torch would device-assert
-    }
-    if (dlogits != nullptr) {
+    __syncwarp();
+
+    if (row < B) {
+      float x[C];
+      int y[H];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         float t[V];
+        const uint4 raw = reinterpret_cast<const uint4*>(sx + lane_ * kRowBytes)[v];
+        if constexpr (sizeof(T) == 4) {
+          t[0] = __uint_as_float(raw.x); t[1] = __uint_as_float(raw.y); t[2] = __uint_as_float(raw.z); t[3] = __uint_as_float(raw.w);
+        } else {
+          const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-        for (int i = 0; i < V; ++i) t[i] = x[v * V + i];
-        VecIO<T>::store(reinterpret_cast<T*>(sx + lane_ * kRowBytes) + v * V, t);    // row -> slab (generic st)
+          for (int q = 0; q < 4; ++q) {
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+              t[2 * q] = __uint_as_float(w[q] << 16); t[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+            } else {
+              const __half2 hh = *reinterpret_cast<const __half2*>(&w[q]);
+              const float2 f = __half22float2(hh);
+              t[2 * q] = f.x; t[2 * q + 1] = f.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) x[v * V + i] = t[i];
+      }
+      {
+        const int4 a = reinterpret_cast<const int4*>(sy + lane_ * H)[0];
+        const int4 b = reinterpret_cast<const int4*>(sy + lane_ * H)[1];
+        y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        constexpr int kMaxNc = 5;
+        const int o = kOff[h], nc = kOff[h + 1] - kOff[h];
+        float e[kMaxNc];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kMaxNc; ++c) if (c < nc) { e[c] = x[o + c] * k2; mx = fmaxf(mx, e[c]); }
+        const int yy = y[h];
+        const bool in_range = yy >= 0;
+        const bool ignored = yy == -1;
+        float vy = 0.f, se = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxNc; ++c) if (c < nc) {
+          vy = (c == yy) ? e[c] : vy;
+          e[c] = ex2f_approx(e[c] - mx);
+          se += e[c];
+        }
+        const float g = in_range ? gsc[h] : 0.f;
+        const float rg = rcpf_approx(se) * g;
+#pragma unroll
+        for (int c = 0; c < kMaxNc; ++c) if (c < nc) x[o + c] = fmaf(e[c], rg, (c == yy) ? -g : 0.f);
+        const float hl = 0.6931471805599453f * (mx + lg2f_approx(se) - vy);
+        head_loss[h] += in_range ? hl : (ignored ? 0.f : NAN);     // out-of-range label: torch would device-assert
+      }
+      if (dlogits != nullptr) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float t[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) t[i] = x[v * V + i];
+          VecIO<T>::store(reinterpret_cast<T*>(sx + lane_ * kRowBytes) + v * V, t);    // row -> slab
+        }
       }
     }
-  }
-  if (dlogits != nullptr) {
-    __syncwarp();
-    uint4* gdst = reinterpret_cast<uint4*>(dlogits + wrow0 * C);
-    const int nvec = wrows * kRowBytes / 16;
+    if (dlogits != nullptr) {
+      __syncwarp();
+      uint4* gdst = reinterpret_cast<uint4*>(dlogits + wrow0 * C);
+      const int nvec = wrows * kRowBytes / 16;
 #pragma unroll
-    for (int v = 0; v < kRowBytes / 16; ++v) {
-      const int i = lane_ + 32 * v;
-      if (i < nvec) gdst[i] = reinterpret_cast<const uint4*>(sx)[i];
+      for (int v = 0; v < kRowBytes / 16; ++v) {
+        const int i = lane_ + 32 * v;
+        if (i < nvec) gdst[i] = reinterpret_cast<const uint4*>(sx)[i];
+      }
     }
+    __syncwarp();     // slab is reused by the next tile
   }
 
   const int lane = tid & 31, warp = tid >> 5;
@@ -611,6 +620,7 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
     SM3_REQUIRE(class_counts_host[h] >= 1, SM3_ERR_SHAPE, "multihead_ce: head %d has %d classes", h, class_counts_host[h]);
     meta.offset[h + 1] = meta.offset[h] + class_counts_host[h];
     meta.weight[h] = weights_host ? weights_host[h] : 1.0f;
+    meta.gs[h] = grad_scale * meta.weight[h] * inv_T / ((float)B * (float)H);
   }
   meta.C = meta.offset[H];
   SM3_REQUIRE(meta.C <= kMaxClassesTotal, SM3_ERR_SHAPE, "multihead_ce: %d total classes > %d", meta.C, kMaxClassesTotal);
@@ -618,7 +628,7 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
   float* ws = (float*)workspace;
   SM3_CHECK_CUDA(cudaMemsetAsync(ws, 0, kWsPartials * sizeof(float), st));
   if (use_ignore_index) {
-    heads_count_kernel<<<1, 1024, 0, st>>>(labels, B, H, ignore_index, ws);
+    heads_count_kernel<<<1, 1024, 0, st>>>(labels, B, H, ignore_index, ws, meta, inv_T, grad_scale);
     SM3_CHECK_CUDA(cudaGetLastError());
   }
   const unsigned grid = (unsigned)((B + kHeadThreads - 1) / kHeadThreads);
@@ -628,7 +638,8 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
   for (int h = 0; fixed && h < 8; ++h) fixed = (class_counts_host[h] == kSm3Layout[h]);
   SM3_DISPATCH_DTYPE(dtype, T, {
     if (fixed && aligned16(logits) && aligned16(labels) && (dlogits == nullptr || aligned16(dlogits))) {
-      multihead_ce_sm3_kernel<T><<<grid, kHeadThreads, 0, st>>>((const T*)logits, labels, B, meta, inv_T,
+      const unsigned pgrid = grid < (unsigned)num_sms() * 8u ? grid : (unsigned)num_sms() * 8u;
+      multihead_ce_sm3_kernel<T><<<pgrid, kHeadThreads, 0, st>>>((const T*)logits, labels, B, meta, inv_T,
           use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
     } else if (fixed) {
       SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -45,8 +45,7 @@ l2norm_fwd_small_kernel(const TIn* __restrict__ pa, int64_t rows_a, const TIn* _
   const int lane = threadIdx.x & 31;
   const int64_t rows = rows_a + rows_b;
   const bool have = lane < D / kChunk;
-  const int64_t gstride = (int64_t)gridDim.x * kWarpsPerBlock * kRows;
-  for (int64_t row0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kRows; row0 < rows; row0 += gstride) {
+  const int64_t row0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kRows;
   float v[kRows][kChunk];
 #pragma unroll
   for (int r = 0; r < kRows; ++r) {
@@ -76,7 +75,6 @@ l2norm_fwd_small_kernel(const TIn* __restrict__ pa, int64_t rows_a, const TIn* _
       if (lane == 0) inv_norm[row] = inv;
     }
   }
-  }
 }
 
 template <typename TZ, typename TOut>
@@ -88,8 +86,7 @@ l2norm_bwd_small_kernel(const float* __restrict__ dz, int n_partials, int64_t pa
   const int lane = threadIdx.x & 31;
   const int64_t rows = rows_a + rows_b;
   const bool have = lane < D / kChunk;
-  const int64_t gstride = (int64_t)gridDim.x * kWarpsPerBlock * R;
-  for (int64_t row0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * R; row0 < rows; row0 += gstride) {
+  const int64_t row0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * R;
   float gv[R][kChunk], zv[R][kChunk];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -125,7 +122,6 @@ l2norm_bwd_small_kernel(const float* __restrict__ dz, int n_partials, int64_t pa
       for (int i = 0; i < kChunk; ++i) gv[r][i] = (gv[r][i] - zv[r][i] * dot) * inv;
       store8<TOut>(dst + lane * kChunk, gv[r]);
     }
-  }
   }
 }
 
