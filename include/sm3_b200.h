@@ -184,6 +184,14 @@ int sm3_infonce_host(const void* p1_host, const void* p2_host, int n_pairs, int 
                      float temperature, float* loss_host, void* dp1_host, void* dp2_host, void* device_scratch,
                      size_t scratch_bytes, int algo, void* stream);
 
+/* Device-pointer form of the same fused step: ONE call enqueues normalise -> K2 -> loss -> K3 -> normalise-backward on
+ * `stream` (no copies, no synchronisation).  loss = weight * mean-CE (device scalar); dp1/dp2 may both be NULL
+ * (forward only).  precision follows `algo` (AUTO = tcgen05 on bf16 rows when D allows, else the fp32 FMA kernels). */
+size_t sm3_infonce_step_scratch_bytes(int n_pairs, int D, int io_dtype, int algo);
+int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_dtype, float temperature, float weight,
+                     float* loss, void* dp1, void* dp2, void* device_scratch, size_t scratch_bytes, int algo,
+                     void* stream);
+
 /* debug / bring-up: single-tile tcgen05 probe used by tests/test_umma_probe.py (not a product path).
  *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */
 int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,

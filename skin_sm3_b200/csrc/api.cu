@@ -176,6 +176,46 @@ HostPlan plan_host(int n, int D, int io_dtype, int algo) {
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// device-pointer fused step: normalise -> K2 -> loss -> K3 -> normalise-backward enqueued by ONE call
+// (no host<->device copies, no synchronisation).  Same scratch layout as the host entry.
+// ---------------------------------------------------------------------------------------------------
+extern "C" size_t sm3_infonce_step_scratch_bytes(int n_pairs, int D, int io_dtype, int algo) {
+  if (n_pairs < 1 || D < 1 || !dtype_ok(io_dtype)) return 0;
+  return plan_host(n_pairs, D, io_dtype, algo).total;
+}
+
+extern "C" int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_dtype, float temperature,
+                                float weight, float* loss, void* dp1, void* dp2, void* device_scratch,
+                                size_t scratch_bytes, int algo, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(p1 && p2 && loss && device_scratch, SM3_ERR_SHAPE, "infonce_step: null pointer");
+  SM3_REQUIRE((dp1 == nullptr) == (dp2 == nullptr), SM3_ERR_SHAPE, "infonce_step: dp1/dp2 must both be given or both NULL");
+  SM3_REQUIRE(n_pairs >= 1 && D >= 1 && dtype_ok(io_dtype), SM3_ERR_SHAPE, "infonce_step: bad shape/dtype");
+  SM3_REQUIRE(temperature > 0.f, SM3_ERR_SHAPE, "infonce_step: temperature must be > 0");
+  HostPlan h = plan_host(n_pairs, D, io_dtype, algo);
+  if (h.algo == SM3_ALGO_TC && !(aligned16(p1) && aligned16(p2))) { h = plan_host(n_pairs, D, io_dtype, SM3_ALGO_SIMT); }
+  SM3_REQUIRE(scratch_bytes >= h.total, SM3_ERR_WORKSPACE, "infonce_step: scratch %zu < %zu", scratch_bytes, h.total);
+  char* base = (char*)device_scratch;
+  const int64_t n = n_pairs, m = 2 * n;
+  const float inv_T = 1.0f / temperature;
+  int rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f, st);
+  if (rc) return rc;
+  rc = sm3_infonce_fwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T, (float*)(base + h.pos),
+                       (float*)(base + h.lse), (float*)(base + h.nsum), base + h.ws, h.ws_bytes, h.algo, st);
+  if (rc) return rc;
+  rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, weight / (float)m, loss, 0,
+                        dp1 ? (float*)(base + h.gpos) : nullptr, dp1 ? (float*)(base + h.glse) : nullptr, st);
+  if (rc || !dp1) return rc;
+  const int np = sm3_infonce_bwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T,
+                                 (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
+                                 (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
+                                 base + h.ws, h.ws_bytes, h.algo, st);
+  if (np < 0) return np;
+  return sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
+                        dp1, n, dp2, n, D, io_dtype, st);
+}
+
 extern "C" size_t sm3_infonce_host_scratch_bytes(int n_pairs, int D, int io_dtype, int algo) {
   if (n_pairs < 1 || D < 1 || !dtype_ok(io_dtype)) return 0;
   return plan_host(n_pairs, D, io_dtype, algo).total;

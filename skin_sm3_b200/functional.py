@@ -298,6 +298,26 @@ class _FusedInfoNCE(torch.autograd.Function):
         w, rank = _group_info(group)
         n_local = p1.shape[0]
         n_global = n_local * w
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if w == 1 and _PROFILE is None:
+            # single GPU: the whole step is enqueued by one C call (launch-bound shapes: ~8 launches, no Python
+            # between them)
+            p1c, p2c = _contig(p1), _contig(p2)
+            dev, d = p1c.device, p1c.shape[1]
+            io = dtype_code(p1c)
+            with torch.cuda.device(dev):
+                nbytes = lib().sm3_infonce_step_scratch_bytes(n_local, d, io, algo)
+                scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                dp1 = torch.empty_like(p1c) if need_grad else None
+                dp2 = torch.empty_like(p2c) if need_grad else None
+                check(lib().sm3_infonce_step(ptr(p1c), ptr(p2c), n_local, d, io, temperature, weight, ptr(loss),
+                                             ptr(dp1), ptr(dp2), ptr(scratch), scratch.numel(), algo, stream_ptr()),
+                      "sm3_infonce_step")
+            if need_grad:
+                ctx.save_for_backward(dp1, dp2)
+            ctx.comm_used = "none"
+            return loss
         pbuf = _resolve_comm(comm, w, z_dtype, n_global, p1.shape[1], p1.device, group)
         slot = pbuf.next_slot() if pbuf is not None else 0
         _mark("start")
@@ -312,7 +332,6 @@ class _FusedInfoNCE(torch.autograd.Function):
         _mark("gather_z")
         pos, lse, nsum = core.stats_fwd(z, z_cols, n_local, rank * n_local, n_global, temperature, algo)
         _mark("stats_fwd")
-        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         loss, g_pos, g_lse = core.loss(pos, lse, weight / (2 * n_local), want_grads=need_grad)
         _mark("loss")
         if need_grad:

@@ -206,6 +206,26 @@ def test_fused_scalar_loss_and_grad_scaling(sm3):
     assert relerr(p2.grad.cpu().numpy() / 32768.0, g["dp2_f64"]) < 1e-4
 
 
+def test_fused_step_entry_matches_composed_path(sm3):
+    """sm3_infonce_step (one C call) == the Python-composed sequence of the same kernels, bit for bit."""
+    from skin_sm3_b200 import functional as F3
+    g = load("infonce_n200_d64_T02_corr")
+    T = float(g["temperature"])
+    for prec, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        outs = []
+        for profiled in (False, True):
+            F3._PROFILE = (lambda name: None) if profiled else None
+            try:
+                a = cuda(g["p1"], dt).requires_grad_(True); b = cuda(g["p2"], dt).requires_grad_(True)
+                loss = sm3.fused_infonce(a, b, T, precision=prec)
+                loss.backward()
+                outs.append((loss.item(), a.grad.clone(), b.grad.clone()))
+            finally:
+                F3._PROFILE = None
+        assert outs[0][0] == outs[1][0]
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
 def test_host_buffer_entry(sm3):
     g = load("infonce_n64_d128_T01")
     T, n, d = float(g["temperature"]), int(g["n"]), int(g["d"])
