@@ -131,6 +131,26 @@ int sm3_peer_multicast_rows(const void* src, int n_local, int pair_offset, int n
 int sm3_peer_multicast_stats(const float* g_pos, const float* g_lse, const float* neg_sum, int n_local, int pair_offset,
                              int n_global, void* multicast_dst, void* stream);
 
+/* Split barrier on a small symmetric flag buffer (>= 64 uint32 per rank, zero-initialised once): `signal` makes this
+ * rank's earlier stores visible and writes `epoch` into slot (channel, rank) of every peer's flags; `wait` blocks the
+ * stream until all `world` slots of `channel` in MY flags reached `epoch` (epochs only grow; channel in [0,4)).   */
+int sm3_peer_signal(void* const* peer_flags_host, int world, int rank, int channel, unsigned epoch, void* stream);
+int sm3_peer_wait(const void* my_flags, int world, int channel, unsigned epoch, void* stream);
+
+/* "Remote" halves of K2 / K3 (tcgen05 path, n_local % 128 == 0, world > 1): visit only the column tiles owned by other
+ * ranks.  The local block is an ordinary call with n_global = n_local, pair_offset = 0 on the local rows -- it needs no
+ * remote data and is enqueued while the exchange is in flight.
+ *   fwd_remote : neg_sum = neg_sum_local + remote part ; lse_neg = inv_T + log(neg_sum)   (pos comes from the local call)
+ *   bwd_remote : partial dz slabs for the remote columns (returns n_partials); add the local call's slabs.           */
+size_t sm3_infonce_remote_workspace_bytes(int n_local, int n_global, int D, int backward);
+int sm3_infonce_fwd_remote(const void* z_rows, const void* z_cols, int n_local, int pair_offset, int n_global, int D,
+                           int dtype, float inv_T, const float* neg_sum_local, float* pos_unused, float* lse_neg,
+                           float* neg_sum, void* workspace, size_t workspace_bytes, void* stream);
+int sm3_infonce_bwd_remote_packed(const void* z_rows, const void* z_cols, int n_local, int pair_offset, int n_global,
+                                  int D, int dtype, float inv_T, const float* g_pos_rows, const float* g_lse_rows,
+                                  const float* neg_sum_rows, const float* stats_cols, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* loss half of nn.CrossEntropyLoss()(logits, 0) on the sufficient statistics, fused with its own
  * gradient (tools/backbone_train.py:101-121):
  *   loss   = scale * sum_i softplus(lse_neg_i - pos_i)             (scale = weight / M_global)
@@ -191,6 +211,19 @@ size_t sm3_infonce_step_scratch_bytes(int n_pairs, int D, int io_dtype, int algo
 int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_dtype, float temperature, float weight,
                      float* loss, void* dp1, void* dp2, void* device_scratch, size_t scratch_bytes, int algo,
                      void* stream);
+
+/* Multi-rank form: this rank's 2*n_local rows against all world*n_local pairs, negatives exchanged over NVLink peer
+ * memory, the whole step enqueued by ONE call on two streams (exchange on stream_side, kernels on stream_main; the
+ * local column block runs while the exchange is in flight).  z_cols_mine / stats_mine / flags_mine are this rank's
+ * symmetric buffers ([2*n_global, D] bf16, [2*n_global, 4] fp32, >= 64 uint32), *_peers_host the HOST arrays of the
+ * `world` peer-mapped pointers of the same buffers; `epoch` must grow by one per call and be identical on all ranks.
+ * Needs n_local % 128 == 0 and D in {64,128,192,256}.  loss = weight * mean over this rank's rows (DDP convention). */
+size_t sm3_infonce_step_peer_scratch_bytes(int n_local, int n_global, int D);
+int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local, int rank, int world, int D, int io_dtype,
+                          float temperature, float weight, float* loss, void* dp1, void* dp2, void* z_cols_mine,
+                          void* const* z_peers_host, void* stats_mine, void* const* stats_peers_host, void* flags_mine,
+                          void* const* flags_peers_host, unsigned epoch, void* device_scratch, size_t scratch_bytes,
+                          void* stream_main, void* stream_side);
 
 /* debug / bring-up: single-tile tcgen05 probe used by tests/test_umma_probe.py (not a product path).
  *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */

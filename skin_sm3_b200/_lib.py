@@ -40,6 +40,11 @@ SIGNATURES = {
     "sm3_peer_scatter_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(_vp), _i, _vp]),
     "sm3_peer_multicast_rows": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sm3_peer_multicast_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "sm3_peer_signal": (_i, [C.POINTER(_vp), _i, _i, _i, C.c_uint, _vp]),
+    "sm3_peer_wait": (_i, [_vp, _i, _i, C.c_uint, _vp]),
+    "sm3_infonce_remote_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "sm3_infonce_fwd_remote": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sm3_infonce_bwd_remote_packed": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sm3_infonce_loss": (_i, [_vp, _vp, _i64, _f, _vp, _i, _vp, _vp, _vp]),
     "sm3_multihead_ce_workspace_bytes": (_sz, [_i64, _i]),
     "sm3_multihead_ce": (_i, [_vp, _i, _vp, _i64, _i, C.POINTER(_i), C.POINTER(_f), _f, _i, _i64, _vp, _vp, _f,
@@ -51,6 +56,9 @@ SIGNATURES = {
     "sm3_infonce_host": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "sm3_infonce_step_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "sm3_infonce_step": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "sm3_infonce_step_peer_scratch_bytes": (_sz, [_i, _i, _i]),
+    "sm3_infonce_step_peer": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp,
+                                   C.POINTER(_vp), _vp, C.POINTER(_vp), C.c_uint, _vp, _sz, _vp, _vp]),
     "sm3_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 

@@ -177,6 +177,47 @@ HostPlan plan_host(int n, int D, int io_dtype, int algo) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
+// "remote" halves of the row-sharded kernels: only the column tiles owned by OTHER ranks are visited (tcgen05 path).
+// The local block is an ordinary single-rank call on the local rows (n_global = n_local, pair_offset = 0); it needs
+// no remote data, so it runs while the exchange is in flight.  See skin_sm3_b200/functional.py (_FusedInfoNCE).
+// ---------------------------------------------------------------------------------------------------
+extern "C" size_t sm3_infonce_remote_workspace_bytes(int n_local, int n_global, int D, int backward) {
+  InfoNceProblem pb{nullptr, nullptr, n_local, 0, n_global, D, SM3_BF16, 1.0f};
+  pb.skip_local = 1;
+  return infonce_tc_workspace(pb, backward);
+}
+
+extern "C" int sm3_infonce_fwd_remote(const void* z_rows, const void* z_cols, int n_local, int pair_offset,
+                                      int n_global, int D, int dtype, float inv_T, const float* neg_sum_local,
+                                      float* pos_unused, float* lse_neg, float* neg_sum, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  InfoNceProblem pb{z_rows, z_cols, n_local, pair_offset, n_global, D, dtype, inv_T};
+  pb.skip_local = 1;
+  pb.extra_neg_sum = neg_sum_local;
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  SM3_REQUIRE(neg_sum_local && pos_unused && lse_neg && neg_sum && workspace, SM3_ERR_SHAPE, "infonce_fwd_remote: null pointer");
+  SM3_REQUIRE(infonce_tc_supported(pb), SM3_ERR_DTYPE, "infonce_fwd_remote: needs the tcgen05 path (bf16 rows, D in {64,128,192,256})");
+  return infonce_tc_fwd(pb, pos_unused, lse_neg, neg_sum, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sm3_infonce_bwd_remote_packed(const void* z_rows, const void* z_cols, int n_local, int pair_offset,
+                                             int n_global, int D, int dtype, float inv_T, const float* g_pos_rows,
+                                             const float* g_lse_rows, const float* neg_sum_rows,
+                                             const float* stats_cols, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+  InfoNceProblem pb{z_rows, z_cols, n_local, pair_offset, n_global, D, dtype, inv_T};
+  pb.skip_local = 1;
+  pb.col_stride = 4;
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  SM3_REQUIRE(g_pos_rows && g_lse_rows && neg_sum_rows && stats_cols && workspace, SM3_ERR_SHAPE, "infonce_bwd_remote: null pointer");
+  SM3_REQUIRE(infonce_tc_supported(pb), SM3_ERR_DTYPE, "infonce_bwd_remote: needs the tcgen05 path (bf16 rows, D in {64,128,192,256})");
+  return infonce_tc_bwd(pb, g_pos_rows, g_lse_rows, neg_sum_rows, stats_cols, stats_cols + 1, stats_cols + 2, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // device-pointer fused step: normalise -> K2 -> loss -> K3 -> normalise-backward enqueued by ONE call
 // (no host<->device copies, no synchronisation).  Same scratch layout as the host entry.
 // ---------------------------------------------------------------------------------------------------
@@ -214,6 +255,132 @@ extern "C" int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int
   if (np < 0) return np;
   return sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
                         dp1, n, dp2, n, D, io_dtype, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-rank fused step with the peer-memory exchange, enqueued by ONE call on two streams:
+//   main: normalise | local K2 | wait | remote K2 | loss | local K3 | wait | remote K3 | normalise-backward
+//   side:           scatter z + signal            ....        scatter stats + signal
+// (at 8 ranks the per-rank GPU work is ~0.7 ms; a Python-orchestrated step of ~25 launches is CPU-bound there)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct PeerPlan {
+  size_t z, inv, pos, lse_l, ns_l, lse, nsum, gpos, glse, ws_f, ws_f_bytes, ws_b, ws_b_bytes, total;
+};
+PeerPlan plan_peer(int n_local, int n_global, int D) {
+  PeerPlan h{};
+  const size_t m = 2 * (size_t)n_local;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  h.z = take(m * D * 2);
+  h.inv = take(m * 4); h.pos = take(m * 4); h.lse_l = take(m * 4); h.ns_l = take(m * 4);
+  h.lse = take(m * 4); h.nsum = take(m * 4); h.gpos = take(m * 4); h.glse = take(m * 4);
+  InfoNceProblem loc{nullptr, nullptr, n_local, 0, n_local, D, SM3_BF16, 1.f};
+  InfoNceProblem rem{nullptr, nullptr, n_local, 0, n_global, D, SM3_BF16, 1.f};
+  rem.skip_local = 1;
+  const size_t f0 = infonce_tc_workspace(loc, 0), f1 = infonce_tc_workspace(rem, 0);
+  h.ws_f_bytes = f0 > f1 ? f0 : f1;
+  h.ws_f = take(h.ws_f_bytes);
+  h.ws_b_bytes = infonce_tc_workspace(loc, 1) + infonce_tc_workspace(rem, 1) + 1024;
+  h.ws_b = take(h.ws_b_bytes);
+  h.total = o;
+  return h;
+}
+cudaEvent_t* peer_events() {
+  static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (ev[0] == nullptr) {
+    if (cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
+  }
+  return ev;
+}
+int fill_peer_ptrs(PeerPtrs& pp, void* const* host, int world) {
+  SM3_REQUIRE(host != nullptr && world >= 2 && world <= 16, SM3_ERR_SHAPE, "infonce_step_peer: world=%d not in [2,16]", world);
+  pp.world = world;
+  for (int r = 0; r < world; ++r) {
+    SM3_REQUIRE(host[r] != nullptr && aligned16(host[r]), SM3_ERR_SHAPE, "infonce_step_peer: bad peer pointer %d", r);
+    pp.p[r] = host[r];
+  }
+  return SM3_OK;
+}
+}  // namespace
+
+extern "C" size_t sm3_infonce_step_peer_scratch_bytes(int n_local, int n_global, int D) {
+  if (n_local < 1 || n_global < n_local || D % 64 != 0 || D < 64 || D > 256) return 0;
+  return plan_peer(n_local, n_global, D).total;
+}
+
+extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local, int rank, int world, int D,
+                                     int io_dtype, float temperature, float weight, float* loss, void* dp1, void* dp2,
+                                     void* z_cols_mine, void* const* z_peers_host, void* stats_mine,
+                                     void* const* stats_peers_host, void* flags_mine, void* const* flags_peers_host,
+                                     unsigned epoch, void* device_scratch, size_t scratch_bytes, void* stream_main,
+                                     void* stream_side) {
+  cudaStream_t sm = (cudaStream_t)stream_main, ss = (cudaStream_t)stream_side;
+  SM3_REQUIRE(p1 && p2 && loss && z_cols_mine && stats_mine && flags_mine && device_scratch, SM3_ERR_SHAPE,
+              "infonce_step_peer: null pointer");
+  SM3_REQUIRE((dp1 == nullptr) == (dp2 == nullptr), SM3_ERR_SHAPE, "infonce_step_peer: dp1/dp2 must both be given or both NULL");
+  SM3_REQUIRE(world >= 2 && rank >= 0 && rank < world && n_local >= 128 && n_local % 128 == 0, SM3_ERR_SHAPE,
+              "infonce_step_peer: needs world >= 2 and n_local %% 128 == 0 (got world=%d n_local=%d)", world, n_local);
+  SM3_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256 && dtype_ok(io_dtype) && temperature > 0.f, SM3_ERR_DTYPE,
+              "infonce_step_peer: D must be in {64,128,192,256}");
+  SM3_REQUIRE(stream_side != stream_main, SM3_ERR_SHAPE, "infonce_step_peer: the side stream must differ from the main stream");
+  const int n_global = n_local * world, off = rank * n_local;
+  const PeerPlan h = plan_peer(n_local, n_global, D);
+  SM3_REQUIRE(scratch_bytes >= h.total, SM3_ERR_WORKSPACE, "infonce_step_peer: scratch %zu < %zu", scratch_bytes, h.total);
+  PeerPtrs zp, sp, fp;
+  int rc = fill_peer_ptrs(zp, z_peers_host, world);
+  if (rc) return rc;
+  if ((rc = fill_peer_ptrs(sp, stats_peers_host, world))) return rc;
+  if ((rc = fill_peer_ptrs(fp, flags_peers_host, world))) return rc;
+  cudaEvent_t* ev = peer_events();
+  SM3_REQUIRE(ev != nullptr, SM3_ERR_CUDA, "infonce_step_peer: cudaEventCreate failed");
+  char* base = (char*)device_scratch;
+  const int64_t n = n_local, m = 2 * n;
+  const float inv_T = 1.0f / temperature;
+  float *pos = (float*)(base + h.pos), *lse_l = (float*)(base + h.lse_l), *ns_l = (float*)(base + h.ns_l);
+  float *lse = (float*)(base + h.lse), *nsum = (float*)(base + h.nsum), *gpos = (float*)(base + h.gpos), *glse = (float*)(base + h.glse);
+  void* z = base + h.z;
+
+  rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, sm);
+  if (rc) return rc;
+  // ---- exchange of the normalised rows on the side stream, local column block meanwhile ----
+  SM3_CHECK_CUDA(cudaEventRecord(ev[0], sm));
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(ss, ev[0], 0));
+  if ((rc = peer_scatter_rows_launch(z, n_local, off, n_global, D * 2, zp, ss))) return rc;
+  if ((rc = peer_signal_launch(fp, rank, 0, epoch, ss))) return rc;
+  SM3_CHECK_CUDA(cudaEventRecord(ev[1], ss));
+  rc = sm3_infonce_fwd(z, z, n_local, 0, n_local, D, SM3_BF16, inv_T, pos, lse_l, ns_l, base + h.ws_f, h.ws_f_bytes,
+                       SM3_ALGO_TC, sm);
+  if (rc) return rc;
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(sm, ev[1], 0));
+  if ((rc = peer_wait_launch((const unsigned*)flags_mine, world, 0, epoch, sm))) return rc;
+  rc = sm3_infonce_fwd_remote(z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T, ns_l, pos, lse, nsum,
+                              base + h.ws_f, h.ws_f_bytes, sm);
+  if (rc) return rc;
+  rc = sm3_infonce_loss(pos, lse, m, weight / (float)m, loss, 0, dp1 ? gpos : nullptr, dp1 ? glse : nullptr, sm);
+  if (rc || !dp1) return rc;
+  // ---- exchange of the 12-byte row statistics, local column block of the backward meanwhile ----
+  SM3_CHECK_CUDA(cudaEventRecord(ev[0], sm));
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(ss, ev[0], 0));
+  if ((rc = peer_scatter_stats_launch(gpos, glse, nsum, n_local, off, n_global, sp, ss))) return rc;
+  if ((rc = peer_signal_launch(fp, rank, 1, epoch, ss))) return rc;
+  SM3_CHECK_CUDA(cudaEventRecord(ev[1], ss));
+  InfoNceProblem loc{nullptr, nullptr, n_local, 0, n_local, D, SM3_BF16, 1.f};
+  const size_t wsl = infonce_tc_workspace(loc, 1);
+  const int np_l = sm3_infonce_bwd(z, z, n_local, 0, n_local, D, SM3_BF16, inv_T, gpos, glse, nsum, gpos, glse, nsum,
+                                   base + h.ws_b, wsl, SM3_ALGO_TC, sm);
+  if (np_l < 0) return np_l;
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(sm, ev[1], 0));
+  if ((rc = peer_wait_launch((const unsigned*)flags_mine, world, 1, epoch, sm))) return rc;
+  const size_t slab = (size_t)np_l * m * D * 4;
+  const int np_r = sm3_infonce_bwd_remote_packed(z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T, gpos, glse,
+                                                 nsum, (const float*)stats_mine, base + h.ws_b + slab,
+                                                 h.ws_b_bytes - slab, sm);
+  if (np_r < 0) return np_r;
+  return sm3_l2norm_bwd((const float*)(base + h.ws_b), np_l + np_r, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f,
+                        dp1, n, dp2, n, D, io_dtype, sm);
 }
 
 extern "C" size_t sm3_infonce_host_scratch_bytes(int n_pairs, int D, int io_dtype, int algo) {

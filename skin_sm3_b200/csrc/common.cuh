@@ -144,12 +144,19 @@ int l2norm_bwd_launch(const float* dz_partials, int n_partials, float scale, con
                       const float* inv_norm, float eps, void* dp_a, int64_t rows_a, void* dp_b, int64_t rows_b, int D,
                       int dp_dtype, cudaStream_t st);
 
+struct PeerPtrs {           // destination buffers of a peer scatter (one per rank, this rank included)
+  void* p[16];
+  int world;
+};
 struct InfoNceProblem {
   const void* z_rows;
   const void* z_cols;
   int n_local, pair_offset, n_global, D, dtype;
   float inv_T;
   int col_stride = 1;   // backward: element stride of the per-column statistic arrays (4 = packed float4 rows)
+  int skip_local = 0;   // 1: visit only the column tiles owned by OTHER ranks (the local block is computed separately,
+                        //    overlapped with the cross-rank exchange); needs n_local % 128 == 0
+  const float* extra_neg_sum = nullptr;   // forward, skip_local: neg_sum of the local block, added in the finalize
 };
 size_t infonce_simt_workspace(const InfoNceProblem& pb, int backward);
 int infonce_simt_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
@@ -165,11 +172,9 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
                    const float* gpos_c, const float* glse_c, const float* nsum_c, void* ws, size_t ws_bytes,
                    cudaStream_t st);
 int infonce_finalize_launch(const float* partial_sums, int n_partials, int64_t rows, float inv_T, float* neg_sum,
-                            float* lse_neg, cudaStream_t st);
-struct PeerPtrs {           // destination buffers of a peer scatter (one per rank, this rank included)
-  void* p[16];
-  int world;
-};
+                            float* lse_neg, cudaStream_t st, const float* extra = nullptr);
+int peer_signal_launch(const PeerPtrs& flags, int rank, int channel, unsigned epoch, cudaStream_t st);
+int peer_wait_launch(const unsigned* my_flags, int world, int channel, unsigned epoch, cudaStream_t st);
 int peer_scatter_rows_launch(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
                              const PeerPtrs& peers, cudaStream_t st);
 int peer_scatter_stats_launch(const float* g_pos, const float* g_lse, const float* nsum, int n_local, int pair_offset,

@@ -521,10 +521,11 @@ bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __re
 
 // ---------------- InfoNCE tail kernels ----------------
 __global__ void infonce_finalize_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, float inv_T,
-                                        float* __restrict__ neg_sum, float* __restrict__ lse_neg) {
+                                        float* __restrict__ neg_sum, float* __restrict__ lse_neg,
+                                        const float* __restrict__ extra) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
-  float s = 0.f;
+  float s = extra ? extra[i] : 0.f;
   for (int k = 0; k < n_partials; ++k) s += partial[(int64_t)k * rows + i];
   neg_sum[i] = s;
   lse_neg[i] = inv_T + logf(s);     // s == 0 (no negatives, N == 1) -> -inf, CE([pos,-inf],0) = 0
@@ -577,10 +578,10 @@ infonce_loss_kernel(const float* __restrict__ pos, const float* __restrict__ lse
 }  // namespace
 
 int infonce_finalize_launch(const float* partial_sums, int n_partials, int64_t rows, float inv_T, float* neg_sum,
-                            float* lse_neg, cudaStream_t st) {
+                            float* lse_neg, cudaStream_t st, const float* extra) {
   if (rows == 0) return SM3_OK;
   infonce_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(partial_sums, n_partials, rows, inv_T,
-                                                                           neg_sum, lse_neg);
+                                                                           neg_sum, lse_neg, extra);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }

@@ -47,7 +47,8 @@ struct TcParams {
   int n_local, pair_offset, n_global, D;
   int m_rows, m_cols;
   float inv_T, c2;
-  int tiles_per_split, col_tiles;
+  int tiles_per_split, col_tiles;   // col_tiles counts the tiles actually visited (local tiles excluded in skip mode)
+  int skip_a, skip_b, skip_len;     // skip mode: original tile indices of the two local ranges and their length
   const __nv_bfloat16* z_rows;
   float* pos;
   float* partial;      // fwd: [splits][m_rows]
@@ -226,7 +227,13 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   // 32-64 KB tile at the same time and serialise on the few L2 slices holding it (measured: the forward kernel was
   // bimodal, 1.7 ms or 3.5-6 ms at cfg4, depending on whether the CTAs happened to run in lockstep).
   const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
-  auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_tiles ? t - n_tiles : t); };
+  auto tile_of = [&](int it) {
+    int t = it + rot;
+    t = t_begin + (t >= n_tiles ? t - n_tiles : t);
+    if (t >= p.skip_a) t += p.skip_len;        // skip mode: hop over the column tiles owned by this rank
+    if (t >= p.skip_b) t += p.skip_len;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
@@ -425,7 +432,13 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
   const int n_tiles = t_end - t_begin;
   const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
-  auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_tiles ? t - n_tiles : t); };
+  auto tile_of = [&](int it) {
+    int t = it + rot;
+    t = t_begin + (t >= n_tiles ? t - n_tiles : t);
+    if (t >= p.skip_a) t += p.skip_len;        // skip mode: hop over the column tiles owned by this rank
+    if (t >= p.skip_b) t += p.skip_len;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
@@ -643,7 +656,13 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   // 32-64 KB tile at the same time and serialise on the few L2 slices holding it (measured: the forward kernel was
   // bimodal, 1.7 ms or 3.5-6 ms at cfg4, depending on whether the CTAs happened to run in lockstep).
   const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
-  auto tile_of = [&](int it) { const int t = it + rot; return t_begin + (t >= n_tiles ? t - n_tiles : t); };
+  auto tile_of = [&](int it) {
+    int t = it + rot;
+    t = t_begin + (t >= n_tiles ? t - n_tiles : t);
+    if (t >= p.skip_a) t += p.skip_len;        // skip mode: hop over the column tiles owned by this rank
+    if (t >= p.skip_b) t += p.skip_len;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
@@ -884,6 +903,7 @@ TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
   pl.bm = bwd ? kBM : tc_fwd_rows_per_cta(m_rows, m_cols);
   pl.row_tiles = (m_rows + pl.bm - 1) / pl.bm;
   pl.col_tiles = (m_cols + bn - 1) / bn;
+  if (pb.skip_local) pl.col_tiles -= 2 * (pb.n_local / bn);
   int max_splits = 32;
   if (bwd) {   // bound the fp32 partial-gradient workspace to ~1 GiB
     const size_t per = (size_t)m_rows * pb.D * 4;
@@ -895,7 +915,15 @@ TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
   return pl;
 }
 
-void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p) {
+void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p, int bn) {
+  if (pb.skip_local) {
+    p.skip_len = pb.n_local / bn;
+    p.skip_a = pb.pair_offset / bn;
+    p.skip_b = (pb.n_global + pb.pair_offset) / bn;
+  } else {
+    p.skip_len = 0;
+    p.skip_a = p.skip_b = 0x7fffffff;
+  }
   p.n_local = pb.n_local; p.pair_offset = pb.pair_offset; p.n_global = pb.n_global; p.D = pb.D;
   p.m_rows = 2 * pb.n_local; p.m_cols = 2 * pb.n_global;
   p.inv_T = pb.inv_T; p.c2 = pb.inv_T * kLog2eTC;
@@ -1004,10 +1032,12 @@ int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* 
                   pb.pair_offset + pb.n_local <= pb.n_global && pb.n_global <= (1 << 29),
               SM3_ERR_SHAPE, "infonce: bad row block (n_local=%d offset=%d n_global=%d)", pb.n_local, pb.pair_offset,
               pb.n_global);
+  SM3_REQUIRE(!pb.skip_local || (pb.n_local % 128 == 0 && pb.n_global > pb.n_local), SM3_ERR_SHAPE,
+              "infonce(tc): skip_local needs n_local %% 128 == 0 and more than one rank");
   SM3_REQUIRE(ws_bytes >= infonce_tc_workspace(pb, 0), SM3_ERR_WORKSPACE, "infonce(tc) fwd: workspace too small");
   const TcPlan pl = tc_plan(pb, false);
   TcParams p{};
-  fill_params(pb, pl, p);
+  fill_params(pb, pl, p, 128);
   p.pos = pos;
   p.partial = (float*)ws;
   CUtensorMap tmap;
@@ -1020,7 +1050,7 @@ int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* 
     default: rc = launch_fwd<4>(tmap, p, pl, st); break;
   }
   if (rc) return rc;
-  return infonce_finalize_launch(p.partial, pl.splits, p.m_rows, pb.inv_T, neg_sum, lse_neg, st);
+  return infonce_finalize_launch(p.partial, pl.splits, p.m_rows, pb.inv_T, neg_sum, lse_neg, st, pb.extra_neg_sum);
 }
 
 int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* glse_r, const float* nsum_r,
@@ -1030,10 +1060,12 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
                   pb.pair_offset + pb.n_local <= pb.n_global && pb.n_global <= (1 << 29),
               SM3_ERR_SHAPE, "infonce: bad row block (n_local=%d offset=%d n_global=%d)", pb.n_local, pb.pair_offset,
               pb.n_global);
+  SM3_REQUIRE(!pb.skip_local || (pb.n_local % 128 == 0 && pb.n_global > pb.n_local), SM3_ERR_SHAPE,
+              "infonce(tc): skip_local needs n_local %% 128 == 0 and more than one rank");
   SM3_REQUIRE(ws_bytes >= infonce_tc_workspace(pb, 1), SM3_ERR_WORKSPACE, "infonce(tc) bwd: workspace too small");
   const TcPlan pl = tc_plan(pb, true);
   TcParams p{};
-  fill_params(pb, pl, p);
+  fill_params(pb, pl, p, 64);
   p.gpos_r = gpos_r; p.glse_r = glse_r; p.nsum_r = nsum_r; p.gpos_c = gpos_c; p.cstride = pb.col_stride;
   p.dz_partial = (float*)ws;
   float* acol = (float*)((char*)ws + bwd_acol_offset(pb, pl));

@@ -67,7 +67,44 @@ peer_scatter_stats_kernel(const float* __restrict__ g_pos, const float* __restri
   for (int r = 0; r < peers.world; ++r) reinterpret_cast<float4*>(peers.p[r])[g] = val;
 }
 
+// Split cross-rank barrier on a small symmetric flag buffer (one 32-bit slot per (channel, source rank), epochs only
+// grow): `signal` publishes this rank's earlier stores to every peer, `wait` blocks the stream until every peer has
+// signalled the same epoch.  Work that does not need remote data is enqueued between the two.
+__global__ void peer_signal_kernel(PeerPtrs flags, int rank, int channel, unsigned epoch) {
+  const int r = threadIdx.x;
+  if (r >= flags.world) return;
+  __threadfence_system();
+  unsigned* dst = reinterpret_cast<unsigned*>(flags.p[r]) + channel * 16 + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+}
+__global__ void peer_wait_kernel(const unsigned* __restrict__ my_flags, int world, int channel, unsigned epoch) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const unsigned* src = my_flags + channel * 16 + r;
+  const long long t0 = clock64();
+  unsigned v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if (clock64() - t0 > 20000000000LL) {      // ~10 s: a missing peer must fail loudly, not hang the GPU
+      printf("sm3: peer wait timeout (channel %d, peer %d, have %u, want %u)\n", channel, r, v, epoch);
+      __trap();
+    }
+  } while (true);
+}
+
 }  // namespace
+
+int peer_signal_launch(const PeerPtrs& flags, int rank, int channel, unsigned epoch, cudaStream_t st) {
+  peer_signal_kernel<<<1, 32, 0, st>>>(flags, rank, channel, epoch);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+int peer_wait_launch(const unsigned* my_flags, int world, int channel, unsigned epoch, cudaStream_t st) {
+  peer_wait_kernel<<<1, 32, 0, st>>>(my_flags, world, channel, epoch);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
 
 int peer_scatter_rows_launch(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,
                              const PeerPtrs& peers, cudaStream_t st) {
@@ -128,6 +165,20 @@ static int fill_peers(PeerPtrs& pp, void* const* peers_host, int world) {
     pp.p[r] = peers_host[r];
   }
   return SM3_OK;
+}
+
+extern "C" int sm3_peer_signal(void* const* peer_flags_host, int world, int rank, int channel, unsigned epoch,
+                               void* stream) {
+  SM3_REQUIRE(channel >= 0 && channel < 4 && rank >= 0 && rank < world, SM3_ERR_SHAPE, "peer_signal: bad channel/rank");
+  PeerPtrs pp;
+  int rc = fill_peers(pp, peer_flags_host, world);
+  if (rc) return rc;
+  return peer_signal_launch(pp, rank, channel, epoch, (cudaStream_t)stream);
+}
+
+extern "C" int sm3_peer_wait(const void* my_flags, int world, int channel, unsigned epoch, void* stream) {
+  SM3_REQUIRE(my_flags && world >= 1 && world <= 16 && channel >= 0 && channel < 4, SM3_ERR_SHAPE, "peer_wait: bad argument");
+  return peer_wait_launch((const unsigned*)my_flags, world, channel, epoch, (cudaStream_t)stream);
 }
 
 extern "C" int sm3_peer_scatter_rows(const void* src, int n_local, int pair_offset, int n_global, int row_bytes,

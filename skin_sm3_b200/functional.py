@@ -18,6 +18,7 @@ Everything here requires CUDA tensors and the built extension; there is no CPU /
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -152,6 +153,46 @@ class core:
                                                        ptr(nsum_r), ptr(stats_cols), ptr(ws), ws.numel(), algo,
                                                        stream_ptr()), "sm3_infonce_bwd_packed")
         return ws, npart
+
+    @staticmethod
+    def stats_fwd_remote(z_rows, z_cols, n_local, pair_offset, n_global, temperature, nsum_local, pos_local):
+        """K2 over the column tiles owned by other ranks; adds nsum_local.  -> (lse_neg, neg_sum) totals."""
+        dev = require_cuda(z_rows, z_cols)
+        d = z_rows.shape[1]
+        out = torch.empty((2, 2 * n_local), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = lib().sm3_infonce_remote_workspace_bytes(n_local, n_global, d, 0)
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+            check(lib().sm3_infonce_fwd_remote(ptr(z_rows), ptr(z_cols), n_local, pair_offset, n_global, d,
+                                               dtype_code(z_rows), 1.0 / temperature, ptr(nsum_local), ptr(pos_local),
+                                               ptr(out[0]), ptr(out[1]), ptr(ws), ws.numel(), stream_ptr()),
+                  "sm3_infonce_fwd_remote")
+        return out[0], out[1]
+
+    @staticmethod
+    def stats_bwd_split(z, z_cols, n_local, pair_offset, n_global, temperature, g_pos, g_lse, nsum, stats_cols,
+                        between=None):
+        """Row-local backward as local block + remote blocks into ONE slab buffer.  `between()` is called after the
+        local block has been enqueued (the caller waits for the peers' statistics there).  -> (ws, n_partials)."""
+        dev = require_cuda(z, z_cols)
+        d = z.shape[1]
+        m = 2 * n_local
+        with torch.cuda.device(dev):
+            b_l = lib().sm3_infonce_workspace_bytes(n_local, n_local, d, dtype_code(z), ALGO_TC, 1)
+            b_r = lib().sm3_infonce_remote_workspace_bytes(n_local, n_global, d, 1)
+            ws = torch.empty(int(b_l) + int(b_r) + 1024, dtype=torch.uint8, device=dev)
+            np_l = check(lib().sm3_infonce_bwd(ptr(z), ptr(z), n_local, 0, n_local, d, dtype_code(z), 1.0 / temperature,
+                                               ptr(g_pos), ptr(g_lse), ptr(nsum), ptr(g_pos), ptr(g_lse), ptr(nsum),
+                                               ptr(ws), int(b_l), ALGO_TC, stream_ptr()), "sm3_infonce_bwd(local)")
+            if between is not None:
+                between()
+            off = np_l * m * d * 4
+            np_r = check(lib().sm3_infonce_bwd_remote_packed(ptr(z), ptr(z_cols), n_local, pair_offset, n_global, d,
+                                                             dtype_code(z), 1.0 / temperature, ptr(g_pos), ptr(g_lse),
+                                                             ptr(nsum), ptr(stats_cols), ws.data_ptr() + off,
+                                                             ws.numel() - off, stream_ptr()),
+                         "sm3_infonce_bwd_remote_packed")
+        return ws, np_l + np_r
 
     @staticmethod
     def sum_partials(ws: torch.Tensor, n_partials: int, m: int, d: int) -> torch.Tensor:
@@ -323,6 +364,75 @@ class _FusedInfoNCE(torch.autograd.Function):
         _mark("start")
         z, inv = core.normalize_pair(p1, p2, z_dtype)
         _mark("normalize")
+        # Overlapping the exchange with the local column block pays once the local block is a small part of the work
+        # (measured on B200: slower at 2 ranks, where splitting K2/K3 in halves costs more than the exchange; faster
+        # from 4 ranks).  SM3_PEER_OVERLAP=0|1 forces it.
+        ov_env = os.environ.get("SM3_PEER_OVERLAP")
+        overlap = (pbuf is not None and n_local % 128 == 0 and algo == ALGO_TC and
+                   (ov_env == "1" or (ov_env is None and w >= 4)))
+        if overlap and _PROFILE is None and pbuf.multicast is False:
+            # ---- the whole overlapped step enqueued by one C call (two streams) ----
+            p1c, p2c = _contig(p1), _contig(p2)
+            dev, d = p1c.device, p1c.shape[1]
+            main = torch.cuda.current_stream()
+            with torch.cuda.device(dev):
+                nbytes = lib().sm3_infonce_step_peer_scratch_bytes(n_local, n_global, d)
+                scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                dp1 = torch.empty_like(p1c) if need_grad else None
+                dp2 = torch.empty_like(p2c) if need_grad else None
+                scratch.record_stream(pbuf.side)
+                check(lib().sm3_infonce_step_peer(ptr(p1c), ptr(p2c), n_local, rank, w, d, dtype_code(p1c), temperature,
+                                                  weight, ptr(loss), ptr(dp1), ptr(dp2), ptr(pbuf.z[slot]),
+                                                  pbuf.zp[slot], ptr(pbuf.st[slot]), pbuf.stp[slot], ptr(pbuf.flags),
+                                                  pbuf.fp, pbuf.step & 0x7FFFFFFF, ptr(scratch), scratch.numel(),
+                                                  main.cuda_stream, pbuf.side.cuda_stream), "sm3_infonce_step_peer")
+            if need_grad:
+                ctx.save_for_backward(dp1, dp2)
+            ctx.comm_used = "peer-overlap"
+            return loss
+        if overlap:
+            # ---- exchange on a side stream, local column block on the main stream, then the remote blocks ----
+            main = torch.cuda.current_stream()
+            epoch = pbuf.step                                   # next_slot() already advanced it: unique, growing
+            off = rank * n_local
+            pbuf.side.wait_stream(main)
+            z.record_stream(pbuf.side)
+            with torch.cuda.stream(pbuf.side):
+                pbuf.store_z(slot, z, n_local)                  # NVLink stores into every rank's z_cols[slot]
+                pbuf.signal(0, epoch)
+            pos, lse_l, ns_l = core.stats_fwd(z, z, n_local, 0, n_local, temperature, algo)   # local block
+            _mark("stats_fwd_local")
+            main.wait_stream(pbuf.side)
+            pbuf.wait(0, epoch)
+            _mark("gather_z")
+            z_cols = pbuf.z[slot]
+            lse, nsum = core.stats_fwd_remote(z, z_cols, n_local, off, n_global, temperature, ns_l, pos)
+            _mark("stats_fwd")
+            loss, g_pos, g_lse = core.loss(pos, lse, weight / (2 * n_local), want_grads=need_grad)
+            _mark("loss")
+            if need_grad:
+                pbuf.side.wait_stream(main)
+                for t in (g_pos, g_lse, nsum):
+                    t.record_stream(pbuf.side)
+                with torch.cuda.stream(pbuf.side):
+                    pbuf.store_stats(slot, g_pos, g_lse, nsum, n_local)
+                    pbuf.signal(1, epoch)
+
+                def _between():
+                    _mark("stats_bwd_local")
+                    main.wait_stream(pbuf.side)
+                    pbuf.wait(1, epoch)
+                    _mark("gather_stats")
+
+                ws, npart = core.stats_bwd_split(z, z_cols, n_local, off, n_global, temperature, g_pos, g_lse, nsum,
+                                                 pbuf.st[slot], _between)
+                _mark("stats_bwd")
+                dp1, dp2 = core.normalize_bwd(ws, npart, 1.0, z, inv, n_local, n_local, p1.dtype)
+                _mark("normalize_bwd")
+                ctx.save_for_backward(dp1, dp2)
+            ctx.comm_used = "peer-overlap"
+            return loss
         if w == 1:
             z_cols = z
         elif pbuf is not None:

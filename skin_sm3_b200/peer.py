@@ -62,7 +62,47 @@ class PeerBuffers:
         # either way -- so multicast is opt-in (SM3_PEER_MULTICAST=1).
         want_mc = os.environ.get("SM3_PEER_MULTICAST", "0") == "1"
         self.multicast = want_mc and all(self.zmc) and all(self.stmc)
+        # split barrier (signal / wait) on a zero-initialised symmetric flag buffer + a side stream for the exchange
+        try:
+            self.flags = symm.empty((64,), dtype=torch.int32, device=device)
+            self.flags.zero_()
+            self.fh = symm.rendezvous(self.flags, self.group)
+            self.fp = (C.c_void_p * self.world)(*self.fh.buffer_ptrs)
+            self.fh.barrier(channel=2)           # nobody signals before everybody has zeroed its flags
+        except Exception as e:
+            raise PeerUnavailable(f"symmetric-memory flag buffer failed: {e!r}") from e
+        self.side = torch.cuda.Stream(device=device)
         self.step = 0
+
+    # ---- split barrier ----
+    def signal(self, channel: int, epoch: int) -> None:
+        check(lib().sm3_peer_signal(self.fp, self.world, self.rank, channel, epoch & 0x7FFFFFFF, stream_ptr()),
+              "sm3_peer_signal")
+
+    def wait(self, channel: int, epoch: int) -> None:
+        check(lib().sm3_peer_wait(ptr(self.flags), self.world, channel, epoch & 0x7FFFFFFF, stream_ptr()),
+              "sm3_peer_wait")
+
+    def store_z(self, slot: int, z_local: torch.Tensor, n_local: int) -> None:
+        """scatter kernel only (no barrier): the caller brackets it with signal()/wait()."""
+        with torch.cuda.device(z_local.device):
+            if self.multicast:
+                check(lib().sm3_peer_multicast_rows(ptr(z_local), n_local, self.rank * n_local, self.n_global,
+                                                    self.d * 2, self.zmc[slot], stream_ptr()), "sm3_peer_multicast_rows")
+            else:
+                check(lib().sm3_peer_scatter_rows(ptr(z_local), n_local, self.rank * n_local, self.n_global, self.d * 2,
+                                                  self.zp[slot], self.world, stream_ptr()), "sm3_peer_scatter_rows")
+
+    def store_stats(self, slot: int, g_pos, g_lse, nsum, n_local: int) -> None:
+        with torch.cuda.device(g_pos.device):
+            if self.multicast:
+                check(lib().sm3_peer_multicast_stats(ptr(g_pos), ptr(g_lse), ptr(nsum), n_local, self.rank * n_local,
+                                                     self.n_global, self.stmc[slot], stream_ptr()),
+                      "sm3_peer_multicast_stats")
+            else:
+                check(lib().sm3_peer_scatter_stats(ptr(g_pos), ptr(g_lse), ptr(nsum), n_local, self.rank * n_local,
+                                                   self.n_global, self.stp[slot], self.world, stream_ptr()),
+                      "sm3_peer_scatter_stats")
 
     def next_slot(self) -> int:
         k = self.step % self.DEPTH

@@ -71,7 +71,7 @@ def main():
         F3.core = OracleCore
         F3.require_cuda = lambda *t: torch.device("cpu")
     results = {}
-    cases = [(64 * world, 128, 0.1, "bf16"), (48 * world, 128, 0.5, "fp32")] if backend == "nccl" else \
+    cases = [(128 * world, 128, 0.1, "bf16"), (48 * world, 128, 0.5, "fp32")] if backend == "nccl" else \
             [(6 * world, 16, 0.1, "fp32"), (5 * world, 8, 0.5, "fp32")]
     for n_global, d, T, precision in cases:
         g = torch.Generator().manual_seed(1234 + n_global)
@@ -114,13 +114,22 @@ def main():
         if backend == "nccl" and precision == "bf16":
             # NVLink peer-memory exchange (symmetric memory) must give the same numbers as the NCCL path;
             # three steps exercise the double-buffered slots.
-            for _ in range(3):
+            for it3 in range(6):
+                # even: split-barrier overlap (it3 % 4 == 0: one C call; == 2: Python-orchestrated), odd: blocking barrier
+                os.environ["SM3_PEER_OVERLAP"] = "1" if it3 % 2 == 0 else "0"
+                F3._PROFILE = (lambda name: None) if it3 % 4 == 2 else None
                 a3 = P1[sl].to(dev).requires_grad_(True)
                 b3 = P2[sl].to(dev).requires_grad_(True)
                 l3 = sm3.fused_infonce(a3, b3, T, precision=precision, group=dist.group.WORLD, comm="peer")
                 l3.backward()
                 assert abs(l3.item() - l2.item()) <= 1e-6 * abs(l2.item()) + 1e-7, (l3.item(), l2.item())
-                assert torch.equal(a3.grad, a2.grad) and torch.equal(b3.grad, b2.grad), "peer path != nccl path"
+                e4 = (a3.grad.double() - a2.grad.double()).abs().max().item() / a2.grad.double().abs().max().item()
+                e5 = (b3.grad.double() - b2.grad.double()).abs().max().item() / b2.grad.double().abs().max().item()
+                # blocking-barrier path: same kernels, same order -> identical; overlapped path sums the local and
+                # remote column blocks separately -> fp32 reassociation + 1-ulp bf16 flips only
+                lim = 1e-2 if it3 % 2 == 0 else 0.0
+                assert e4 <= lim and e5 <= lim, ("peer path != nccl path", it3, e4, e5)
+            F3._PROFILE = None
         results[f"{n_global}x{d}"] = (loss_global, ref_loss, float(e1), float(e2))
     if rank == 0 and out_path:
         with open(out_path, "w") as f:
