@@ -217,13 +217,15 @@ int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_
  * local column block runs while the exchange is in flight).  z_cols_mine / stats_mine / flags_mine are this rank's
  * symmetric buffers ([2*n_global, D] bf16, [2*n_global, 4] fp32, >= 64 uint32), *_peers_host the HOST arrays of the
  * `world` peer-mapped pointers of the same buffers; `epoch` must grow by one per call and be identical on all ranks.
- * Needs n_local % 128 == 0 and D in {64,128,192,256}.  loss = weight * mean over this rank's rows (DDP convention). */
+ * overlap = 1: local column block computed while the exchange is in flight (needs n_local % 128 == 0); overlap = 0:
+ * exchange, barrier and full-width kernels back to back on stream_main.  D in {64,128,192,256}.
+ * loss = weight * mean over this rank's rows (DDP convention).                                                     */
 size_t sm3_infonce_step_peer_scratch_bytes(int n_local, int n_global, int D);
 int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local, int rank, int world, int D, int io_dtype,
                           float temperature, float weight, float* loss, void* dp1, void* dp2, void* z_cols_mine,
                           void* const* z_peers_host, void* stats_mine, void* const* stats_peers_host, void* flags_mine,
-                          void* const* flags_peers_host, unsigned epoch, void* device_scratch, size_t scratch_bytes,
-                          void* stream_main, void* stream_side);
+                          void* const* flags_peers_host, unsigned epoch, int overlap, void* device_scratch,
+                          size_t scratch_bytes, void* stream_main, void* stream_side);
 
 /* debug / bring-up: single-tile tcgen05 probe used by tests/test_umma_probe.py (not a product path).
  *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */

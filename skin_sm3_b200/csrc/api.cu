@@ -281,7 +281,11 @@ PeerPlan plan_peer(int n_local, int n_global, int D) {
   const size_t f0 = infonce_tc_workspace(loc, 0), f1 = infonce_tc_workspace(rem, 0);
   h.ws_f_bytes = f0 > f1 ? f0 : f1;
   h.ws_f = take(h.ws_f_bytes);
-  h.ws_b_bytes = infonce_tc_workspace(loc, 1) + infonce_tc_workspace(rem, 1) + 1024;
+  InfoNceProblem full{nullptr, nullptr, n_local, 0, n_global, D, SM3_BF16, 1.f};
+  const size_t split_b = infonce_tc_workspace(loc, 1) + infonce_tc_workspace(rem, 1) + 1024;
+  const size_t full_b = infonce_tc_workspace(full, 1), full_f = infonce_tc_workspace(full, 0);
+  h.ws_b_bytes = split_b > full_b ? split_b : full_b;
+  if (h.ws_b_bytes < full_f) h.ws_b_bytes = full_f;
   h.ws_b = take(h.ws_b_bytes);
   h.total = o;
   return h;
@@ -315,17 +319,19 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
                                      int io_dtype, float temperature, float weight, float* loss, void* dp1, void* dp2,
                                      void* z_cols_mine, void* const* z_peers_host, void* stats_mine,
                                      void* const* stats_peers_host, void* flags_mine, void* const* flags_peers_host,
-                                     unsigned epoch, void* device_scratch, size_t scratch_bytes, void* stream_main,
-                                     void* stream_side) {
+                                     unsigned epoch, int overlap, void* device_scratch, size_t scratch_bytes,
+                                     void* stream_main, void* stream_side) {
   cudaStream_t sm = (cudaStream_t)stream_main, ss = (cudaStream_t)stream_side;
   SM3_REQUIRE(p1 && p2 && loss && z_cols_mine && stats_mine && flags_mine && device_scratch, SM3_ERR_SHAPE,
               "infonce_step_peer: null pointer");
   SM3_REQUIRE((dp1 == nullptr) == (dp2 == nullptr), SM3_ERR_SHAPE, "infonce_step_peer: dp1/dp2 must both be given or both NULL");
-  SM3_REQUIRE(world >= 2 && rank >= 0 && rank < world && n_local >= 128 && n_local % 128 == 0, SM3_ERR_SHAPE,
-              "infonce_step_peer: needs world >= 2 and n_local %% 128 == 0 (got world=%d n_local=%d)", world, n_local);
+  SM3_REQUIRE(world >= 2 && rank >= 0 && rank < world && n_local >= 1, SM3_ERR_SHAPE,
+              "infonce_step_peer: needs world >= 2 (got world=%d n_local=%d)", world, n_local);
+  SM3_REQUIRE(!overlap || n_local % 128 == 0, SM3_ERR_SHAPE, "infonce_step_peer: overlap needs n_local %% 128 == 0");
   SM3_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256 && dtype_ok(io_dtype) && temperature > 0.f, SM3_ERR_DTYPE,
               "infonce_step_peer: D must be in {64,128,192,256}");
-  SM3_REQUIRE(stream_side != stream_main, SM3_ERR_SHAPE, "infonce_step_peer: the side stream must differ from the main stream");
+  SM3_REQUIRE(!overlap || stream_side != stream_main, SM3_ERR_SHAPE,
+              "infonce_step_peer: the side stream must differ from the main stream");
   const int n_global = n_local * world, off = rank * n_local;
   const PeerPlan h = plan_peer(n_local, n_global, D);
   SM3_REQUIRE(scratch_bytes >= h.total, SM3_ERR_WORKSPACE, "infonce_step_peer: scratch %zu < %zu", scratch_bytes, h.total);
@@ -345,6 +351,25 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
 
   rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, sm);
   if (rc) return rc;
+  if (!overlap) {
+    // ---- everything on the main stream: exchange, barrier, full-width kernels (best below ~8 ranks) ----
+    if ((rc = peer_scatter_rows_launch(z, n_local, off, n_global, D * 2, zp, sm))) return rc;
+    if ((rc = peer_signal_launch(fp, rank, 0, epoch, sm))) return rc;
+    if ((rc = peer_wait_launch((const unsigned*)flags_mine, world, 0, epoch, sm))) return rc;
+    rc = sm3_infonce_fwd(z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T, pos, lse, nsum, base + h.ws_b,
+                         h.ws_b_bytes, SM3_ALGO_TC, sm);
+    if (rc) return rc;
+    rc = sm3_infonce_loss(pos, lse, m, weight / (float)m, loss, 0, dp1 ? gpos : nullptr, dp1 ? glse : nullptr, sm);
+    if (rc || !dp1) return rc;
+    if ((rc = peer_scatter_stats_launch(gpos, glse, nsum, n_local, off, n_global, sp, sm))) return rc;
+    if ((rc = peer_signal_launch(fp, rank, 1, epoch, sm))) return rc;
+    if ((rc = peer_wait_launch((const unsigned*)flags_mine, world, 1, epoch, sm))) return rc;
+    const int np = sm3_infonce_bwd_packed(z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T, gpos, glse, nsum,
+                                          (const float*)stats_mine, base + h.ws_b, h.ws_b_bytes, SM3_ALGO_TC, sm);
+    if (np < 0) return np;
+    return sm3_l2norm_bwd((const float*)(base + h.ws_b), np, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, dp1, n,
+                          dp2, n, D, io_dtype, sm);
+  }
   // ---- exchange of the normalised rows on the side stream, local column block meanwhile ----
   SM3_CHECK_CUDA(cudaEventRecord(ev[0], sm));
   SM3_CHECK_CUDA(cudaStreamWaitEvent(ss, ev[0], 0));

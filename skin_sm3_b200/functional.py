@@ -364,14 +364,14 @@ class _FusedInfoNCE(torch.autograd.Function):
         _mark("start")
         z, inv = core.normalize_pair(p1, p2, z_dtype)
         _mark("normalize")
-        # Overlapping the exchange with the local column block pays once the local block is a small part of the work
-        # (measured on B200: slower at 2 ranks, where splitting K2/K3 in halves costs more than the exchange; faster
-        # from 4 ranks).  SM3_PEER_OVERLAP=0|1 forces it.
+        # Overlapping the exchange with the local column block (SM3_PEER_OVERLAP=1) is implemented and verified, but on
+        # B200 it does not pay yet: splitting K2/K3 into a local and a remote launch costs about what the hidden
+        # exchange saves (8 ranks: 0.754 ms overlapped vs 0.703 ms back to back), so it is opt-in.
         ov_env = os.environ.get("SM3_PEER_OVERLAP")
         overlap = (pbuf is not None and n_local % 128 == 0 and algo == ALGO_TC and
-                   (ov_env == "1" or (ov_env is None and w >= 4)))
-        if overlap and _PROFILE is None and pbuf.multicast is False:
-            # ---- the whole overlapped step enqueued by one C call (two streams) ----
+                   ov_env == "1")
+        if pbuf is not None and algo == ALGO_TC and _PROFILE is None and pbuf.multicast is False:
+            # ---- the whole multi-rank step enqueued by one C call (exchange overlapped or back to back) ----
             p1c, p2c = _contig(p1), _contig(p2)
             dev, d = p1c.device, p1c.shape[1]
             main = torch.cuda.current_stream()
@@ -385,11 +385,12 @@ class _FusedInfoNCE(torch.autograd.Function):
                 check(lib().sm3_infonce_step_peer(ptr(p1c), ptr(p2c), n_local, rank, w, d, dtype_code(p1c), temperature,
                                                   weight, ptr(loss), ptr(dp1), ptr(dp2), ptr(pbuf.z[slot]),
                                                   pbuf.zp[slot], ptr(pbuf.st[slot]), pbuf.stp[slot], ptr(pbuf.flags),
-                                                  pbuf.fp, pbuf.step & 0x7FFFFFFF, ptr(scratch), scratch.numel(),
-                                                  main.cuda_stream, pbuf.side.cuda_stream), "sm3_infonce_step_peer")
+                                                  pbuf.fp, pbuf.step & 0x7FFFFFFF, int(overlap), ptr(scratch),
+                                                  scratch.numel(), main.cuda_stream, pbuf.side.cuda_stream),
+                      "sm3_infonce_step_peer")
             if need_grad:
                 ctx.save_for_backward(dp1, dp2)
-            ctx.comm_used = "peer-overlap"
+            ctx.comm_used = "peer-overlap" if overlap else "peer"
             return loss
         if overlap:
             # ---- exchange on a side stream, local column block on the main stream, then the remote blocks ----
