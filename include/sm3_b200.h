@@ -204,6 +204,23 @@ int sm3_infonce_host(const void* p1_host, const void* p2_host, int n_pairs, int 
                      float temperature, float* loss_host, void* dp1_host, void* dp2_host, void* device_scratch,
                      size_t scratch_bytes, int algo, void* stream);
 
+/* Pipelined form of the host-buffer entry (what bench.py's `e2e` times): the handle owns three streams (H2D | kernels |
+ * D2H) and `depth` I/O slots inside the caller's `device_scratch`, so the copies of step k+1 and k-1 overlap the
+ * kernels of step k.  `submit` enqueues one step and returns a ticket (>= 0) without synchronising, except that it
+ * first waits for the ticket `depth` submits ago (its slot is reused); `wait` blocks the host until that ticket's loss
+ * and gradients are in the host buffers given to its submit.  Host buffers should be pinned (pageable memory works but
+ * serialises the copies) and stay untouched until the ticket has been waited for.  dp1_host/dp2_host may both be NULL
+ * (forward only).  One handle = one device (the current device at create) and one submitting thread at a time.      */
+#define SM3_PIPE_MAX_DEPTH 4
+typedef struct sm3_host_pipe sm3_host_pipe;
+size_t sm3_host_pipe_scratch_bytes(int n_pairs, int D, int io_dtype, int algo, int depth);
+int sm3_host_pipe_create(sm3_host_pipe** out, int n_pairs, int D, int io_dtype, int algo, int depth,
+                         void* device_scratch, size_t scratch_bytes);
+int64_t sm3_host_pipe_submit(sm3_host_pipe* pipe, const void* p1_host, const void* p2_host, float temperature,
+                             float* loss_host, void* dp1_host, void* dp2_host);
+int sm3_host_pipe_wait(sm3_host_pipe* pipe, int64_t ticket);
+int sm3_host_pipe_destroy(sm3_host_pipe* pipe);
+
 /* Device-pointer form of the same fused step: ONE call enqueues normalise -> K2 -> loss -> K3 -> normalise-backward on
  * `stream` (no copies, no synchronisation).  loss = weight * mean-CE (device scalar); dp1/dp2 may both be NULL
  * (forward only).  precision follows `algo` (AUTO = tcgen05 on bf16 rows when D allows, else the fp32 FMA kernels). */

@@ -54,6 +54,11 @@ SIGNATURES = {
     "sm3_sim_topk": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _i64, _vp, _vp, _vp]),
     "sm3_infonce_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "sm3_infonce_host": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "sm3_host_pipe_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sm3_host_pipe_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _sz]),
+    "sm3_host_pipe_submit": (_i64, [_vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "sm3_host_pipe_wait": (_i, [_vp, _i64]),
+    "sm3_host_pipe_destroy": (_i, [_vp]),
     "sm3_infonce_step_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "sm3_infonce_step": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "sm3_infonce_step_peer_scratch_bytes": (_sz, [_i, _i, _i]),

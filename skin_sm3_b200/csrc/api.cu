@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <new>
+
 #include "common.cuh"
 
 namespace sm3 {
@@ -451,5 +453,140 @@ extern "C" int sm3_infonce_host(const void* p1_host, const void* p2_host, int n_
     SM3_CHECK_CUDA(cudaMemcpyAsync(dp2_host, base + h.dp2, in_bytes, cudaMemcpyDeviceToHost, st));
   }
   SM3_CHECK_CUDA(cudaStreamSynchronize(st));
+  return SM3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pipelined host-buffer entry: three streams owned by the handle (H2D | kernels | D2H) and `depth` I/O slots, so the
+// copies of step k+1 and k-1 run on the copy engines while the kernels of step k occupy the SMs.  Everything else
+// (normalised rows, statistics, partial-gradient workspace) is touched by the kernel stream only and exists once.
+// ---------------------------------------------------------------------------------------------------
+struct sm3_host_pipe {
+  int n_pairs, D, io_dtype, algo, depth, device;
+  size_t in_bytes, io_stride, step_bytes, total;
+  char* base;
+  cudaStream_t s_h2d, s_run, s_d2h;
+  cudaEvent_t ev_in[SM3_PIPE_MAX_DEPTH], ev_run[SM3_PIPE_MAX_DEPTH], ev_out[SM3_PIPE_MAX_DEPTH];
+  int busy[SM3_PIPE_MAX_DEPTH];
+  int64_t next_ticket;
+};
+
+namespace {
+// per-slot I/O block: p1 | p2 | dp1 | dp2 | loss
+size_t pipe_io_stride(size_t in_bytes) { return 4 * align_up(in_bytes) + 256; }
+}  // namespace
+
+extern "C" size_t sm3_host_pipe_scratch_bytes(int n_pairs, int D, int io_dtype, int algo, int depth) {
+  if (n_pairs < 1 || D < 1 || !dtype_ok(io_dtype) || depth < 1 || depth > SM3_PIPE_MAX_DEPTH) return 0;
+  const size_t in_bytes = (size_t)n_pairs * D * dtype_size(io_dtype);
+  return align_up(plan_host(n_pairs, D, io_dtype, algo).total) + (size_t)depth * pipe_io_stride(in_bytes);
+}
+
+extern "C" int sm3_host_pipe_create(sm3_host_pipe** out, int n_pairs, int D, int io_dtype, int algo, int depth,
+                                    void* device_scratch, size_t scratch_bytes) {
+  SM3_REQUIRE(out != nullptr && device_scratch != nullptr, SM3_ERR_SHAPE, "host_pipe_create: null pointer");
+  *out = nullptr;
+  SM3_REQUIRE(n_pairs >= 1 && D >= 1 && dtype_ok(io_dtype), SM3_ERR_SHAPE, "host_pipe_create: bad shape/dtype");
+  SM3_REQUIRE(depth >= 1 && depth <= SM3_PIPE_MAX_DEPTH, SM3_ERR_SHAPE, "host_pipe_create: depth %d not in [1,%d]", depth,
+              SM3_PIPE_MAX_DEPTH);
+  const size_t need = sm3_host_pipe_scratch_bytes(n_pairs, D, io_dtype, algo, depth);
+  SM3_REQUIRE(scratch_bytes >= need, SM3_ERR_WORKSPACE, "host_pipe_create: scratch %zu < %zu", scratch_bytes, need);
+  SM3_REQUIRE(aligned16(device_scratch), SM3_ERR_SHAPE, "host_pipe_create: scratch must be 16-byte aligned");
+  sm3_host_pipe* hp = new (std::nothrow) sm3_host_pipe();
+  SM3_REQUIRE(hp != nullptr, SM3_ERR_CUDA, "host_pipe_create: out of host memory");
+  hp->n_pairs = n_pairs; hp->D = D; hp->io_dtype = io_dtype; hp->algo = algo; hp->depth = depth;
+  hp->in_bytes = (size_t)n_pairs * D * dtype_size(io_dtype);
+  hp->io_stride = pipe_io_stride(hp->in_bytes);
+  hp->step_bytes = align_up(plan_host(n_pairs, D, io_dtype, algo).total);
+  hp->total = need;
+  hp->base = (char*)device_scratch;
+  hp->next_ticket = 0;
+  hp->s_h2d = hp->s_run = hp->s_d2h = nullptr;
+  for (int i = 0; i < SM3_PIPE_MAX_DEPTH; ++i) { hp->ev_in[i] = hp->ev_run[i] = hp->ev_out[i] = nullptr; hp->busy[i] = 0; }
+  cudaError_t e = cudaGetDevice(&hp->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_h2d, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_run, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_d2h, cudaStreamNonBlocking);
+  for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&hp->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&hp->ev_run[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&hp->ev_out[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    set_error("host_pipe_create: %s", cudaGetErrorString(e));
+    sm3_host_pipe_destroy(hp);
+    return SM3_ERR_CUDA;
+  }
+  *out = hp;
+  return SM3_OK;
+}
+
+extern "C" int sm3_host_pipe_destroy(sm3_host_pipe* hp) {
+  if (hp == nullptr) return SM3_OK;
+  if (hp->s_d2h) cudaStreamSynchronize(hp->s_d2h);
+  if (hp->s_run) cudaStreamSynchronize(hp->s_run);
+  if (hp->s_h2d) cudaStreamSynchronize(hp->s_h2d);
+  for (int i = 0; i < SM3_PIPE_MAX_DEPTH; ++i) {
+    if (hp->ev_in[i]) cudaEventDestroy(hp->ev_in[i]);
+    if (hp->ev_run[i]) cudaEventDestroy(hp->ev_run[i]);
+    if (hp->ev_out[i]) cudaEventDestroy(hp->ev_out[i]);
+  }
+  if (hp->s_h2d) cudaStreamDestroy(hp->s_h2d);
+  if (hp->s_run) cudaStreamDestroy(hp->s_run);
+  if (hp->s_d2h) cudaStreamDestroy(hp->s_d2h);
+  delete hp;
+  return SM3_OK;
+}
+
+extern "C" int64_t sm3_host_pipe_submit(sm3_host_pipe* hp, const void* p1_host, const void* p2_host, float temperature,
+                                        float* loss_host, void* dp1_host, void* dp2_host) {
+  SM3_REQUIRE(hp && p1_host && p2_host && loss_host, SM3_ERR_SHAPE, "host_pipe_submit: null pointer");
+  SM3_REQUIRE((dp1_host == nullptr) == (dp2_host == nullptr), SM3_ERR_SHAPE,
+              "host_pipe_submit: dp1_host/dp2_host must both be given or both NULL");
+  SM3_REQUIRE(temperature > 0.f, SM3_ERR_SHAPE, "host_pipe_submit: temperature must be > 0");
+  int dev = -1;
+  SM3_CHECK_CUDA(cudaGetDevice(&dev));
+  SM3_REQUIRE(dev == hp->device, SM3_ERR_SHAPE, "host_pipe_submit: handle belongs to device %d, current device is %d",
+              hp->device, dev);
+  const int64_t ticket = hp->next_ticket;
+  const int s = (int)(ticket % hp->depth);
+  // back-pressure: the previous occupant of this slot must have delivered its results to the host
+  if (hp->busy[s]) SM3_CHECK_CUDA(cudaEventSynchronize(hp->ev_out[s]));
+  char* io = hp->base + hp->step_bytes + (size_t)s * hp->io_stride;
+  const size_t a = align_up(hp->in_bytes);
+  char *p1 = io, *p2 = io + a, *dp1 = io + 2 * a, *dp2 = io + 3 * a;
+  float* loss = (float*)(io + 4 * a);
+  // H2D: the slot's input block was last read by the kernels of ticket - depth (ev_run[s])
+  if (hp->busy[s]) SM3_CHECK_CUDA(cudaStreamWaitEvent(hp->s_h2d, hp->ev_run[s], 0));
+  SM3_CHECK_CUDA(cudaMemcpyAsync(p1, p1_host, hp->in_bytes, cudaMemcpyHostToDevice, hp->s_h2d));
+  SM3_CHECK_CUDA(cudaMemcpyAsync(p2, p2_host, hp->in_bytes, cudaMemcpyHostToDevice, hp->s_h2d));
+  SM3_CHECK_CUDA(cudaEventRecord(hp->ev_in[s], hp->s_h2d));
+  // kernels: wait for the inputs; the slot's output block is free because ev_out[s] was synchronised above
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(hp->s_run, hp->ev_in[s], 0));
+  const int rc = sm3_infonce_step(p1, p2, hp->n_pairs, hp->D, hp->io_dtype, temperature, 1.0f, loss,
+                                  dp1_host ? dp1 : nullptr, dp1_host ? dp2 : nullptr, hp->base, hp->step_bytes, hp->algo,
+                                  hp->s_run);
+  if (rc) return rc;
+  SM3_CHECK_CUDA(cudaEventRecord(hp->ev_run[s], hp->s_run));
+  // D2H
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(hp->s_d2h, hp->ev_run[s], 0));
+  SM3_CHECK_CUDA(cudaMemcpyAsync(loss_host, loss, 4, cudaMemcpyDeviceToHost, hp->s_d2h));
+  if (dp1_host) {
+    SM3_CHECK_CUDA(cudaMemcpyAsync(dp1_host, dp1, hp->in_bytes, cudaMemcpyDeviceToHost, hp->s_d2h));
+    SM3_CHECK_CUDA(cudaMemcpyAsync(dp2_host, dp2, hp->in_bytes, cudaMemcpyDeviceToHost, hp->s_d2h));
+  }
+  SM3_CHECK_CUDA(cudaEventRecord(hp->ev_out[s], hp->s_d2h));
+  hp->busy[s] = 1;
+  hp->next_ticket = ticket + 1;
+  return ticket;
+}
+
+extern "C" int sm3_host_pipe_wait(sm3_host_pipe* hp, int64_t ticket) {
+  SM3_REQUIRE(hp != nullptr, SM3_ERR_SHAPE, "host_pipe_wait: null handle");
+  SM3_REQUIRE(ticket >= 0 && ticket < hp->next_ticket, SM3_ERR_SHAPE, "host_pipe_wait: unknown ticket %lld",
+              (long long)ticket);
+  // a ticket older than the slot's current occupant was already synchronised by the submit that replaced it
+  if (ticket + hp->depth < hp->next_ticket) return SM3_OK;
+  SM3_CHECK_CUDA(cudaEventSynchronize(hp->ev_out[ticket % hp->depth]));
   return SM3_OK;
 }

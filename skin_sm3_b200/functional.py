@@ -641,3 +641,59 @@ class HostInfoNCE:
                                          self.dp1.data_ptr(), self.dp2.data_ptr(), ptr(self.scratch),
                                          self.scratch.numel(), self.algo, stream_ptr()), "sm3_infonce_host")
         return self.loss, self.dp1, self.dp2
+
+
+class HostInfoNCEPipeline:
+    """Pipelined front end of the host-buffer entry (``sm3_host_pipe_*``): ``submit`` enqueues H2D -> fused fwd+bwd ->
+    D2H for one batch on the handle's own three streams and returns a ticket; ``wait(ticket)`` blocks until that
+    step's loss and gradients are in pinned host memory and returns them.  With ``depth`` >= 2 the copies of
+    neighbouring steps overlap the kernels, so host-to-host throughput approaches the device-resident rate."""
+
+    def __init__(self, n_pairs: int, d: int, dtype: torch.dtype = torch.bfloat16, algo: int = ALGO_AUTO, depth: int = 2,
+                 device: Optional[torch.device] = None):
+        import ctypes as C
+        self.n, self.d, self.dtype, self.depth = n_pairs, d, dtype, depth
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        code = _lib._DTYPES[dtype]
+        with torch.cuda.device(self.device):
+            nbytes = lib().sm3_host_pipe_scratch_bytes(n_pairs, d, code, algo, depth)
+            if nbytes == 0:
+                raise ValueError("bad shape / depth for HostInfoNCEPipeline")
+            self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            torch.cuda.synchronize(self.device)       # the handle's streams do not order against torch's allocator
+            h = C.c_void_p()
+            check(lib().sm3_host_pipe_create(C.byref(h), n_pairs, d, code, algo, depth, ptr(self.scratch),
+                                             self.scratch.numel()), "sm3_host_pipe_create")
+        self._h = h
+        self._next = 0
+        self.out = [(torch.empty(1, dtype=torch.float32).pin_memory(), torch.empty((n_pairs, d), dtype=dtype).pin_memory(),
+                     torch.empty((n_pairs, d), dtype=dtype).pin_memory()) for _ in range(depth)]
+        self.h2d_bytes = 2 * n_pairs * d * self.out[0][1].element_size()
+        self.d2h_bytes = 4 + self.h2d_bytes
+
+    def submit(self, p1_host: torch.Tensor, p2_host: torch.Tensor, temperature: float) -> int:
+        assert not p1_host.is_cuda and p1_host.dtype == self.dtype and tuple(p1_host.shape) == (self.n, self.d)
+        assert not p2_host.is_cuda and p2_host.dtype == self.dtype and tuple(p2_host.shape) == (self.n, self.d)
+        with torch.cuda.device(self.device):
+            loss, dp1, dp2 = self.out[self._next % self.depth]
+            t = check(lib().sm3_host_pipe_submit(self._h, p1_host.data_ptr(), p2_host.data_ptr(), temperature,
+                                                 loss.data_ptr(), dp1.data_ptr(), dp2.data_ptr()), "sm3_host_pipe_submit")
+        self._next = t + 1
+        return t
+
+    def wait(self, ticket: int):
+        """-> (loss[1] fp32, dp1, dp2) pinned host tensors of that ticket (valid until `depth` more submits)."""
+        with torch.cuda.device(self.device):
+            check(lib().sm3_host_pipe_wait(self._h, ticket), "sm3_host_pipe_wait")
+        return self.out[ticket % self.depth]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().sm3_host_pipe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

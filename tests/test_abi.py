@@ -43,6 +43,13 @@ def test_argument_validation_without_gpu():
     assert rc == -1
     assert l.sm3_infonce_host_scratch_bytes(0, 128, 2, 0) == 0
     assert l.sm3_multihead_ce_workspace_bytes(512, 8) > 0
+    # pipelined host entry: size query and handle validation are host-only
+    assert l.sm3_host_pipe_scratch_bytes(4096, 128, 2, 0, 2) > l.sm3_infonce_host_scratch_bytes(4096, 128, 2, 0)
+    assert l.sm3_host_pipe_scratch_bytes(4096, 128, 2, 0, 9) == 0
+    h = ctypes.c_void_p()
+    assert l.sm3_host_pipe_create(ctypes.byref(h), 4096, 128, 2, 0, 2, None, 0) == -1 and not h
+    assert l.sm3_host_pipe_wait(None, 0) == -1 and b"null handle" in l.sm3_last_error()
+    assert l.sm3_host_pipe_destroy(None) == 0
 
 
 def test_product_refuses_cpu_tensors():

@@ -238,6 +238,40 @@ def test_host_buffer_entry(sm3):
         assert relerr(d1.float().numpy(), r1) < tg and relerr(d2.float().numpy(), r2) < tg
 
 
+def test_host_pipeline_matches_synchronous_entry(sm3):
+    """sm3_host_pipe_* (three streams, slots reused every `depth` submits) == sm3_infonce_host on the same batches, bit
+    for bit, with several different batches in flight and more tickets than slots."""
+    n, d, T = 384, 128, 0.1
+    gen = torch.Generator().manual_seed(11)
+    batches = [(torch.randn(n, d, generator=gen).bfloat16().pin_memory(),
+                torch.randn(n, d, generator=gen).bfloat16().pin_memory()) for _ in range(7)]
+    sync = sm3.HostInfoNCE(n, d, torch.bfloat16, sm3.ALGO_TC)
+    want = []
+    for p1, p2 in batches:
+        l, d1, d2 = sync(p1, p2, T)
+        want.append((l.clone(), d1.clone(), d2.clone()))
+    for depth in (1, 2, 3):
+        pipe = sm3.HostInfoNCEPipeline(n, d, torch.bfloat16, sm3.ALGO_TC, depth)
+        tickets, got = [], []
+        for p1, p2 in batches:
+            tickets.append(pipe.submit(p1, p2, T))
+            if len(tickets) == depth:
+                got.append(tuple(t.clone() for t in pipe.wait(tickets.pop(0))))
+        for t in tickets:
+            got.append(tuple(x.clone() for x in pipe.wait(t)))
+        pipe.close()
+        assert len(got) == len(want)
+        for (l, d1, d2), (rl, r1, r2) in zip(got, want):
+            assert torch.equal(l, rl) and torch.equal(d1, r1) and torch.equal(d2, r2)
+    # forward-only tickets and argument validation
+    pipe = sm3.HostInfoNCEPipeline(n, d, torch.bfloat16, sm3.ALGO_TC, 2)
+    with pytest.raises(RuntimeError, match="ticket"):
+        pipe.wait(5)
+    pipe.close()
+    with pytest.raises(ValueError):
+        sm3.HostInfoNCEPipeline(n, d, torch.bfloat16, sm3.ALGO_TC, 9)
+
+
 def test_known_answers_at_full_size(sm3):
     """Size-independent properties at BASELINE config-4 scale (N=32768, D=256, M=65536 rows)."""
     n, d, T = 32768, 256, 0.1
