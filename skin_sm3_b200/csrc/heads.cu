@@ -5,6 +5,8 @@
 // K4 replaces the reference's 8-head loops: tools/mlc_eval.py:159-162, tools/backbone_eval.py:102-105,
 // tools/backbone_train.py:178-181, tools/mlc_train.py:255-261 (+ ignore_index=-100 at :381).
 // K5 has no reference counterpart; it mirrors torch's binary_cross_entropy_with_logits.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -240,11 +242,27 @@ multihead_ce_kernel(const T* __restrict__ logits, const int64_t* __restrict__ la
   }
 }
 
-// SM3 layout fast path (24 logits = 5,3,2,3,3,3,3,2; 8 int64 labels): one row per thread straight from global
-// memory.  A row is 48 B (16-bit logits) or 96 B (fp32) => 3 / 6 aligned 128-bit loads per thread, 4 for the labels,
-// all issued before first use; consecutive lanes touch consecutive rows, so every fetched sector is consumed by the
-// warp.  No shared-memory transposition, no block barriers on the data path.
-template <typename T>
+// SM3 layout fast path (24 logits = 5,3,2,3,3,3,3,2; 8 int64 labels).  Each warp moves its 32 rows as ONE contiguous
+// span (48 or 96 B of logits + 64 B of labels per row) with 16-byte transactions into a per-warp shared-memory slab,
+// then every lane works on its own row in registers and the gradient goes back out through the same slab.  No block
+// barriers on the data path.
+// kAsync: the slab is double buffered and filled with cp.async, two tiles ahead of the softmaxes: the copies hold no
+// registers, so each warp keeps ~7 KB in flight through its (long, instruction-bound) compute phase.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T> struct CeSlab {
+  static constexpr int kRowBytes = 24 * (int)sizeof(T);          // 48 or 96
+  static constexpr int kX = 32 * kRowBytes;                      // logits / gradient bytes per warp and buffer
+  static constexpr int kY = 32 * 8 * 8;                          // raw int64 labels per warp and buffer
+  static constexpr int bytes(bool async) { return (kHeadThreads / 32) * (async ? 2 : 1) * (kX + kY); }
+};
+
+template <typename T, bool kAsync>
 __global__ void __launch_bounds__(kHeadThreads)
 multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels, int64_t B, HeadMeta meta,
                         float inv_T, int use_ignore, int64_t ignore_index, float* __restrict__ loss_out,
@@ -253,17 +271,16 @@ multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict_
   constexpr int kOff[9] = {0, 5, 8, 10, 13, 16, 19, 22, 24};
   constexpr int V = VecIO<T>::N;            // 4 (fp32) or 8 (16-bit)
   constexpr int NV = C / V;                 // 6 or 3 vectors per row
-  constexpr int kRowBytes = C * (int)sizeof(T);                 // 48 or 96
-  constexpr int kSlabX = 32 * kRowBytes;                        // logits / gradient slab per warp
-  constexpr int kSlabY = 32 * H * 4;                            // labels as int32 (ignore / out-of-range pre-decoded)
-  __shared__ __align__(16) unsigned char slab[(kHeadThreads / 32) * (kSlabX + kSlabY)];
+  constexpr int kRowBytes = CeSlab<T>::kRowBytes;
+  constexpr int kVX = kRowBytes / 16;       // 16-byte vectors per lane and tile (logits); 4 more for the labels
+  constexpr int kBuf = CeSlab<T>::kX + CeSlab<T>::kY;
+  extern __shared__ __align__(16) unsigned char slab[];
   __shared__ float red[(kHeadThreads / 32) * H];
   __shared__ bool is_last;
   (void)grad_scale;
   const int tid = threadIdx.x;
   const int lane_ = tid & 31, warp_ = tid >> 5;
-  unsigned char* sx = slab + warp_ * (kSlabX + kSlabY);
-  int* sy = reinterpret_cast<int*>(sx + kSlabX);
+  unsigned char* wslab = slab + warp_ * (kAsync ? 2 : 1) * kBuf;
 
   // per-head gradient scales: host-computed when nothing can be ignored, else from the counting kernel (no barrier)
   float gsc[H];
@@ -275,37 +292,50 @@ multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict_
 #pragma unroll
   for (int h = 0; h < H; ++h) head_loss[h] = 0.f;
 
-  // persistent loop over 256-row tiles: one loss reduction per CTA instead of one per tile
   const int64_t n_tiles = (B + kHeadThreads - 1) / kHeadThreads;
+  // global -> slab `buf` of this warp: the warp's rows of `tile` (warp-coalesced 16-byte transactions)
+  auto fetch = [&](int64_t tile, int buf) {
+    const int64_t wrow0 = tile * kHeadThreads + warp_ * 32;
+    const int wrows = (int)max((int64_t)0, min((int64_t)32, B - wrow0));
+    uint4* dx_ = reinterpret_cast<uint4*>(wslab + buf * kBuf);
+    uint4* dy_ = reinterpret_cast<uint4*>(wslab + buf * kBuf + CeSlab<T>::kX);
+    const uint4* gx = reinterpret_cast<const uint4*>(logits + wrow0 * C);
+    const uint4* gy = reinterpret_cast<const uint4*>(labels + wrow0 * H);
+    const int nvx = wrows * kVX, nvy = wrows * 4;
+    if constexpr (kAsync) {
+#pragma unroll
+      for (int v = 0; v < kVX; ++v) { const int i = lane_ + 32 * v; if (i < nvx) cp_async16(dx_ + i, gx + i); }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { const int i = lane_ + 32 * v; if (i < nvy) cp_async16(dy_ + i, gy + i); }
+    } else {
+      uint4 rx[kVX], ry[4];
+#pragma unroll
+      for (int v = 0; v < kVX; ++v) { const int i = lane_ + 32 * v; rx[v] = i < nvx ? __ldg(gx + i) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { const int i = lane_ + 32 * v; ry[v] = i < nvy ? __ldg(gy + i) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+      for (int v = 0; v < kVX; ++v) dx_[lane_ + 32 * v] = rx[v];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) dy_[lane_ + 32 * v] = ry[v];
+    }
+  };
+  if constexpr (kAsync) {       // two tiles in flight before the first softmax (empty groups keep the count uniform)
+    if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x, 0);
+    cp_async_commit();
+    if ((int64_t)blockIdx.x + gridDim.x < n_tiles) fetch((int64_t)blockIdx.x + gridDim.x, 1);
+    cp_async_commit();
+  }
+
+  // persistent loop over 256-row tiles: one loss reduction per CTA instead of one per tile
+  int buf = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t wrow0 = tile * kHeadThreads + warp_ * 32;
     const int64_t row = wrow0 + lane_;
     const int wrows = (int)max((int64_t)0, min((int64_t)32, B - wrow0));
-    // ---- warp-coalesced global -> per-warp slab (the warp's 32 rows are one contiguous span) ----
-    {
-      const uint4* gsrc = reinterpret_cast<const uint4*>(logits + wrow0 * C);
-      const int nvec = wrows * kRowBytes / 16;
-#pragma unroll
-      for (int v = 0; v < kRowBytes / 16; ++v) {
-        const int i = lane_ + 32 * v;
-        if (i < nvec) reinterpret_cast<uint4*>(sx)[i] = __ldg(gsrc + i);
-      }
-      const longlong2* lsrc = reinterpret_cast<const longlong2*>(labels + wrow0 * H);
-      const int nl = wrows * H / 2;
-#pragma unroll
-      for (int v = 0; v < H / 2; ++v) {
-        const int i = lane_ + 32 * v;                               // label pair i = (row i / 4, heads 2*(i%4), +1)
-        if (i < nl) {
-          const longlong2 t = __ldg(lsrc + i);
-          const int h0 = (2 * i) & (H - 1);
-          int2 o;   // -1: ignored, -2: out of range, else the class id
-          o.x = (use_ignore && t.x == ignore_index) ? -1 : ((unsigned long long)t.x < (unsigned long long)(kOff[h0 + 1] - kOff[h0]) ? (int)t.x : -2);
-          o.y = (use_ignore && t.y == ignore_index) ? -1 : ((unsigned long long)t.y < (unsigned long long)(kOff[h0 + 2] - kOff[h0 + 1]) ? (int)t.y : -2);
-          reinterpret_cast<int2*>(sy)[i] = o;
-        }
-      }
-    }
+    if constexpr (kAsync) cp_async_wait<1>(); else fetch(tile, 0);
     __syncwarp();
+    unsigned char* sx = wslab + buf * kBuf;
+    const long long* sy = reinterpret_cast<const long long*>(sx + CeSlab<T>::kX);
 
     if (row < B) {
       float x[C];
@@ -332,10 +362,16 @@ multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict_
 #pragma unroll
         for (int i = 0; i < V; ++i) x[v * V + i] = t[i];
       }
-      {
-        const int4 a = reinterpret_cast<const int4*>(sy + lane_ * H)[0];
-        const int4 b = reinterpret_cast<const int4*>(sy + lane_ * H)[1];
-        y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+      {   // -1: ignored, -2: out of range, else the class id
+        const longlong2* yr = reinterpret_cast<const longlong2*>(sy + lane_ * H);
+#pragma unroll
+        for (int q = 0; q < H / 2; ++q) {
+          const longlong2 t = yr[q];
+          y[2 * q] = (use_ignore && t.x == ignore_index) ? -1
+                     : ((unsigned long long)t.x < (unsigned long long)(kOff[2 * q + 1] - kOff[2 * q]) ? (int)t.x : -2);
+          y[2 * q + 1] = (use_ignore && t.y == ignore_index) ? -1
+                         : ((unsigned long long)t.y < (unsigned long long)(kOff[2 * q + 2] - kOff[2 * q + 1]) ? (int)t.y : -2);
+        }
       }
 #pragma unroll
       for (int h = 0; h < H; ++h) {
@@ -382,8 +418,15 @@ multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict_
         if (i < nvec) gdst[i] = reinterpret_cast<const uint4*>(sx)[i];
       }
     }
-    __syncwarp();     // slab is reused by the next tile
+    __syncwarp();     // slab is reused by a later tile
+    if constexpr (kAsync) {
+      const int64_t t2 = tile + 2 * (int64_t)gridDim.x;
+      if (t2 < n_tiles) fetch(t2, buf);
+      cp_async_commit();
+      buf ^= 1;
+    }
   }
+  if constexpr (kAsync) cp_async_wait<0>();
 
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -430,29 +473,44 @@ multihead_ce_sm3_kernel(const T* __restrict__ logits, const int64_t* __restrict_
 // ---------------- K5: BCE with logits ----------------
 constexpr int kBceThreads = 256;
 
-template <typename TX, typename TT, bool kHasPW>
+// kProd (unweighted form only): the kernel is co-limited by the MUFU pipe (3 transcendentals per element against
+// 6 bytes of traffic), so the per-element log is replaced by ONE log per 8 elements of the running product of
+// (1 + e^-|x|) -- each factor lies in (1, 2], the product of 8 in (1, 256] -- which leaves 2.125 MUFU ops per element.
+template <typename TX, typename TT, bool kHasPW, bool kProd>
 __global__ void __launch_bounds__(kBceThreads)
 bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __restrict__ pos_weight, int64_t n,
            int C, float inv_n, float* __restrict__ loss_out, TX* __restrict__ dx, float grad_scale,
            float* __restrict__ ws, int vec_ok) {
+  static_assert(!(kHasPW && kProd), "the product form needs unweighted log terms");
   __shared__ float red[32];
   __shared__ bool is_last;
   float acc = 0.f;
+  float prod = 1.f;
   const float gscale = inv_n * grad_scale;
   auto elem = [&](float xv, float tv, int64_t idx) -> float {
     // e = exp(-|x|), r = 1/(1+e):  softplus(-x) = max(-x,0) - log(r),  sigmoid(x) = x >= 0 ? r : 1 - r
     const float e = ex2f_approx(-1.4426950408889634f * fabsf(xv));
-    const float r = rcpf_approx(1.0f + e);
-    const float sp = fmaxf(-xv, 0.f) - 0.6931471805599453f * lg2f_approx(r);
+    const float w = 1.0f + e;
+    const float r = rcpf_approx(w);
     const float sig = xv >= 0.f ? r : 1.0f - r;
-    if constexpr (kHasPW) {
-      const float lw = fmaf(__ldg(pos_weight + (idx % C)) - 1.f, tv, 1.f);
-      acc += fmaf(1.f - tv, xv, lw * sp);
-      return ((1.f - tv) - lw * (1.f - sig)) * gscale;
-    } else {
-      acc += fmaf(1.f - tv, xv, sp);
+    if constexpr (kProd) {
+      prod *= w;
+      acc += fmaf(1.f - tv, xv, fmaxf(-xv, 0.f));
       return (sig - tv) * gscale;
+    } else {
+      const float sp = fmaxf(-xv, 0.f) - 0.6931471805599453f * lg2f_approx(r);
+      if constexpr (kHasPW) {
+        const float lw = fmaf(__ldg(pos_weight + (idx % C)) - 1.f, tv, 1.f);
+        acc += fmaf(1.f - tv, xv, lw * sp);
+        return ((1.f - tv) - lw * (1.f - sig)) * gscale;
+      } else {
+        acc += fmaf(1.f - tv, xv, sp);
+        return (sig - tv) * gscale;
+      }
     }
+  };
+  auto fold = [&]() {       // product form: one log per 8 elements
+    if constexpr (kProd) { acc = fmaf(0.6931471805599453f, lg2f_approx(prod), acc); prod = 1.f; }
   };
   const int64_t stride = (int64_t)gridDim.x * kBceThreads;
   const int64_t gid = (int64_t)blockIdx.x * kBceThreads + threadIdx.x;
@@ -490,15 +548,18 @@ bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __re
     if (two) { load8x(v2, xb); load8t(v2, tb); }
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = elem(xa[i], ta[i], v * 8 + i);
+    fold();
     store8(v, g);
     if (two) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = elem(xb[i], tb[i], v2 * 8 + i);
+      fold();
       store8(v2, g);
     }
   }
   for (int64_t e = n8 * 8 + gid; e < n; e += stride) {
     const float g = elem(to_f32(x[e]), to_f32(t[e]), e);
+    fold();
     if (dx != nullptr) dx[e] = from_f32<TX>(g);
   }
   const float bs = block_sum(acc, red);
@@ -640,8 +701,22 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
   SM3_DISPATCH_DTYPE(dtype, T, {
     if (fixed && aligned16(logits) && aligned16(labels) && (dlogits == nullptr || aligned16(dlogits))) {
       const unsigned pgrid = grid < (unsigned)num_sms() * 8u ? grid : (unsigned)num_sms() * 8u;
-      multihead_ce_sm3_kernel<T><<<pgrid, kHeadThreads, 0, st>>>((const T*)logits, labels, B, meta, inv_T,
-          use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
+      const char* ev = getenv("SM3_CE_VARIANT");           // 0 = load -> compute -> store per tile, 1 = cp.async ring
+      if (ev && ev[0] == '1') {
+        const int smem3 = CeSlab<T>::bytes(true);
+        static const int per_sm = [&] {
+          int n = 0;
+          cudaFuncSetAttribute(multihead_ce_sm3_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, multihead_ce_sm3_kernel<T, true>, kHeadThreads, smem3) != cudaSuccess || n < 1) n = 2;
+          return n;
+        }();
+        const unsigned cap = (unsigned)(num_sms() * per_sm);
+        multihead_ce_sm3_kernel<T, true><<<grid < cap ? grid : cap, kHeadThreads, smem3, st>>>((const T*)logits, labels, B,
+            meta, inv_T, use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
+      } else {
+        multihead_ce_sm3_kernel<T, false><<<pgrid, kHeadThreads, CeSlab<T>::bytes(false), st>>>((const T*)logits, labels, B,
+            meta, inv_T, use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
+      }
     } else if (fixed) {
       SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       multihead_ce_kernel<T, true><<<grid, kHeadThreads, smem, st>>>((const T*)logits, labels, B, meta, inv_T,
@@ -681,13 +756,18 @@ extern "C" int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_d
   SM3_CHECK_CUDA(cudaMemsetAsync(ws, 0, 16, st));
   const int vec_ok = aligned16(x) && aligned16(t) && (dx == nullptr || aligned16(dx));
   const float inv_n = 1.0f / (float)n;
+  const char* ev = getenv("SM3_BCE_VARIANT");            // 0 = one log per element, 1 = one log per 8 (default)
+  const bool prod = !(ev && ev[0] == '0');
   SM3_DISPATCH_DTYPE(x_dtype, TX, SM3_DISPATCH_DTYPE(t_dtype, TT, {
     if (pos_weight != nullptr)
-      bce_kernel<TX, TT, true><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n, loss,
-                                                             (TX*)dx, grad_scale, ws, vec_ok);
+      bce_kernel<TX, TT, true, false><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n,
+                                                                    loss, (TX*)dx, grad_scale, ws, vec_ok);
+    else if (prod)
+      bce_kernel<TX, TT, false, true><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n,
+                                                                    loss, (TX*)dx, grad_scale, ws, vec_ok);
     else
-      bce_kernel<TX, TT, false><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n, loss,
-                                                              (TX*)dx, grad_scale, ws, vec_ok);
+      bce_kernel<TX, TT, false, false><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n,
+                                                                     loss, (TX*)dx, grad_scale, ws, vec_ok);
   }));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;

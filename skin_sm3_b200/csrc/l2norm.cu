@@ -1,6 +1,8 @@
 // K1: row L2 normalisation forward / backward (HBM-bound, 128-bit vectorised, one warp per row).
 // Replaces F.normalize(features, dim=1) -- reference src/models/simclr.py:62,138,294 -- and its autograd
 // backward.  Algorithmic bytes: fwd M*D*(b_in + b_out) + 4M ; bwd M*D*(4*n_partials + b_z + b_dp) + 4M.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sm3 {
@@ -125,6 +127,114 @@ l2norm_bwd_small_kernel(const float* __restrict__ dz, int n_partials, int64_t pa
   }
 }
 
+// ---------------- D <= 256, persistent: grid-stride over 4-row groups, the NEXT group's 16-byte loads are issued
+// (raw, still packed) before the current group is reduced and stored, so every warp keeps 64 B per lane in flight for
+// its whole life instead of only until its first reduction, and no time is lost to block turnover.  kStream adds
+// evict-first cache hints (ld.global.cs / st.global.cs) for inputs/outputs far larger than L2. ----------------
+template <typename T> struct Raw8 {
+  static constexpr int NV = (int)sizeof(T) * 8 / 16;      // 16-byte vectors per 8 elements: 1 (16-bit) or 2 (fp32)
+  uint4 v[NV];
+};
+template <typename T, bool kStream>
+__device__ __forceinline__ void raw_load8(const T* p, Raw8<T>& r) {
+#pragma unroll
+  for (int i = 0; i < Raw8<T>::NV; ++i)
+    r.v[i] = kStream ? __ldcs(reinterpret_cast<const uint4*>(p) + i) : __ldg(reinterpret_cast<const uint4*>(p) + i);
+}
+template <typename T>
+__device__ __forceinline__ void raw_unpack8(const Raw8<T>& r, float (&o)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    o[0] = __uint_as_float(r.v[0].x); o[1] = __uint_as_float(r.v[0].y); o[2] = __uint_as_float(r.v[0].z); o[3] = __uint_as_float(r.v[0].w);
+    o[4] = __uint_as_float(r.v[1].x); o[5] = __uint_as_float(r.v[1].y); o[6] = __uint_as_float(r.v[1].z); o[7] = __uint_as_float(r.v[1].w);
+  } else {
+    const uint32_t w[4] = {r.v[0].x, r.v[0].y, r.v[0].z, r.v[0].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if constexpr (sizeof(T) == 2 && !__is_same(T, __half)) {          // bf16: the fp32 bit pattern is the high half
+        o[2 * q] = __uint_as_float(w[q] << 16); o[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+        o[2 * q] = f.x; o[2 * q + 1] = f.y;
+      }
+    }
+  }
+}
+template <typename T, bool kStream>
+__device__ __forceinline__ void store8s(T* p, const float (&o)[8]) {
+  if constexpr (!kStream) {
+    store8<T>(p, o);
+  } else if constexpr (sizeof(T) == 4) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+    __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(o[4], o[5], o[6], o[7]));
+  } else {
+    uint4 v;
+    if constexpr (__is_same(T, __half)) {
+      __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+    } else {
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    }
+    __stcs(reinterpret_cast<uint4*>(p), v);
+  }
+}
+
+template <typename TIn> struct PersistRows { static constexpr int R = sizeof(TIn) == 4 ? 2 : 4; };
+
+template <typename TIn, typename TOut, bool kStream>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_fwd_persist_kernel(const TIn* __restrict__ pa, int64_t rows_a, const TIn* __restrict__ pb, int64_t rows_b, int D,
+                          TOut* __restrict__ z, float* __restrict__ inv_norm, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = rows_a + rows_b;
+  const bool have = lane < D / kChunk;
+  constexpr int kRows = PersistRows<TIn>::R;           // 64 B per lane in flight either way
+  const int64_t n_groups = (rows + kRows - 1) / kRows;
+  const int64_t gstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  int64_t grp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  Raw8<TIn> cur[kRows], nxt[kRows];
+  auto issue = [&](int64_t g, Raw8<TIn> (&dst)[kRows]) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int64_t row = g * kRows + r;
+      if (row < rows && have) {
+        const TIn* src = row < rows_a ? pa + row * D : pb + (row - rows_a) * D;
+        raw_load8<TIn, kStream>(src + lane * kChunk, dst[r]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < Raw8<TIn>::NV; ++i) dst[r].v[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  if (grp < n_groups) issue(grp, cur);
+  for (; grp < n_groups; grp += gstride) {
+    if (grp + gstride < n_groups) issue(grp + gstride, nxt);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int64_t row = grp * kRows + r;
+      float v[kChunk];
+      raw_unpack8<TIn>(cur[r], v);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) ss = fmaf(v[i], v[i], ss);
+      ss = warp_sum(ss);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+      if (row < rows) {
+        if (have) {
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) v[i] *= inv;
+          store8s<TOut, kStream>(z + row * D + lane * kChunk, v);
+        }
+        if (lane == 0) inv_norm[row] = inv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) cur[r] = nxt[r];
+  }
+}
+
 // ---------------- forward ----------------
 template <typename TIn, typename TOut, bool kVec>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -230,6 +340,22 @@ l2norm_bwd_kernel(const float* __restrict__ dz, int n_partials, int64_t partial_
   }
 }
 
+template <typename K>
+int resident_ctas(K kernel, int threads) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 2;
+  return n;
+}
+
+// SM3_K1_FWD_VARIANT: 0 = one short-lived CTA per 32 rows, 1 = persistent + register prefetch, 2 = 1 with evict-first
+// hints, unset = by size (the streaming form only when input + output exceed the 126 MB L2).
+int k1_fwd_variant(int64_t rows, int D, int bytes_per_elem) {
+  const char* e = getenv("SM3_K1_FWD_VARIANT");
+  if (e && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
+  (void)rows; (void)D; (void)bytes_per_elem;
+  return 0;
+}
+
 }  // namespace
 
 int l2norm_fwd_launch(const void* p_a, int64_t rows_a, const void* p_b, int64_t rows_b, int D, int p_dtype, void* z,
@@ -242,6 +368,27 @@ int l2norm_fwd_launch(const void* p_a, int64_t rows_a, const void* p_b, int64_t 
   if (vec && D <= 32 * kChunk) {
     const int64_t want4 = (rows + kWarpsPerBlock * kRows - 1) / (kWarpsPerBlock * kRows);
     const unsigned g4 = (unsigned)(want4 < 0x7fffffff ? want4 : 0x7fffffff);
+    const int variant = k1_fwd_variant(rows, D, dtype_size(p_dtype) + dtype_size(z_dtype));
+    if (variant != 0) {
+      // persistent grid: exactly as many CTAs as are resident at once (occupancy query, cached per instantiation)
+      const int rpw = dtype_size(p_dtype) == 4 ? 2 : 4;                        // PersistRows<TIn>::R
+      const int64_t wantp = (rows + kWarpsPerBlock * rpw - 1) / (kWarpsPerBlock * rpw);
+      SM3_DISPATCH_DTYPE(p_dtype, TIn, SM3_DISPATCH_DTYPE(z_dtype, TOut, {
+        if (variant == 2) {
+          static const int per_sm = resident_ctas(l2norm_fwd_persist_kernel<TIn, TOut, true>, kWarpsPerBlock * 32);
+          const int64_t cap = (int64_t)num_sms() * per_sm;
+          l2norm_fwd_persist_kernel<TIn, TOut, true><<<(unsigned)(wantp < cap ? wantp : cap), kWarpsPerBlock * 32, 0, st>>>(
+              (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);
+        } else {
+          static const int per_sm = resident_ctas(l2norm_fwd_persist_kernel<TIn, TOut, false>, kWarpsPerBlock * 32);
+          const int64_t cap = (int64_t)num_sms() * per_sm;
+          l2norm_fwd_persist_kernel<TIn, TOut, false><<<(unsigned)(wantp < cap ? wantp : cap), kWarpsPerBlock * 32, 0, st>>>(
+              (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);
+        }
+      }));
+      SM3_CHECK_CUDA(cudaGetLastError());
+      return SM3_OK;
+    }
     SM3_DISPATCH_DTYPE(p_dtype, TIn, SM3_DISPATCH_DTYPE(z_dtype, TOut, {
       l2norm_fwd_small_kernel<TIn, TOut><<<g4, kWarpsPerBlock * 32, 0, st>>>(
           (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);

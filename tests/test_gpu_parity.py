@@ -57,9 +57,13 @@ def run_term(sm3, p1, p2, T, precision):
 # ---------------------------------------------------------------------------------------------------
 # K1
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["0", "1", "2"])     # SM3_K1_FWD_VARIANT: per-block | persistent | + evict-first
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("shape", [(7, 8), (33, 5), (64, 128), (130, 256), (9, 512), (5, 1030)])
-def test_l2norm_forward_backward(sm3, dtype, shape):
+@pytest.mark.parametrize("shape", [(7, 8), (33, 5), (64, 128), (130, 256), (9, 512), (5, 1030), (70001, 256)])
+def test_l2norm_forward_backward(sm3, monkeypatch, dtype, shape, variant):
+    if variant != "0" and not (shape[1] % 8 == 0 and shape[1] <= 256):
+        pytest.skip("the persistent forward only exists for D % 8 == 0, D <= 256")
+    monkeypatch.setenv("SM3_K1_FWD_VARIANT", variant)
     g = torch.Generator().manual_seed(1)
     p = torch.randn(*shape, generator=g).to(dtype)
     p[1] = 0                                            # eps-clamp row
@@ -329,9 +333,11 @@ def test_multihead_ce_matches_reference_loops(sm3):
     assert relerr(x.grad.cpu().numpy(), g["dc_grad"]) < 1e-4
 
 
+@pytest.mark.parametrize("variant", ["0", "1"])          # SM3_CE_VARIANT: synchronous slab | cp.async double buffer
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("B", [1, 64, 257, 4096, 100003])
-def test_multihead_ce_vs_oracle(sm3, dtype, B):
+@pytest.mark.parametrize("B", [1, 64, 257, 4096, 100003, 700001])
+def test_multihead_ce_vs_oracle(sm3, monkeypatch, dtype, B, variant):
+    monkeypatch.setenv("SM3_CE_VARIANT", variant)
     rng = np.random.default_rng(B)
     nc = list(sm3.NUM_CLASSES)
     x = torch.from_numpy(rng.normal(size=(B, 24)).astype(np.float32) * 2).to(dtype)
@@ -352,9 +358,11 @@ def test_multihead_ce_vs_oracle(sm3, dtype, B):
     assert relerr(xc.grad.float().cpu().numpy(), gref) < tol
 
 
+@pytest.mark.parametrize("variant", ["0", "1"])          # SM3_BCE_VARIANT: one log per element | per 8 elements
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("shape", [(1, 24), (37, 24), (512, 24), (1001, 5), (65536, 24)])
-def test_bce_with_logits_vs_torch_oracle(sm3, dtype, shape):
+@pytest.mark.parametrize("shape", [(1, 24), (37, 24), (512, 24), (1001, 5), (65536, 24), (300007, 24)])
+def test_bce_with_logits_vs_torch_oracle(sm3, monkeypatch, dtype, shape, variant):
+    monkeypatch.setenv("SM3_BCE_VARIANT", variant)
     rng = np.random.default_rng(shape[0])
     x = torch.from_numpy(rng.normal(size=shape).astype(np.float32) * 3).to(dtype)
     t = torch.from_numpy((rng.random(shape) < 0.3).astype(np.float32))
