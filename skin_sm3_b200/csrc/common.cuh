@@ -129,6 +129,26 @@ __device__ __forceinline__ int positive_of(int g, int n_global) {
   return g < n_global ? g + n_global : g - n_global;
 }
 
+// Cross-rank flag wait used INSIDE kernels (fused exchange): one thread spins until every peer has published `epoch`
+// on `channel` of this rank's flag buffer (slot layout: flags[channel * 16 + source_rank], epochs only grow).  The
+// acquire at system scope orders this thread's later reads after the peers' stores; a missing peer traps after ~10 s
+// instead of hanging the GPU.
+__device__ __forceinline__ void peer_flags_wait_all(const unsigned* flags, int world, int channel, unsigned epoch) {
+  const long long t0 = clock64();
+  for (int r = 0; r < world; ++r) {
+    const unsigned* src = flags + channel * 16 + r;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 20000000000LL) {
+        printf("sm3: in-kernel peer wait timeout (channel %d, peer %d, have %u, want %u)\n", channel, r, v, epoch);
+        __trap();
+      }
+    } while (true);
+  }
+}
+
 // dtype dispatch helper for host code
 #define SM3_DISPATCH_DTYPE(dt, T, ...)                       \
   do {                                                       \
@@ -157,7 +177,28 @@ struct InfoNceProblem {
   int skip_local = 0;   // 1: visit only the column tiles owned by OTHER ranks (the local block is computed separately,
                         //    overlapped with the cross-rank exchange); needs n_local % 128 == 0
   const float* extra_neg_sum = nullptr;   // forward, skip_local: neg_sum of the local block, added in the finalize
+  // fused exchange (tcgen05 path): the kernel itself waits for the peers' flags before it touches the first column tile
+  // another rank owns (local tiles are visited first), instead of a separate wait kernel in front of it
+  const unsigned* wait_flags = nullptr;
+  int wait_world = 0, wait_channel = 0;
+  unsigned wait_epoch = 0;
+  const float* acol_direct = nullptr;     // backward: a_j = g_lse_j / neg_sum_j already materialised per global column
+                                          // (written by the owners over NVLink) -> no prep kernel; g_pos_cols likewise
+  int no_finalize = 0;                    // forward: leave the per-split partial sums in the workspace (the fused
+                                          // loss kernel folds them)
 };
+struct PeerFused {          // what the fused exchange kernels need to publish to every rank
+  PeerPtrs data;            // destination buffers (z_cols or stats), one per rank
+  PeerPtrs flags;           // flag buffers, one per rank
+  unsigned* counter;        // local zero-initialised word: CTA ticket for the "last block signals" pattern
+  int rank, channel;
+  unsigned epoch;
+};
+int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pair_offset, int n_global, int D, int p_dtype,
+                          void* z_local, float* inv_norm, float eps, const PeerFused& pf, cudaStream_t st);
+int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
+                              int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
+                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st);
 size_t infonce_simt_workspace(const InfoNceProblem& pb, int backward);
 int infonce_simt_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
                      cudaStream_t st);

@@ -56,7 +56,34 @@ struct TcParams {
   int cstride;         // element stride of gpos_c (1, or 4 for packed peer-exchanged statistics)
   const float* acol;   // bwd: a_j = g_lse_j / neg_sum_j, zero padded to a multiple of 64
   float* dz_partial;   // bwd: [splits][m_rows][D]
+  // fused exchange: flags to wait for before the first column tile owned by another rank (nullptr = no waiting), and
+  // the two local column-tile ranges [loc_a, loc_a + loc_len), [loc_b, loc_b + loc_len) in this kernel's tile units
+  const unsigned* wait_flags;
+  int wait_world, wait_channel;
+  unsigned wait_epoch;
+  int loc_a, loc_b, loc_len;
 };
+
+// Per-CTA starting rotation of the column-tile order.  Default: pseudo-random (decorrelates the CTAs of a wave, see the
+// forward kernel).  Fused exchange: start inside this rank's own column range when the CTA's split touches it, so the
+// tiles that need no remote data are visited while the peers' rows are still in flight.
+__device__ __forceinline__ int tile_rotation(const TcParams& p, int t_begin, int n_tiles) {
+  if (n_tiles <= 0) return 0;
+  const unsigned h = blockIdx.x * 37u + blockIdx.y * 11u;
+  if (p.wait_flags != nullptr) {
+    const int t_end = t_begin + n_tiles;
+    const int s0 = max(t_begin, p.loc_a), e0 = min(t_end, p.loc_a + p.loc_len);
+    if (s0 < e0) return s0 - t_begin + (int)(h % (unsigned)(e0 - s0));
+    const int s1 = max(t_begin, p.loc_b), e1 = min(t_end, p.loc_b + p.loc_len);
+    if (s1 < e1) return s1 - t_begin + (int)(h % (unsigned)(e1 - s1));
+  }
+  return (int)(h % (unsigned)n_tiles);
+}
+__device__ __forceinline__ bool tile_is_local(const TcParams& p, int t) {
+  return (unsigned)(t - p.loc_a) < (unsigned)p.loc_len || (unsigned)(t - p.loc_b) < (unsigned)p.loc_len;
+}
+// generic-proxy acquire of the peers' flags -> async-proxy (TMA) reads of the rows they published
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // TMA descriptor (driver entry point fetched through the runtime: no link-time libcuda dependency)
@@ -226,7 +253,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   // Column tiles are visited in a per-CTA rotated order.  All row blocks of a wave would otherwise sweep the SAME
   // 32-64 KB tile at the same time and serialise on the few L2 slices holding it (measured: the forward kernel was
   // bimodal, 1.7 ms or 3.5-6 ms at cfg4, depending on whether the CTAs happened to run in lockstep).
-  const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
+  const int rot = tile_rotation(p, t_begin, n_tiles);
   auto tile_of = [&](int it) {
     int t = it + rot;
     t = t_begin + (t >= n_tiles ? t - n_tiles : t);
@@ -253,13 +280,23 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   if (warp == 0) {
     // =========================== TMA producer (warp-uniform loop, one elected lane issues) ===========
     if (elect_one()) prefetch_tensormap(&tmap_cols);
+    bool remote_ready = (p.wait_flags == nullptr);
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE;
       const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      const int tile = tile_of(it);
+      if (!remote_ready && !tile_is_local(p, tile)) {     // fused exchange: the peers' rows must have landed
+        if (elect_one()) {
+          peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch);
+          fence_proxy_async_global();
+        }
+        __syncwarp();
+        remote_ready = true;
+      }
       mbar_wait(bar_empty(s), ph ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
-        const int row = tile_of(it) * BN;
+        const int row = tile * BN;
 #pragma unroll
         for (int pnl = 0; pnl < DP; ++pnl)
           tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
@@ -431,7 +468,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
   const int n_tiles = t_end - t_begin;
-  const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
+  const int rot = tile_rotation(p, t_begin, n_tiles);
   auto tile_of = [&](int it) {
     int t = it + rot;
     t = t_begin + (t >= n_tiles ? t - n_tiles : t);
@@ -459,13 +496,23 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one()) prefetch_tensormap(&tmap_cols);
+    bool remote_ready = (p.wait_flags == nullptr);
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE;
       const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      const int tile = tile_of(it);
+      if (!remote_ready && !tile_is_local(p, tile)) {     // fused exchange: the peers' rows must have landed
+        if (elect_one()) {
+          peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch);
+          fence_proxy_async_global();
+        }
+        __syncwarp();
+        remote_ready = true;
+      }
       mbar_wait(bar_empty(s), ph ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
-        const int row = tile_of(it) * BN;
+        const int row = tile * BN;
 #pragma unroll
         for (int pnl = 0; pnl < DP; ++pnl)
           tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
@@ -626,7 +673,10 @@ __global__ void tc_bwd_prep_kernel(const float* __restrict__ glse, const float* 
   acol[j] = a;
 }
 
-template <int DP, int NG>
+// kWait (fused exchange): the per-column statistics (acol, gpos_c) are written by their owner ranks over NVLink while
+// this kernel is already running; every softmax warp waits for the peers' flags before the first column tile another
+// rank owns and reads the statistics with L2-coherent loads (ld.global.cg) instead of the read-only path.
+template <int DP, int NG, bool kWait>
 __global__ void __launch_bounds__(64 + 256 * NG, 1)
 infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
   using C = BwdCfg<DP>;
@@ -655,7 +705,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   // Column tiles are visited in a per-CTA rotated order.  All row blocks of a wave would otherwise sweep the SAME
   // 32-64 KB tile at the same time and serialise on the few L2 slices holding it (measured: the forward kernel was
   // bimodal, 1.7 ms or 3.5-6 ms at cfg4, depending on whether the CTAs happened to run in lockstep).
-  const int rot = n_tiles > 0 ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)n_tiles) : 0;
+  const int rot = tile_rotation(p, t_begin, n_tiles);
   auto tile_of = [&](int it) {
     int t = it + rot;
     t = t_begin + (t >= n_tiles ? t - n_tiles : t);
@@ -788,8 +838,17 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     }
     const float c2 = p.c2;
 
+    bool remote_ready = !kWait;
     for (int it = grp; it < n_tiles; it += NG) {
       const int as = it & 1;
+      const int tile = tile_of(it);
+      if constexpr (kWait) {
+        if (!remote_ready && !tile_is_local(p, tile)) {   // the owners' statistics must have landed
+          if (lane == 0) peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch);
+          __syncwarp();
+          remote_ready = true;
+        }
+      }
       mbar_wait(bar_sfull(as), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       if (warp == 2 && lane == 0) SM3_TR(3, it);
@@ -798,7 +857,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       tmem_ld_x32(taddr, v);
       tmem_ld_wait(v);
       if (warp == 2 && lane == 0) SM3_TR(4, it);
-      const int cb = tile_of(it) * BN + half * 32;
+      const int cb = tile * BN + half * 32;
       const bool need = (cb + 32 > p.m_cols) ||
                         (valid && ((unsigned)(g - cb) < 32u || (unsigned)(pj - cb) < 32u));
       uint32_t h[16];
@@ -806,7 +865,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       if (!__any_sync(0xffffffffu, need)) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 aj = __ldg(ap + i);
+          const float4 aj = kWait ? __ldcg(ap + i) : __ldg(ap + i);
           const float e0 = ex2(fmaf(__uint_as_float(v[4 * i]), c2, -c2)) * (a_i + aj.x);
           const float e1 = ex2(fmaf(__uint_as_float(v[4 * i + 1]), c2, -c2)) * (a_i + aj.y);
           const float e2 = ex2(fmaf(__uint_as_float(v[4 * i + 2]), c2, -c2)) * (a_i + aj.z);
@@ -822,8 +881,8 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
           const float s = __uint_as_float(v[i]);
           float x = 0.f;
           if (valid && col < p.m_cols && col != g) {
-            if (col == pj) x = gp_i + p.gpos_c[(size_t)col * p.cstride];
-            else x = ex2(fmaf(s, c2, -c2)) * (a_i + p.acol[col]);
+            if (col == pj) x = gp_i + (kWait ? __ldcg(p.gpos_c + (size_t)col * p.cstride) : p.gpos_c[(size_t)col * p.cstride]);
+            else x = ex2(fmaf(s, c2, -c2)) * (a_i + (kWait ? __ldcg(p.acol + col) : p.acol[col]));
           }
           hv[i] = x;
         }
@@ -924,6 +983,11 @@ void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p, int bn
     p.skip_len = 0;
     p.skip_a = p.skip_b = 0x7fffffff;
   }
+  p.wait_flags = pb.wait_flags; p.wait_world = pb.wait_world; p.wait_channel = pb.wait_channel;
+  p.wait_epoch = pb.wait_epoch;
+  p.loc_len = pb.n_local / bn;                      // only consulted when wait_flags != nullptr (n_local % 128 == 0)
+  p.loc_a = pb.pair_offset / bn;
+  p.loc_b = (pb.n_global + pb.pair_offset) / bn;
   p.n_local = pb.n_local; p.pair_offset = pb.pair_offset; p.n_global = pb.n_global; p.D = pb.D;
   p.m_rows = 2 * pb.n_local; p.m_cols = 2 * pb.n_global;
   p.inv_T = pb.inv_T; p.c2 = pb.inv_T * kLog2eTC;
@@ -991,17 +1055,18 @@ int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cud
     default: return launch_fwd_ng<DP, 1, 2>(tmap, p, pl, st);
   }
 }
-template <int DP, int NG>
+template <int DP, int NG, bool kWait>
 int launch_bwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP, NG, kWait>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)BwdCfg<DP>::SMEM));
-  infonce_tc_bwd_kernel<DP, NG><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, BwdCfg<DP>::SMEM, st>>>(tmap, p);
+  infonce_tc_bwd_kernel<DP, NG, kWait><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, BwdCfg<DP>::SMEM, st>>>(tmap, p);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
 template <int DP>
 int launch_bwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  return tc_groups() == 1 ? launch_bwd_ng<DP, 1>(tmap, p, pl, st) : launch_bwd_ng<DP, 2>(tmap, p, pl, st);
+  if (p.wait_flags != nullptr) return launch_bwd_ng<DP, 1, true>(tmap, p, pl, st);
+  return tc_groups() == 1 ? launch_bwd_ng<DP, 1, false>(tmap, p, pl, st) : launch_bwd_ng<DP, 2, false>(tmap, p, pl, st);
 }
 
 size_t bwd_acol_offset(const InfoNceProblem& pb, const TcPlan& pl) {
@@ -1034,6 +1099,8 @@ int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* 
               pb.n_global);
   SM3_REQUIRE(!pb.skip_local || (pb.n_local % 128 == 0 && pb.n_global > pb.n_local), SM3_ERR_SHAPE,
               "infonce(tc): skip_local needs n_local %% 128 == 0 and more than one rank");
+  SM3_REQUIRE(pb.wait_flags == nullptr || (pb.n_local % 128 == 0 && !pb.skip_local), SM3_ERR_SHAPE,
+              "infonce(tc): in-kernel peer waits need n_local %% 128 == 0");
   SM3_REQUIRE(ws_bytes >= infonce_tc_workspace(pb, 0), SM3_ERR_WORKSPACE, "infonce(tc) fwd: workspace too small");
   const TcPlan pl = tc_plan(pb, false);
   TcParams p{};
@@ -1050,6 +1117,7 @@ int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* 
     default: rc = launch_fwd<4>(tmap, p, pl, st); break;
   }
   if (rc) return rc;
+  if (pb.no_finalize) return pl.splits;             // the caller folds the [splits][m_rows] partial sums itself
   return infonce_finalize_launch(p.partial, pl.splits, p.m_rows, pb.inv_T, neg_sum, lse_neg, st, pb.extra_neg_sum);
 }
 
@@ -1068,11 +1136,17 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
   fill_params(pb, pl, p, 64);
   p.gpos_r = gpos_r; p.glse_r = glse_r; p.nsum_r = nsum_r; p.gpos_c = gpos_c; p.cstride = pb.col_stride;
   p.dz_partial = (float*)ws;
-  float* acol = (float*)((char*)ws + bwd_acol_offset(pb, pl));
-  p.acol = acol;
-  const int m_pad = (p.m_cols + 63) / 64 * 64 + 64;
-  tc_bwd_prep_kernel<<<(m_pad + 255) / 256, 256, 0, st>>>(glse_c, nsum_c, pb.col_stride, p.m_cols, m_pad, acol);
-  SM3_CHECK_CUDA(cudaGetLastError());
+  SM3_REQUIRE(pb.wait_flags == nullptr || (pb.n_local % 128 == 0 && !pb.skip_local && pb.acol_direct != nullptr),
+              SM3_ERR_SHAPE, "infonce(tc): in-kernel peer waits need n_local %% 128 == 0 and materialised column statistics");
+  if (pb.acol_direct != nullptr) {
+    p.acol = pb.acol_direct;                        // written by the owner ranks (fused exchange): no prep kernel
+  } else {
+    float* acol = (float*)((char*)ws + bwd_acol_offset(pb, pl));
+    p.acol = acol;
+    const int m_pad = (p.m_cols + 63) / 64 * 64 + 64;
+    tc_bwd_prep_kernel<<<(m_pad + 255) / 256, 256, 0, st>>>(glse_c, nsum_c, pb.col_stride, p.m_cols, m_pad, acol);
+    SM3_CHECK_CUDA(cudaGetLastError());
+  }
   CUtensorMap tmap;
   int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 64);
   if (rc) return rc;

@@ -348,12 +348,15 @@ int resident_ctas(K kernel, int threads) {
 }
 
 // SM3_K1_FWD_VARIANT: 0 = one short-lived CTA per 32 rows, 1 = persistent + register prefetch, 2 = 1 with evict-first
-// hints, unset = by size (the streaming form only when input + output exceed the 126 MB L2).
-int k1_fwd_variant(int64_t rows, int D, int bytes_per_elem) {
+// hints.  Unset = by shape, from the measurements on B200 at 2M x 256 (tools/hbm_variants.py, fraction of the 6.5 TB/s
+// copy rate): 16-bit rows 0.71 / 0.85 / 0.88 for variants 0 / 1 / 2 (and 20 -> 16 us at the L2-resident 65536 x 256),
+// fp32 rows 1.08 / 0.93 / 0.95 (the read-heavy form is already past the copy rate).  The evict-first hints are only used
+// when input + output cannot stay in the 126 MB L2 anyway, so that K2 still finds a small z there.
+int k1_fwd_variant(int64_t rows, int D, int in_bytes, int out_bytes) {
   const char* e = getenv("SM3_K1_FWD_VARIANT");
   if (e && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
-  (void)rows; (void)D; (void)bytes_per_elem;
-  return 0;
+  if (in_bytes == 4) return 0;
+  return rows * (int64_t)D * (in_bytes + out_bytes) > (int64_t)96 << 20 ? 2 : 1;
 }
 
 }  // namespace
@@ -368,7 +371,7 @@ int l2norm_fwd_launch(const void* p_a, int64_t rows_a, const void* p_b, int64_t 
   if (vec && D <= 32 * kChunk) {
     const int64_t want4 = (rows + kWarpsPerBlock * kRows - 1) / (kWarpsPerBlock * kRows);
     const unsigned g4 = (unsigned)(want4 < 0x7fffffff ? want4 : 0x7fffffff);
-    const int variant = k1_fwd_variant(rows, D, dtype_size(p_dtype) + dtype_size(z_dtype));
+    const int variant = k1_fwd_variant(rows, D, dtype_size(p_dtype), dtype_size(z_dtype));
     if (variant != 0) {
       // persistent grid: exactly as many CTAs as are resident at once (occupancy query, cached per instantiation)
       const int rpw = dtype_size(p_dtype) == 4 ? 2 : 4;                        // PersistRows<TIn>::R

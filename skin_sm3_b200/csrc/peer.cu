@@ -93,7 +93,175 @@ __global__ void peer_wait_kernel(const unsigned* __restrict__ my_flags, int worl
   } while (true);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused exchange kernels (SM3_PEER_FUSED=1, sm3_infonce_step_peer mode 2).  The producing kernel itself publishes to
+// every rank and signals, the consuming tcgen05 kernel itself waits (peer_flags_wait_all in its prologue path), so a
+// multi-rank step is 5 launches instead of 13 and the cross-rank latency hides behind the local column block.
+// "Last block signals": every CTA fences its peer stores at system scope and takes a ticket; the CTA that draws the
+// last ticket knows all stores of the grid are visible, resets the ticket word and releases the epoch to every peer.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void last_block_signal(const PeerFused& pf, bool* smem_flag) {
+  __syncthreads();                                   // every thread's peer stores precede thread 0's fence
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned t = atomicAdd(pf.counter, 1u);
+    *smem_flag = (t == total - 1);
+  }
+  __syncthreads();
+  if (*smem_flag && threadIdx.x < pf.flags.world) {
+    if (threadIdx.x == 0) *pf.counter = 0u;          // next launch starts from zero (same stream => ordered)
+    __threadfence_system();
+    unsigned* dst = reinterpret_cast<unsigned*>(pf.flags.p[threadIdx.x]) + pf.channel * 16 + pf.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(pf.epoch) : "memory");
+  }
+}
+
+// K1 forward + scatter: normalise this rank's rows (first halves from pa, second halves from pb), keep the bf16 rows
+// locally (A operand of K2/K3, normalise-backward) and store them into every rank's z_cols at the global row index.
+// One warp per 4 rows, D % 8 == 0, D <= 256 (lane < D/8 owns one 16-byte vector of the row).
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+l2norm_scatter_kernel(const TIn* __restrict__ pa, const TIn* __restrict__ pb, int n_local, int pair_offset, int n_global,
+                      int D, __nv_bfloat16* __restrict__ z_local, float* __restrict__ inv_norm, float eps, PeerFused pf) {
+  __shared__ bool is_last;
+  constexpr int kR = 4;
+  const int lane = threadIdx.x & 31;
+  const int rows = 2 * n_local;
+  const bool have = lane < D / 8;
+  const int vpr = D / 8;
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kR;
+  float v[kR][8];
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const int row = row0 + r;
+    if (row < rows && have) {
+      const TIn* src = row < n_local ? pa + (size_t)row * D : pb + (size_t)(row - n_local) * D;
+      if constexpr (sizeof(TIn) == 4) {
+        float a[4], b[4];
+        VecIO<float>::load(reinterpret_cast<const float*>(src) + lane * 8, a);
+        VecIO<float>::load(reinterpret_cast<const float*>(src) + lane * 8 + 4, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[r][i] = a[i]; v[r][4 + i] = b[i]; }
+      } else {
+        VecIO<TIn>::load(src + lane * 8, v[r]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[r][i] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const int row = row0 + r;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss = fmaf(v[r][i], v[r][i], ss);
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+    if (row < rows) {
+      if (have) {
+        uint4 pk;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[r][2 * i] * inv, v[r][2 * i + 1] * inv);
+        reinterpret_cast<uint4*>(z_local)[(size_t)row * vpr + lane] = pk;
+        const size_t off = (size_t)global_row(row, n_local, pair_offset, n_global) * vpr + lane;
+#pragma unroll 4
+        for (int q = 0; q < pf.data.world; ++q) reinterpret_cast<uint4*>(pf.data.p[q])[off] = pk;
+      }
+      if (lane == 0) inv_norm[row] = inv;
+    }
+  }
+  last_block_signal(pf, &is_last);
+}
+
+// CE on the sufficient statistics + its gradient + the backward exchange, one launch:
+//   neg_sum_i = sum_k partial[k][i] ; lse_i = inv_T + log(neg_sum_i) ; loss = scale * sum_i softplus(lse_i - pos_i)
+//   g_lse_i = scale * sigmoid(lse_i - pos_i) = -g_pos_i ; a_i = g_lse_i / neg_sum_i
+// (g_pos, g_lse, neg_sum) stay local for this rank's rows of K3; (a_i, g_pos_i) go to every rank's column planes
+// stats[0 .. M_g) = a, stats[M_g .. 2 M_g) = g_pos at the global row index.  The loss is folded by the last CTA in a
+// fixed order (deterministic), which then signals.
+__global__ void __launch_bounds__(256)
+loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, const float* __restrict__ pos, int n_local,
+                          int pair_offset, int n_global, float inv_T, float scale, float* __restrict__ loss,
+                          float* __restrict__ g_pos, float* __restrict__ g_lse, float* __restrict__ neg_sum,
+                          float* __restrict__ block_ws, PeerFused pf) {
+  __shared__ float red[32];
+  __shared__ bool is_last;
+  const int rows = 2 * n_local;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (i < rows) {
+    float s = 0.f;
+    for (int k = 0; k < n_partials; ++k) s += partial[(size_t)k * rows + i];
+    const float lse = inv_T + logf(s);               // s == 0 (a single pair: no negatives) -> -inf, term = 0
+    const float x = lse - pos[i];
+    const float e = __expf(-fabsf(x));
+    const float r = __frcp_rn(1.0f + e);
+    const float g = scale * (x >= 0.f ? r : e * r);  // scale * sigmoid(x)
+    term = fmaxf(x, 0.f) + log1pf(e);
+    g_lse[i] = g;
+    g_pos[i] = -g;
+    neg_sum[i] = s;
+    const float a = s > 0.f ? g / s : 0.f;
+    const size_t gr = (size_t)global_row(i, n_local, pair_offset, n_global);
+    const size_t m_cols = (size_t)2 * n_global;
+#pragma unroll 4
+    for (int q = 0; q < pf.data.world; ++q) {
+      float* st = reinterpret_cast<float*>(pf.data.p[q]);
+      st[gr] = a;
+      st[m_cols + gr] = -g;
+    }
+  }
+  const float bs = block_sum(term, red);
+  if (threadIdx.x == 0) block_ws[blockIdx.x] = bs;
+  // ticket + signal; the CTA that draws the last ticket also folds the block sums
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned t = atomicAdd(pf.counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(block_ws + b);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) { *loss = s * scale; *pf.counter = 0u; }
+    if (threadIdx.x < pf.flags.world) {
+      __threadfence_system();
+      unsigned* dst = reinterpret_cast<unsigned*>(pf.flags.p[threadIdx.x]) + pf.channel * 16 + pf.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(pf.epoch) : "memory");
+    }
+  }
+}
+
 }  // namespace
+
+int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pair_offset, int n_global, int D, int p_dtype,
+                          void* z_local, float* inv_norm, float eps, const PeerFused& pf, cudaStream_t st) {
+  SM3_REQUIRE(D % 8 == 0 && D >= 8 && D <= 256, SM3_ERR_SHAPE, "l2norm_scatter: D=%d", D);
+  SM3_REQUIRE(aligned16(p_a) && aligned16(p_b) && aligned16(z_local), SM3_ERR_SHAPE, "l2norm_scatter: unaligned rows");
+  const unsigned grid = (unsigned)((2 * (int64_t)n_local + 31) / 32);
+  SM3_DISPATCH_DTYPE(p_dtype, TIn, {
+    l2norm_scatter_kernel<TIn><<<grid, 256, 0, st>>>((const TIn*)p_a, (const TIn*)p_b, n_local, pair_offset, n_global, D,
+                                                     (__nv_bfloat16*)z_local, inv_norm, eps, pf);
+  });
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
+                              int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
+                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st) {
+  const unsigned grid = (unsigned)((2 * (int64_t)n_local + 255) / 256);
+  loss_stats_scatter_kernel<<<grid, 256, 0, st>>>(partial, n_partials, pos, n_local, pair_offset, n_global, inv_T, scale,
+                                                  loss, g_pos, g_lse, neg_sum, block_ws, pf);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
 
 int peer_signal_launch(const PeerPtrs& flags, int rank, int channel, unsigned epoch, cudaStream_t st) {
   peer_signal_kernel<<<1, 32, 0, st>>>(flags, rank, channel, epoch);

@@ -355,6 +355,13 @@ def test_multihead_ce_vs_oracle(sm3, monkeypatch, dtype, B, variant):
         return
     assert abs(loss.item() - ref) < 2e-5 * abs(ref)
     tol = 1e-4 if dtype == torch.float32 else 1e-2
+    if dtype == torch.float16 and B > 200000:
+        # d loss / d logit ~ 1 / (8 B) ~ 1e-7 sits at the fp16 subnormal step (6e-8): the stored gradient is quantised
+        # to a few percent whatever computes it (torch's own fp16 CE backward included); use a GradScaler-like factor
+        xs = x.cuda().requires_grad_(True)
+        (sm3.multihead_ce(xs, torch.from_numpy(y).cuda(), weights=w, temperature=0.5, ignore_index=-100) * 1024.0).backward()
+        assert relerr(xs.grad.float().cpu().numpy() / 1024.0, gref) < tol
+        return
     assert relerr(xc.grad.float().cpu().numpy(), gref) < tol
 
 
