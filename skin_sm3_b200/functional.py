@@ -499,6 +499,11 @@ class _MultiHeadCE(torch.autograd.Function):
     def forward(ctx, logits, labels, class_counts, weights, inv_t, ignore_index, use_ignore):
         import ctypes as C
         dev = require_cuda(logits, labels)
+        ctx.in_dtype = logits.dtype
+        if logits.dtype == torch.float16:
+            # fp16 cannot hold d loss / d logit ~ 1 / (H B) before the upstream (GradScaler) factor is applied: compute
+            # in fp32 like the reference does under autocast (CE is an fp32 op there) and round once, after scaling
+            logits = logits.float()
         logits = _contig(logits)
         labels = _contig(labels.to(torch.int64))
         b, c_total = logits.shape
@@ -523,7 +528,7 @@ class _MultiHeadCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dlogits,) = ctx.saved_tensors
-        return dlogits * g.to(dlogits.dtype), None, None, None, None, None, None
+        return (dlogits * g.to(dlogits.dtype)).to(ctx.in_dtype), None, None, None, None, None, None
 
 
 def multihead_ce(outputs, labels: torch.Tensor, weights: Optional[Sequence[float]] = None, temperature: float = 1.0,
@@ -548,6 +553,9 @@ class _BCEWithLogits(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, t, pos_weight):
         dev = require_cuda(x, t, pos_weight)
+        ctx.in_dtype = x.dtype
+        if x.dtype == torch.float16:
+            x = x.float()              # see _MultiHeadCE: the 1/(B C) gradient is rounded to fp16 only after upstream scaling
         x = _contig(x)
         t = _contig(t)
         if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
@@ -570,7 +578,7 @@ class _BCEWithLogits(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dx,) = ctx.saved_tensors
-        return dx * g.to(dx.dtype), None, None
+        return (dx * g.to(dx.dtype)).to(ctx.in_dtype), None, None
 
 
 def bce_with_logits(x: torch.Tensor, target: torch.Tensor, pos_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
