@@ -232,10 +232,16 @@ int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_
 /* Multi-rank form: this rank's 2*n_local rows against all world*n_local pairs, negatives exchanged over NVLink peer
  * memory, the whole step enqueued by ONE call on two streams (exchange on stream_side, kernels on stream_main; the
  * local column block runs while the exchange is in flight).  z_cols_mine / stats_mine / flags_mine are this rank's
- * symmetric buffers ([2*n_global, D] bf16, [2*n_global, 4] fp32, >= 64 uint32), *_peers_host the HOST arrays of the
+ * symmetric buffers ([2*n_global, D] bf16, [2*n_global, 4] fp32, >= 64 uint32 (128 for mode 2)), *_peers_host the HOST arrays of the
  * `world` peer-mapped pointers of the same buffers; `epoch` must grow by one per call and be identical on all ranks.
- * overlap = 1: local column block computed while the exchange is in flight (needs n_local % 128 == 0); overlap = 0:
- * exchange, barrier and full-width kernels back to back on stream_main.  D in {64,128,192,256}.
+ * overlap (mode) = 0: exchange, barrier and full-width kernels back to back on stream_main (13 launches);
+ *   1: local column block computed while the exchange runs on stream_side (needs n_local % 128 == 0);
+ *   2: fused exchange, 5 launches on stream_main: the normalise kernel stores its rows into every rank's z_cols and
+ *      signals, the loss kernel does the same for the backward statistics, and K2 / K3 wait for the peers' flags
+ *      inside the kernel, visiting this rank's own column tiles first (needs n_local % 128 == 0; flags buffers of
+ *      >= 128 uint32, zero-initialised: words [64, 66) are local ticket counters; the stats buffer then holds the
+ *      planes a_j = g_lse_j / neg_sum_j at [0, 2*n_global) and g_pos_j at [2*n_global, 4*n_global)).
+ * D in {64,128,192,256}.
  * loss = weight * mean over this rank's rows (DDP convention).                                                     */
 size_t sm3_infonce_step_peer_scratch_bytes(int n_local, int n_global, int D);
 int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local, int rank, int world, int D, int io_dtype,

@@ -329,10 +329,11 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
   SM3_REQUIRE((dp1 == nullptr) == (dp2 == nullptr), SM3_ERR_SHAPE, "infonce_step_peer: dp1/dp2 must both be given or both NULL");
   SM3_REQUIRE(world >= 2 && rank >= 0 && rank < world && n_local >= 1, SM3_ERR_SHAPE,
               "infonce_step_peer: needs world >= 2 (got world=%d n_local=%d)", world, n_local);
-  SM3_REQUIRE(!overlap || n_local % 128 == 0, SM3_ERR_SHAPE, "infonce_step_peer: overlap needs n_local %% 128 == 0");
+  SM3_REQUIRE(overlap >= 0 && overlap <= 2, SM3_ERR_SHAPE, "infonce_step_peer: mode %d not in {0,1,2}", overlap);
+  SM3_REQUIRE(!overlap || n_local % 128 == 0, SM3_ERR_SHAPE, "infonce_step_peer: modes 1 and 2 need n_local %% 128 == 0");
   SM3_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256 && dtype_ok(io_dtype) && temperature > 0.f, SM3_ERR_DTYPE,
               "infonce_step_peer: D must be in {64,128,192,256}");
-  SM3_REQUIRE(!overlap || stream_side != stream_main, SM3_ERR_SHAPE,
+  SM3_REQUIRE(overlap != 1 || stream_side != stream_main, SM3_ERR_SHAPE,
               "infonce_step_peer: the side stream must differ from the main stream");
   const int n_global = n_local * world, off = rank * n_local;
   const PeerPlan h = plan_peer(n_local, n_global, D);
@@ -351,6 +352,33 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
   float *lse = (float*)(base + h.lse), *nsum = (float*)(base + h.nsum), *gpos = (float*)(base + h.gpos), *glse = (float*)(base + h.glse);
   void* z = base + h.z;
 
+  if (overlap == 2) {
+    // ---- fused exchange: 5 launches.  The producers publish + signal themselves, K2 / K3 wait inside the kernel and
+    //      visit this rank's own column tiles first (see peer.cu, infonce_tc.cu). ----
+    SM3_REQUIRE(aligned16(p1) && aligned16(p2), SM3_ERR_SHAPE, "infonce_step_peer: fused mode needs 16-byte aligned rows");
+    unsigned* counters = (unsigned*)flags_mine + 64;          // two local ticket words behind the 64 flag slots
+    PeerFused pz{zp, fp, counters, rank, 0, epoch};
+    rc = l2norm_scatter_launch(p1, p2, n_local, off, n_global, D, io_dtype, z, (float*)(base + h.inv), 1e-12f, pz, sm);
+    if (rc) return rc;
+    InfoNceProblem pf{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
+    pf.wait_flags = (const unsigned*)flags_mine; pf.wait_world = world; pf.wait_channel = 0; pf.wait_epoch = epoch;
+    pf.no_finalize = 1;
+    SM3_REQUIRE(infonce_tc_supported(pf), SM3_ERR_DTYPE, "infonce_step_peer: tcgen05 path unavailable");
+    const int splits = infonce_tc_fwd(pf, pos, lse, nsum, base + h.ws_b, h.ws_b_bytes, sm);
+    if (splits < 0) return splits;
+    PeerFused ps{sp, fp, counters + 1, rank, 1, epoch};
+    rc = loss_stats_scatter_launch((const float*)(base + h.ws_b), splits, pos, n_local, off, n_global, inv_T,
+                                   weight / (float)m, loss, gpos, glse, nsum, lse_l /* per-CTA loss sums */, ps, sm);
+    if (rc || !dp1) return rc;
+    InfoNceProblem pk{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
+    pk.wait_flags = (const unsigned*)flags_mine; pk.wait_world = world; pk.wait_channel = 1; pk.wait_epoch = epoch;
+    pk.acol_direct = (const float*)stats_mine;                 // planes written by the owners: a_j | g_pos_j
+    const float* gpos_cols = (const float*)stats_mine + (size_t)2 * n_global;
+    const int np = infonce_tc_bwd(pk, gpos, glse, nsum, gpos_cols, gpos_cols, gpos_cols, base + h.ws_b, h.ws_b_bytes, sm);
+    if (np < 0) return np;
+    return sm3_l2norm_bwd((const float*)(base + h.ws_b), np, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, dp1, n,
+                          dp2, n, D, io_dtype, sm);
+  }
   rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, sm);
   if (rc) return rc;
   if (!overlap) {

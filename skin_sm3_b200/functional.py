@@ -370,6 +370,10 @@ class _FusedInfoNCE(torch.autograd.Function):
         ov_env = os.environ.get("SM3_PEER_OVERLAP")
         overlap = (pbuf is not None and n_local % 128 == 0 and algo == ALGO_TC and
                    ov_env == "1")
+        # SM3_PEER_FUSED=1: the producers scatter + signal themselves and K2 / K3 wait inside the kernel (5 launches
+        # per step instead of 13; sm3_infonce_step_peer mode 2).  Opt-in until it has been measured at 8 ranks.
+        fused = (pbuf is not None and n_local % 128 == 0 and algo == ALGO_TC and
+                 os.environ.get("SM3_PEER_FUSED") == "1")
         if pbuf is not None and algo == ALGO_TC and _PROFILE is None and pbuf.multicast is False:
             # ---- the whole multi-rank step enqueued by one C call (exchange overlapped or back to back) ----
             p1c, p2c = _contig(p1), _contig(p2)
@@ -385,12 +389,12 @@ class _FusedInfoNCE(torch.autograd.Function):
                 check(lib().sm3_infonce_step_peer(ptr(p1c), ptr(p2c), n_local, rank, w, d, dtype_code(p1c), temperature,
                                                   weight, ptr(loss), ptr(dp1), ptr(dp2), ptr(pbuf.z[slot]),
                                                   pbuf.zp[slot], ptr(pbuf.st[slot]), pbuf.stp[slot], ptr(pbuf.flags),
-                                                  pbuf.fp, pbuf.step & 0x7FFFFFFF, int(overlap), ptr(scratch),
+                                                  pbuf.fp, pbuf.step & 0x7FFFFFFF, 2 if fused else int(overlap), ptr(scratch),
                                                   scratch.numel(), main.cuda_stream, pbuf.side.cuda_stream),
                       "sm3_infonce_step_peer")
             if need_grad:
                 ctx.save_for_backward(dp1, dp2)
-            ctx.comm_used = "peer-overlap" if overlap else "peer"
+            ctx.comm_used = "peer-fused" if fused else ("peer-overlap" if overlap else "peer")
             return loss
         if overlap:
             # ---- exchange on a side stream, local column block on the main stream, then the remote blocks ----

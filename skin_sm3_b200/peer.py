@@ -64,7 +64,8 @@ class PeerBuffers:
         self.multicast = want_mc and all(self.zmc) and all(self.stmc)
         # split barrier (signal / wait) on a zero-initialised symmetric flag buffer + a side stream for the exchange
         try:
-            self.flags = symm.empty((64,), dtype=torch.int32, device=device)
+            # 64 flag slots (channel * 16 + source rank) + local ticket words of the fused exchange kernels
+            self.flags = symm.empty((128,), dtype=torch.int32, device=device)
             self.flags.zero_()
             self.fh = symm.rendezvous(self.flags, self.group)
             self.fp = (C.c_void_p * self.world)(*self.fh.buffer_ptrs)

@@ -130,7 +130,33 @@ def main():
                 lim = 1e-2 if it3 % 2 == 0 else 0.0
                 assert e4 <= lim and e5 <= lim, ("peer path != nccl path", it3, e4, e5)
             F3._PROFILE = None
+            os.environ["SM3_PEER_OVERLAP"] = "0"
         results[f"{n_global}x{d}"] = (loss_global, ref_loss, float(e1), float(e2))
+    if backend == "nccl":
+        # Fused exchange (SM3_PEER_FUSED=1: scatter + signal inside the producers, waits inside K2 / K3) against the
+        # NCCL path on FRESH inputs every step, so a read of a stale slot or of rows that have not landed yet shows up
+        # as a mismatch; several column splits and many tiles per rank.
+        for n_local, d, T in ((1024, 256, 0.1), (384, 128, 0.2)):
+            for step in range(6):
+                g = torch.Generator().manual_seed(99 + step + 1000 * rank)
+                p1 = torch.randn(n_local, d, generator=g).bfloat16()
+                p2 = (p1.float() + 0.5 * torch.randn(n_local, d, generator=g)).bfloat16()
+                outs = []
+                for fused in ("0", "1"):
+                    os.environ["SM3_PEER_FUSED"] = fused
+                    a4 = p1.to(dev).requires_grad_(True)
+                    b4 = p2.to(dev).requires_grad_(True)
+                    l4 = sm3.fused_infonce(a4, b4, T, precision="bf16", group=dist.group.WORLD,
+                                           comm="peer" if fused == "1" else "nccl")
+                    l4.backward()
+                    outs.append((l4.item(), a4.grad.double(), b4.grad.double()))
+                os.environ["SM3_PEER_FUSED"] = "0"
+                (l_n, ga_n, gb_n), (l_f, ga_f, gb_f) = outs
+                assert abs(l_f - l_n) <= 2e-6 * abs(l_n), ("fused loss", step, l_f, l_n)
+                ea = (ga_f - ga_n).abs().max().item() / ga_n.abs().max().item()
+                eb = (gb_f - gb_n).abs().max().item() / gb_n.abs().max().item()
+                assert ea <= 1e-2 and eb <= 1e-2, ("fused grads", n_local, step, ea, eb)
+        results["fused"] = "ok"
     if rank == 0 and out_path:
         with open(out_path, "w") as f:
             f.write(repr(results))

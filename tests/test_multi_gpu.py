@@ -20,4 +20,5 @@ def test_sharded_infonce_nccl(tmp_path):
            str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert len(eval(out.read_text())) == 2
+    res = eval(out.read_text())
+    assert len(res) == 3 and res["fused"] == "ok"
