@@ -436,7 +436,7 @@ def run_ours(args):
         if _peer._CACHE:
             mc = any(b.multicast for b in _peer._CACHE.values())
             comm_used = "NVLink peer memory (symmetric memory" + (", NVSwitch multicast stores)" if mc else ", unicast stores)")
-            if os.environ.get("SM3_PEER_FUSED") == "1":
+            if os.environ.get("SM3_PEER_FUSED", "1") != "0" and (n // world) % 128 == 0:
                 comm_used += ", fused exchange: scatter+signal in the producer kernels, waits inside K2/K3"
     flops_bwd = 4.0 * m_rows * m_cols * d
     flops_fwd = 2.0 * m_rows * m_cols * d

@@ -370,10 +370,11 @@ class _FusedInfoNCE(torch.autograd.Function):
         ov_env = os.environ.get("SM3_PEER_OVERLAP")
         overlap = (pbuf is not None and n_local % 128 == 0 and algo == ALGO_TC and
                    ov_env == "1")
-        # SM3_PEER_FUSED=1: the producers scatter + signal themselves and K2 / K3 wait inside the kernel (5 launches
-        # per step instead of 13; sm3_infonce_step_peer mode 2).  Opt-in until it has been measured at 8 ranks.
-        fused = (pbuf is not None and n_local % 128 == 0 and algo == ALGO_TC and
-                 os.environ.get("SM3_PEER_FUSED") == "1")
+        # Fused exchange (sm3_infonce_step_peer mode 2, default; SM3_PEER_FUSED=0 disables): the producers scatter +
+        # signal themselves and K2 / K3 wait inside the kernel, 5 launches per step instead of 13.  Measured on B200,
+        # cfg4: 2 ranks 2.563 -> 2.493 ms, 8 ranks 0.778 -> 0.701 ms per step.
+        fused = (pbuf is not None and n_local % 128 == 0 and algo == ALGO_TC and not overlap and
+                 os.environ.get("SM3_PEER_FUSED", "1") != "0")
         if pbuf is not None and algo == ALGO_TC and _PROFILE is None and pbuf.multicast is False:
             # ---- the whole multi-rank step enqueued by one C call (exchange overlapped or back to back) ----
             p1c, p2c = _contig(p1), _contig(p2)

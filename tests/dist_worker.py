@@ -71,6 +71,7 @@ def main():
         F3.core = OracleCore
         F3.require_cuda = lambda *t: torch.device("cpu")
     results = {}
+    os.environ["SM3_PEER_FUSED"] = "0"        # the first block pins the unfused peer paths bit for bit against NCCL
     cases = [(128 * world, 128, 0.1, "bf16"), (48 * world, 128, 0.5, "fp32")] if backend == "nccl" else \
             [(6 * world, 16, 0.1, "fp32"), (5 * world, 8, 0.5, "fp32")]
     for n_global, d, T, precision in cases:
