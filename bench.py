@@ -494,9 +494,119 @@ def run_ours(args):
             except Exception as e:
                 line["cfg2"]["gpu_reference_port"] = {"error": repr(e)[:200]}
         try:
+            line["cfg4_sweep"] = cfg4_sweep(sm3, args.steps, flush)
+        except Exception as e:
+            line["cfg4_sweep"] = {"error": repr(e)[:300]}
+        try:
             line["heads"] = heads_probe(sm3, pk)
         except Exception as e:   # the head probe must never take the headline down
             line["heads"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cfg4_sweep(sm3, steps, flush, d=256, T=0.1):
+    """SURVEY 8d config 4 on one GPU: N in {8192, 16384, 32768}, D = 256, a single term and the four style-0 terms
+    (derm + clinic + 0.5 cross + 0.5 cross) enqueued by one grouped call.  Device-timed, inputs resident."""
+    out = []
+    for n in (8192, 16384, 32768):
+        g = torch.Generator().manual_seed(SEED + n)
+        pairs = [(torch.randn(n, d, generator=g).bfloat16().cuda().requires_grad_(True),
+                  torch.randn(n, d, generator=g).bfloat16().cuda().requires_grad_(True)) for _ in range(4)]
+        row = {"global_pairs": n, "dim": d}
+        for name, fn, terms in (("one_term", lambda: sm3.fused_infonce(pairs[0][0], pairs[0][1], T, precision="bf16"), 1),
+                                ("four_terms", lambda: sm3.fused_infonce_multi(pairs, T, [1, 1, 0.5, 0.5], precision="bf16"), 4)):
+            for _ in range(2):
+                fn().backward()
+            ms = []
+            for _ in range(max(3, min(steps, 8))):
+                for a, b in pairs:
+                    a.grad = b.grad = None
+                flush.add_(1.0)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn().backward()
+                e1.record()
+                ms.append((e0, e1))
+            torch.cuda.synchronize()
+            t = sum(a.elapsed_time(b) for a, b in ms) / len(ms)
+            flops = terms * 6.0 * (2 * n) ** 2 * d
+            row[name] = {"ms_per_step": round(t, 4), "pairs_per_s": round(n / (t * 1e-3), 1),
+                         "tc_frac_of_burst_peak": round(flops / (t * 1e-3) / 1e12 / peaks()["tflops"], 3)}
+        out.append(row)
+        del pairs
+    return out
+
+
+def run_cfg3(args):
+    """the pretraining step of tools/backbone_train.py:95-130 (style 0) on synthetic 224 x 224 pairs,
+    256 pairs per GPU, dual ResNet-50 branches (stock torchvision / cuDNN, out of scope) + the drop-in SimCLRSkinV32 whose
+    four loss terms run on the fused kernels; with N > 1 ranks: SyncBatchNorm + DDP as the script does
+    (backbone_train.py:510,522) and global negatives.  Timed twice: fused loss path, and the reference's materialising
+    op sequence (oracle/ref_port.py on the GPU) in the same model -- the loss is a small share of this step."""
+    import torch.nn as nn
+    world, rank, local = dist_setup(args.gpus)
+    from skin_sm3_b200 import dropin, functional as F3
+    dropin.install()
+    from src.models.simclr import SimCLRSkinV32
+    n_local, T, d = 256, 0.1, 128
+    torch.manual_seed(SEED)
+    model = SimCLRSkinV32("resnet50", weights=None, proj_dim=d, temperature=T).cuda().to(memory_format=torch.channels_last)
+    if world > 1:
+        os.environ["SM3_GLOBAL_NEGATIVES"] = "1"
+        model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        model = nn.parallel.DistributedDataParallel(model, device_ids=[local])
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-6)
+    crit = nn.CrossEntropyLoss().cuda()
+    g = torch.Generator().manual_seed(SEED + rank)
+    imgs = [torch.randn(n_local, 3, 224, 224, generator=g).cuda().to(memory_format=torch.channels_last) for _ in range(4)]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = model([imgs[0], imgs[1]], [imgs[2], imgs[3]], 0)
+            loss = crit(*outs[0]) + crit(*outs[1]) + 0.5 * crit(*outs[2][0]) + 0.5 * crit(*outs[2][1])
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(k):
+        for _ in range(2):
+            step()
+        barrier(world)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            loss = step()
+        e1.record(); e1.synchronize()
+        barrier(world)
+        return max_over_ranks(e0.elapsed_time(e1), world) / k, float(loss)
+
+    k = max(2, min(args.steps, 6))
+    with ClockSampler(local) as clk:
+        ms_fused, loss_fused = timed(k)
+    line = {"metric": "contrastive pairs/sec (fwd+bwd)", "value": n_local * world / (ms_fused * 1e-3), "unit": "pairs/s",
+            "n_gpus": world, "steps": k, "warmup": 2, "ms_per_step": ms_fused, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 autocast", "data": "synthetic",
+            "config": {"workload": "cfg3: SM3 pretraining step, dual ResNet-50 branches, 224x224, 256 pairs/GPU, style 0 "
+                                   "(4 InfoNCE terms), SGD step included", "pairs_per_gpu": n_local, "dim": d,
+                       "temperature": T, "backbone": "torchvision resnet50 (stock cuDNN, out of scope)"},
+            "loss": loss_fused, "clocks": clk.summary()}
+    if world == 1 and not args.no_extras:
+        from oracle import ref_port                      # context only: the reference's op sequence in the same model
+        orig = F3.cal_logits
+        F3.cal_logits = lambda p1, p2, temperature, precision="auto", group=None: ref_port.port_cal_logits(p1.float(), p2.float(), temperature)
+        try:
+            ms_ref, loss_ref = timed(k)
+        finally:
+            F3.cal_logits = orig
+        line["reference_loss_path_same_model"] = {"ms_per_step": ms_ref, "loss": loss_ref,
+                                                  "loss_path_saving_ms": ms_ref - ms_fused,
+                                                  "what": "identical step with the reference's materialising _cal_logits op "
+                                                          "sequence (port, fp32) in place of the fused kernels"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -511,7 +621,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS["cfg4" if args.workload == "cfg3" else args.workload]
     n, d, T = wl["n"], wl["d"], wl["T"]
     reps = max(1, args.steps)
     r = cpu_reference(n, d, T, budget_s=60.0, max_reps=min(reps, 8))
@@ -534,12 +644,14 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg3"], default="cfg4")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / cfg2 / heads (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg3":
+        run_cfg3(args)
     else:
         run_ours(args)
 

@@ -229,6 +229,17 @@ int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_
                      float* loss, void* dp1, void* dp2, void* device_scratch, size_t scratch_bytes, int algo,
                      void* stream);
 
+/* Grouped form: `num_terms` independent terms of ONE shape enqueued by one call -- the derm / clinic / cross / cross
+ * terms of SimCLRSkinV3 style 0 (tools/backbone_train.py:101-121: loss = derm + clinic + 0.5*cross1 + 0.5*cross2).
+ * p1/p2/dp1/dp2 are HOST arrays of `num_terms` device pointers (dp arrays may both be NULL: forward only),
+ * weights_host a HOST array (NULL = all 1); loss = sum_t weights[t] * mean-CE_t in one device scalar.  The terms run
+ * back to back on `stream` and share one step's scratch (size from sm3_infonce_step_multi_scratch_bytes).           */
+size_t sm3_infonce_step_multi_scratch_bytes(int n_pairs, int D, int io_dtype, int algo);
+int sm3_infonce_step_multi(int num_terms, const void* const* p1_host_array, const void* const* p2_host_array, int n_pairs,
+                           int D, int io_dtype, float temperature, const float* weights_host, float* loss,
+                           void* const* dp1_host_array, void* const* dp2_host_array, void* device_scratch,
+                           size_t scratch_bytes, int algo, void* stream);
+
 /* Multi-rank form: this rank's 2*n_local rows against all world*n_local pairs, negatives exchanged over NVLink peer
  * memory, the whole step enqueued by ONE call on two streams (exchange on stream_side, kernels on stream_main; the
  * local column block runs while the exchange is in flight).  z_cols_mine / stats_mine / flags_mine are this rank's

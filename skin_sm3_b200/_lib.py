@@ -61,6 +61,9 @@ SIGNATURES = {
     "sm3_host_pipe_destroy": (_i, [_vp]),
     "sm3_infonce_step_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "sm3_infonce_step": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "sm3_infonce_step_multi_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "sm3_infonce_step_multi": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _f, C.POINTER(_f), _vp,
+                                    C.POINTER(_vp), C.POINTER(_vp), _vp, _sz, _i, _vp]),
     "sm3_infonce_step_peer_scratch_bytes": (_sz, [_i, _i, _i]),
     "sm3_infonce_step_peer": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp,
                                    C.POINTER(_vp), _vp, C.POINTER(_vp), C.c_uint, _i, _vp, _sz, _vp, _vp]),

@@ -228,9 +228,9 @@ extern "C" size_t sm3_infonce_step_scratch_bytes(int n_pairs, int D, int io_dtyp
   return plan_host(n_pairs, D, io_dtype, algo).total;
 }
 
-extern "C" int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_dtype, float temperature,
-                                float weight, float* loss, void* dp1, void* dp2, void* device_scratch,
-                                size_t scratch_bytes, int algo, void* stream) {
+static int step_impl(const void* p1, const void* p2, int n_pairs, int D, int io_dtype, float temperature, float weight,
+                     float* loss, int accumulate, void* dp1, void* dp2, void* device_scratch, size_t scratch_bytes,
+                     int algo, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SM3_REQUIRE(p1 && p2 && loss && device_scratch, SM3_ERR_SHAPE, "infonce_step: null pointer");
   SM3_REQUIRE((dp1 == nullptr) == (dp2 == nullptr), SM3_ERR_SHAPE, "infonce_step: dp1/dp2 must both be given or both NULL");
@@ -247,7 +247,7 @@ extern "C" int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int
   rc = sm3_infonce_fwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T, (float*)(base + h.pos),
                        (float*)(base + h.lse), (float*)(base + h.nsum), base + h.ws, h.ws_bytes, h.algo, st);
   if (rc) return rc;
-  rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, weight / (float)m, loss, 0,
+  rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, weight / (float)m, loss, accumulate,
                         dp1 ? (float*)(base + h.gpos) : nullptr, dp1 ? (float*)(base + h.glse) : nullptr, st);
   if (rc || !dp1) return rc;
   const int np = sm3_infonce_bwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T,
@@ -257,6 +257,47 @@ extern "C" int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int
   if (np < 0) return np;
   return sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
                         dp1, n, dp2, n, D, io_dtype, st);
+}
+
+extern "C" int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_dtype, float temperature,
+                                float weight, float* loss, void* dp1, void* dp2, void* device_scratch,
+                                size_t scratch_bytes, int algo, void* stream) {
+  return step_impl(p1, p2, n_pairs, D, io_dtype, temperature, weight, loss, 0, dp1, dp2, device_scratch, scratch_bytes,
+                   algo, stream);
+}
+
+// Grouped form: `num_terms` independent InfoNCE terms of one shape (the derm / clinic / cross / cross terms of
+// SimCLRSkinV3 style 0, tools/backbone_train.py:101-121) enqueued by ONE call; loss = sum_t weights[t] * CE_t in one
+// device scalar.  The terms run back to back on `stream` and share the scratch of a single step.
+extern "C" int sm3_infonce_step_multi(int num_terms, const void* const* p1_host_array, const void* const* p2_host_array,
+                                      int n_pairs, int D, int io_dtype, float temperature, const float* weights_host,
+                                      float* loss, void* const* dp1_host_array, void* const* dp2_host_array,
+                                      void* device_scratch, size_t scratch_bytes, int algo, void* stream) {
+  SM3_REQUIRE(num_terms >= 1 && num_terms <= 64, SM3_ERR_SHAPE, "infonce_step_multi: num_terms=%d not in [1,64]", num_terms);
+  SM3_REQUIRE(p1_host_array && p2_host_array && loss && device_scratch, SM3_ERR_SHAPE, "infonce_step_multi: null pointer");
+  SM3_REQUIRE((dp1_host_array == nullptr) == (dp2_host_array == nullptr), SM3_ERR_SHAPE,
+              "infonce_step_multi: dp1/dp2 arrays must both be given or both NULL");
+  SM3_REQUIRE(n_pairs >= 1 && D >= 1 && dtype_ok(io_dtype) && temperature > 0.f, SM3_ERR_SHAPE,
+              "infonce_step_multi: bad shape/dtype/temperature");
+  const size_t need = plan_host(n_pairs, D, io_dtype, algo).total;
+  SM3_REQUIRE(scratch_bytes >= need, SM3_ERR_WORKSPACE, "infonce_step_multi: scratch %zu < %zu", scratch_bytes, need);
+  for (int t = 0; t < num_terms; ++t) {
+    SM3_REQUIRE(p1_host_array[t] && p2_host_array[t], SM3_ERR_SHAPE, "infonce_step_multi: term %d has a null input", t);
+    void* d1 = dp1_host_array ? dp1_host_array[t] : nullptr;
+    void* d2 = dp2_host_array ? dp2_host_array[t] : nullptr;
+    SM3_REQUIRE((d1 == nullptr) == (d2 == nullptr), SM3_ERR_SHAPE, "infonce_step_multi: term %d: dp1/dp2 mismatch", t);
+    const float w = weights_host ? weights_host[t] : 1.0f;
+    // the loss kernel of term t > 0 adds into the scalar written by term 0 (same stream => ordered)
+    const int rc = step_impl(p1_host_array[t], p2_host_array[t], n_pairs, D, io_dtype, temperature, w, loss, t > 0, d1, d2,
+                             device_scratch, scratch_bytes, algo, stream);
+    if (rc) return rc;
+  }
+  return SM3_OK;
+}
+
+extern "C" size_t sm3_infonce_step_multi_scratch_bytes(int n_pairs, int D, int io_dtype, int algo) {
+  if (n_pairs < 1 || D < 1 || !dtype_ok(io_dtype)) return 0;
+  return plan_host(n_pairs, D, io_dtype, algo).total;
 }
 
 // ---------------------------------------------------------------------------------------------------

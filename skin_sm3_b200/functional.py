@@ -496,6 +496,62 @@ def fused_infonce(p1: torch.Tensor, p2: torch.Tensor, temperature: float, precis
     return _FusedInfoNCE.apply(p1, p2, float(temperature), z_dtype, algo, group, float(weight), comm)
 
 
+class _FusedInfoNCEMulti(torch.autograd.Function):
+    """Several same-shape terms through sm3_infonce_step_multi: one C call, one device scalar."""
+
+    @staticmethod
+    def forward(ctx, temperature, algo, weights, *ps):
+        import ctypes as C
+        t = len(ps) // 2
+        p1s = [_contig(p) for p in ps[:t]]
+        p2s = [_contig(p) for p in ps[t:]]
+        dev = require_cuda(*p1s, *p2s)
+        n, d = p1s[0].shape
+        io = dtype_code(p1s[0])
+        need_grad = any(ctx.needs_input_grad[3:])
+        with torch.cuda.device(dev):
+            nbytes = lib().sm3_infonce_step_multi_scratch_bytes(n, d, io, algo)
+            scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            d1 = [torch.empty_like(p) for p in p1s] if need_grad else None
+            d2 = [torch.empty_like(p) for p in p2s] if need_grad else None
+            arr = lambda ts: (C.c_void_p * t)(*[x.data_ptr() for x in ts])       # noqa: E731
+            check(lib().sm3_infonce_step_multi(t, arr(p1s), arr(p2s), n, d, io, temperature, (C.c_float * t)(*weights),
+                                               ptr(loss), arr(d1) if need_grad else None, arr(d2) if need_grad else None,
+                                               ptr(scratch), scratch.numel(), algo, stream_ptr()),
+                  "sm3_infonce_step_multi")
+        if need_grad:
+            ctx.save_for_backward(*d1, *d2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None, None) + tuple(dp * g.to(dp.dtype) for dp in ctx.saved_tensors)
+
+
+def fused_infonce_multi(pairs, temperature: float, weights: Optional[Sequence[float]] = None,
+                        precision: str = "auto") -> torch.Tensor:
+    """``sum_t weights[t] * CrossEntropy(_cal_logits(p1_t, p2_t, T))`` for several same-shape terms in one call -- the
+    derm / clinic / cross / cross terms of SimCLRSkinV3 style 0 (``loss = derm + clinic + 0.5*cross1 + 0.5*cross2``,
+    tools/backbone_train.py:101-121).  ``pairs``: sequence of ``(p1, p2)`` projector outputs ``[N, D]``.  Single
+    process (each rank its own negatives); the sharded form is ``fused_infonce(group=...)`` per term."""
+    pairs = list(pairs)
+    if not pairs:
+        raise ValueError("fused_infonce_multi needs at least one (p1, p2) pair")
+    shape, dtype = pairs[0][0].shape, pairs[0][0].dtype
+    for p1, p2 in pairs:
+        if p1.dim() != 2 or p1.shape != shape or p2.shape != shape or p1.dtype != dtype or p2.dtype != dtype:
+            raise ValueError("fused_infonce_multi expects [N, D] tensors of one shape and dtype")
+    if temperature <= 0:
+        raise ValueError("temperature must be > 0")
+    require_cuda(*[p for pr in pairs for p in pr])
+    _, algo = pick_precision(pairs[0][0], precision)
+    w = [1.0] * len(pairs) if weights is None else [float(x) for x in weights]
+    if len(w) != len(pairs):
+        raise ValueError("one weight per term")
+    return _FusedInfoNCEMulti.apply(float(temperature), algo, tuple(w), *[p[0] for p in pairs], *[p[1] for p in pairs])
+
+
 # ------------------------------------------------------------------------------------------------------
 # heads
 # ------------------------------------------------------------------------------------------------------

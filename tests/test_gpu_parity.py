@@ -230,6 +230,34 @@ def test_fused_step_entry_matches_composed_path(sm3):
         assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
 
 
+def test_grouped_terms_match_separate_calls(sm3):
+    """sm3_infonce_step_multi: the four style-0 terms (derm + clinic + 0.5 cross1 + 0.5 cross2) in one call ==
+    four fused_infonce calls: gradients bit for bit, loss to fp32 summation order; and against the oracle."""
+    n, d, T = 200, 128, 0.1
+    gen = torch.Generator().manual_seed(5)
+    w = [1.0, 1.0, 0.5, 0.5]
+    for dt, prec, tl, tg in ((torch.bfloat16, "bf16", 2e-2, 2e-2), (torch.float32, "fp32", 1e-5, 1e-4)):
+        base = [(torch.randn(n, d, generator=gen).to(dt), torch.randn(n, d, generator=gen).to(dt)) for _ in range(4)]
+        ps = [(a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)) for a, b in base]
+        loss = sm3.fused_infonce_multi(ps, T, w, precision=prec)
+        (loss * 3.0).backward()
+        qs = [(a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)) for a, b in base]
+        sep = sum(wi * sm3.fused_infonce(a, b, T, precision=prec) for wi, (a, b) in zip(w, qs))
+        (sep * 3.0).backward()
+        assert abs(loss.item() - sep.item()) <= 1e-6 * abs(sep.item())
+        ref_total = 0.0
+        for wi, (a, b), (qa, qb), (ha, hb) in zip(w, ps, qs, base):
+            assert torch.equal(a.grad, qa.grad) and torch.equal(b.grad, qb.grad)
+            rl, r1, r2 = O.infonce_closed_form(ha.float().numpy(), hb.float().numpy(), T)
+            ref_total += wi * rl
+            assert relerr(a.grad.float().cpu().numpy() / (3.0 * wi), r1) < tg
+        assert abs(loss.item() - ref_total) <= tl * abs(ref_total)
+    with pytest.raises(ValueError):
+        sm3.fused_infonce_multi([], T)
+    with pytest.raises(ValueError):
+        sm3.fused_infonce_multi(ps[:2], T, [1.0])
+
+
 def test_host_buffer_entry(sm3):
     g = load("infonce_n64_d128_T01")
     T, n, d = float(g["temperature"]), int(g["n"]), int(g["d"])
