@@ -38,7 +38,9 @@ WORKLOADS = {
 }
 SEED = 3407
 COMM = os.environ.get("SM3_COMM", "auto")     # multi-rank exchange: auto (peer memory if available) | peer | nccl
-KERNELS_PER_STEP = 7   # l2norm_fwd, infonce_fwd, finalize, loss, bwd_prep, infonce_bwd, l2norm_bwd
+# our kernels per step on the production path (one GPU: l2norm_fwd, infonce_fwd, finalize+loss, bwd_prep, infonce_bwd,
+# l2norm_bwd; multi-rank fused exchange: l2norm+scatter, infonce_fwd, loss+stats scatter, infonce_bwd, l2norm_bwd)
+KERNELS_PER_STEP = {True: 6, False: 5}
 
 
 def ncu_traffic():
@@ -454,7 +456,7 @@ def run_ours(args):
                         "sync_value = one synchronous sm3_infonce_host call per step") if world == 1 else
                        ("skin_sm3_b200.fused_infonce(group=WORLD) fed from / drained to pinned host memory on two copy "
                         "streams, 2 slots; sync_value = drained after every step")},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "gpu_launches": KERNELS_PER_STEP[world == 1] * args.steps,
         "stages_ms": {k: round(v, 4) for k, v in stages.items()},
         "clocks": clk.summary(),
     }

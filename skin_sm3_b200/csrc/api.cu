@@ -244,11 +244,30 @@ static int step_impl(const void* p1, const void* p2, int n_pairs, int D, int io_
   const float inv_T = 1.0f / temperature;
   int rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f, st);
   if (rc) return rc;
-  rc = sm3_infonce_fwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T, (float*)(base + h.pos),
-                       (float*)(base + h.lse), (float*)(base + h.nsum), base + h.ws, h.ws_bytes, h.algo, st);
-  if (rc) return rc;
-  rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, weight / (float)m, loss, accumulate,
-                        dp1 ? (float*)(base + h.gpos) : nullptr, dp1 ? (float*)(base + h.glse) : nullptr, st);
+  if (h.algo == SM3_ALGO_TC) {
+    // K2 leaves its per-split partial row sums in the workspace; ONE multi-CTA kernel folds them and does the CE on
+    // the statistics + its gradient (instead of a finalize launch and a single-CTA reduction over all 2N rows)
+    InfoNceProblem pb{base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T};
+    pb.no_finalize = 1;
+    SM3_REQUIRE(infonce_tc_supported(pb), SM3_ERR_DTYPE, "infonce_step: tcgen05 path unavailable for this shape");
+    const int splits = infonce_tc_fwd(pb, (float*)(base + h.pos), (float*)(base + h.lse), (float*)(base + h.nsum),
+                                      base + h.ws, h.ws_bytes, st);
+    if (splits < 0) return splits;
+    unsigned* ticket = (unsigned*)(base + h.loss + 64);
+    SM3_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    PeerFused none{};
+    none.counter = ticket;
+    rc = loss_stats_scatter_launch((const float*)(base + h.ws), splits, (const float*)(base + h.pos), n_pairs, 0, n_pairs,
+                                   inv_T, weight / (float)m, loss, (float*)(base + h.gpos), (float*)(base + h.glse),
+                                   (float*)(base + h.nsum), (float*)(base + h.lse) /* per-CTA loss sums */, none, st,
+                                   accumulate);
+  } else {
+    rc = sm3_infonce_fwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T, (float*)(base + h.pos),
+                         (float*)(base + h.lse), (float*)(base + h.nsum), base + h.ws, h.ws_bytes, h.algo, st);
+    if (rc) return rc;
+    rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, weight / (float)m, loss, accumulate,
+                          dp1 ? (float*)(base + h.gpos) : nullptr, dp1 ? (float*)(base + h.glse) : nullptr, st);
+  }
   if (rc || !dp1) return rc;
   const int np = sm3_infonce_bwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T,
                                  (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
@@ -495,29 +514,15 @@ extern "C" int sm3_infonce_host(const void* p1_host, const void* p2_host, int n_
   SM3_REQUIRE(scratch_bytes >= h.total, SM3_ERR_WORKSPACE, "infonce_host: scratch %zu < %zu", scratch_bytes, h.total);
   char* base = (char*)device_scratch;
   const size_t in_bytes = (size_t)n_pairs * D * dtype_size(io_dtype);
-  const int64_t n = n_pairs, m = 2 * n;
-  const float inv_T = 1.0f / temperature;
   SM3_CHECK_CUDA(cudaMemcpyAsync(base + h.p1, p1_host, in_bytes, cudaMemcpyHostToDevice, st));
   SM3_CHECK_CUDA(cudaMemcpyAsync(base + h.p2, p2_host, in_bytes, cudaMemcpyHostToDevice, st));
-  int rc = sm3_l2norm_fwd(base + h.p1, n, base + h.p2, n, D, io_dtype, base + h.z, h.z_dtype, (float*)(base + h.inv),
-                          1e-12f, st);
-  if (rc) return rc;
-  rc = sm3_infonce_fwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T, (float*)(base + h.pos),
-                       (float*)(base + h.lse), (float*)(base + h.nsum), base + h.ws, h.ws_bytes, h.algo, st);
-  if (rc) return rc;
-  rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, 1.0f / (float)m, (float*)(base + h.loss), 0,
-                        (float*)(base + h.gpos), (float*)(base + h.glse), st);
+  const bool grads = dp1_host && dp2_host;
+  const int rc = step_impl(base + h.p1, base + h.p2, n_pairs, D, io_dtype, temperature, 1.0f, (float*)(base + h.loss), 0,
+                           grads ? base + h.dp1 : nullptr, grads ? base + h.dp2 : nullptr, device_scratch, scratch_bytes,
+                           algo, stream);
   if (rc) return rc;
   SM3_CHECK_CUDA(cudaMemcpyAsync(loss_host, base + h.loss, 4, cudaMemcpyDeviceToHost, st));
-  if (dp1_host && dp2_host) {
-    const int np = sm3_infonce_bwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T,
-                                   (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
-                                   (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
-                                   base + h.ws, h.ws_bytes, h.algo, st);
-    if (np < 0) return np;
-    rc = sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
-                        base + h.dp1, n, base + h.dp2, n, D, io_dtype, st);
-    if (rc) return rc;
+  if (grads) {
     SM3_CHECK_CUDA(cudaMemcpyAsync(dp1_host, base + h.dp1, in_bytes, cudaMemcpyDeviceToHost, st));
     SM3_CHECK_CUDA(cudaMemcpyAsync(dp2_host, base + h.dp2, in_bytes, cudaMemcpyDeviceToHost, st));
   }

@@ -46,6 +46,14 @@ inline int num_sms() {
   return n;
 }
 
+// resident CTAs per SM of a kernel (occupancy query): the grid of a persistent kernel is num_sms() * this
+template <typename K>
+inline int resident_ctas(K kernel, int threads, size_t dyn_smem = 0) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn_smem) != cudaSuccess || n < 1) n = 2;
+  return n;
+}
+
 // ---- scalar dtype conversion ------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
@@ -198,7 +206,7 @@ int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pai
                           void* z_local, float* inv_norm, float eps, const PeerFused& pf, cudaStream_t st);
 int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
                               int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
-                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st);
+                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate = 0);
 size_t infonce_simt_workspace(const InfoNceProblem& pb, int backward);
 int infonce_simt_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
                      cudaStream_t st);

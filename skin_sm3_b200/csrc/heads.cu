@@ -717,8 +717,10 @@ extern "C" int sm3_multihead_ce(const void* logits, int dtype, const int64_t* la
         multihead_ce_sm3_kernel<T, true><<<grid < cap ? grid : cap, kHeadThreads, smem3, st>>>((const T*)logits, labels, B,
             meta, inv_T, use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
       } else {
-        multihead_ce_sm3_kernel<T, false><<<pgrid, kHeadThreads, CeSlab<T>::bytes(false), st>>>((const T*)logits, labels, B,
-            meta, inv_T, use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
+        static const int per_sm0 = resident_ctas(multihead_ce_sm3_kernel<T, false>, kHeadThreads, CeSlab<T>::bytes(false));
+        const unsigned cap0 = (unsigned)(num_sms() * per_sm0);      // one wave of persistent CTAs
+        multihead_ce_sm3_kernel<T, false><<<grid < cap0 ? grid : cap0, kHeadThreads, CeSlab<T>::bytes(false), st>>>(
+            (const T*)logits, labels, B, meta, inv_T, use_ignore_index, ignore_index, loss, (T*)dlogits, grad_scale, ws);
       }
     } else if (fixed) {
       SM3_CHECK_CUDA(cudaFuncSetAttribute(multihead_ce_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -753,7 +755,7 @@ extern "C" int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_d
   SM3_REQUIRE(dtype_ok(x_dtype) && dtype_ok(t_dtype), SM3_ERR_DTYPE, "bce: bad dtype");
   SM3_REQUIRE(B >= 1 && C >= 1, SM3_ERR_SHAPE, "bce: empty input");
   const int64_t n = B * (int64_t)C;
-  const unsigned grid = bce_grid(n);
+  unsigned grid = bce_grid(n);
   SM3_REQUIRE(workspace_bytes >= (size_t)(kWsPartials + grid) * sizeof(float), SM3_ERR_WORKSPACE, "bce: workspace too small");
   float* ws = (float*)workspace;
   SM3_CHECK_CUDA(cudaMemsetAsync(ws, 0, 16, st));
@@ -766,10 +768,13 @@ extern "C" int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_d
     if (pos_weight != nullptr)
       bce_kernel<TX, TT, true, false><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n,
                                                                     loss, (TX*)dx, grad_scale, ws, vec_ok);
-    else if (prod)
+    else if (prod) {
+      static const int per_sm = resident_ctas(bce_kernel<TX, TT, false, true>, kBceThreads);
+      const unsigned cap = (unsigned)(num_sms() * per_sm);          // one wave of persistent CTAs
+      if (grid > cap) grid = cap;
       bce_kernel<TX, TT, false, true><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n,
                                                                     loss, (TX*)dx, grad_scale, ws, vec_ok);
-    else
+    } else
       bce_kernel<TX, TT, false, false><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n,
                                                                      loss, (TX*)dx, grad_scale, ws, vec_ok);
   }));

@@ -340,13 +340,6 @@ l2norm_bwd_kernel(const float* __restrict__ dz, int n_partials, int64_t partial_
   }
 }
 
-template <typename K>
-int resident_ctas(K kernel, int threads) {
-  int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 2;
-  return n;
-}
-
 // SM3_K1_FWD_VARIANT: 0 = one short-lived CTA per 32 rows, 1 = persistent + register prefetch, 2 = 1 with evict-first
 // hints.  Unset = by shape, from the measurements on B200 at 2M x 256 (tools/hbm_variants.py, fraction of the 6.5 TB/s
 // copy rate): 16-bit rows 0.71 / 0.85 / 0.88 for variants 0 / 1 / 2 (and 20 -> 16 us at the L2-resident 65536 x 256),

@@ -181,12 +181,14 @@ l2norm_scatter_kernel(const TIn* __restrict__ pa, const TIn* __restrict__ pb, in
 //   g_lse_i = scale * sigmoid(lse_i - pos_i) = -g_pos_i ; a_i = g_lse_i / neg_sum_i
 // (g_pos, g_lse, neg_sum) stay local for this rank's rows of K3; (a_i, g_pos_i) go to every rank's column planes
 // stats[0 .. M_g) = a, stats[M_g .. 2 M_g) = g_pos at the global row index.  The loss is folded by the last CTA in a
-// fixed order (deterministic), which then signals.
+// fixed order (deterministic), which then signals.  With pf.data.world == pf.flags.world == 0 nothing is published:
+// that is the single-GPU "finalize + loss" kernel (one multi-CTA launch instead of a finalize launch and a 1-CTA
+// reduction over all rows).
 __global__ void __launch_bounds__(256)
 loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, const float* __restrict__ pos, int n_local,
                           int pair_offset, int n_global, float inv_T, float scale, float* __restrict__ loss,
                           float* __restrict__ g_pos, float* __restrict__ g_lse, float* __restrict__ neg_sum,
-                          float* __restrict__ block_ws, PeerFused pf) {
+                          float* __restrict__ block_ws, PeerFused pf, int accumulate) {
   __shared__ float red[32];
   __shared__ bool is_last;
   const int rows = 2 * n_local;
@@ -229,7 +231,7 @@ loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, con
     float s = 0.f;
     for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += __ldcg(block_ws + b);
     s = block_sum(s, red);
-    if (threadIdx.x == 0) { *loss = s * scale; *pf.counter = 0u; }
+    if (threadIdx.x == 0) { *loss = (accumulate ? *loss : 0.f) + s * scale; *pf.counter = 0u; }
     if (threadIdx.x < pf.flags.world) {
       __threadfence_system();
       unsigned* dst = reinterpret_cast<unsigned*>(pf.flags.p[threadIdx.x]) + pf.channel * 16 + pf.rank;
@@ -255,10 +257,10 @@ int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pai
 
 int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
                               int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
-                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st) {
+                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate) {
   const unsigned grid = (unsigned)((2 * (int64_t)n_local + 255) / 256);
   loss_stats_scatter_kernel<<<grid, 256, 0, st>>>(partial, n_partials, pos, n_local, pair_offset, n_global, inv_T, scale,
-                                                  loss, g_pos, g_lse, neg_sum, block_ws, pf);
+                                                  loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
