@@ -475,7 +475,9 @@ class _FusedInfoNCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         dp1, dp2 = ctx.saved_tensors
-        return dp1 * g.to(dp1.dtype), dp2 * g.to(dp2.dtype), None, None, None, None, None, None
+        # one multi-tensor launch (vectorised) instead of two broadcast multiplies
+        o1, o2 = torch._foreach_mul((dp1, dp2), g.to(dp1.dtype))
+        return o1, o2, None, None, None, None, None, None
 
 
 def fused_infonce(p1: torch.Tensor, p2: torch.Tensor, temperature: float, precision: str = "auto", group=None,
@@ -526,7 +528,7 @@ class _FusedInfoNCEMulti(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return (None, None, None) + tuple(dp * g.to(dp.dtype) for dp in ctx.saved_tensors)
+        return (None, None, None) + tuple(torch._foreach_mul(ctx.saved_tensors, g.to(ctx.saved_tensors[0].dtype)))
 
 
 def fused_infonce_multi(pairs, temperature: float, weights: Optional[Sequence[float]] = None,
