@@ -475,8 +475,12 @@ class _FusedInfoNCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         dp1, dp2 = ctx.saved_tensors
-        # one multi-tensor launch (vectorised) instead of two broadcast multiplies
-        o1, o2 = torch._foreach_mul((dp1, dp2), g.to(dp1.dtype))
+        if dp1.numel() >= (1 << 22):
+            # large gradients: one vectorised multi-tensor launch (cfg4: ~15 us instead of 2 x 20 us of broadcast mul)
+            o1, o2 = torch._foreach_mul((dp1, dp2), g.to(dp1.dtype))
+        else:
+            # small ones: multi_tensor_apply's 64K-element chunks leave most SMs idle (cfg2: 18 us vs 2 x 2.5 us)
+            o1, o2 = dp1 * g.to(dp1.dtype), dp2 * g.to(dp2.dtype)
         return o1, o2, None, None, None, None, None, None
 
 
@@ -528,7 +532,11 @@ class _FusedInfoNCEMulti(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return (None, None, None) + tuple(torch._foreach_mul(ctx.saved_tensors, g.to(ctx.saved_tensors[0].dtype)))
+        dps = ctx.saved_tensors
+        gg = g.to(dps[0].dtype)
+        if dps[0].numel() >= (1 << 22):
+            return (None, None, None) + tuple(torch._foreach_mul(dps, gg))
+        return (None, None, None) + tuple(dp * gg for dp in dps)
 
 
 def fused_infonce_multi(pairs, temperature: float, weights: Optional[Sequence[float]] = None,
