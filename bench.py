@@ -389,6 +389,11 @@ def heads_probe(sm3, pk):
             ms = e0.elapsed_time(e1) / reps
             out[f"{op}_{name}"] = {"us": round(ms * 1e3, 2), "GB/s": round(nbytes / ms / 1e6, 1),
                                    "frac_hbm": round(nbytes / ms / 1e6 / pk["hbm"], 3)}
+    tr = ncu_traffic()
+    for k, v in out.items():                      # DRAM bytes per launch from the committed ncu --set full capture
+        if k in tr:
+            v["algorithmic_bytes"] = tr[k]["algorithmic_bytes"]
+            v["traffic"] = tr[k]["dram_bytes_per_launch"]
     return out
 
 
