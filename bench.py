@@ -214,6 +214,26 @@ def time_device(sm3, p1, p2, T, group, world, steps, warmup, flush, profile=True
     return total_ms, stage_avg, float(loss.item())
 
 
+def time_graph(sm3, p1, p2, T, steps, warmup, flush):
+    """The same single-GPU step replayed from a CUDA graph (skin_sm3_b200.GraphedInfoNCE): no Python / autograd between
+    the kernels.  Device-timed per replay, L2 flushed between replays.  -> ms per step"""
+    gr = sm3.GraphedInfoNCE(p1.shape[0], p1.shape[1], T, dtype=torch.bfloat16, precision="bf16")
+    gr.p1.copy_(p1.cuda()); gr.p2.copy_(p2.cuda())
+    for _ in range(warmup):
+        gr.replay()
+    recs = []
+    for _ in range(steps):
+        if flush is not None:
+            flush.add_(1.0)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gr.replay()
+        e1.record()
+        recs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in recs) / len(recs)
+
+
 def time_e2e(sm3, p1, p2, T, group, world, steps, warmup, depth=2):
     """Same metric end to end: every step copies its inputs from pinned host memory (H2D), runs the fused fwd+bwd and
     copies the loss and both gradients back to pinned host memory (D2H), all inside the timed region.  The steps go
@@ -480,6 +500,13 @@ def run_ours(args):
         line["roofline_fwd"] = {"bound": "tensor", "kernel": "infonce_tc_fwd_kernel (K2; includes the finalize kernel)",
                                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
     line["step_tc_frac"] = (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12 / pk["tflops"]
+    if world == 1:
+        try:
+            gms = time_graph(sm3, p1, p2, T, args.steps, args.warmup, flush)
+            line["cuda_graph"] = {"ms_per_step": gms, "value": n / (gms * 1e-3), "unit": "pairs/s",
+                                  "what": "same step replayed from a CUDA graph (GraphedInfoNCE), device-timed"}
+        except Exception as e:
+            line["cuda_graph"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_extras:
         line["cpu_baseline"] = cpu_reference(n, d, T)
         if args.workload != "cfg2":     # configs[1] rides along in the same line
@@ -488,10 +515,17 @@ def run_ours(args):
             _, st2, _ = time_device(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup, flush)          # per-stage events
             ms2, _, _ = time_device(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup, flush, profile=False)
             e2, e2s, _, _ = time_e2e(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup)
+            try:
+                g2 = time_graph(sm3, q1, q2, w2["T"], args.steps, args.warmup, flush)
+            except Exception as e:
+                g2 = None
+                print(f"[bench] cfg2 graph replay failed: {e!r}", file=sys.stderr)
             f2 = 6.0 * (2 * w2["n"]) ** 2 * w2["d"]
             line["cfg2"] = {"workload": w2["name"], "value": w2["n"] / (ms2 / args.steps * 1e-3), "unit": "pairs/s",
                             "ms_per_step": ms2 / args.steps, "e2e_value": w2["n"] / (e2 / args.steps * 1e-3),
                             "e2e_sync_value": w2["n"] / (e2s / args.steps * 1e-3),
+                            "cuda_graph_value": (w2["n"] / (g2 * 1e-3)) if g2 else None,
+                            "cuda_graph_ms_per_step": g2,
                             "step_tc_frac": f2 / (ms2 / args.steps * 1e-3) / 1e12 / pk["tflops"],
                             "stages_ms": {k: round(v, 4) for k, v in st2.items()},
                             "cpu_baseline": cpu_reference(w2["n"], w2["d"], w2["T"], budget_s=12.0, max_reps=4)}
