@@ -655,13 +655,20 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int DP> struct BwdCfg {
+// NS = S/H stages in TMEM.  2 at D = 256 (all 512 columns in use).  At D <= 128 TMEM has room for 4, which keeps four
+// tiles of the chain  S-MMA -> tcgen05.ld -> exp -> tcgen05.st -> dZ-MMA  in flight.  Measured on B200 at cfg2
+// (4096 x 128): 83.7 -> 81.5 us for the backward stage, i.e. the chain latency is NOT what holds this shape at 0.7 us
+// per 128 x 64 tile (MMA work: 0.27 us); the next suspect is the issue rate of the small N = 64 / K = 16 MMAs.
+template <int DP, int NS> struct BwdCfg {
   static constexpr int BN = 64;
   static constexpr uint32_t PANEL = BN * 128;          // 8 KB: 64 rows x 64 bf16
   static constexpr uint32_t STAGE = DP * PANEL;        // <= 32 KB
-  static constexpr int NSTAGE = 4;
+  static constexpr int NSTAGE = NS + 2;                // smem ring: tiles it .. it+NS are live, one more in flight
   static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 + 256;
-  // TMEM columns: A [0, 32*DP) | S/H stage 0 [128,192) | stage 1 [192,256) | dZ [256, 256 + 64*DP)
+  // TMEM columns: A [0, 32*DP) | S/H stage i [128 + 64 i, 192 + 64 i), i < NS | dZ [128 + 64 NS, 128 + 64 NS + 64*DP)
+  static constexpr uint32_t kColS = 128, kColDZ = 128 + 64 * NS;
+  static_assert(kColDZ + 64 * DP <= 512, "TMEM budget");
+  static_assert(8 * (2 * NSTAGE + 2 * NS + 3) <= 256, "barrier block");
 };
 
 __global__ void tc_bwd_prep_kernel(const float* __restrict__ glse, const float* __restrict__ nsum, int stride,
@@ -676,10 +683,11 @@ __global__ void tc_bwd_prep_kernel(const float* __restrict__ glse, const float* 
 // kWait (fused exchange): the per-column statistics (acol, gpos_c) are written by their owner ranks over NVLink while
 // this kernel is already running; every softmax warp waits for the peers' flags before the first column tile another
 // rank owns and reads the statistics with L2-coherent loads (ld.global.cg) instead of the read-only path.
-template <int DP, int NG, bool kWait>
+template <int DP, int NG, bool kWait, int NS>
 __global__ void __launch_bounds__(64 + 256 * NG, 1)
 infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
-  using C = BwdCfg<DP>;
+  using C = BwdCfg<DP, NS>;
+  static_assert(NS % NG == 0, "each softmax group must keep its own S/H stages");
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
   constexpr int D = 64 * DP;
   extern __shared__ uint8_t smem_raw[];
@@ -691,10 +699,10 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   auto bar_full = [&](int i) { return bars + 8u * i; };
   auto bar_empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
   auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
-  auto bar_hfull = [&](int i) { return bars + 8u * (2 * NSTAGE + 2 + i); };
-  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 4);
-  const uint32_t bar_dzfull = bars + 8u * (2 * NSTAGE + 5);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 6));
+  auto bar_hfull = [&](int i) { return bars + 8u * (2 * NSTAGE + NS + i); };
+  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 2 * NS);
+  const uint32_t bar_dzfull = bars + 8u * (2 * NSTAGE + 2 * NS + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 2 * NS + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * kBM;
@@ -716,7 +724,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_hfull(i), 8); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_hfull(i), 8); }
     mbar_init(bar_aready, 8 * NG);
     mbar_init(bar_dzfull, 1);
     fence_barrier_init();
@@ -729,7 +737,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t kColS = 128, kColDZ = 256;
+  constexpr uint32_t kColS = C::kColS, kColDZ = C::kColDZ;
 
   if (warp == 0) {
     // =========================== TMA producer (warp-uniform loop, one elected lane issues) ===========
@@ -753,7 +761,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     constexpr uint32_t idesc_z = make_idesc_bf16(128, D, 0, 1);      // dZ += H  * Zc     (B MN-major)
     constexpr uint32_t dhi = smem_desc_hi(1024);
     auto issue_s = [&](int it) {
-      const int s = it % NSTAGE, as = it & 1;
+      const int s = it % NSTAGE, as = it % NS;
       mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem + kColS + (uint32_t)as * 64u;
@@ -769,11 +777,12 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     };
     mbar_wait(bar_aready, 0);
     tc_fence_after();
-    if (n_tiles > 0) issue_s(0);
-    if (n_tiles > 1) issue_s(1);
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+      if (i < n_tiles) issue_s(i);
     for (int it = 0; it < n_tiles; ++it) {
-      const int s = it % NSTAGE, as = it & 1;
-      mbar_wait(bar_hfull(as), (uint32_t)(it >> 1) & 1u);
+      const int s = it % NSTAGE, as = it % NS;
+      mbar_wait(bar_hfull(as), (uint32_t)(it / NS) & 1u);
       tc_fence_after();
       SM3_TR(0, it);
       const uint32_t h_tmem = tmem + kColS + (uint32_t)as * 64u;
@@ -789,7 +798,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       }
       __syncwarp();
       SM3_TR(1, it);
-      if (it + 2 < n_tiles) issue_s(it + 2);   // in-order tensor pipe: overwrites S/H stage `as` only after dZ(it)
+      if (it + NS < n_tiles) issue_s(it + NS);   // in-order tensor pipe: overwrites S/H stage `as` only after dZ(it)
       SM3_TR(2, it);
     }
     if (elect_one()) umma_commit(bar_dzfull);
@@ -840,7 +849,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
 
     bool remote_ready = !kWait;
     for (int it = grp; it < n_tiles; it += NG) {
-      const int as = it & 1;
+      const int as = it % NS;
       const int tile = tile_of(it);
       if constexpr (kWait) {
         if (!remote_ready && !tile_is_local(p, tile)) {   // the owners' statistics must have landed
@@ -849,7 +858,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
           remote_ready = true;
         }
       }
-      mbar_wait(bar_sfull(as), (uint32_t)(it >> 1) & 1u);
+      mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u);
       tc_fence_after();
       if (warp == 2 && lane == 0) SM3_TR(3, it);
       const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)as * 64u + (uint32_t)half * 32u;
@@ -1055,18 +1064,33 @@ int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cud
     default: return launch_fwd_ng<DP, 1, 2>(tmap, p, pl, st);
   }
 }
-template <int DP, int NG, bool kWait>
+template <int DP, int NG, bool kWait, int NS>
 int launch_bwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP, NG, kWait>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BwdCfg<DP>::SMEM));
-  infonce_tc_bwd_kernel<DP, NG, kWait><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, BwdCfg<DP>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP, NG, kWait, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BwdCfg<DP, NS>::SMEM));
+  infonce_tc_bwd_kernel<DP, NG, kWait, NS><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, BwdCfg<DP, NS>::SMEM, st>>>(tmap, p);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
+// S/H stages of the backward: 4 for D <= 128 (latency-bound chain, TMEM has room), 2 otherwise; SM3_TC_BWD_NS=2 forces 2.
+int tc_bwd_stages(int dp) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("SM3_TC_BWD_NS");
+    forced = (e && e[0] == '2') ? 2 : 0;
+  }
+  if (forced == 2 || dp > 2) return 2;
+  return 4;
+}
 template <int DP>
 int launch_bwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  if (p.wait_flags != nullptr) return launch_bwd_ng<DP, 1, true>(tmap, p, pl, st);
-  return tc_groups() == 1 ? launch_bwd_ng<DP, 1, false>(tmap, p, pl, st) : launch_bwd_ng<DP, 2, false>(tmap, p, pl, st);
+  // (the in-kernel-wait form of the multi-rank fused exchange stays on 2 stages until it has been run on >= 2 GPUs)
+  if (p.wait_flags != nullptr) return launch_bwd_ng<DP, 1, true, 2>(tmap, p, pl, st);
+  if constexpr (DP <= 2) {
+    if (tc_bwd_stages(DP) == 4)
+      return tc_groups() == 1 ? launch_bwd_ng<DP, 1, false, 4>(tmap, p, pl, st) : launch_bwd_ng<DP, 2, false, 4>(tmap, p, pl, st);
+  }
+  return tc_groups() == 1 ? launch_bwd_ng<DP, 1, false, 2>(tmap, p, pl, st) : launch_bwd_ng<DP, 2, false, 2>(tmap, p, pl, st);
 }
 
 size_t bwd_acol_offset(const InfoNceProblem& pb, const TcPlan& pl) {
