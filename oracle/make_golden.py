@@ -203,6 +203,55 @@ def gen_model():
     print("model goldens written")
 
 
+def gen_kmeans():
+    """tools/mlc_train.py::cluster_memory (the REAL function) on CPU: a 1-process gloo group stands in for the job and
+    Tensor.cuda is made the identity (the function hard-codes .cuda()).  The random initial centroids come from
+    torch.randperm on the default generator (:144), so re-seeding reproduces the indices for the fixture."""
+    import importlib
+    import types
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+        created = True
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        mt = importlib.import_module("tools.mlc_train")
+        args = types.SimpleNamespace(world_size=1, rank=0)
+        out = {}
+        cases = [("a", 413, 64, 5, 0.35), ("b", 640, 256, 3, 0.6), ("c", 96, 16, 2, 0.5), ("d", 24, 8, 6, 0.05)]
+        for tag, n, d, k, noise in cases:
+            g = torch.Generator().manual_seed(SEED + n + d + k)
+            true_c = nn.functional.normalize(torch.randn(k if tag != "d" else 3, d, generator=g), dim=1)
+            lab = torch.randint(0, true_c.shape[0], (n,), generator=g)
+            emb = nn.functional.normalize(true_c[lab] + noise * torch.randn(n, d, generator=g), dim=1)
+            if tag == "d":                      # duplicates of three points -> clusters run empty (the `mask` path :173)
+                emb = nn.functional.normalize(true_c[lab], dim=1)
+            index = torch.randperm(n, generator=g)
+            proto = nn.Linear(d, k, bias=False)
+            torch.manual_seed(SEED + 17 * k)
+            with torch.no_grad():
+                assign = mt.cluster_memory(args, proto, k, index, emb)
+            torch.manual_seed(SEED + 17 * k)
+            init_idx = torch.randperm(n)[:k]
+            out[f"{tag}_emb"] = _np(emb)
+            out[f"{tag}_index"] = _np(index)
+            out[f"{tag}_init_idx"] = _np(init_idx)
+            out[f"{tag}_assign"] = _np(assign)
+            out[f"{tag}_centroids"] = _np(proto.weight)
+            out[f"{tag}_seed"] = np.int64(SEED + 17 * k)
+        out["cases"] = np.array([c[0] for c in cases])
+        np.savez_compressed(os.path.join(OUT, "kmeans.npz"), **out)
+        print("kmeans.npz", {c[0]: np.bincount(out[f"{c[0]}_assign"][out[f"{c[0]}_assign"] >= 0]).tolist() for c in cases})
+    finally:
+        torch.Tensor.cuda = orig_cuda
+        if created:
+            dist.destroy_process_group()
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -215,7 +264,12 @@ def main():
     gen_heads()
     gen_knn()
     gen_model()
+    gen_kmeans()
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "kmeans":      # regenerate one fixture without touching the others
+        os.makedirs(OUT, exist_ok=True)
+        gen_kmeans()
+    else:
+        main()

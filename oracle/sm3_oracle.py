@@ -272,3 +272,36 @@ def knn_predict(query, bank, bank_labels, num_classes: int, k: int, temperature:
     for c in range(num_classes):
         scores[:, c] = (w * (lab == c)).sum(axis=1)
     return np.argsort(-scores, axis=1, kind="stable"), scores
+
+
+# --------------------------------------------------------------------------------------
+# N4: DeepCluster spherical k-means of the memory bank (tools/mlc_train.py:116-189)
+# --------------------------------------------------------------------------------------
+def spherical_kmeans(emb: np.ndarray, init_idx: np.ndarray, n_iters: int = 10, dtype=np.float32):
+    """cluster_memory's rank-0 loop restated: centroids = emb[init_idx] (mlc_train.py:144-145); n_iters times
+    E step = argmax of emb @ centroids.T (:150-152), M step = mean of each non-empty cluster (:157-172) followed by
+    L2 normalisation of ALL centroids (:175); one final E step (:150-155).  Returns (assignments [n], centroids [K, D]).
+    dtype float32 mirrors the reference's arithmetic; argmax ties resolve to the lower centroid index."""
+    emb = np.asarray(emb, dtype)
+    cent = emb[np.asarray(init_idx)].copy()
+    k = cent.shape[0]
+    assign = None
+    for it in range(n_iters + 1):
+        assign = np.argmax(emb @ cent.T, axis=1)
+        if it == n_iters:
+            break
+        for c in range(k):
+            members = emb[assign == c]
+            if len(members) > 0:
+                cent[c] = members.sum(axis=0, dtype=dtype) / dtype(len(members))
+        norm = np.sqrt((cent.astype(np.float64) ** 2).sum(axis=1, keepdims=True)).astype(dtype)
+        cent = cent / np.maximum(norm, dtype(1e-12))
+    return assign.astype(np.int64), cent
+
+
+def cluster_memory(index: np.ndarray, emb: np.ndarray, init_idx: np.ndarray, n_iters: int = 10):
+    """assignments[index[i]] = cluster of emb[i] (mlc_train.py:119-121, 178-182); -100 where no sample points."""
+    a, cent = spherical_kmeans(emb, init_idx, n_iters)
+    out = np.full(len(index), -100, np.int64)
+    out[np.asarray(index)] = a
+    return out, cent

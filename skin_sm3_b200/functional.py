@@ -691,6 +691,73 @@ def knn_predict(query: torch.Tensor, bank: torch.Tensor, bank_labels: torch.Tens
 
 
 # ------------------------------------------------------------------------------------------------------
+# DeepCluster memory-bank clustering (N4)
+# ------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def spherical_kmeans(emb: torch.Tensor, init_idx: torch.Tensor, n_iters: int = 10):
+    """The rank-0 loop of ``cluster_memory`` (reference tools/mlc_train.py:144-176) without leaving the GPU: centroids
+    start at ``emb[init_idx]``; E step = ``sm3_sim_topk`` with k = 1 (argmax of ``emb @ centroids.T``, never
+    materialised, ties to the lower centroid); M step = per-cluster mean as a one-hot GEMM (deterministic, no
+    ``.cpu().numpy()`` / scipy.sparse / Python loop over clusters as at :161-172) for the non-empty clusters, then row
+    L2-normalisation of all centroids (K1).  Returns (assignments int64 [n], centroids fp32 [K, D])."""
+    require_cuda(emb, init_idx)
+    if emb.dim() != 2 or init_idx.dim() != 1:
+        raise ValueError("spherical_kmeans expects emb [n, D] and init_idx [K]")
+    emb = _contig(emb.float())
+    cent = _contig(emb[init_idx.long()].clone())
+    k = cent.shape[0]
+    assign = None
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False          # the cluster sums must be fp32 sums whatever the script set
+    try:
+        for it in range(n_iters + 1):
+            _, idx = sim_topk(emb, cent, 1)
+            assign = idx[:, 0]
+            if it == n_iters:
+                break
+            onehot = torch.nn.functional.one_hot(assign, k).to(emb.dtype)        # [n, K]
+            counts = onehot.sum(0)                                               # exact in fp32 below 2^24 samples
+            sums = onehot.t() @ emb                                              # [K, D]
+            keep = (counts > 0).unsqueeze(1)
+            cent = torch.where(keep, sums / counts.clamp(min=1.0).unsqueeze(1), cent)
+            cent = l2_normalize(_contig(cent))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return assign, cent
+
+
+@torch.no_grad()
+def cluster_memory(args, prototypes, K: int, local_memory_index: torch.Tensor, local_memory_embeddings: torch.Tensor,
+                   nmb_kmeans_iters: int = 10) -> torch.Tensor:
+    """Drop-in for ``cluster_memory`` of tools/mlc_train.py:116-189 (same signature, same return value, same side
+    effect ``prototypes.weight.copy_(centroids)``).  Every rank all-gathers the bank and runs the identical
+    deterministic k-means on its own GPU instead of gathering to rank 0, looping in Python there and broadcasting the
+    result; only the K initial indices -- ``torch.randperm`` on rank 0's default generator, as at :144 -- are broadcast."""
+    dev = require_cuda(local_memory_embeddings)
+    index = local_memory_index.to(dev).long()
+    emb = _contig(local_memory_embeddings)
+    world = int(getattr(args, "world_size", 1))
+    if world > 1:
+        all_emb = torch.empty((world * emb.shape[0], emb.shape[1]), dtype=emb.dtype, device=dev)
+        all_idx = torch.empty(world * index.shape[0], dtype=index.dtype, device=dev)
+        dist.all_gather_into_tensor(all_emb, emb)
+        dist.all_gather_into_tensor(all_idx, _contig(index))
+    else:
+        all_emb, all_idx = emb, index
+    n = all_emb.shape[0]
+    if n < K:
+        raise ValueError("please reduce the number of centroids")          # reference :146
+    init = torch.randperm(n)[:K].to(dev) if int(getattr(args, "rank", 0)) == 0 else torch.empty(K, dtype=torch.long, device=dev)
+    if world > 1:
+        dist.broadcast(init, 0)
+    assign, centroids = spherical_kmeans(all_emb, init, nmb_kmeans_iters)
+    assignments = torch.full((n,), -100, dtype=torch.long, device=dev)
+    assignments[all_idx] = assign
+    prototypes.weight.copy_(centroids.to(prototypes.weight.dtype))
+    return assignments
+
+
+# ------------------------------------------------------------------------------------------------------
 # host-buffer entry (the call bench.py times end to end)
 # ------------------------------------------------------------------------------------------------------
 class HostInfoNCE:

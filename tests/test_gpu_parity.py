@@ -522,3 +522,31 @@ def test_in_batch_retrieval_top1_is_the_positive(sm3):
     assert relerr(vals.cpu().numpy(), g["top5_val"]) < 1e-5
     n = int(g["n"])
     assert (idx[:, 0].cpu().numpy() == (np.arange(2 * n) + n) % (2 * n)).all()   # correlated pairs: positive is top-1
+
+
+# ---------------------------------------------------------------------------------------------------
+# N4: DeepCluster memory-bank k-means against the reference's cluster_memory (golden)
+# ---------------------------------------------------------------------------------------------------
+def test_cluster_memory_matches_reference(sm3):
+    import types
+    g = load("kmeans")
+    for c in g["cases"]:
+        emb, index, init = g[f"{c}_emb"], g[f"{c}_index"], g[f"{c}_init_idx"]
+        k, d = len(init), emb.shape[1]
+        a, cent = sm3.spherical_kmeans(cuda(emb), torch.from_numpy(init).cuda())
+        ra, rcent = O.spherical_kmeans(emb, init)
+        assert (a.cpu().numpy() == ra).all(), c
+        assert np.abs(cent.cpu().numpy() - g[f"{c}_centroids"]).max() < 1e-5, c
+        # the drop-in: same signature and side effect as tools/mlc_train.py::cluster_memory, same RNG consumption
+        proto = torch.nn.Linear(d, k, bias=False).cuda()
+        torch.manual_seed(int(g[f"{c}_seed"]))
+        out = sm3.cluster_memory(types.SimpleNamespace(world_size=1, rank=0), proto, k, torch.from_numpy(index).cuda(),
+                                 cuda(emb))
+        assert (out.cpu().numpy() == g[f"{c}_assign"]).all(), c
+        assert np.abs(proto.weight.detach().cpu().numpy() - g[f"{c}_centroids"]).max() < 1e-5, c
+    # k = 1 retrieval (the E step) against the oracle on its own
+    q = torch.randn(300, 96, generator=torch.Generator().manual_seed(3)).cuda()
+    b = torch.randn(7, 96, generator=torch.Generator().manual_seed(4)).cuda()
+    v, i = sm3.sim_topk(q, b, 1)
+    rv, ri = O.knn_topk(q.cpu().numpy(), b.cpu().numpy(), 1)
+    assert (i.cpu().numpy() == ri).all() and relerr(v.cpu().numpy(), rv) < 1e-5

@@ -196,3 +196,16 @@ def test_torch_port_heads():
     outs = list(torch.split(torch.from_numpy(g["eval_logits"]), nc, dim=1))
     l = ref_port.port_multihead_ce(outs, torch.from_numpy(g["eval_labels"]), g["eval_weights"])
     assert abs(l.item() - float(g["eval_loss"])) < 1e-12
+
+
+def test_kmeans_oracle_matches_reference_cluster_memory():
+    """oracle.cluster_memory vs tools/mlc_train.py::cluster_memory (real function, run by oracle/make_golden.py):
+    assignments exact -- including the case whose clusters run empty -- and centroids to fp32 rounding."""
+    g = np.load(os.path.join(GOLDEN, "kmeans.npz"))
+    for c in g["cases"]:
+        a, cent = O.cluster_memory(g[f"{c}_index"], g[f"{c}_emb"], g[f"{c}_init_idx"])
+        assert (a == g[f"{c}_assign"]).all(), c
+        assert np.abs(cent - g[f"{c}_centroids"]).max() < 1e-6, c
+        # the initial indices are what torch.randperm gives for the recorded seed (how the product reproduces them)
+        torch.manual_seed(int(g[f"{c}_seed"]))
+        assert (torch.randperm(len(g[f"{c}_emb"]))[: len(g[f"{c}_init_idx"])].numpy() == g[f"{c}_init_idx"]).all()
