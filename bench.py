@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- contrastive pairs/sec (fwd+bwd) of the fused cross-modal InfoNCE hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2|cfg1|cfg3] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 WORKLOADS = {
+    "cfg1": dict(n=64, d=128, T=0.1, name="cfg1: SM3 contrastive loss fwd+bwd, batch 64 x dim 128 (the reference's own CPU-runnable case)"),
     "cfg4": dict(n=32768, d=256, T=0.1, name="cfg4: fused cross-modal InfoNCE fwd+bwd, global batch 32768 x dim 256, bf16"),
     "cfg2": dict(n=4096, d=128, T=0.1, name="cfg2: fused cross-modal InfoNCE fwd+bwd, batch 4096 x dim 128, bf16"),
 }

@@ -24,6 +24,17 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_reference_arm_runs_the_reference_sized_case_in_full():
+    """cfg1 (batch 64 x dim 128, BASELINE.json configs[0]) is small enough that the reference arm times the FULL
+    materialising step, not a row-block sample."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                        "--steps", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    assert d["config"]["global_pairs"] == 64 and d["config"]["dim"] == 128
+    assert d["cpu_baseline"]["sample"].startswith("full step")
+
+
 def test_ours_arm_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
