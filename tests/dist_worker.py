@@ -158,6 +158,36 @@ def main():
                 eb = (gb_f - gb_n).abs().max().item() / gb_n.abs().max().item()
                 assert ea <= 1e-2 and eb <= 1e-2, ("fused grads", n_local, step, ea, eb)
         results["fused"] = "ok"
+    # ---- N4: the DeepCluster clustering drop-in across ranks (bank sharded by rank, identical result everywhere) ----
+    import types
+    gk = np.load(os.path.join(ROOT, "tests", "golden", "kmeans.npz"))
+    if backend == "gloo":                     # CPU stand-ins for the two kernels the k-means is built from
+        def cpu_topk(q, b, k, exclude_self_offset=-1):
+            sim = q.double() @ b.double().T
+            order = torch.from_numpy(np.argsort(-sim.numpy(), axis=1, kind="stable")[:, :k].copy())
+            return torch.gather(sim, 1, order).float(), order
+        F3.sim_topk = cpu_topk
+        F3.l2_normalize = lambda p, eps=1e-12, out_dtype=None: torch.nn.functional.normalize(p, dim=1, eps=eps)
+    for c in ("a", "c"):
+        emb, index, init = gk[f"{c}_emb"], gk[f"{c}_index"], gk[f"{c}_init_idx"]
+        n = (len(emb) // world) * world       # equal shards (DistributedSampler semantics)
+        emb, index = emb[:n], index[:n]
+        index = np.argsort(np.argsort(index))                 # still a permutation of range(n) after the truncation
+        k, d = len(init), emb.shape[1]
+        nl = n // world
+        proto = torch.nn.Linear(d, k, bias=False).to(dev)
+        torch.manual_seed(4321)               # only rank 0's draw is used (broadcast), as in the reference
+        if rank != 0:
+            torch.manual_seed(99 + rank)
+        a = F3.cluster_memory(types.SimpleNamespace(world_size=world, rank=rank), proto, k,
+                              torch.from_numpy(index[rank * nl:(rank + 1) * nl]).to(dev),
+                              torch.from_numpy(emb[rank * nl:(rank + 1) * nl]).to(dev))
+        torch.manual_seed(4321)
+        init0 = torch.randperm(n)[:k].numpy()
+        ref_a, ref_c = O.cluster_memory(index, emb, init0)
+        assert (a.cpu().numpy() == ref_a).all(), ("cluster_memory assignments", c, rank)
+        assert np.abs(proto.weight.detach().cpu().numpy() - ref_c).max() < 1e-5
+    results["kmeans"] = "ok"
     if rank == 0 and out_path:
         with open(out_path, "w") as f:
             f.write(repr(results))

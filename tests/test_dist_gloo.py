@@ -22,6 +22,7 @@ def test_sharded_infonce_host_logic_gloo(tmp_path, world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = eval(out.read_text())
+    assert res.pop("kmeans") == "ok"          # N4 drop-in: sharded bank, identical clustering on every rank
     assert len(res) == 2
     for loss, ref, e1, e2 in res.values():
         assert abs(loss - ref) < 1e-6 * abs(ref) and e1 < 1e-5 and e2 < 1e-5
