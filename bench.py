@@ -393,7 +393,7 @@ def heads_probe(sm3, pk):
         out[op] = {"us": round(ms * 1e3, 2), "GB/s": round(nbytes / ms / 1e6, 1),
                    "frac_hbm": round(nbytes / ms / 1e6 / pk["hbm"], 3)}
     del p, z, inv, dz
-    for name, B in (("b512", 512), ("b4M", 1 << 22)):
+    for name, B in (("b512", 512), ("b4096", 4096), ("b4M", 1 << 22)):     # cfg5 size, cfg2 size, bandwidth size
         x = torch.randn(B, 24, device="cuda", dtype=torch.bfloat16, requires_grad=True)
         y = torch.stack([torch.randint(0, c, (B,), device="cuda") for c in sm3.NUM_CLASSES], 1)
         t = torch.nn.functional.one_hot(y[:, 0], 24).to(torch.bfloat16)
