@@ -261,6 +261,11 @@ int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local, int rank,
                           void* const* flags_peers_host, unsigned epoch, int overlap, void* device_scratch,
                           size_t scratch_bytes, void* stream_main, void* stream_side);
 
+/* debug / tuning: drop the cached values of the SM3_TC_* environment knobs (SM3_TC_GROUPS, SM3_TC_POLY, SM3_TC_BWD_NS;
+ * SM3_TC_FWD_BM, SM3_TC_FWD_SPLITS, SM3_TC_BWD_SPLITS and the HBM-kernel variant selectors are read at every launch)
+ * so that a sweep can change them inside one process.  Not a product path.                                       */
+void sm3_debug_reload_env(void);
+
 /* debug / bring-up: single-tile tcgen05 probe used by tests/test_umma_probe.py (not a product path).
  *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */
 int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,

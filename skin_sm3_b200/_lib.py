@@ -67,6 +67,7 @@ SIGNATURES = {
     "sm3_infonce_step_peer_scratch_bytes": (_sz, [_i, _i, _i]),
     "sm3_infonce_step_peer": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp,
                                    C.POINTER(_vp), _vp, C.POINTER(_vp), C.c_uint, _i, _vp, _sz, _vp, _vp]),
+    "sm3_debug_reload_env": (None, []),
     "sm3_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 

@@ -979,6 +979,13 @@ TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
     if ((size_t)max_splits > cap) max_splits = cap < 1 ? 1 : (int)cap;
   }
   pl.splits = tc_pick_splits(pl.row_tiles, pl.col_tiles, bwd ? 6 : (pl.bm == 256 ? 3 : 4), max_splits);
+  if (const char* e = getenv(bwd ? "SM3_TC_BWD_SPLITS" : "SM3_TC_FWD_SPLITS")) {     // tuning override (sweeps)
+    const int want = atoi(e);
+    if (want >= 1 && want <= max_splits && want <= pl.col_tiles) {
+      const int tps = (pl.col_tiles + want - 1) / want;
+      pl.splits = (pl.col_tiles + tps - 1) / tps;          // no empty split
+    }
+  }
   pl.tiles_per_split = (pl.col_tiles + pl.splits - 1) / pl.splits;
   return pl;
 }
@@ -1007,8 +1014,11 @@ void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p, int bn
 // number of softmax warp groups (8 warps each): tuning knob, SM3_TC_GROUPS=1|2.  Measured on B200 (cfg4): one group
 // is faster in the forward (1.93 vs 2.57 ms: with 3 TMEM S stages two tiles in flight starve the MMA warp of a free
 // stage) and equal in the backward, so 1 is the default.
+// The tuning knobs are read from the environment once and cached; sm3_debug_reload_env() drops the cache so that a
+// sweep (tools/tc_sweep.py) can change them inside one process.
+int g_knob_groups = 0, g_knob_poly = -1, g_knob_bwd_ns = -1;
 int tc_groups() {
-  static int g = 0;
+  int& g = g_knob_groups;
   if (g == 0) {
     const char* e = getenv("SM3_TC_GROUPS");
     g = (e && e[0] == '2') ? 2 : 1;
@@ -1021,7 +1031,7 @@ int tc_groups() {
 // load), where trading one MUFU op for ~11 FMA/ALU ops shortens the cycle count per tile (trace build: 1550 -> 1350)
 // but not the wall time; measured 1.74 / 1.78 / 1.80 ms for POLY = 0 / 2 / 3 at cfg4.
 int tc_poly() {
-  static int v = -1;
+  int& v = g_knob_poly;
   if (v < 0) {
     const char* e = getenv("SM3_TC_POLY");
     v = e ? atoi(e) : 0;
@@ -1074,7 +1084,7 @@ int launch_bwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, 
 }
 // S/H stages of the backward: 4 for D <= 128 (latency-bound chain, TMEM has room), 2 otherwise; SM3_TC_BWD_NS=2 forces 2.
 int tc_bwd_stages(int dp) {
-  static int forced = -1;
+  int& forced = g_knob_bwd_ns;
   if (forced < 0) {
     const char* e = getenv("SM3_TC_BWD_NS");
     forced = (e && e[0] == '2') ? 2 : 0;
@@ -1185,6 +1195,12 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
 }
 
 }  // namespace sm3
+
+extern "C" void sm3_debug_reload_env(void) {
+  sm3::g_knob_groups = 0;
+  sm3::g_knob_poly = -1;
+  sm3::g_knob_bwd_ns = -1;
+}
 
 #ifdef SM3_TRACE
 extern "C" int sm3_debug_read_trace(long long* host, int n) {

@@ -17,6 +17,8 @@ for poly in 0 2; do for ns in 4 2; do for grp in 1 2; do
   SM3_TC_POLY=$poly SM3_TC_BWD_NS=$ns SM3_TC_GROUPS=$grp timeout 40 python bench.py --workload cfg2 --steps 30 --no-extras 2>/dev/null \
     | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('poly=$poly ns=$ns groups=$grp', d['ms_per_step'], d['cuda_graph'])"
 done; done; done > gpurun_out/cfg2_knobs.txt 2>&1
+# 2b. K2 / K3 timed on their own over every knob combination, one process (D = 128 shapes + cfg4)
+timeout 150 python tools/tc_sweep.py --out gpurun_out/tc_sweep.jsonl > gpurun_out/tc_sweep.log 2>&1
 # 3. N4 timing: cluster_memory at the Derm7pt bank size (413 train samples x 512, K = 5) and at 100k x 512
 timeout 60 python - > gpurun_out/kmeans_timing.txt 2>&1 <<'PY'
 import sys, time, types, torch
