@@ -542,6 +542,12 @@ def run_ours(args):
             line["heads"] = heads_probe(sm3, pk)
         except Exception as e:   # the head probe must never take the headline down
             line["heads"] = {"error": repr(e)}
+        for key, probe in (("small_shapes", small_shapes_probe), ("tc_kernels_cfg2", tc_kernel_probe),
+                           ("kmeans", kmeans_probe)):
+            try:
+                line[key] = probe(sm3)
+            except Exception as e:
+                line[key] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -579,6 +585,99 @@ def cfg4_sweep(sm3, steps, flush, d=256, T=0.1):
                          "tc_frac_of_burst_peak": round(flops / (t * 1e-3) / 1e12 / peaks()["tflops"], 3)}
         out.append(row)
         del pairs
+    return out
+
+
+def _ev_us(fn, reps=30, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); e1.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def small_shapes_probe(sm3):
+    """The reference's REAL batch sizes (run.sh: 96 pairs over 2 GPUs = 48 per rank; 256 per rank in cfg3), D = 128: the
+    step is launch-bound, so what matters is launches and host time.  Per size: the eager op (Python + autograd + one C
+    call), the CUDA-graph replay, the four style-0 terms in one grouped call, and the reference's materialising op
+    sequence (oracle/ref_port.py, context only) on the same GPU.  Microseconds per step, back-to-back launches."""
+    from oracle import ref_port
+    out = []
+    for n in (48, 256, 1024):
+        d, T = 128, 0.1
+        g = torch.Generator().manual_seed(SEED + n)
+        pairs = [(torch.randn(n, d, generator=g).bfloat16().cuda().requires_grad_(True),
+                  torch.randn(n, d, generator=g).bfloat16().cuda().requires_grad_(True)) for _ in range(4)]
+        a, b = pairs[0]
+        gr = sm3.GraphedInfoNCE(n, d, T, dtype=torch.bfloat16, precision="bf16")
+        gr.p1.copy_(a.detach()); gr.p2.copy_(b.detach())
+        a32, b32 = a.detach().float(), b.detach().float()
+
+        def eager():
+            a.grad = b.grad = None
+            sm3.fused_infonce(a, b, T, precision="bf16").backward()
+
+        def grouped():
+            sm3.fused_infonce_multi(pairs, T, [1, 1, 0.5, 0.5], precision="bf16").backward()
+
+        out.append({"pairs": n, "dim": d,
+                    "eager_us": round(_ev_us(eager), 1), "cuda_graph_us": round(_ev_us(gr.replay), 1),
+                    "four_terms_grouped_us": round(_ev_us(grouped), 1),
+                    "reference_port_gpu_us": round(_ev_us(lambda: ref_port.port_infonce_step(a32, b32, T), reps=10), 1)})
+    return out
+
+
+def tc_kernel_probe(sm3):
+    """K2 and K3 timed on their own at cfg2 (4096 x 128, the D = 128 regime of every reference config), for the knob values
+    that have been parity-checked on B200: forward rows per CTA 256 / 128 and FMA-pipe exponentials 0 / 2 per 8; backward
+    S/H stages 4 / 2.  Feeds DESIGN.md section 9 item 1.  Microseconds per launch (finalize / prep kernels included)."""
+    n, d, T = 4096, 128, 0.1
+    z, _ = sm3.core.normalize_pair(torch.randn(2 * n, d, device="cuda"), None, torch.bfloat16)
+    pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
+    _, gp, gl = sm3.core.loss(pos, lse, 1.0 / (2 * n))
+    knobs = ("SM3_TC_FWD_BM", "SM3_TC_POLY", "SM3_TC_BWD_NS")
+    saved = {k: os.environ.get(k) for k in knobs}
+    out = {}
+    try:
+        for bm, poly in (("256", "0"), ("256", "2"), ("128", "0")):      # the combinations that have run on B200 before
+            os.environ["SM3_TC_FWD_BM"], os.environ["SM3_TC_POLY"] = bm, poly
+            sm3.lib().sm3_debug_reload_env()
+            out[f"fwd_bm{bm}_poly{poly}_us"] = round(_ev_us(lambda: sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)), 1)
+        os.environ.pop("SM3_TC_FWD_BM", None); os.environ.pop("SM3_TC_POLY", None)
+        for ns in ("4", "2"):
+            os.environ["SM3_TC_BWD_NS"] = ns
+            sm3.lib().sm3_debug_reload_env()
+            out[f"bwd_stages{ns}_us"] = round(_ev_us(
+                lambda: sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)), 1)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        sm3.lib().sm3_debug_reload_env()
+    return out
+
+
+def kmeans_probe(sm3):
+    """N4: one DeepCluster clustering (10 iterations + final assignment, K = 5, D = 512) at the Derm7pt bank size and at
+    100k samples; milliseconds, host-timed with a device sync on both sides (the function never syncs itself)."""
+    out = {}
+    for n in (413, 100000):
+        emb = torch.nn.functional.normalize(torch.randn(n, 512, device="cuda"), dim=1)
+        init = torch.randperm(n)[:5].cuda()
+        for _ in range(2):
+            sm3.spherical_kmeans(emb, init)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            sm3.spherical_kmeans(emb, init)
+        torch.cuda.synchronize()
+        out[f"n{n}_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
     return out
 
 
