@@ -542,12 +542,15 @@ def run_ours(args):
             line["heads"] = heads_probe(sm3, pk)
         except Exception as e:   # the head probe must never take the headline down
             line["heads"] = {"error": repr(e)}
-        for key, probe in (("small_shapes", small_shapes_probe), ("tc_kernels_cfg2", tc_kernel_probe),
-                           ("kmeans", kmeans_probe)):
-            try:
-                line[key] = probe(sm3)
-            except Exception as e:
-                line[key] = {"error": repr(e)[:300]}
+        # The newest probes run in a CHILD process with a timeout: whatever happens there (exception, device trap, hang)
+        # cannot touch the headline numbers above or keep this process from printing its line.
+        import subprocess
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-child"], capture_output=True,
+                               text=True, timeout=120)
+            line.update(json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]))
+        except Exception as e:
+            line["extras_child"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -778,6 +781,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_extras_child():
+    """Child of the default bench run (see run_ours): probes whose failure must not reach the parent."""
+    import skin_sm3_b200 as sm3
+    torch.cuda.set_device(0)
+    out = {}
+    for key, probe in (("small_shapes", small_shapes_probe), ("tc_kernels_cfg2", tc_kernel_probe),
+                       ("kmeans", kmeans_probe)):
+        try:
+            out[key] = probe(sm3)
+        except Exception as e:
+            out[key] = {"error": repr(e)[:300]}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -786,9 +803,12 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["cfg3"], default="cfg4")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / cfg2 / heads (profiling runs)")
+    ap.add_argument("--extras-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.extras_child:
+        run_extras_child()
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg3":
         run_cfg3(args)
