@@ -548,7 +548,12 @@ def run_ours(args):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-child"], capture_output=True,
                                text=True, timeout=120)
-            line.update(json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]))
+            got = _last_json(r.stdout)
+            line.update(got if got is not None else {"extras_child": {"error": (r.stderr or "no output")[-300:]}})
+        except subprocess.TimeoutExpired as e:
+            got = _last_json(e.stdout.decode() if isinstance(e.stdout, bytes) else e.stdout)
+            line.update(got or {})
+            line["extras_child"] = {"error": "timeout after 120 s"}
         except Exception as e:
             line["extras_child"] = {"error": repr(e)[:300]}
     if rank == 0:
@@ -589,6 +594,17 @@ def cfg4_sweep(sm3, steps, flush, d=256, T=0.1):
         out.append(row)
         del pairs
     return out
+
+
+def _last_json(text):
+    """Last line of `text` that parses as a JSON object (a crashed child may leave a truncated final line)."""
+    for l in reversed((text or "").splitlines()):
+        if l.startswith("{"):
+            try:
+                return json.loads(l)
+            except ValueError:
+                continue
+    return None
 
 
 def _ev_us(fn, reps=30, warm=3):
@@ -663,6 +679,57 @@ def tc_kernel_probe(sm3):
             else:
                 os.environ[k] = v
         sm3.lib().sm3_debug_reload_env()
+    return out
+
+
+def tc_experimental_probe(sm3, emit):
+    """Knob combinations that have NOT been run on a B200 yet (two softmax groups with 4 backward stages, FMA-pipe
+    exponentials in the 128-row forward, forced split counts), at the D = 128 shapes.  Only ever called from the
+    extras child: each result is checked against the default configuration's output ("ok") and emitted immediately,
+    so a trap in one combination costs the combinations after it, nothing else."""
+    knobs = ("SM3_TC_FWD_BM", "SM3_TC_POLY", "SM3_TC_GROUPS", "SM3_TC_BWD_NS", "SM3_TC_FWD_SPLITS", "SM3_TC_BWD_SPLITS")
+
+    def set_knobs(cfg):
+        for k in knobs:
+            os.environ.pop(k, None)
+        os.environ.update({k: str(v) for k, v in cfg.items()})
+        sm3.lib().sm3_debug_reload_env()
+
+    out = []
+    for n in (4096, 1024, 256):
+        d, T = 128, 0.1
+        z, _ = sm3.core.normalize_pair(torch.randn(2 * n, d, device="cuda"), None, torch.bfloat16)
+        set_knobs({})
+        pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
+        _, gp, gl = sm3.core.loss(pos, lse, 1.0 / (2 * n))
+        ws, npart = sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)
+        dz_ref = sm3.core.sum_partials(ws, npart, 2 * n, d).clone()
+        fwd = [{"SM3_TC_FWD_BM": 128, "SM3_TC_POLY": 2}, {"SM3_TC_FWD_BM": 128, "SM3_TC_GROUPS": 2},
+               {"SM3_TC_FWD_BM": 128, "SM3_TC_GROUPS": 2, "SM3_TC_POLY": 2},
+               {"SM3_TC_FWD_SPLITS": 2}, {"SM3_TC_FWD_SPLITS": 8}, {"SM3_TC_FWD_BM": 128, "SM3_TC_FWD_SPLITS": 8}]
+        bwd = [{"SM3_TC_GROUPS": 2, "SM3_TC_BWD_NS": 4}, {"SM3_TC_GROUPS": 2, "SM3_TC_BWD_NS": 2},
+               {"SM3_TC_BWD_SPLITS": 1}, {"SM3_TC_BWD_SPLITS": 3}, {"SM3_TC_BWD_SPLITS": 4},
+               {"SM3_TC_BWD_SPLITS": 4, "SM3_TC_GROUPS": 2}]
+        for kind, cfgs in (("fwd", fwd), ("bwd", bwd)):
+            for cfg in cfgs:
+                rec = {"kernel": kind, "pairs": n, **cfg}
+                try:
+                    set_knobs(cfg)
+                    if kind == "fwd":
+                        p2, _, n2 = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
+                        rec["ok"] = bool(torch.allclose(p2, pos, rtol=1e-5, atol=1e-6) and torch.allclose(n2, nsum, rtol=1e-3))
+                        rec["us"] = round(_ev_us(lambda: sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)), 1)
+                    else:
+                        w2, np2 = sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)
+                        dz = sm3.core.sum_partials(w2, np2, 2 * n, d)
+                        rec["ok"] = bool((dz - dz_ref).abs().max().item() <= 2e-2 * dz_ref.abs().max().item())
+                        rec["us"] = round(_ev_us(
+                            lambda: sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)), 1)
+                except Exception as e:
+                    rec["error"] = repr(e)[:200]
+                out.append(rec)
+                emit(out)
+    set_knobs({})
     return out
 
 
@@ -792,7 +859,17 @@ def run_extras_child():
             out[key] = probe(sm3)
         except Exception as e:
             out[key] = {"error": repr(e)[:300]}
-    print(json.dumps(out))
+        print(json.dumps(out), flush=True)          # cumulative: the parent keeps the last complete line
+
+    def emit(partial):
+        out["tc_experimental"] = partial
+        print(json.dumps(out), flush=True)
+
+    try:
+        tc_experimental_probe(sm3, emit)            # last: combinations that have never run on the hardware
+    except Exception as e:
+        out["tc_experimental_error"] = repr(e)[:300]
+        print(json.dumps(out), flush=True)
 
 
 def main():
