@@ -733,6 +733,58 @@ def tc_experimental_probe(sm3, emit):
     return out
 
 
+def hbm_experimental_probe(sm3, emit):
+    """Opt-in variants of the HBM-bound kernels that have not run on hardware yet (extras child only): the persistent
+    normalise-backward (SM3_K1_BWD_VARIANT=1) and the deep-prefetch BCE kernels (SM3_BCE_VARIANT=2|3), each checked
+    against the default's output and timed at the bandwidth-sized shapes of `heads`."""
+    out = []
+    pk = peaks()
+
+    def rec(name, variant, ms, nbytes, ok):
+        out.append({"kernel": name, "variant": variant, "us": round(ms * 1e3, 2), "frac_hbm": round(nbytes / ms / 1e6 / pk["hbm"], 3),
+                    "ok": bool(ok)})
+        emit(out)
+
+    try:
+        for M, D, parts in ((1 << 21, 256, 1), (65536, 256, 2)):
+            z, inv = sm3.core.normalize_pair(torch.randn(M, D, device="cuda", dtype=torch.bfloat16), None, torch.bfloat16)
+            dz = torch.randn(parts, M, D, device="cuda", dtype=torch.float32)
+            nbytes = M * D * (4 * parts + 2 + 2) + 4 * M
+            ref = None
+            for v in ("0", "1"):
+                os.environ["SM3_K1_BWD_VARIANT"] = v
+                o, _ = sm3.core.normalize_bwd(dz, parts, 1.0, z, inv, M, 0, torch.bfloat16)
+                ref = o.clone() if ref is None else ref
+                us = _ev_us(lambda: sm3.core.normalize_bwd(dz, parts, 1.0, z, inv, M, 0, torch.bfloat16), reps=10)
+                rec(f"l2norm_bwd_{M}x{D}_p{parts}", v, us / 1e3, nbytes, torch.equal(o, ref))
+            del z, inv, dz, ref
+    except Exception as e:
+        out.append({"kernel": "l2norm_bwd", "error": repr(e)[:200]}); emit(out)
+    finally:
+        os.environ.pop("SM3_K1_BWD_VARIANT", None)
+    try:
+        B = 1 << 22
+        x = torch.randn(B, 24, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        t = (torch.rand(B, 24, device="cuda") < 0.3).to(torch.bfloat16)
+        ref = None
+        for v in ("1", "2", "3"):
+            os.environ["SM3_BCE_VARIANT"] = v
+            x.grad = None
+            loss = sm3.bce_with_logits(x, t)
+            loss.backward()
+            cur = (float(loss.detach()), x.grad.float().clone())
+            ref = cur if ref is None else ref
+            ok = abs(cur[0] - ref[0]) <= 1e-5 * abs(ref[0]) and \
+                (cur[1] - ref[1]).abs().max().item() <= 1e-2 * ref[1].abs().max().item()
+            us = _ev_us(lambda: sm3.bce_with_logits(x, t), reps=20)
+            rec("bce_b4M", v, us / 1e3, B * 24 * 6, ok)
+    except Exception as e:
+        out.append({"kernel": "bce", "error": repr(e)[:200]}); emit(out)
+    finally:
+        os.environ.pop("SM3_BCE_VARIANT", None)
+    return out
+
+
 def kmeans_probe(sm3):
     """N4: one DeepCluster clustering (10 iterations + final assignment, K = 5, D = 512) at the Derm7pt bank size and at
     100k samples; milliseconds, host-timed with a device sync on both sides (the function never syncs itself)."""
@@ -861,15 +913,16 @@ def run_extras_child():
             out[key] = {"error": repr(e)[:300]}
         print(json.dumps(out), flush=True)          # cumulative: the parent keeps the last complete line
 
-    def emit(partial):
-        out["tc_experimental"] = partial
-        print(json.dumps(out), flush=True)
-
-    try:
-        tc_experimental_probe(sm3, emit)            # last: combinations that have never run on the hardware
-    except Exception as e:
-        out["tc_experimental_error"] = repr(e)[:300]
-        print(json.dumps(out), flush=True)
+    # last: code that has never run on the hardware, each result checked against the default's and emitted at once
+    for key, probe in (("hbm_experimental", hbm_experimental_probe), ("tc_experimental", tc_experimental_probe)):
+        def emit(partial, key=key):
+            out[key] = partial
+            print(json.dumps(out), flush=True)
+        try:
+            probe(sm3, emit)
+        except Exception as e:
+            out[key + "_error"] = repr(e)[:300]
+            print(json.dumps(out), flush=True)
 
 
 def main():

@@ -580,6 +580,94 @@ bce_kernel(const TX* __restrict__ x, const TT* __restrict__ t, const float* __re
   }
 }
 
+// Experimental K5 variant (SM3_BCE_VARIANT=2|3, 16-bit logits and targets, no pos_weight, n % 8 == 0): FOUR 8-element
+// chunks per thread are requested (packed, 8 registers per chunk) before the first one is consumed -- twice the bytes in
+// flight of bce_kernel at the same occupancy; kNewton additionally takes 1 / (1 + e) from a linear seed + 2 Newton steps
+// on the FMA pipe (1.2e-5 relative, below 16-bit output rounding) so that ONE MUFU op per element is left (+ one log
+// per 8).  Not a default until measured.
+template <typename T>
+__device__ __forceinline__ void unpack8_16(const uint4& r, float (&o)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      o[2 * q] = __uint_as_float(w[q] << 16); o[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+    } else {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+      o[2 * q] = f.x; o[2 * q + 1] = f.y;
+    }
+  }
+}
+
+template <typename TX, typename TT, bool kNewton>
+__global__ void __launch_bounds__(kBceThreads)
+bce_deep_kernel(const TX* __restrict__ x, const TT* __restrict__ t, int64_t n8, float inv_n, float* __restrict__ loss_out,
+                TX* __restrict__ dx, float grad_scale, float* __restrict__ ws) {
+  static_assert(sizeof(TX) == 2 && sizeof(TT) == 2, "16-bit inputs only");
+  constexpr int U = 4;
+  __shared__ float red[32];
+  __shared__ bool is_last;
+  float acc = 0.f;
+  const float gscale = inv_n * grad_scale;
+  const int64_t stride = (int64_t)gridDim.x * kBceThreads;
+  const int64_t gid = (int64_t)blockIdx.x * kBceThreads + threadIdx.x;
+  const uint4* xv4 = reinterpret_cast<const uint4*>(x);
+  const uint4* tv4 = reinterpret_cast<const uint4*>(t);
+  for (int64_t v0 = gid; v0 < n8; v0 += U * stride) {
+    uint4 rx[U], rt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < n8) { rx[u] = __ldg(xv4 + v); rt[u] = __ldg(tv4 + v); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < n8) {
+        float xs[8], ts[8], g[8];
+        unpack8_16<TX>(rx[u], xs);
+        unpack8_16<TT>(rt[u], ts);
+        float prod = 1.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float e = ex2f_approx(-1.4426950408889634f * fabsf(xs[i]));
+          const float w = 1.0f + e;
+          float r;
+          if constexpr (kNewton) {
+            r = fmaf(w, -0.47058823529f, 1.41176470588f);      // 24/17 - 8/17 w : |rel err| <= 1/17 on [1, 2]
+            r = r * fmaf(-w, r, 2.0f);
+            r = r * fmaf(-w, r, 2.0f);
+          } else {
+            r = rcpf_approx(w);
+          }
+          const float sig = xs[i] >= 0.f ? r : 1.0f - r;
+          prod *= w;
+          acc += fmaf(1.f - ts[i], xs[i], fmaxf(-xs[i], 0.f));
+          g[i] = (sig - ts[i]) * gscale;
+        }
+        acc = fmaf(0.6931471805599453f, lg2f_approx(prod), acc);
+        if (dx != nullptr) VecIO<TX>::store(dx + v * 8, g);
+      }
+    }
+  }
+  const float bs = block_sum(acc, red);
+  if (threadIdx.x == 0) ws[kWsPartials + blockIdx.x] = bs;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kBceThreads) s += __ldcg(ws + kWsPartials + b);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) { *loss_out = s * inv_n; *reinterpret_cast<unsigned*>(ws) = 0u; }
+  }
+}
+
 // ---------------- InfoNCE tail kernels ----------------
 __global__ void infonce_finalize_kernel(const float* __restrict__ partial, int n_partials, int64_t rows, float inv_T,
                                         float* __restrict__ neg_sum, float* __restrict__ lse_neg,
@@ -762,8 +850,31 @@ extern "C" int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_d
   const int vec_ok = aligned16(x) && aligned16(t) && (dx == nullptr || aligned16(dx));
   const float inv_n = 1.0f / (float)n;
   // SM3_BCE_VARIANT: 0 = one log per element, 1 = one log per 8 elements (default; B200, 4M x 24 bf16: 125 -> 116 us)
+  //                  2 / 3 = experimental deep-prefetch kernels (bce_deep_kernel), opt-in only
   const char* ev = getenv("SM3_BCE_VARIANT");
   const bool prod = !(ev && ev[0] == '0');
+  const int deep = (ev && (ev[0] == '2' || ev[0] == '3')) ? ev[0] - '0' : 0;
+  if (deep && pos_weight == nullptr && vec_ok && n % 8 == 0 && x_dtype != SM3_F32 && t_dtype != SM3_F32) {
+    const int64_t n8 = n / 8;
+#define SM3_BCE_DEEP(TX, TT)                                                                                         \
+    do {                                                                                                             \
+      const int per_sm = deep == 3 ? resident_ctas(bce_deep_kernel<TX, TT, true>, kBceThreads)                       \
+                                   : resident_ctas(bce_deep_kernel<TX, TT, false>, kBceThreads);                     \
+      int64_t g = (n8 + kBceThreads * 4 - 1) / (kBceThreads * 4);                                                    \
+      const int64_t cap = (int64_t)num_sms() * per_sm;                                                               \
+      if (g > cap) g = cap;                                                                                          \
+      if (g > (int64_t)grid) g = grid;          /* the workspace was sized for `grid` CTAs */                        \
+      if (deep == 3) bce_deep_kernel<TX, TT, true><<<(unsigned)g, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, n8, inv_n, loss, (TX*)dx, grad_scale, ws); \
+      else bce_deep_kernel<TX, TT, false><<<(unsigned)g, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, n8, inv_n, loss, (TX*)dx, grad_scale, ws); \
+    } while (0)
+    if (x_dtype == SM3_BF16 && t_dtype == SM3_BF16) SM3_BCE_DEEP(__nv_bfloat16, __nv_bfloat16);
+    else if (x_dtype == SM3_BF16) SM3_BCE_DEEP(__nv_bfloat16, __half);
+    else if (t_dtype == SM3_BF16) SM3_BCE_DEEP(__half, __nv_bfloat16);
+    else SM3_BCE_DEEP(__half, __half);
+#undef SM3_BCE_DEEP
+    SM3_CHECK_CUDA(cudaGetLastError());
+    return SM3_OK;
+  }
   SM3_DISPATCH_DTYPE(x_dtype, TX, SM3_DISPATCH_DTYPE(t_dtype, TT, {
     if (pos_weight != nullptr)
       bce_kernel<TX, TT, true, false><<<grid, kBceThreads, 0, st>>>((const TX*)x, (const TT*)t, pos_weight, n, C, inv_n,

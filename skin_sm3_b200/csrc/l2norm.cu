@@ -235,6 +235,72 @@ l2norm_fwd_persist_kernel(const TIn* __restrict__ pa, int64_t rows_a, const TIn*
   }
 }
 
+// Experimental (SM3_K1_BWD_VARIANT=1, 16-bit z, D <= 256): the backward in the same persistent form -- a warp owns
+// 2-row groups and requests the next group's first gradient slab (fp32, two 16-byte vectors per lane and row) and z row
+// (one vector) before it reduces the current group.  Further slabs (n_partials > 1) are read in the loop as before.
+template <typename TZ, typename TOut>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_bwd_persist_kernel(const float* __restrict__ dz, int n_partials, int64_t partial_stride, float scale,
+                          const TZ* __restrict__ z, const float* __restrict__ inv_norm, float inv_eps,
+                          TOut* __restrict__ dpa, int64_t rows_a, TOut* __restrict__ dpb, int64_t rows_b, int D) {
+  static_assert(sizeof(TZ) == 2, "16-bit z rows");
+  constexpr int R = 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = rows_a + rows_b;
+  const bool have = lane < D / kChunk;
+  const int64_t n_groups = (rows + R - 1) / R;
+  const int64_t gstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  int64_t grp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  Raw8<float> cg[R], ng[R];
+  Raw8<TZ> cz[R], nz[R];
+  auto issue = [&](int64_t g, Raw8<float> (&dg)[R], Raw8<TZ> (&dzr)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = g * R + r;
+      if (row < rows && have) {
+        raw_load8<float, false>(dz + row * D + lane * kChunk, dg[r]);
+        raw_load8<TZ, false>(z + row * D + lane * kChunk, dzr[r]);
+      } else {
+        dg[r].v[0] = dg[r].v[1] = make_uint4(0u, 0u, 0u, 0u);
+        dzr[r].v[0] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  if (grp < n_groups) issue(grp, cg, cz);
+  for (; grp < n_groups; grp += gstride) {
+    if (grp + gstride < n_groups) issue(grp + gstride, ng, nz);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = grp * R + r;
+      float gv[kChunk], zv[kChunk];
+      raw_unpack8<float>(cg[r], gv);
+      raw_unpack8<TZ>(cz[r], zv);
+      if (row < rows && have) {
+        for (int k = 1; k < n_partials; ++k) {
+          float t[kChunk];
+          load8<float>(dz + k * partial_stride + row * D + lane * kChunk, t);
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) gv[i] += t[i];
+        }
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) { gv[i] *= scale; dot = fmaf(gv[i], zv[i], dot); }
+      dot = warp_sum(dot);
+      if (row < rows && have) {
+        const float inv = inv_norm[row];
+        if (inv >= inv_eps) dot = 0.f;          // ||p|| <= eps: F.normalize divides by the constant eps
+        TOut* dst = row < rows_a ? dpa + row * D : dpb + (row - rows_a) * D;
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) gv[i] = (gv[i] - zv[i] * dot) * inv;
+        store8<TOut>(dst + lane * kChunk, gv);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { cg[r] = ng[r]; cz[r] = nz[r]; }
+  }
+}
+
 // ---------------- forward ----------------
 template <typename TIn, typename TOut, bool kVec>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -416,6 +482,22 @@ int l2norm_bwd_launch(const float* dz_partials, int n_partials, float scale, con
   if (vec && D <= 32 * kChunk) {
     const int64_t want2 = (rows + kWarpsPerBlock * 2 - 1) / (kWarpsPerBlock * 2);
     const unsigned g2 = (unsigned)(want2 < 0x7fffffff ? want2 : 0x7fffffff);
+    const char* ev = getenv("SM3_K1_BWD_VARIANT");           // 1 = experimental persistent + prefetch form (opt-in)
+    if (ev && ev[0] == '1' && z_dtype != SM3_F32) {
+#define SM3_K1_BWD_PERSIST(TZ, TOut)                                                                                 \
+      do {                                                                                                           \
+        static const int per_sm = resident_ctas(l2norm_bwd_persist_kernel<TZ, TOut>, kWarpsPerBlock * 32);           \
+        const int64_t cap = (int64_t)num_sms() * per_sm;                                                             \
+        l2norm_bwd_persist_kernel<TZ, TOut><<<(unsigned)(want2 < cap ? want2 : cap), kWarpsPerBlock * 32, 0, st>>>(  \
+            dz_partials, n_partials, rows * (int64_t)D, scale, (const TZ*)z, inv_norm, inv_eps, (TOut*)dp_a, rows_a, \
+            (TOut*)dp_b, rows_b, D);                                                                                 \
+      } while (0)
+      if (z_dtype == SM3_BF16) { SM3_DISPATCH_DTYPE(dp_dtype, TOut, { SM3_K1_BWD_PERSIST(__nv_bfloat16, TOut); }); }
+      else { SM3_DISPATCH_DTYPE(dp_dtype, TOut, { SM3_K1_BWD_PERSIST(__half, TOut); }); }
+#undef SM3_K1_BWD_PERSIST
+      SM3_CHECK_CUDA(cudaGetLastError());
+      return SM3_OK;
+    }
     SM3_DISPATCH_DTYPE(z_dtype, TZ, SM3_DISPATCH_DTYPE(dp_dtype, TOut, {
       l2norm_bwd_small_kernel<TZ, TOut><<<g2, kWarpsPerBlock * 32, 0, st>>>(
           dz_partials, n_partials, rows * (int64_t)D, scale, (const TZ*)z, inv_norm, inv_eps, (TOut*)dp_a, rows_a,

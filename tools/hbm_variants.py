@@ -80,6 +80,20 @@ def main():
     os.environ.pop("SM3_K1_FWD_VARIANT", None)
     del p
 
+    # ---- K1 backward: default vs the experimental persistent form ----
+    M, D = 1 << 21, 256
+    z, inv = sm3.core.normalize_pair(torch.randn(M, D, device="cuda", dtype=torch.bfloat16), None, torch.bfloat16)
+    dz = torch.randn(M, D, device="cuda", dtype=torch.float32)
+    ref = None
+    for v in ("0", "1"):
+        os.environ["SM3_K1_BWD_VARIANT"] = v
+        o, _ = sm3.core.normalize_bwd(dz, 1, 1.0, z, inv, M, 0, torch.bfloat16)
+        ref = o.clone() if ref is None else ref
+        ms = ev_time(lambda: sm3.core.normalize_bwd(dz, 1, 1.0, z, inv, M, 0, torch.bfloat16), reps=10)
+        emit("l2norm_bwd_2Mx256 bf16", v, ms, M * D * 8 + 4 * M, torch.equal(o, ref))
+    os.environ.pop("SM3_K1_BWD_VARIANT", None)
+    del z, inv, dz, ref
+
     # ---- K4 / K5 at B = 4M rows x 24 logits, and the reference-sized B = 512 ----
     for B in (1 << 22, 512):
         x = torch.randn(B, 24, device="cuda", dtype=torch.bfloat16, requires_grad=True)
@@ -99,7 +113,7 @@ def main():
             emit(f"ce8_b{B}", v, ms, B * 24 * 4 + B * 64 + 4, ok)
         os.environ.pop("SM3_CE_VARIANT", None)
         ref = None
-        for v in ("0", "1"):
+        for v in ("0", "1", "2", "3"):                  # 2 / 3: experimental deep-prefetch kernels
             os.environ["SM3_BCE_VARIANT"] = v
             x.grad = None
             loss = sm3.bce_with_logits(x, t)
@@ -107,7 +121,8 @@ def main():
             cur = (float(loss), x.grad.clone())
             if ref is None:
                 ref = cur
-            ok = abs(cur[0] - ref[0]) <= 2e-6 * abs(ref[0]) and torch.equal(cur[1], ref[1])
+            ok = abs(cur[0] - ref[0]) <= 2e-6 * abs(ref[0]) and \
+                (cur[1].float() - ref[1].float()).abs().max().item() <= 1e-2 * ref[1].float().abs().max().item()
             ms = ev_time(lambda: sm3.bce_with_logits(x, t))
             emit(f"bce_b{B}", v, ms, B * 24 * 6, ok, {"loss": cur[0]})
         os.environ.pop("SM3_BCE_VARIANT", None)
