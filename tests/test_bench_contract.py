@@ -42,3 +42,28 @@ def test_ours_arm_fails_loudly_without_cuda():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--no-extras"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and not r.stdout.strip().startswith("{")
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """The recorded B200 line (profiles/r01_bench_final.json) has every key the bench contract names, the roofline is
+    self-consistent (frac = achieved / peak, achieved = algorithmic flops / the measured stage time) and the end-to-end
+    figure really moved its bytes."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "pairs/s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    n = d["config"]["global_pairs"]
+    assert abs(d["value"] - n / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    m = 2 * n
+    assert r["flops_per_launch"] == 4.0 * m * m * d["config"]["dim"]
+    assert abs(r["achieved"] - r["flops_per_launch"] / (d["stages_ms"]["stats_bwd"] * 1e-3) / 1e12) < 0.01 * r["achieved"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 2 * n * d["config"]["dim"] * 2 and e["d2h_bytes_per_step"] == e["h2d_bytes_per_step"] + 4
+    assert 0 < e["value"] <= d["value"] * 1.05 and e["value"] != d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert not bad & set(d["clocks"]["reasons"])
