@@ -8,6 +8,11 @@ Reference being replaced (paths relative to the reference checkout):
   * ``multihead_ce``            the 8-head CE loops                        tools/mlc_eval.py:159-162,
                                                                            tools/mlc_train.py:255-261
   * ``bce_with_logits``         north_star's multi-hot head loss (no reference counterpart)
+  * ``fused_infonce_multi``     the four style-0 terms of one step in one call  tools/backbone_train.py:101-121
+  * ``sim_topk`` / ``knn_predict``  KNNOnlineEvaluator.predict                 src/models/evaluator.py:43-83
+  * ``cluster_memory`` / ``spherical_kmeans``  DeepCluster memory-bank k-means tools/mlc_train.py:116-189
+  * ``HostInfoNCE`` / ``HostInfoNCEPipeline`` / ``GraphedInfoNCE``  host-buffer, pipelined and CUDA-graph front ends of
+                                the fused step (new capability; bench.py's ``e2e`` and small-shape numbers)
 
 ``cal_logits`` returns *sufficient-statistics logits* ``[M, 2] = [pos/T, log sum_neg exp(s/T)]`` with
 all-zero labels: the training script's own ``nn.CrossEntropyLoss()(logits, labels)`` then yields exactly
