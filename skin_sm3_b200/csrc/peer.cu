@@ -109,6 +109,9 @@ __device__ __forceinline__ void last_block_signal(const PeerFused& pf, bool* sme
     *smem_flag = (t == total - 1);
   }
   __syncthreads();
+  // Every CTA's stores were made visible system-wide by its thread 0's fence BEFORE its ticket; the CTA that sees the
+  // last ticket therefore runs strictly after all of them, and so does each of its lanes below (ordered behind thread
+  // 0's atomic by the barrier above): lane r publishes the epoch to rank r with its own fence + release store.
   if (*smem_flag && threadIdx.x < pf.flags.world) {
     if (threadIdx.x == 0) *pf.counter = 0u;          // next launch starts from zero (same stream => ordered)
     __threadfence_system();
