@@ -39,9 +39,9 @@ WORKLOADS = {
 }
 SEED = 3407
 COMM = os.environ.get("SM3_COMM", "auto")     # multi-rank exchange: auto (peer memory if available) | peer | nccl
-# our kernels per step on the production path (one GPU: l2norm_fwd, infonce_fwd, finalize+loss, bwd_prep, infonce_bwd,
-# l2norm_bwd; multi-rank fused exchange: l2norm+scatter, infonce_fwd, loss+stats scatter, infonce_bwd, l2norm_bwd)
-KERNELS_PER_STEP = {True: 6, False: 5}
+# our kernels per step on the production path: normalise (+ NVLink row scatter when sharded), K2, CE on the statistics
+# (+ a_j, + statistics scatter), K3, normalise-backward -- one C call -- and the upstream-scale kernel of .backward()
+KERNELS_PER_STEP = 6
 
 
 def ncu_traffic():
@@ -157,13 +157,42 @@ def max_over_ranks(x: float, world: int) -> float:
     return float(t.item())
 
 
-def synth(n_global, d, rank, world, device):
-    """p1, p2 ~ N(0,1) (the projector ends in an affine-free BatchNorm, simclr.py:26), bf16, this rank's pairs."""
+def synth(n_global, d, rank, world, device=None, seed=SEED):
+    """p1, p2 ~ N(0,1) (the projector ends in an affine-free BatchNorm, simclr.py:26), bf16.  The GLOBAL batch is drawn
+    from one seed and every rank takes its slice of pairs, so the N = 1 / 2 / 4 / 8 runs compute the SAME problem and
+    their (rank-averaged) losses must agree.  -> (p1_local, p2_local, (P1_global, P2_global))"""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    P1 = torch.randn(n_global, d, generator=g).bfloat16()
+    P2 = torch.randn(n_global, d, generator=g).bfloat16()
     n_local = n_global // world
-    g = torch.Generator(device="cpu").manual_seed(SEED + rank)
-    p1 = torch.randn(n_local, d, generator=g).bfloat16()
-    p2 = torch.randn(n_local, d, generator=g).bfloat16()
-    return p1, p2
+    sl = slice(rank * n_local, (rank + 1) * n_local)
+    return P1[sl].contiguous(), P2[sl].contiguous(), (P1, P2)
+
+
+def stage_times(sm3, p1, p2, T, group, world, steps, flush):
+    """Per-stage device times of the PRODUCTION path (the one C call `value` times): libsm3's stage-timing facility
+    records CUDA events between the kernels inside sm3_infonce_step / sm3_infonce_step_peer.  -> {stage: ms}"""
+    import ctypes as C
+    lib = sm3.lib()
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda().requires_grad_(True)
+    acc, names = {}, []
+    lib.sm3_stage_timing(1)
+    try:
+        for _ in range(max(3, min(steps, 10))):
+            if flush is not None:
+                flush.add_(1.0)
+            a.grad = b.grad = None
+            sm3.fused_infonce(a, b, T, precision="bf16", group=group, comm=COMM).backward()
+            buf = (C.c_float * 8)()
+            k = lib.sm3_stage_timing_read(buf, 8)
+            names = [x for x in lib.sm3_stage_timing_names().decode().split(",") if x][:k]
+            for nm, v in zip(names, list(buf)[:k]):
+                acc.setdefault(nm, []).append(float(v))
+    finally:
+        lib.sm3_stage_timing(0)
+    torch.cuda.synchronize()
+    return {k: sum(v) / len(v) for k, v in acc.items()}
 
 
 def time_device(sm3, p1, p2, T, group, world, steps, warmup, flush, profile=True):
@@ -339,36 +368,88 @@ def time_e2e(sm3, p1, p2, T, group, world, steps, warmup, depth=2):
     return ms_pipe, ms_sync, h2d, d2h
 
 
-def cpu_reference(n, d, T, budget_s=20.0, max_reps=8):
-    """The reference's materialising CPU path (oracle/ref_port.py, an op-for-op torch port pinned to the real
-    reference by tests/test_oracle_golden.py) on the host cores.  Bounded sample -> pairs/s."""
-    from oracle import ref_port
+def _real_reference():
+    """The reference's own code (src/models/simclr.py:290-322 + nn.CrossEntropyLoss, tools/backbone_train.py:531), imported
+    unmodified from oracle/_ref/skin_sm3 (vendored by oracle/vendor_ref.py; see there).  None when it is not there."""
+    from oracle import vendor_ref
+    root = vendor_ref.ref_root()
+    if root is None:
+        return None
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    try:
+        from src.models.simclr import SimCLRSkinV3
+    except Exception as e:  # pragma: no cover
+        print(f"[bench] reference import failed: {e!r}", file=sys.stderr)
+        return None
+    import torch.nn as nn
+    ident, crit = nn.Identity(), nn.CrossEntropyLoss()
+
+    def step(p1, p2, T):
+        a = p1.detach().clone().requires_grad_(True)
+        b = p2.detach().clone().requires_grad_(True)
+        logits, labels = SimCLRSkinV3._cal_logits(None, a, b, ident, ident, T)     # `self` is unused by the reference
+        loss = crit(logits, labels)
+        loss.backward()
+        return loss.detach(), a.grad, b.grad
+    return step
+
+
+def _ref_sample_pairs(n, d, budget_s):
+    """Largest sub-problem (pairs) of the reference's O(M^2)-memory step that fits the host and the time budget: ~7 live
+    [M, M] fp32 tensors at the peak, measured 3.0 GB at N = 4096."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 16e9
+    cap = n
+    while cap > 64 and (2 * cap) ** 2 * 4 * 12 > 0.5 * avail:
+        cap //= 2
+    return cap
+
+
+def cpu_reference(n, d, T, budget_s=20.0, reps=None, warmup=1):
+    """The reference's CPU implementation of the path on the box's host cores, `reps` (+ `warmup`) timed steps of a BOUNDED
+    sample: the full step when it is small, else the same step on the largest square sub-problem N_s that fits memory and
+    the time budget, scaled to the full configuration by (N / N_s)^2 (the step's work and memory are O(N^2)); the figure is
+    then marked "estimated".  kind = "reference" (the real code, vendored) or "port" (oracle/ref_port.py) when absent."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    step = _real_reference()
+    kind = "reference" if step is not None else "port"
+    if step is None:
+        from oracle import ref_port
+        step = ref_port.port_infonce_step
     g = torch.Generator().manual_seed(SEED)
-    p1 = torch.randn(n, d, generator=g)
-    p2 = torch.randn(n, d, generator=g)
-    m = 2 * n
-    full = m * m * 4 * 8 < 24e9                    # ~8 live [M,M] fp32 temporaries must fit comfortably
-    if full:
-        fn = lambda: ref_port.port_infonce_step(p1, p2, T)           # noqa: E731
-        scale, sample = 1.0, f"full step N={n} D={d} fp32 (reference op sequence, {cores} threads)"
-    else:
-        rows = 512
-        fn = lambda: ref_port.port_infonce_step_rowblock(p1, p2, T, 1024, rows)   # noqa: E731
-        scale = m / rows
-        sample = (f"row block of {rows}/{m} logits rows x all {m} columns of N={n} D={d} fp32 "
-                  f"(full [M,M] step needs ~{m * m * 4 * 6 / 1e9:.0f} GB); time scaled x{scale:.0f}")
-    fn()
+    n_s = _ref_sample_pairs(n, d, budget_s)
+    total_reps = (reps or 3) + warmup
+    # shrink until (reps + warmup) steps fit the budget: probe a small size, extrapolate quadratically
+    probe = min(n_s, 512)
+    q1, q2 = torch.randn(probe, d, generator=g), torch.randn(probe, d, generator=g)
+    step(q1, q2, T)
+    t0 = time.perf_counter(); step(q1, q2, T); t_probe = time.perf_counter() - t0
+    while n_s > probe and 1.5 * t_probe * (n_s / probe) ** 2 * total_reps > budget_s:   # 1.5: the step is superquadratic once it leaves the caches
+        n_s //= 2
+    p1, p2 = torch.randn(n_s, d, generator=g), torch.randn(n_s, d, generator=g)
+    for _ in range(warmup):
+        step(p1, p2, T)
     times = []
-    t_start = time.perf_counter()
-    while len(times) < max_reps and (time.perf_counter() - t_start) < budget_s:
+    for _ in range(reps or 3):
         t0 = time.perf_counter()
-        fn()
+        step(p1, p2, T)
         times.append(time.perf_counter() - t0)
-    t = statistics.median(times) * scale
-    return dict(value=n / t, unit="pairs/s", cores=cores, kind="port", sample=sample, ms_per_step=t * 1e3,
-                reps=len(times))
+    t_s = statistics.median(times)
+    scale = (n / n_s) ** 2
+    what = "SimCLRSkinV3._cal_logits + nn.CrossEntropyLoss, fwd+bwd" if kind == "reference" else "op-for-op port of _cal_logits + CE"
+    if n_s == n:
+        sample = f"full step N={n} D={d} fp32 ({what}, {cores} threads)"
+    else:
+        sample = (f"{what} on a square sub-problem N_s={n_s} of N={n} (D={d}, fp32, {cores} threads; the full step needs "
+                  f"~{(2 * n) ** 2 * 4 * 7 / 1e9:.0f} GB); time scaled x{scale:.0f} = (N/N_s)^2")
+    out = dict(value=n / (t_s * scale), unit="pairs/s", cores=cores, kind=kind, sample=sample,
+               sample_pairs=n_s, sample_ms_per_step=t_s * 1e3, reps=len(times), estimated=(n_s != n), scale_factor=scale)
+    return out
 
 
 def heads_probe(sm3, pk):
@@ -435,6 +516,74 @@ def gpu_reference_port(n, d, T, reps=5):
             "what": f"reference op sequence (port) on this GPU, fp32, N={n} D={d}; not the headline baseline"}
 
 
+def config_of(wl, n, d, T, world):
+    """The `config` object of a bench line: identical for our arm and the reference arm of the same workload / N."""
+    return {"workload": wl["name"], "global_pairs": n, "rows_per_rank": 2 * n // world, "dim": d, "temperature": T,
+            "terms": 1, "sharding": f"row-block x{world}, global negatives" if world > 1 else "single GPU",
+            "l2": "256 MB flush write between timed steps (inputs are L2-sized by design)"}
+
+
+def comm_description(n, world):
+    if world == 1:
+        return "none"
+    from skin_sm3_b200 import peer as _peer
+    if COMM == "nccl":
+        return "NCCL all-gather"
+    used = "NVLink peer memory (symmetric memory"
+    mc = bool(_peer._CACHE) and any(b.multicast for b in _peer._CACHE.values())
+    used += ", NVSwitch multicast stores)" if mc else ", unicast stores)"
+    if os.environ.get("SM3_PEER_FUSED", "1") != "0" and (n // world) % 128 == 0:
+        used += ", fused exchange: scatter+signal in the producer kernels, waits inside K2/K3"
+    return used
+
+
+def parity_block(sm3, p1, p2, full, n, d, T, group, world, rank):
+    """Checked OUTSIDE every timed region, on the production path and at the benchmarked size: the loss (rank mean) and the
+    gradient of a row sample of rank 0's shard against oracle.infonce_rowblock (fp32-GEMM mode: pinned to the reference
+    goldens to 1e-5, tests/test_oracle_golden.py), and, when sharded, the fused NVLink exchange against the NCCL path.
+    The oracle is the checker here, never the thing measured."""
+    import numpy as np
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda().requires_grad_(True)
+    loss = sm3.fused_infonce(a, b, T, precision="bf16", group=group, comm=COMM)
+    loss.backward()
+    out = {"loss_local": float(loss)}
+    gl = loss.detach().clone().double()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(gl)
+        gl /= world
+        a2 = p1.cuda().requires_grad_(True)
+        b2 = p2.cuda().requires_grad_(True)
+        l2 = sm3.fused_infonce(a2, b2, T, precision="bf16", group=group, comm="nccl")
+        l2.backward()
+        e = max(float((a.grad.float() - a2.grad.float()).abs().max() / a2.grad.float().abs().max()),
+                float((b.grad.float() - b2.grad.float()).abs().max() / b2.grad.float().abs().max()))
+        out["fused_vs_nccl_grad_relerr"] = max_over_ranks(e, world)
+        out["fused_vs_nccl_loss_relerr"] = max_over_ranks(abs(float(loss) - float(l2)) / abs(float(l2)), world)
+    out["loss"] = float(gl)
+    if rank == 0:
+        from oracle import sm3_oracle as O                      # checker only
+        nl = n // world
+        rng = np.random.default_rng(11)
+        loc = np.unique(np.concatenate([np.arange(32), np.arange(nl - 32, nl), rng.choice(nl, min(nl, 64), replace=False)]))
+        rows = np.concatenate([loc, n + loc])                   # rank 0 owns pairs [0, nl): global rows loc and n + loc
+        t0 = time.perf_counter()
+        ref_loss, ref_dp, _ = O.infonce_rowblock(full[0].float().numpy(), full[1].float().numpy(), T, rows,
+                                                 matmul_dtype=np.float32, threads=os.cpu_count())
+        got = torch.cat([a.grad[torch.from_numpy(loc).cuda()], b.grad[torch.from_numpy(loc).cuda()]]).float().cpu().numpy()
+        # the sharded op returns d(sum over ranks of the per-rank mean losses)/dp = world x d(global mean loss)/dp
+        got = got / world
+        out.update({"loss_oracle_rowblock": ref_loss, "loss_relerr": abs(float(gl) - ref_loss) / abs(ref_loss),
+                    "grad_relerr_rowblock": float(np.abs(got - ref_dp).max() / np.abs(ref_dp).max()),
+                    "rows_checked": int(len(rows)), "tolerance": 2e-2, "oracle_seconds": round(time.perf_counter() - t0, 1),
+                    "oracle": "oracle.sm3_oracle.infonce_rowblock (fp32 GEMM, fp64 accumulation) on the same bf16-rounded inputs"})
+        out["ok"] = bool(out["loss_relerr"] <= 2e-2 and out["grad_relerr_rowblock"] <= 2e-2 and
+                         out.get("fused_vs_nccl_grad_relerr", 0.0) <= 1e-2)
+    barrier(world)
+    return out
+
+
 def run_ours(args):
     import skin_sm3_b200 as sm3
     world, rank, local = dist_setup(args.gpus)
@@ -446,60 +595,65 @@ def run_ours(args):
     n, d, T = wl["n"], wl["d"], wl["T"]
     assert n % world == 0
     pk = peaks()
-    p1, p2 = synth(n, d, rank, world, "cuda")
+    p1, p2, full = synth(n, d, rank, world)
     flush = torch.zeros(64 * 1024 * 1024, device="cuda")            # 256 MB > 126 MB L2
     with ClockSampler(local) as clk:
-        total_ms, stages, loss = time_device(sm3, p1, p2, T, group, world, args.steps, args.warmup, flush)
-        # `value` is measured on the production path (the whole step enqueued by ONE C call, no per-stage event marks, no
-        # Python between the kernels); the profiled pass above only supplies the per-kernel durations for the roofline.
-        total_ms, _, loss = time_device(sm3, p1, p2, T, group, world, args.steps, args.warmup, flush, profile=False)
+        # `value`: the production path (the whole step enqueued by ONE C call, no event marks, no Python between kernels)
+        total_ms, _, _ = time_device(sm3, p1, p2, T, group, world, args.steps, args.warmup, flush, profile=False)
     e2e_ms, e2e_sync_ms, h2d, d2h = time_e2e(sm3, p1, p2, T, group, world, args.steps, args.warmup)
+    # per-kernel durations of the SAME production path (events recorded inside the C call), a separate pass
+    stages = stage_times(sm3, p1, p2, T, group, world, args.steps, flush)
+    stage_source = "events inside sm3_infonce_step%s (production path)" % ("" if world == 1 else "_peer")
+    if not stages:       # NCCL / unfused exchange: no single C call -> Python-composed sequence of the same kernels
+        _, stages, _ = time_device(sm3, p1, p2, T, group, world, max(3, args.steps // 2), 2, flush, profile=True)
+        stages = {{"stats_fwd": "infonce_fwd", "stats_bwd": "infonce_bwd"}.get(k, k): v for k, v in stages.items()}
+        stage_source = "CUDA events between the Python-composed kernels (exchange path without a one-call step)"
+    parity = parity_block(sm3, p1, p2, full, n, d, T, group, world, rank)
     ms_step = total_ms / args.steps
     m_cols, m_rows = 2 * n, 2 * n // world
-    comm_used = "none"
-    if world > 1:
-        from skin_sm3_b200 import peer as _peer
-        comm_used = "NCCL all-gather"
-        if _peer._CACHE:
-            mc = any(b.multicast for b in _peer._CACHE.values())
-            comm_used = "NVLink peer memory (symmetric memory" + (", NVSwitch multicast stores)" if mc else ", unicast stores)")
-            if os.environ.get("SM3_PEER_FUSED", "1") != "0" and (n // world) % 128 == 0:
-                comm_used += ", fused exchange: scatter+signal in the producer kernels, waits inside K2/K3"
+    comm_used = comm_description(n, world)
     flops_bwd = 4.0 * m_rows * m_cols * d
     flops_fwd = 2.0 * m_rows * m_cols * d
     line = {
         "metric": "contrastive pairs/sec (fwd+bwd)", "value": n / (ms_step * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": wl["name"], "global_pairs": n, "rows_per_rank": m_rows, "dim": d, "temperature": T,
-                   "terms": 1, "sharding": (f"row-block x{world}, global negatives exchanged over " + comm_used) if world > 1 else "single GPU",
-                   "l2": "256 MB flush write between timed steps (inputs are L2-sized by design)"},
-        "loss": loss,
+        "config": config_of(wl, n, d, T, world),
+        "exchange": comm_used,
+        "loss": parity["loss"],
         "e2e": {"value": n / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                 "sync_value": n / (e2e_sync_ms / args.steps * 1e-3), "sync_ms_per_step": e2e_sync_ms / args.steps,
                 "api": ("sm3_host_pipe_submit/wait (C ABI, pinned host buffers, 2-slot copy/compute pipeline); "
-                        "sync_value = one synchronous sm3_infonce_host call per step") if world == 1 else
-                       ("skin_sm3_b200.fused_infonce(group=WORLD) fed from / drained to pinned host memory on two copy "
-                        "streams, 2 slots; sync_value = drained after every step")},
-        "gpu_launches": KERNELS_PER_STEP[world == 1] * args.steps,
+                        "sync_value = one synchronous sm3_infonce_host call per step") if world == 1 else E2E_MULTI_API},
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
         "stages_ms": {k: round(v, 4) for k, v in stages.items()},
         "clocks": clk.summary(),
+        "parity": parity,
     }
-    t_bwd = stages.get("stats_bwd")
-    t_fwd = stages.get("stats_fwd")
+    tr = ncu_traffic()
+    t_bwd, t_fwd = stages.get("infonce_bwd"), stages.get("infonce_fwd")
     if t_bwd:
         ach = flops_bwd / (t_bwd * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "infonce_tc_bwd_kernel (K3; includes its 1-block prep kernel)",
+        kname = "infonce_tc_bwd_kernel" if d > 128 else "infonce_tc_bwd2_kernel"
+        line["roofline"] = {"bound": "tensor", "kernel": kname + " (K3)" + (", incl. in-kernel waits for the peers' statistics" if world > 1 else ""),
                             "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                            "traffic": (ncu_traffic().get("infonce_tc_bwd_kernel", {}).get("dram_bytes_per_launch")
-                                        if (args.workload == "cfg4" and world == 1) else None),
-                            "traffic_source": ncu_traffic().get("source"),
-                            "peak_source": pk["source"] + ", burst bf16", "flops_per_launch": flops_bwd}
-    if t_fwd:
-        ach = flops_fwd / (t_fwd * 1e-3) / 1e12
-        line["roofline_fwd"] = {"bound": "tensor", "kernel": "infonce_tc_fwd_kernel (K2; includes the finalize kernel)",
-                                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
+                            "traffic": (tr.get(args.workload, {}).get("bwd_dram_bytes_per_launch") if world == 1 else None),
+                            "traffic_source": tr.get("source"), "stage_source": stage_source,
+                            "peak_source": pk["source"] + ", burst bf16", "flops_per_launch": flops_bwd,
+                            "launch_ms": t_bwd, "frac_of_sustained": ach / pk["tflops_sustained"] if pk["tflops_sustained"] else None}
+        r = line["roofline"]
+        if t_fwd:
+            achf = flops_fwd / (t_fwd * 1e-3) / 1e12
+            r["fwd"] = {"kernel": "infonce_tc_fwd2_kernel (K2)" + (", incl. in-kernel waits for the peers' rows" if world > 1 else ""),
+                        "achieved": achf, "frac": achf / pk["tflops"], "launch_ms": t_fwd, "flops_per_launch": flops_fwd,
+                        "traffic": (tr.get(args.workload, {}).get("fwd_dram_bytes_per_launch") if world == 1 else None)}
+        r["step"] = {"achieved": (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12,
+                     "frac": (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12 / pk["tflops"],
+                     "what": "algorithmic 6 M^2 D / W per rank over the whole timed step"}
+        r["stages_ms"] = line["stages_ms"]
+        r["parity"] = {k: parity.get(k) for k in ("ok", "loss", "loss_oracle_rowblock", "loss_relerr", "grad_relerr_rowblock",
+                                                  "fused_vs_nccl_grad_relerr", "rows_checked", "tolerance") if k in parity}
     line["step_tc_frac"] = (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12 / pk["tflops"]
     if world == 1:
         try:
@@ -509,58 +663,94 @@ def run_ours(args):
         except Exception as e:
             line["cuda_graph"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_extras:
-        line["cpu_baseline"] = cpu_reference(n, d, T)
-        if args.workload != "cfg2":     # configs[1] rides along in the same line
-            w2 = WORKLOADS["cfg2"]
-            q1, q2 = synth(w2["n"], w2["d"], 0, 1, "cuda")
-            _, st2, _ = time_device(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup, flush)          # per-stage events
-            ms2, _, _ = time_device(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup, flush, profile=False)
-            e2, e2s, _, _ = time_e2e(sm3, q1, q2, w2["T"], None, 1, args.steps, args.warmup)
+        line["cpu_baseline"] = cpu_reference(n, d, T, budget_s=25.0, reps=2)
+        r = line.get("roofline", {})
+        if args.workload != "cfg2":     # configs[1] rides along, inside `roofline` so the driver's record keeps it
             try:
-                g2 = time_graph(sm3, q1, q2, w2["T"], args.steps, args.warmup, flush)
+                r["cfg2"] = cfg2_block(sm3, pk, args, flush)
             except Exception as e:
-                g2 = None
-                print(f"[bench] cfg2 graph replay failed: {e!r}", file=sys.stderr)
-            f2 = 6.0 * (2 * w2["n"]) ** 2 * w2["d"]
-            line["cfg2"] = {"workload": w2["name"], "value": w2["n"] / (ms2 / args.steps * 1e-3), "unit": "pairs/s",
-                            "ms_per_step": ms2 / args.steps, "e2e_value": w2["n"] / (e2 / args.steps * 1e-3),
-                            "e2e_sync_value": w2["n"] / (e2s / args.steps * 1e-3),
-                            "cuda_graph_value": (w2["n"] / (g2 * 1e-3)) if g2 else None,
-                            "cuda_graph_ms_per_step": g2,
-                            "step_tc_frac": f2 / (ms2 / args.steps * 1e-3) / 1e12 / pk["tflops"],
-                            "stages_ms": {k: round(v, 4) for k, v in st2.items()},
-                            "cpu_baseline": cpu_reference(w2["n"], w2["d"], w2["T"], budget_s=12.0, max_reps=4)}
-            try:
-                line["cfg2"]["gpu_reference_port"] = gpu_reference_port(w2["n"], w2["d"], w2["T"])
-            except Exception as e:
-                line["cfg2"]["gpu_reference_port"] = {"error": repr(e)[:200]}
+                r["cfg2"] = {"error": repr(e)[:300]}
         try:
             line["cfg4_sweep"] = cfg4_sweep(sm3, args.steps, flush)
+            r["cfg4_sweep"] = line["cfg4_sweep"]
         except Exception as e:
             line["cfg4_sweep"] = {"error": repr(e)[:300]}
         try:
-            line["heads"] = heads_probe(sm3, pk)
+            r["hbm_kernels"] = heads_probe(sm3, pk)
         except Exception as e:   # the head probe must never take the headline down
-            line["heads"] = {"error": repr(e)}
-        # The newest probes run in a CHILD process with a timeout: whatever happens there (exception, device trap, hang)
+            r["hbm_kernels"] = {"error": repr(e)}
+        # The remaining probes run in a CHILD process with a timeout: whatever happens there (exception, device trap, hang)
         # cannot touch the headline numbers above or keep this process from printing its line.
         import subprocess
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-child"], capture_output=True,
-                               text=True, timeout=120)
-            got = _last_json(r.stdout)
-            line.update(got if got is not None else {"extras_child": {"error": (r.stderr or "no output")[-300:]}})
+            rr = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-child"], capture_output=True,
+                                text=True, timeout=150)
+            got = _last_json(rr.stdout)
+            r.update(got if got is not None else {"extras_child": {"error": (rr.stderr or "no output")[-300:]}})
         except subprocess.TimeoutExpired as e:
             got = _last_json(e.stdout.decode() if isinstance(e.stdout, bytes) else e.stdout)
-            line.update(got or {})
-            line["extras_child"] = {"error": "timeout after 120 s"}
+            r.update(got or {})
+            r["extras_child"] = {"error": "timeout after 150 s"}
         except Exception as e:
-            line["extras_child"] = {"error": repr(e)[:300]}
+            r["extras_child"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+E2E_MULTI_API = ("skin_sm3_b200.fused_infonce(group=WORLD) fed from / drained to pinned host memory on two copy "
+                 "streams, 2 slots; sync_value = drained after every step")
+
+
+def cfg2_block(sm3, pk, args, flush):
+    """BASELINE configs[1] (4096 x 128): production step (eager op), CUDA-graph replay, e2e, per-kernel rooflines from the
+    production path's stage events, full-size parity against the fp64 closed form, the reference on the host cores and
+    the reference's op sequence on this GPU."""
+    import numpy as np
+    w2 = WORKLOADS["cfg2"]
+    n2, d2, T2 = w2["n"], w2["d"], w2["T"]
+    q1, q2, _ = synth(n2, d2, 0, 1)
+    ms2, _, _ = time_device(sm3, q1, q2, T2, None, 1, args.steps, args.warmup, flush, profile=False)
+    st2 = stage_times(sm3, q1, q2, T2, None, 1, args.steps, flush)
+    e2, e2s, _, _ = time_e2e(sm3, q1, q2, T2, None, 1, args.steps, args.warmup)
+    try:
+        g2 = time_graph(sm3, q1, q2, T2, args.steps, args.warmup, flush)
+    except Exception as e:
+        g2 = None
+        print(f"[bench] cfg2 graph replay failed: {e!r}", file=sys.stderr)
+    m2 = 2 * n2
+    f2 = 6.0 * m2 ** 2 * d2
+    tr = ncu_traffic().get("cfg2", {})
+    blk = {"workload": w2["name"], "value": n2 / (ms2 / args.steps * 1e-3), "unit": "pairs/s",
+           "ms_per_step": ms2 / args.steps, "e2e_value": n2 / (e2 / args.steps * 1e-3),
+           "e2e_sync_value": n2 / (e2s / args.steps * 1e-3),
+           "cuda_graph_value": (n2 / (g2 * 1e-3)) if g2 else None, "cuda_graph_ms_per_step": g2,
+           "step_frac": f2 / (ms2 / args.steps * 1e-3) / 1e12 / pk["tflops"],
+           "cuda_graph_step_frac": (f2 / (g2 * 1e-3) / 1e12 / pk["tflops"]) if g2 else None,
+           "stages_ms": {k: round(v, 4) for k, v in st2.items()}}
+    for key, nm, fl in (("bwd", "infonce_bwd", 4.0 * m2 * m2 * d2), ("fwd", "infonce_fwd", 2.0 * m2 * m2 * d2)):
+        if st2.get(nm):
+            ach = fl / (st2[nm] * 1e-3) / 1e12
+            blk[key] = {"launch_us": round(st2[nm] * 1e3, 2), "achieved": ach, "frac": ach / pk["tflops"], "unit": "TFLOP/s",
+                        "flops_per_launch": fl, "traffic": tr.get(key + "_dram_bytes_per_launch")}
+    # parity at this size: every gradient element against the fp64 closed form (the checker, outside all timing)
+    from oracle import sm3_oracle as O
+    a, b = q1.cuda().requires_grad_(True), q2.cuda().requires_grad_(True)
+    loss = sm3.fused_infonce(a, b, T2, precision="bf16")
+    loss.backward()
+    ref_loss, r1, r2 = O.infonce_closed_form(q1.float().numpy(), q2.float().numpy(), T2, chunk=2048)
+    blk["parity"] = {"loss": float(loss), "loss_oracle": ref_loss, "loss_relerr": abs(float(loss) - ref_loss) / abs(ref_loss),
+                     "grad_relerr_all_rows": float(max(np.abs(a.grad.float().cpu().numpy() - r1).max() / np.abs(r1).max(),
+                                                       np.abs(b.grad.float().cpu().numpy() - r2).max() / np.abs(r2).max())),
+                     "tolerance": 2e-2}
+    blk["cpu_baseline"] = cpu_reference(n2, d2, T2, budget_s=12.0, reps=2)
+    try:
+        blk["gpu_reference_port"] = gpu_reference_port(n2, d2, T2)
+    except Exception as e:
+        blk["gpu_reference_port"] = {"error": repr(e)[:200]}
+    return blk
 
 
 def cfg4_sweep(sm3, steps, flush, d=256, T=0.1):
@@ -651,27 +841,26 @@ def small_shapes_probe(sm3):
 
 
 def tc_kernel_probe(sm3):
-    """K2 and K3 timed on their own at cfg2 (4096 x 128, the D = 128 regime of every reference config), for the knob values
-    that have been parity-checked on B200: forward rows per CTA 256 / 128 and FMA-pipe exponentials 0 / 2 per 8; backward
-    S/H stages 4 / 2.  Feeds DESIGN.md section 9 item 1.  Microseconds per launch (finalize / prep kernels included)."""
-    n, d, T = 4096, 128, 0.1
-    z, _ = sm3.core.normalize_pair(torch.randn(2 * n, d, device="cuda"), None, torch.bfloat16)
-    pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
-    _, gp, gl = sm3.core.loss(pos, lse, 1.0 / (2 * n))
-    knobs = ("SM3_TC_FWD_BM", "SM3_TC_POLY", "SM3_TC_BWD_NS")
+    """K2 / K3 launch times at cfg2 (4096 x 128: the D = 128 regime of every reference config) and at N = 8192 x 256 from the
+    production path's stage events, for the kernel variants selectable at run time: backward form 1 (softmax warps split
+    the tile's columns) vs 2 (tile-alternating groups, a_j through shared memory), S/H stages, FMA-pipe exponentials in
+    the forward.  Microseconds per launch."""
+    knobs = ("SM3_TC_FWD_BM", "SM3_TC_POLY", "SM3_TC_BWD_NS", "SM3_TC_BWD_V")
     saved = {k: os.environ.get(k) for k in knobs}
     out = {}
     try:
-        for bm, poly in (("256", "0"), ("256", "2"), ("128", "0")):      # the combinations that have run on B200 before
-            os.environ["SM3_TC_FWD_BM"], os.environ["SM3_TC_POLY"] = bm, poly
-            sm3.lib().sm3_debug_reload_env()
-            out[f"fwd_bm{bm}_poly{poly}_us"] = round(_ev_us(lambda: sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)), 1)
-        os.environ.pop("SM3_TC_FWD_BM", None); os.environ.pop("SM3_TC_POLY", None)
-        for ns in ("4", "2"):
-            os.environ["SM3_TC_BWD_NS"] = ns
-            sm3.lib().sm3_debug_reload_env()
-            out[f"bwd_stages{ns}_us"] = round(_ev_us(
-                lambda: sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)), 1)
+        for n, d in ((4096, 128), (8192, 256)):
+            p1, p2, _ = synth(n, d, 0, 1, seed=SEED + n)
+            for name, cfg in (("default", {}), ("bwd_v1", {"SM3_TC_BWD_V": "1"}), ("bwd_v2", {"SM3_TC_BWD_V": "2"}),
+                              ("bwd_v2_ns2", {"SM3_TC_BWD_V": "2", "SM3_TC_BWD_NS": "2"}),
+                              ("fwd_poly0", {"SM3_TC_POLY": "0"}), ("fwd_poly2", {"SM3_TC_POLY": "2"})):
+                for k in knobs:
+                    os.environ.pop(k, None)
+                os.environ.update(cfg)
+                sm3.lib().sm3_debug_reload_env()
+                st = stage_times(sm3, p1, p2, 0.1, None, 1, 10, None)
+                out[f"n{n}_d{d}_{name}"] = {"fwd_us": round(st.get("infonce_fwd", 0) * 1e3, 1),
+                                            "bwd_us": round(st.get("infonce_bwd", 0) * 1e3, 1)}
     finally:
         for k, v in saved.items():
             if v is None:
@@ -679,109 +868,6 @@ def tc_kernel_probe(sm3):
             else:
                 os.environ[k] = v
         sm3.lib().sm3_debug_reload_env()
-    return out
-
-
-def tc_experimental_probe(sm3, emit):
-    """Knob combinations that have NOT been run on a B200 yet (two softmax groups with 4 backward stages, FMA-pipe
-    exponentials in the 128-row forward, forced split counts), at the D = 128 shapes.  Only ever called from the
-    extras child: each result is checked against the default configuration's output ("ok") and emitted immediately,
-    so a trap in one combination costs the combinations after it, nothing else."""
-    knobs = ("SM3_TC_FWD_BM", "SM3_TC_POLY", "SM3_TC_GROUPS", "SM3_TC_BWD_NS", "SM3_TC_FWD_SPLITS", "SM3_TC_BWD_SPLITS")
-
-    def set_knobs(cfg):
-        for k in knobs:
-            os.environ.pop(k, None)
-        os.environ.update({k: str(v) for k, v in cfg.items()})
-        sm3.lib().sm3_debug_reload_env()
-
-    out = []
-    for n in (4096, 1024, 256):
-        d, T = 128, 0.1
-        z, _ = sm3.core.normalize_pair(torch.randn(2 * n, d, device="cuda"), None, torch.bfloat16)
-        set_knobs({})
-        pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
-        _, gp, gl = sm3.core.loss(pos, lse, 1.0 / (2 * n))
-        ws, npart = sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)
-        dz_ref = sm3.core.sum_partials(ws, npart, 2 * n, d).clone()
-        fwd = [{"SM3_TC_FWD_BM": 128, "SM3_TC_POLY": 2}, {"SM3_TC_FWD_BM": 128, "SM3_TC_GROUPS": 2},
-               {"SM3_TC_FWD_BM": 128, "SM3_TC_GROUPS": 2, "SM3_TC_POLY": 2},
-               {"SM3_TC_FWD_SPLITS": 2}, {"SM3_TC_FWD_SPLITS": 8}, {"SM3_TC_FWD_BM": 128, "SM3_TC_FWD_SPLITS": 8}]
-        bwd = [{"SM3_TC_GROUPS": 2, "SM3_TC_BWD_NS": 4}, {"SM3_TC_GROUPS": 2, "SM3_TC_BWD_NS": 2},
-               {"SM3_TC_BWD_SPLITS": 1}, {"SM3_TC_BWD_SPLITS": 3}, {"SM3_TC_BWD_SPLITS": 4},
-               {"SM3_TC_BWD_SPLITS": 4, "SM3_TC_GROUPS": 2}]
-        for kind, cfgs in (("fwd", fwd), ("bwd", bwd)):
-            for cfg in cfgs:
-                rec = {"kernel": kind, "pairs": n, **cfg}
-                try:
-                    set_knobs(cfg)
-                    if kind == "fwd":
-                        p2, _, n2 = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
-                        rec["ok"] = bool(torch.allclose(p2, pos, rtol=1e-5, atol=1e-6) and torch.allclose(n2, nsum, rtol=1e-3))
-                        rec["us"] = round(_ev_us(lambda: sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)), 1)
-                    else:
-                        w2, np2 = sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)
-                        dz = sm3.core.sum_partials(w2, np2, 2 * n, d)
-                        rec["ok"] = bool((dz - dz_ref).abs().max().item() <= 2e-2 * dz_ref.abs().max().item())
-                        rec["us"] = round(_ev_us(
-                            lambda: sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)), 1)
-                except Exception as e:
-                    rec["error"] = repr(e)[:200]
-                out.append(rec)
-                emit(out)
-    set_knobs({})
-    return out
-
-
-def hbm_experimental_probe(sm3, emit):
-    """Opt-in variants of the HBM-bound kernels that have not run on hardware yet (extras child only): the persistent
-    normalise-backward (SM3_K1_BWD_VARIANT=1) and the deep-prefetch BCE kernels (SM3_BCE_VARIANT=2|3), each checked
-    against the default's output and timed at the bandwidth-sized shapes of `heads`."""
-    out = []
-    pk = peaks()
-
-    def rec(name, variant, ms, nbytes, ok):
-        out.append({"kernel": name, "variant": variant, "us": round(ms * 1e3, 2), "frac_hbm": round(nbytes / ms / 1e6 / pk["hbm"], 3),
-                    "ok": bool(ok)})
-        emit(out)
-
-    try:
-        for M, D, parts in ((1 << 21, 256, 1), (65536, 256, 2)):
-            z, inv = sm3.core.normalize_pair(torch.randn(M, D, device="cuda", dtype=torch.bfloat16), None, torch.bfloat16)
-            dz = torch.randn(parts, M, D, device="cuda", dtype=torch.float32)
-            nbytes = M * D * (4 * parts + 2 + 2) + 4 * M
-            ref = None
-            for v in ("0", "1"):
-                os.environ["SM3_K1_BWD_VARIANT"] = v
-                o, _ = sm3.core.normalize_bwd(dz, parts, 1.0, z, inv, M, 0, torch.bfloat16)
-                ref = o.clone() if ref is None else ref
-                us = _ev_us(lambda: sm3.core.normalize_bwd(dz, parts, 1.0, z, inv, M, 0, torch.bfloat16), reps=10)
-                rec(f"l2norm_bwd_{M}x{D}_p{parts}", v, us / 1e3, nbytes, torch.equal(o, ref))
-            del z, inv, dz, ref
-    except Exception as e:
-        out.append({"kernel": "l2norm_bwd", "error": repr(e)[:200]}); emit(out)
-    finally:
-        os.environ.pop("SM3_K1_BWD_VARIANT", None)
-    try:
-        B = 1 << 22
-        x = torch.randn(B, 24, device="cuda", dtype=torch.bfloat16, requires_grad=True)
-        t = (torch.rand(B, 24, device="cuda") < 0.3).to(torch.bfloat16)
-        ref = None
-        for v in ("1", "2", "3"):
-            os.environ["SM3_BCE_VARIANT"] = v
-            x.grad = None
-            loss = sm3.bce_with_logits(x, t)
-            loss.backward()
-            cur = (float(loss.detach()), x.grad.float().clone())
-            ref = cur if ref is None else ref
-            ok = abs(cur[0] - ref[0]) <= 1e-5 * abs(ref[0]) and \
-                (cur[1] - ref[1]).abs().max().item() <= 1e-2 * ref[1].abs().max().item()
-            us = _ev_us(lambda: sm3.bce_with_logits(x, t), reps=20)
-            rec("bce_b4M", v, us / 1e3, B * 24 * 6, ok)
-    except Exception as e:
-        out.append({"kernel": "bce", "error": repr(e)[:200]}); emit(out)
-    finally:
-        os.environ.pop("SM3_BCE_VARIANT", None)
     return out
 
 
@@ -877,27 +963,46 @@ def run_cfg3(args):
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (op-for-op port in oracle/ref_port.py;
-    the Python reference itself cannot travel to the GPU box) on all host threads, bounded sample per step."""
+    """Reference arm: the reference's own CPU implementation of the path -- the real SimCLRSkinV3._cal_logits +
+    nn.CrossEntropyLoss, unmodified, from oracle/_ref (oracle/ref_port.py only when that is absent) -- on all host threads,
+    exactly --steps timed steps after --warmup, each a bounded sample of our arm's workload (see cpu_reference)."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     wl = WORKLOADS["cfg4" if args.workload == "cfg3" else args.workload]
     n, d, T = wl["n"], wl["d"], wl["T"]
-    reps = max(1, args.steps)
-    r = cpu_reference(n, d, T, budget_s=60.0, max_reps=min(reps, 8))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    r = cpu_reference(n, d, T, budget_s=150.0, reps=steps, warmup=warmup)
     line = {
         "impl": "reference", "metric": "contrastive pairs/sec (fwd+bwd)", "value": r["value"], "unit": "pairs/s",
-        "n_gpus": world, "steps": r["reps"], "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": r["sample_ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "global_pairs": n, "dim": d, "temperature": T, "terms": 1,
-                   "device": "host CPU"},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": config_of(wl, n, d, T, world),
+        "estimated": r["estimated"], "scale_factor": r["scale_factor"],
+        "note": ("value = pairs/s of the full configuration; ms_per_step = measured time of one sampled step"
+                 + (" (value is an ESTIMATE: sample time x scale_factor)" if r["estimated"] else "")),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "estimated", "scale_factor")},
         "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "device": "host CPU",
     }
     print(json.dumps(line))
+
+
+def retrieval_probe(sm3):
+    """N1: fused similarity + top-k (sm3_sim_topk) against `q @ bank.T; topk` on the same GPU, at the KNN evaluator's
+    shape (src/models/evaluator.py:43-83: k = 200) and at a cfg2-sized in-batch retrieval."""
+    out = {}
+    for name, bq, nb, d, k in (("knn_eval_b512_bank16k_k200", 512, 16384, 128, 200), ("in_batch_8192_k5", 8192, 8192, 128, 5)):
+        q = torch.nn.functional.normalize(torch.randn(bq, d, device="cuda"), dim=1)
+        bank = torch.nn.functional.normalize(torch.randn(nb, d, device="cuda"), dim=1)
+        ours = _ev_us(lambda: sm3.sim_topk(q, bank, k), reps=10)
+        ref = _ev_us(lambda: (q @ bank.T).topk(k, dim=-1), reps=10)
+        v, i = sm3.sim_topk(q, bank, k)
+        rv, ri = (q @ bank.T).topk(k, dim=-1)
+        out[name] = {"ours_us": round(ours, 1), "matmul_topk_us": round(ref, 1),
+                     "index_agreement": float((i == ri).float().mean())}
+    return out
 
 
 def run_extras_child():
@@ -906,23 +1011,12 @@ def run_extras_child():
     torch.cuda.set_device(0)
     out = {}
     for key, probe in (("small_shapes", small_shapes_probe), ("tc_kernels_cfg2", tc_kernel_probe),
-                       ("kmeans", kmeans_probe)):
+                       ("kmeans", kmeans_probe), ("retrieval", retrieval_probe)):
         try:
             out[key] = probe(sm3)
         except Exception as e:
             out[key] = {"error": repr(e)[:300]}
         print(json.dumps(out), flush=True)          # cumulative: the parent keeps the last complete line
-
-    # last: code that has never run on the hardware, each result checked against the default's and emitted at once
-    for key, probe in (("hbm_experimental", hbm_experimental_probe), ("tc_experimental", tc_experimental_probe)):
-        def emit(partial, key=key):
-            out[key] = partial
-            print(json.dumps(out), flush=True)
-        try:
-            probe(sm3, emit)
-        except Exception as e:
-            out[key + "_error"] = repr(e)[:300]
-            print(json.dumps(out), flush=True)
 
 
 def main():

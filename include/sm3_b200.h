@@ -261,6 +261,20 @@ int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local, int rank,
                           void* const* flags_peers_host, unsigned epoch, int overlap, void* device_scratch,
                           size_t scratch_bytes, void* stream_main, void* stream_side);
 
+/* out_t[i] = in_t[i] * (*g_device) for `count` (<= 8) tensors of `numel` elements each, one launch: the upstream scaling
+ * that autograd applies to the gradients the fused steps computed eagerly (GradScaler factor x loss weight,
+ * tools/backbone_train.py:101-125); in/out dtypes may differ (fp32 gradients -> fp16 after the factor). */
+int sm3_scale_grads(const void* const* in_host_array, void* const* out_host_array, int count, int64_t numel,
+                    int in_dtype, int out_dtype, const float* g_device, void* stream);
+
+/* Per-stage timing of the fused steps on the PRODUCTION path (bench / profiling; not thread safe, one step at a time):
+ * while enabled, sm3_infonce_step and sm3_infonce_step_peer (fused mode) record a CUDA event on the launching stream
+ * before the first and after every stage; `read` synchronises on the last event of the most recent step and returns the
+ * number of stages, ms[k] = duration of stage k; `names` = comma-separated stage names of that step. */
+int sm3_stage_timing(int enable);
+int sm3_stage_timing_read(float* ms, int capacity);
+const char* sm3_stage_timing_names(void);
+
 /* debug / tuning: drop the cached values of the SM3_TC_* environment knobs (SM3_TC_GROUPS, SM3_TC_POLY, SM3_TC_BWD_NS;
  * SM3_TC_FWD_BM, SM3_TC_FWD_SPLITS, SM3_TC_BWD_SPLITS and the HBM-kernel variant selectors are read at every launch)
  * so that a sweep can change them inside one process.  Not a product path.                                       */

@@ -12,6 +12,7 @@ What it restates (all citations relative to the reference checkout):
                               (= SimCLR.forward :54-93 with one projector)
 * ``cross_entropy_col0``   -> ``nn.CrossEntropyLoss()(logits, 0)``     tools/backbone_train.py:531,101-121
 * ``infonce_closed_form``  -> the same objective without the [M,M] matrix (chunked, any N) + gradients
+* ``infonce_rowblock``     -> loss + gradient of a chosen set of rows at full benchmark size (cfg4)
 * ``multihead_ce``         -> the 8-head loss loops                    tools/mlc_eval.py:159-162,
                                                                         tools/mlc_train.py:255-261,381
 * ``bce_with_logits``      -> (no reference counterpart: PARITY UNPINNED; restates
@@ -156,6 +157,65 @@ def infonce_closed_form(p1, p2, temperature: float, chunk: int = 1024, upstream:
     clamped = (1.0 / inv) <= 1e-12
     dp = normalize_bwd(dz, z, inv, clamped)
     return loss, dp[:n], dp[n:]
+
+
+def infonce_rowblock(p1, p2, temperature: float, rows, chunk: int = 2048, matmul_dtype=np.float64,
+                     upstream: float = 1.0, threads=None):
+    """Loss of one InfoNCE term and d loss / d p for a chosen set of GLOBAL rows, at sizes where the full fp64
+    closed form above is too slow (cfg4: M = 65536 rows, 4.3e9 logits).
+
+    ``rows`` index the concatenated batch ``p = cat([p1, p2])`` (0 <= row < 2N).  Returns
+    ``(loss, dp_rows [len(rows), D], lse_all [M])`` with the same maths as ``infonce_closed_form``
+    (simclr.py:290-322 + CE backbone_train.py:531 + their autograd backward):
+
+        lse_j  = log sum_{k != j} exp(S_jk)                  for ALL j (one full pass, needed by every row's gradient)
+        dz_i   = sum_j (exp(S_ij - lse_i) + exp(S_ij - lse_j) - 2 [j = pos(i)]) z_j * upstream / (M T)     (j != i)
+        dp_i   = (dz_i - z_i <z_i, dz_i>) / max(||p_i||, 1e-12)
+
+    ``matmul_dtype=np.float64`` is the pinned mode (agrees with the reference goldens to 1e-12, see
+    tests/test_oracle_golden.py).  ``np.float32`` runs the M x M similarity pass as a multi-threaded fp32 GEMM with
+    fp64 row-sum accumulation (torch CPU): relative error <= 1e-5 on loss and gradients (pinned by the same test),
+    three orders of magnitude below the 2e-2 bf16 tolerance it is used to check at full size.
+    """
+    import torch
+    if threads:
+        torch.set_num_threads(int(threads))
+    p = np.concatenate([np.asarray(p1, np.float64), np.asarray(p2, np.float64)], axis=0)
+    n = p1.shape[0]
+    m = 2 * n
+    z, inv = normalize(p)
+    tdt = torch.float64 if matmul_dtype == np.float64 else torch.float32
+    zt = torch.from_numpy(np.ascontiguousarray(z)).to(tdt)
+    inv_t = 1.0 / temperature
+    lse = np.empty(m)
+    pos = np.empty(m)
+    for s in range(0, m, chunk):
+        e = min(m, s + chunk)
+        S = (zt[s:e] @ zt.T) * inv_t                     # simclr.py:300, :320
+        ar = torch.arange(e - s)
+        pj = (torch.arange(s, e) + n) % m
+        pos[s:e] = S[ar, pj].double().numpy()
+        S[ar, torch.arange(s, e)] = -float("inf")        # drop the diagonal (simclr.py:303-307)
+        mx = S.max(dim=1, keepdim=True).values
+        mx = torch.where(torch.isfinite(mx), mx, torch.zeros_like(mx))
+        lse[s:e] = (mx[:, 0].double() + torch.exp(S - mx).sum(dim=1, dtype=torch.float64).log()).numpy()
+    loss = float(np.mean(lse - pos))
+    rows = np.asarray(rows, np.int64)
+    dp = np.empty((len(rows), p.shape[1]))
+    lse_t = torch.from_numpy(lse)
+    z64 = torch.from_numpy(np.ascontiguousarray(z))
+    for s in range(0, len(rows), chunk):
+        r = rows[s:s + chunk]
+        rt = torch.from_numpy(r)
+        S = ((zt[rt] @ zt.T) * inv_t).double()
+        H = torch.exp(S - lse_t[rt][:, None]) + torch.exp(S - lse_t[None, :])
+        ar = torch.arange(len(r))
+        H[ar, rt] = 0.0
+        H[ar, (rt + n) % m] -= 2.0
+        dz = (H @ z64).numpy() * (upstream / (m * temperature))
+        clamped = (1.0 / inv[r]) <= 1e-12
+        dp[s:s + chunk] = normalize_bwd(dz, z[r], inv[r], clamped)
+    return loss, dp, lse
 
 
 def stats_backward(z, n_pairs, temperature, g_pos, g_lse, rows=None, chunk: int = 1024):

@@ -67,6 +67,10 @@ SIGNATURES = {
     "sm3_infonce_step_peer_scratch_bytes": (_sz, [_i, _i, _i]),
     "sm3_infonce_step_peer": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp,
                                    C.POINTER(_vp), _vp, C.POINTER(_vp), C.c_uint, _i, _vp, _sz, _vp, _vp]),
+    "sm3_scale_grads": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _i64, _i, _i, _vp, _vp]),
+    "sm3_stage_timing": (_i, [_i]),
+    "sm3_stage_timing_read": (_i, [_vp, _i]),
+    "sm3_stage_timing_names": (C.c_char_p, []),
     "sm3_debug_reload_env": (None, []),
     "sm3_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }

@@ -19,6 +19,24 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+// ---- stage timing (bench / profiling only): events recorded between the stages of the fused steps ----
+static constexpr int kMaxStages = 8;
+static bool g_stage_timing = false;
+static cudaEvent_t g_stage_ev[kMaxStages + 1] = {};
+static int g_stage_count = 0;                 // events recorded by the most recent step (stages = count - 1)
+static const char* g_stage_names = "";
+static void stage_begin(cudaStream_t st, const char* names) {
+  if (!g_stage_timing) return;
+  g_stage_names = names;
+  g_stage_count = 0;
+  for (int i = 0; i <= kMaxStages; ++i)
+    if (g_stage_ev[i] == nullptr && cudaEventCreate(&g_stage_ev[i]) != cudaSuccess) { g_stage_timing = false; return; }
+  cudaEventRecord(g_stage_ev[g_stage_count++], st);
+}
+static void stage_mark(cudaStream_t st) {
+  if (g_stage_timing && g_stage_count > 0 && g_stage_count <= kMaxStages) cudaEventRecord(g_stage_ev[g_stage_count++], st);
+}
+
 static int pick_algo(const InfoNceProblem& pb, int algo) {
   if (algo == SM3_ALGO_AUTO) return infonce_tc_supported(pb) ? SM3_ALGO_TC : SM3_ALGO_SIMT;
   return algo;
@@ -37,6 +55,22 @@ static int check_problem(const InfoNceProblem& pb) {
 using namespace sm3;
 
 extern "C" int sm3_version(void) { return SM3_ABI_VERSION; }
+
+extern "C" int sm3_stage_timing(int enable) {
+  g_stage_timing = enable != 0;
+  g_stage_count = 0;
+  return SM3_OK;
+}
+extern "C" const char* sm3_stage_timing_names(void) { return g_stage_names; }
+extern "C" int sm3_stage_timing_read(float* ms, int capacity) {
+  SM3_REQUIRE(ms != nullptr && capacity >= 1, SM3_ERR_SHAPE, "stage_timing_read: bad buffer");
+  if (g_stage_count < 2) return 0;
+  SM3_CHECK_CUDA(cudaEventSynchronize(g_stage_ev[g_stage_count - 1]));
+  int n = 0;
+  for (int i = 1; i < g_stage_count && n < capacity; ++i, ++n)
+    SM3_CHECK_CUDA(cudaEventElapsedTime(&ms[n], g_stage_ev[i - 1], g_stage_ev[i]));
+  return n;
+}
 extern "C" const char* sm3_last_error(void) { return get_error(); }
 
 extern "C" int sm3_device_supported(void) {
@@ -242,8 +276,10 @@ static int step_impl(const void* p1, const void* p2, int n_pairs, int D, int io_
   char* base = (char*)device_scratch;
   const int64_t n = n_pairs, m = 2 * n;
   const float inv_T = 1.0f / temperature;
+  stage_begin(st, "normalize,infonce_fwd,loss,infonce_bwd,normalize_bwd");
   int rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f, st);
   if (rc) return rc;
+  stage_mark(st);
   if (h.algo == SM3_ALGO_TC) {
     // K2 leaves its per-split partial row sums in the workspace; ONE multi-CTA kernel folds them and does the CE on
     // the statistics + its gradient (instead of a finalize launch and a single-CTA reduction over all 2N rows)
@@ -253,20 +289,41 @@ static int step_impl(const void* p1, const void* p2, int n_pairs, int D, int io_
     const int splits = infonce_tc_fwd(pb, (float*)(base + h.pos), (float*)(base + h.lse), (float*)(base + h.nsum),
                                       base + h.ws, h.ws_bytes, st);
     if (splits < 0) return splits;
+    stage_mark(st);
     unsigned* ticket = (unsigned*)(base + h.loss + 64);
     SM3_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
     PeerFused none{};
     none.counter = ticket;
+    // the same kernel also materialises a_j = g_lse_j / neg_sum_j where K3 expects it (behind the partial-gradient slabs:
+    // K2's partial sums at the start of the workspace are dead by the time K3 overwrites them), so the backward needs no
+    // prep launch
+    float* acol = (float*)(base + h.ws + infonce_tc_acol_offset(pb));
     rc = loss_stats_scatter_launch((const float*)(base + h.ws), splits, (const float*)(base + h.pos), n_pairs, 0, n_pairs,
                                    inv_T, weight / (float)m, loss, (float*)(base + h.gpos), (float*)(base + h.glse),
                                    (float*)(base + h.nsum), (float*)(base + h.lse) /* per-CTA loss sums */, none, st,
-                                   accumulate);
+                                   accumulate, dp1 ? acol : nullptr);
+    stage_mark(st);
+    if (rc || !dp1) return rc;
+    InfoNceProblem pk{base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T};
+    pk.acol_direct = acol;
+    const int np = infonce_tc_bwd(pk, (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
+                                  (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum), base + h.ws,
+                                  h.ws_bytes, st);
+    if (np < 0) return np;
+    stage_mark(st);
+    rc = sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
+                        dp1, n, dp2, n, D, io_dtype, st);
+    stage_mark(st);
+    return rc;
   } else {
     rc = sm3_infonce_fwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T, (float*)(base + h.pos),
                          (float*)(base + h.lse), (float*)(base + h.nsum), base + h.ws, h.ws_bytes, h.algo, st);
     if (rc) return rc;
+    if (rc) return rc;
+    stage_mark(st);
     rc = sm3_infonce_loss((float*)(base + h.pos), (float*)(base + h.lse), m, weight / (float)m, loss, accumulate,
                           dp1 ? (float*)(base + h.gpos) : nullptr, dp1 ? (float*)(base + h.glse) : nullptr, st);
+    stage_mark(st);
   }
   if (rc || !dp1) return rc;
   const int np = sm3_infonce_bwd(base + h.z, base + h.z, n_pairs, 0, n_pairs, D, h.z_dtype, inv_T,
@@ -274,8 +331,11 @@ static int step_impl(const void* p1, const void* p2, int n_pairs, int D, int io_
                                  (float*)(base + h.gpos), (float*)(base + h.glse), (float*)(base + h.nsum),
                                  base + h.ws, h.ws_bytes, h.algo, st);
   if (np < 0) return np;
-  return sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
-                        dp1, n, dp2, n, D, io_dtype, st);
+  stage_mark(st);
+  rc = sm3_l2norm_bwd((const float*)(base + h.ws), np, 1.0f, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f,
+                      dp1, n, dp2, n, D, io_dtype, st);
+  stage_mark(st);
+  return rc;
 }
 
 extern "C" int sm3_infonce_step(const void* p1, const void* p2, int n_pairs, int D, int io_dtype, float temperature,
@@ -418,17 +478,21 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
     SM3_REQUIRE(aligned16(p1) && aligned16(p2), SM3_ERR_SHAPE, "infonce_step_peer: fused mode needs 16-byte aligned rows");
     unsigned* counters = (unsigned*)flags_mine + 64;          // two local ticket words behind the 64 flag slots
     PeerFused pz{zp, fp, counters, rank, 0, epoch};
+    stage_begin(sm, "normalize_scatter,infonce_fwd,loss_scatter,infonce_bwd,normalize_bwd");
     rc = l2norm_scatter_launch(p1, p2, n_local, off, n_global, D, io_dtype, z, (float*)(base + h.inv), 1e-12f, pz, sm);
     if (rc) return rc;
+    stage_mark(sm);
     InfoNceProblem pf{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
     pf.wait_flags = (const unsigned*)flags_mine; pf.wait_world = world; pf.wait_channel = 0; pf.wait_epoch = epoch;
     pf.no_finalize = 1;
     SM3_REQUIRE(infonce_tc_supported(pf), SM3_ERR_DTYPE, "infonce_step_peer: tcgen05 path unavailable");
     const int splits = infonce_tc_fwd(pf, pos, lse, nsum, base + h.ws_b, h.ws_b_bytes, sm);
     if (splits < 0) return splits;
+    stage_mark(sm);
     PeerFused ps{sp, fp, counters + 1, rank, 1, epoch};
     rc = loss_stats_scatter_launch((const float*)(base + h.ws_b), splits, pos, n_local, off, n_global, inv_T,
                                    weight / (float)m, loss, gpos, glse, nsum, lse_l /* per-CTA loss sums */, ps, sm);
+    stage_mark(sm);
     if (rc || !dp1) return rc;
     InfoNceProblem pk{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
     pk.wait_flags = (const unsigned*)flags_mine; pk.wait_world = world; pk.wait_channel = 1; pk.wait_epoch = epoch;
@@ -436,8 +500,11 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
     const float* gpos_cols = (const float*)stats_mine + (size_t)2 * n_global;
     const int np = infonce_tc_bwd(pk, gpos, glse, nsum, gpos_cols, gpos_cols, gpos_cols, base + h.ws_b, h.ws_b_bytes, sm);
     if (np < 0) return np;
-    return sm3_l2norm_bwd((const float*)(base + h.ws_b), np, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, dp1, n,
-                          dp2, n, D, io_dtype, sm);
+    stage_mark(sm);
+    rc = sm3_l2norm_bwd((const float*)(base + h.ws_b), np, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, dp1, n,
+                        dp2, n, D, io_dtype, sm);
+    stage_mark(sm);
+    return rc;
   }
   rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, sm);
   if (rc) return rc;

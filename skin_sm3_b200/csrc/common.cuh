@@ -139,23 +139,41 @@ __device__ __forceinline__ int positive_of(int g, int n_global) {
 
 // Cross-rank flag wait used INSIDE kernels (fused exchange): one thread spins until every peer has published `epoch`
 // on `channel` of this rank's flag buffer (slot layout: flags[channel * 16 + source_rank], epochs only grow).  The
-// acquire at system scope orders this thread's later reads after the peers' stores; a missing peer traps after ~10 s
-// instead of hanging the GPU.
-__device__ __forceinline__ void peer_flags_wait_all(const unsigned* flags, int world, int channel, unsigned epoch) {
-  const long long t0 = clock64();
+// acquire at system scope orders this thread's later reads after the peers' stores.  A peer may legitimately be late
+// by a long time (dataloader respawn at an epoch boundary, rank-0 checkpoint or evaluation, cudnn autotune), so the
+// wait is bounded in WALL time by `timeout_ns` (host: SM3_PEER_TIMEOUT_S, default 1800 s -- the order of NCCL's own
+// watchdog) and backs off with nanosleep; only past that bound does it trap, so a dead peer cannot hang the GPU for ever.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void peer_flags_wait_all(const unsigned* flags, int world, int channel, unsigned epoch,
+                                                    unsigned long long timeout_ns) {
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
   for (int r = 0; r < world; ++r) {
     const unsigned* src = flags + channel * 16 + r;
     unsigned v;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
       if ((int)(v - epoch) >= 0) break;
-      if (clock64() - t0 > 20000000000LL) {
-        printf("sm3: in-kernel peer wait timeout (channel %d, peer %d, have %u, want %u)\n", channel, r, v, epoch);
-        __trap();
+      if (++spins > 64u) {                     // the first polls are back to back (the common case: data lands within us)
+        __nanosleep(spins > 4096u ? 2000u : 100u);
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > timeout_ns) {
+          printf("sm3: in-kernel peer wait timed out after %llu s (channel %d, peer %d, have %u, want %u); "
+                 "raise SM3_PEER_TIMEOUT_S if ranks may enter the step further apart\n",
+                 timeout_ns / 1000000000ull, channel, r, v, epoch);
+          __trap();
+        }
       }
     } while (true);
   }
 }
+// host side: SM3_PEER_TIMEOUT_S (seconds, default 1800; read once)
+unsigned long long peer_timeout_ns();
 
 // dtype dispatch helper for host code
 #define SM3_DISPATCH_DTYPE(dt, T, ...)                       \
@@ -206,7 +224,10 @@ int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pai
                           void* z_local, float* inv_norm, float eps, const PeerFused& pf, cudaStream_t st);
 int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
                               int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
-                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate = 0);
+                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate = 0,
+                              float* a_local = nullptr);
+// byte offset of the a_j array (padded to a multiple of 64 columns + 64) inside the tcgen05 backward workspace
+size_t infonce_tc_acol_offset(const InfoNceProblem& pb);
 size_t infonce_simt_workspace(const InfoNceProblem& pb, int backward);
 int infonce_simt_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
                      cudaStream_t st);

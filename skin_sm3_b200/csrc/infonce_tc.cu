@@ -61,6 +61,7 @@ struct TcParams {
   const unsigned* wait_flags;
   int wait_world, wait_channel;
   unsigned wait_epoch;
+  unsigned long long wait_timeout_ns;
   int loc_a, loc_b, loc_len;
 };
 
@@ -245,6 +246,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);   // [2*NG - 1][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long bar_limit = 2000000000ull + p.wait_timeout_ns;   // + cross-rank bound in fused-exchange mode
   const int r0 = blockIdx.x * kBM;
   const int split = blockIdx.y;
   const int t_begin = split * p.tiles_per_split;
@@ -287,13 +289,13 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       const int tile = tile_of(it);
       if (!remote_ready && !tile_is_local(p, tile)) {     // fused exchange: the peers' rows must have landed
         if (elect_one()) {
-          peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch);
+          peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch, p.wait_timeout_ns);
           fence_proxy_async_global();
         }
         __syncwarp();
         remote_ready = true;
       }
-      mbar_wait(bar_empty(s), ph ^ 1u);
+      mbar_wait(bar_empty(s), ph ^ 1u, bar_limit);
       if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
         const int row = tile * BN;
@@ -305,15 +307,15 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (warp-uniform loop, one elected lane issues) ============
-    mbar_wait(bar_aready, 0);
+    mbar_wait(bar_aready, 0, bar_limit);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t dhi = smem_desc_hi(1024);
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE, as = it % NS;
       const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u, aph = (uint32_t)(it / NS) & 1u;
-      mbar_wait(bar_sempty(as), aph ^ 1u);
-      mbar_wait(bar_full(s), ph);
+      mbar_wait(bar_sempty(as), aph ^ 1u, bar_limit);
+      mbar_wait(bar_full(s), ph, bar_limit);
       tc_fence_after();
       SM3_TR(0, it);
       const uint32_t d_tmem = tmem + 128u + (uint32_t)as * 128u;
@@ -377,7 +379,7 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     // the S stage by a whole tile of exponentials and starves the MMA warp.)
     for (int it = grp; it < n_tiles; it += NG) {
       const int as = it % NS;
-      mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u);
+      mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u, bar_limit);
       tc_fence_after();
       if (warp == 2 && lane == 0) SM3_TR(3, it);
       const uint32_t taddr = tmem + lane_addr + 128u + (uint32_t)as * 128u + (uint32_t)half * 64u;
@@ -463,6 +465,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);   // [2 row blocks][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long bar_limit = 2000000000ull + p.wait_timeout_ns;   // + cross-rank bound in fused-exchange mode
   const int r0 = blockIdx.x * 256;
   const int split = blockIdx.y;
   const int t_begin = split * p.tiles_per_split;
@@ -503,13 +506,13 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
       const int tile = tile_of(it);
       if (!remote_ready && !tile_is_local(p, tile)) {     // fused exchange: the peers' rows must have landed
         if (elect_one()) {
-          peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch);
+          peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch, p.wait_timeout_ns);
           fence_proxy_async_global();
         }
         __syncwarp();
         remote_ready = true;
       }
-      mbar_wait(bar_empty(s), ph ^ 1u);
+      mbar_wait(bar_empty(s), ph ^ 1u, bar_limit);
       if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
         const int row = tile * BN;
@@ -521,18 +524,18 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    mbar_wait(bar_aready, 0);
+    mbar_wait(bar_aready, 0, bar_limit);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t dhi = smem_desc_hi(1024);
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE;
       const uint32_t sph = (uint32_t)it & 1u;          // each S stage is used once per tile
-      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u);
+      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);
       const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
-        mbar_wait(bar_sempty(rb), sph ^ 1u);
+        mbar_wait(bar_sempty(rb), sph ^ 1u, bar_limit);
         tc_fence_after();
         const uint32_t d_tmem = tmem + kColS + (uint32_t)rb * 128u;
         const uint32_t a_tmem = tmem + (uint32_t)rb * kColA1;
@@ -599,7 +602,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
       const int cb = tile_of(it) * BN + half * 64;
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
-        mbar_wait(bar_sfull(rb), sph);
+        mbar_wait(bar_sfull(rb), sph, bar_limit);
         tc_fence_after();
         const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)rb * 128u + (uint32_t)half * 64u;
         uint32_t a[32], b[32];
@@ -705,6 +708,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 2 * NS + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long bar_limit = 2000000000ull + p.wait_timeout_ns;   // + cross-rank bound in fused-exchange mode
   const int r0 = blockIdx.x * kBM;
   const int split = blockIdx.y;
   const int t_begin = split * p.tiles_per_split;
@@ -745,7 +749,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE;
       const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
-      mbar_wait(bar_empty(s), ph ^ 1u);
+      mbar_wait(bar_empty(s), ph ^ 1u, bar_limit);
       if (elect_one()) {
         mbar_expect_tx(bar_full(s), C::STAGE);
         const int row = tile_of(it) * BN;
@@ -762,7 +766,7 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     constexpr uint32_t dhi = smem_desc_hi(1024);
     auto issue_s = [&](int it) {
       const int s = it % NSTAGE, as = it % NS;
-      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u);
+      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);
       tc_fence_after();
       const uint32_t d_tmem = tmem + kColS + (uint32_t)as * 64u;
       const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
@@ -775,14 +779,14 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       }
       __syncwarp();
     };
-    mbar_wait(bar_aready, 0);
+    mbar_wait(bar_aready, 0, bar_limit);
     tc_fence_after();
 #pragma unroll
     for (int i = 0; i < NS; ++i)
       if (i < n_tiles) issue_s(i);
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE, as = it % NS;
-      mbar_wait(bar_hfull(as), (uint32_t)(it / NS) & 1u);
+      mbar_wait(bar_hfull(as), (uint32_t)(it / NS) & 1u, bar_limit);
       tc_fence_after();
       SM3_TR(0, it);
       const uint32_t h_tmem = tmem + kColS + (uint32_t)as * 64u;
@@ -853,12 +857,12 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       const int tile = tile_of(it);
       if constexpr (kWait) {
         if (!remote_ready && !tile_is_local(p, tile)) {   // the owners' statistics must have landed
-          if (lane == 0) peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch);
+          if (lane == 0) peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch, p.wait_timeout_ns);
           __syncwarp();
           remote_ready = true;
         }
       }
-      mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u);
+      mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u, bar_limit);
       tc_fence_after();
       if (warp == 2 && lane == 0) SM3_TR(3, it);
       const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)as * 64u + (uint32_t)half * 32u;
@@ -908,12 +912,301 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
     }
 
     // ---- epilogue: dZ (TMEM fp32) * 1/T -> global partial ----
-    mbar_wait(bar_dzfull, 0);
+    mbar_wait(bar_dzfull, 0, bar_limit);
     tc_fence_after();
     float* dst = p.dz_partial + ((size_t)split * p.m_rows + (valid ? l : 0)) * D;
 #pragma unroll
     for (int ch = 0; ch < 2 * DP; ++ch) {
       if ((ch % (2 * NG)) == combo) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem + lane_addr + kColDZ + ch * 32, v);
+        tmem_ld_wait(v);
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(dst + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] = make_float4(__uint_as_float(v[4 * i]) * p.inv_T, __uint_as_float(v[4 * i + 1]) * p.inv_T,
+                               __uint_as_float(v[4 * i + 2]) * p.inv_T, __uint_as_float(v[4 * i + 3]) * p.inv_T);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, second form: TILE-ALTERNATING softmax groups + per-column statistics through shared memory.
+//
+// What held the first form at ~1600 clk per 128 x 64 tile at D = 128 (MMA work: 512, MUFU work: 512): all eight softmax
+// warps walked every tile together (the two warps of an SM sub-partition split the tile's columns), so per tile each
+// sub-partition paid, back to back and with nothing to overlap them,  tcgen05.ld latency -> an L2 round trip for the 64
+// a_j values (LDG issued after the barrier) -> 512 MUFU cycles -> tcgen05.st latency.  Here
+//   * warps 2-5 own the even tiles and warps 6-9 the odd ones (one thread = one row x all 64 columns of the tile), so
+//     the two warps sharing a sub-partition are always in DIFFERENT phases of DIFFERENT tiles and the MUFU pipe
+//     stays busy while the other warp sits in its TMEM round trips;
+//   * a_j travels with the column tile: the TMA warp adds one 256-byte bulk copy per stage and the softmax threads
+//     read it with broadcast LDS.128 -- no global-memory latency inside the softmax loop at all.  (Fused exchange: the
+//     TMA warp, not the softmax warps, waits for the owners' statistics before the first remote tile.)
+// TMEM: A [0, 32 DP) | S/H stage i [128 + 64 i, 192 + 64 i) | dZ [128 + 64 NS, 128 + 64 NS + 64 DP).  H (bf16 pairs)
+// overwrites the first 32 columns of the S stage it was computed from.
+// ------------------------------------------------------------------------------------------------
+template <int DP, int NS> struct Bwd2Cfg {
+  static constexpr int BN = 64;
+  static constexpr uint32_t PANEL = BN * 128;          // 8 KB: 64 rows x 64 bf16
+  static constexpr uint32_t STAGE = DP * PANEL;        // <= 32 KB
+  static constexpr uint32_t ACOL = BN * 4;             // 256 B: a_j of the tile's 64 columns
+  static constexpr int NSTAGE = NS + 2;                // smem ring: tiles it .. it+NS are live, one more in flight
+  static constexpr uint32_t SMEM = NSTAGE * (STAGE + ACOL) + 1024 + 256;
+  static constexpr uint32_t kColS = 128, kColDZ = 128 + 64 * NS;
+  static_assert(32 * DP <= 128, "A operand region");
+  static_assert(kColDZ + 64 * DP <= 512, "TMEM budget");
+  static_assert(8 * (2 * NSTAGE + 2 * NS + 3) <= 256, "barrier block");
+};
+
+template <int DP, bool kWait, int NS>
+__global__ void __launch_bounds__(320, 1)
+infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
+  using C = Bwd2Cfg<DP, NS>;
+  static_assert(NS % 2 == 0, "each softmax group keeps its own S/H stages");
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
+  constexpr int D = 64 * DP;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sB = base;
+  const uint32_t sA = sB + NSTAGE * C::STAGE;                       // a_j slots, 256 B per stage
+  const uint32_t bars = sA + NSTAGE * C::ACOL;
+  auto bar_full = [&](int i) { return bars + 8u * i; };
+  auto bar_empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
+  auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
+  auto bar_hfull = [&](int i) { return bars + 8u * (2 * NSTAGE + NS + i); };
+  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 2 * NS);
+  const uint32_t bar_dzfull = bars + 8u * (2 * NSTAGE + 2 * NS + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 2 * NS + 2));
+  const float* acol_smem = reinterpret_cast<const float*>(base_ptr + (sA - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long bar_limit = 2000000000ull + p.wait_timeout_ns;   // + cross-rank bound in fused-exchange mode
+  const int r0 = blockIdx.x * kBM;
+  const int split = blockIdx.y;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
+  const int n_tiles = t_end - t_begin;
+  const int rot = tile_rotation(p, t_begin, n_tiles);   // decorrelates the CTAs' L2 accesses; local tiles first (fused)
+  auto tile_of = [&](int it) {
+    int t = it + rot;
+    t = t_begin + (t >= n_tiles ? t - n_tiles : t);
+    if (t >= p.skip_a) t += p.skip_len;        // skip mode: hop over the column tiles owned by this rank
+    if (t >= p.skip_b) t += p.skip_len;
+    return t;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_hfull(i), 4); }
+    mbar_init(bar_aready, 8);
+    mbar_init(bar_dzfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t kColS = C::kColS, kColDZ = C::kColDZ;
+
+  if (warp == 0) {
+    // =========================== TMA producer: column tile + its 64 a_j ===========================
+    if (elect_one()) prefetch_tensormap(&tmap_cols);
+    bool remote_ready = !kWait;
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE;
+      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      const int tile = tile_of(it);
+      if constexpr (kWait) {
+        if (!remote_ready && !tile_is_local(p, tile)) {   // the owners' statistics (a_j) must have landed
+          if (elect_one()) {
+            peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch, p.wait_timeout_ns);
+            fence_proxy_async_global();
+          }
+          __syncwarp();
+          remote_ready = true;
+        }
+      }
+      mbar_wait(bar_empty(s), ph ^ 1u, bar_limit);
+      if (elect_one()) {
+        mbar_expect_tx(bar_full(s), C::STAGE + C::ACOL);
+        const int row = tile * BN;
+#pragma unroll
+        for (int pnl = 0; pnl < DP; ++pnl)
+          tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
+        bulk_load_1d(sA + s * C::ACOL, p.acol + row, C::ACOL, bar_full(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);     // S  = Zr  * Zc^T   (B K-major)
+    constexpr uint32_t idesc_z = make_idesc_bf16(128, D, 0, 1);      // dZ += H  * Zc     (B MN-major)
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    auto issue_s = [&](int it) {
+      const int s = it % NSTAGE, as = it % NS;
+      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + kColS + (uint32_t)as * 64u;
+      const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4 * DP; ++ks)
+          umma_ts(d_tmem, tmem + ks * 8, desc64(lo0 + (((ks >> 2) * C::PANEL + (ks & 3) * 32) >> 4), dhi), idesc_s,
+                  ks > 0);
+        umma_commit(bar_sfull(as));
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar_aready, 0, bar_limit);
+    tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+      if (i < n_tiles) issue_s(i);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % NSTAGE, as = it % NS;
+      mbar_wait(bar_hfull(as), (uint32_t)(it / NS) & 1u, bar_limit);
+      tc_fence_after();
+      SM3_TR(0, it);
+      const uint32_t h_tmem = tmem + kColS + (uint32_t)as * 64u;     // 64 k-values packed in 32 columns
+      const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, C::PANEL);   // MN-major: LBO = panel stride
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks)
+          umma_ts(tmem + kColDZ, h_tmem + ks * 8, desc64(lo0 + ks * (2048 >> 4), dhi), idesc_z,
+                  (it > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(bar_empty(s));
+      }
+      __syncwarp();
+      SM3_TR(1, it);
+      if (it + NS < n_tiles) issue_s(it + NS);   // in-order tensor pipe: overwrites S/H stage `as` only after dZ(it)
+      SM3_TR(2, it);
+    }
+    if (elect_one()) umma_commit(bar_dzfull);
+    __syncwarp();
+  } else {
+    // =========================== softmax / epilogue warps ===========================
+    const int q = warp & 3;                    // TMEM lane quadrant
+    const int grp = (warp - 2) >> 2;           // group 0 = warps 2-5 (even tiles), group 1 = warps 6-9 (odd tiles)
+    const int row_in_tile = q * 32 + lane;
+    const int l = r0 + row_in_tile;
+    const bool valid = l < p.m_rows;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+
+#pragma unroll
+    for (int ch = 0; ch < DP; ++ch) {
+      if ((ch & 1) == grp) {
+        uint32_t r[32];
+        if (valid) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)l * D + ch * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 v = __ldg(src + i);
+            r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        tmem_st_x32(tmem + lane_addr + ch * 32, r);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_aready);
+
+    const int g = valid ? global_row(l, p.n_local, p.pair_offset, p.n_global) : -1;
+    const int pj = valid ? positive_of(g, p.n_global) : -1;
+    float a_i = 0.f, gp_i = 0.f;
+    if (valid) {
+      const float s = p.nsum_r[l];
+      a_i = s > 0.f ? p.glse_r[l] / s : 0.f;
+      gp_i = p.gpos_r[l];
+    }
+    const float c2 = p.c2;
+
+    for (int it = grp; it < n_tiles; it += 2) {
+      const int as = it % NS, s = it % NSTAGE;
+      const int tile = tile_of(it);
+      mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u, bar_limit);
+      mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);   // completed long ago: makes the TMA-written a_j ours
+      tc_fence_after();
+      if (warp == 2 && lane == 0) SM3_TR(3, it);
+      const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)as * 64u;
+      uint32_t v0[32], v1[32];
+      tmem_ld_x32(taddr, v0);
+      tmem_ld_x32(taddr + 32, v1);
+      tmem_ld_wait(v0);
+      tmem_ld_wait(v1);
+      if (warp == 2 && lane == 0) SM3_TR(4, it);
+      const int cb = tile * BN;
+      const bool need = (cb + BN > p.m_cols) ||
+                        (valid && ((unsigned)(g - cb) < (unsigned)BN || (unsigned)(pj - cb) < (unsigned)BN));
+      const float4* ap = reinterpret_cast<const float4*>(acol_smem + s * BN);
+      uint32_t h[32];
+      if (!__any_sync(0xffffffffu, need)) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 aj = ap[i];                     // broadcast LDS.128
+          const uint32_t* v = i < 8 ? v0 : v1;
+          const int o = 4 * (i & 7);
+          const float e0 = ex2(fmaf(__uint_as_float(v[o]), c2, -c2)) * (a_i + aj.x);
+          const float e1 = ex2(fmaf(__uint_as_float(v[o + 1]), c2, -c2)) * (a_i + aj.y);
+          const float e2 = ex2(fmaf(__uint_as_float(v[o + 2]), c2, -c2)) * (a_i + aj.z);
+          const float e3 = ex2(fmaf(__uint_as_float(v[o + 3]), c2, -c2)) * (a_i + aj.w);
+          h[2 * i] = pack_bf16x2(e0, e1);
+          h[2 * i + 1] = pack_bf16x2(e2, e3);
+        }
+      } else {
+        const float* as_ = acol_smem + s * BN;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = 2 * i + u;
+            const int col = cb + c;
+            const float sv = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
+            float xv = 0.f;
+            if (valid && col < p.m_cols && col != g) {
+              if (col == pj) xv = gp_i + (kWait ? __ldcg(p.gpos_c + (size_t)col * p.cstride) : p.gpos_c[(size_t)col * p.cstride]);
+              else xv = ex2(fmaf(sv, c2, -c2)) * (a_i + as_[c]);
+            }
+            x[u] = xv;
+          }
+          h[i] = pack_bf16x2(x[0], x[1]);
+        }
+      }
+      if (warp == 2 && lane == 0) SM3_TR(5, it);
+      tmem_st_x32(taddr, h);          // H overwrites the first 32 of this thread's own (already consumed) S columns
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hfull(as));
+      if (warp == 2 && lane == 0) SM3_TR(6, it);
+    }
+
+    // ---- epilogue: dZ (TMEM fp32) * 1/T -> global partial ----
+    mbar_wait(bar_dzfull, 0, bar_limit);
+    tc_fence_after();
+    float* dst = p.dz_partial + ((size_t)split * p.m_rows + (valid ? l : 0)) * D;
+#pragma unroll
+    for (int ch = 0; ch < 2 * DP; ++ch) {
+      if ((ch & 1) == grp) {
         uint32_t v[32];
         tmem_ld_x32(tmem + lane_addr + kColDZ + ch * 32, v);
         tmem_ld_wait(v);
@@ -1001,6 +1294,7 @@ void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p, int bn
   }
   p.wait_flags = pb.wait_flags; p.wait_world = pb.wait_world; p.wait_channel = pb.wait_channel;
   p.wait_epoch = pb.wait_epoch;
+  p.wait_timeout_ns = pb.wait_flags != nullptr ? peer_timeout_ns() : 0ull;
   p.loc_len = pb.n_local / bn;                      // only consulted when wait_flags != nullptr (n_local % 128 == 0)
   p.loc_a = pb.pair_offset / bn;
   p.loc_b = (pb.n_global + pb.pair_offset) / bn;
@@ -1016,7 +1310,7 @@ void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p, int bn
 // stage) and equal in the backward, so 1 is the default.
 // The tuning knobs are read from the environment once and cached; sm3_debug_reload_env() drops the cache so that a
 // sweep (tools/tc_sweep.py) can change them inside one process.
-int g_knob_groups = 0, g_knob_poly = -1, g_knob_bwd_ns = -1;
+int g_knob_groups = 0, g_knob_poly = -1, g_knob_bwd_ns = -1, g_knob_bwd_v = -1;
 int tc_groups() {
   int& g = g_knob_groups;
   if (g == 0) {
@@ -1030,13 +1324,16 @@ int tc_groups() {
 // SM3_TC_POLY=0..4.  Default 0: on B200 the kernel runs under the 1 kW power cap (SM clock ~1.3-1.5 GHz under this
 // load), where trading one MUFU op for ~11 FMA/ALU ops shortens the cycle count per tile (trace build: 1550 -> 1350)
 // but not the wall time; measured 1.74 / 1.78 / 1.80 ms for POLY = 0 / 2 / 3 at cfg4.
-int tc_poly() {
+int tc_poly(int dp) {
   int& v = g_knob_poly;
-  if (v < 0) {
+  if (v == -1) {
     const char* e = getenv("SM3_TC_POLY");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 4) v = 0;
+    v = e ? atoi(e) : -2;                       // -2: not set -> by embedding width
+    if (v != -2 && (v < 0 || v > 4)) v = 0;
   }
+  // D <= 128: the forward is MUFU-bound (1024 MUFU cycles vs 512 MMA cycles per 128 x 128 tile), so a quarter of the
+  // exponentials go to the FMA pipes by default; D > 128: MMA and MUFU are level and the chip is power-capped -> 0.
+  if (v == -2) return dp <= 2 ? 2 : 0;
   return v;
 }
 
@@ -1058,15 +1355,15 @@ int launch_fwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cu
 }
 template <int DP>
 int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  if (pl.bm == 256) return tc_poly() == 2 ? launch_fwd2<DP, 2>(tmap, p, pl, st) : launch_fwd2<DP, 0>(tmap, p, pl, st);
+  if (pl.bm == 256) return tc_poly(DP) == 2 ? launch_fwd2<DP, 2>(tmap, p, pl, st) : launch_fwd2<DP, 0>(tmap, p, pl, st);
   if (tc_groups() == 2) {
-    switch (tc_poly()) {
+    switch (tc_poly(DP)) {
       case 0: return launch_fwd_ng<DP, 2, 0>(tmap, p, pl, st);
       case 3: return launch_fwd_ng<DP, 2, 3>(tmap, p, pl, st);
       default: return launch_fwd_ng<DP, 2, 2>(tmap, p, pl, st);
     }
   }
-  switch (tc_poly()) {
+  switch (tc_poly(DP)) {
     case 0: return launch_fwd_ng<DP, 1, 0>(tmap, p, pl, st);
     case 1: return launch_fwd_ng<DP, 1, 1>(tmap, p, pl, st);
     case 3: return launch_fwd_ng<DP, 1, 3>(tmap, p, pl, st);
@@ -1092,8 +1389,34 @@ int tc_bwd_stages(int dp) {
   if (forced == 2 || dp > 2) return 2;
   return 4;
 }
+template <int DP, bool kWait, int NS>
+int launch_bwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd2_kernel<DP, kWait, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Bwd2Cfg<DP, NS>::SMEM));
+  infonce_tc_bwd2_kernel<DP, kWait, NS><<<dim3(pl.row_tiles, pl.splits), 320, Bwd2Cfg<DP, NS>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+// which backward kernel: 2 = tile-alternating softmax groups + a_j through shared memory (infonce_tc_bwd2_kernel),
+// 1 = the first form.  SM3_TC_BWD_V=1|2 overrides; default by embedding width (see tc_bwd_version()).
+int tc_bwd_version(int dp) {
+  int& v = g_knob_bwd_v;
+  if (v < 0) {
+    const char* e = getenv("SM3_TC_BWD_V");
+    v = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }
+  if (v != 0) return v;
+  return dp <= 2 ? 2 : 1;
+}
 template <int DP>
 int launch_bwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
+  if (tc_bwd_version(DP) == 2) {
+    constexpr int NS2 = DP <= 2 ? 4 : 2;
+    const bool two = tc_bwd_stages(DP) == 2;
+    if (p.wait_flags != nullptr)
+      return two ? launch_bwd2<DP, true, 2>(tmap, p, pl, st) : launch_bwd2<DP, true, NS2>(tmap, p, pl, st);
+    return two ? launch_bwd2<DP, false, 2>(tmap, p, pl, st) : launch_bwd2<DP, false, NS2>(tmap, p, pl, st);
+  }
   // (the in-kernel-wait form of the multi-rank fused exchange stays on 2 stages until it has been run on >= 2 GPUs)
   if (p.wait_flags != nullptr) return launch_bwd_ng<DP, 1, true, 2>(tmap, p, pl, st);
   if constexpr (DP <= 2) {
@@ -1109,6 +1432,8 @@ size_t bwd_acol_offset(const InfoNceProblem& pb, const TcPlan& pl) {
 }
 
 }  // namespace
+
+size_t infonce_tc_acol_offset(const InfoNceProblem& pb) { return bwd_acol_offset(pb, tc_plan(pb, true)); }
 
 bool infonce_tc_supported(const InfoNceProblem& pb) {
   static int sm100 = -1;
@@ -1200,6 +1525,7 @@ extern "C" void sm3_debug_reload_env(void) {
   sm3::g_knob_groups = 0;
   sm3::g_knob_poly = -1;
   sm3::g_knob_bwd_ns = -1;
+  sm3::g_knob_bwd_v = -1;
 }
 
 #ifdef SM3_TRACE

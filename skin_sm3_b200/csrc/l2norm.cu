@@ -520,4 +520,64 @@ int l2norm_bwd_launch(const float* dz_partials, int n_partials, float scale, con
   return SM3_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// upstream scaling of eagerly computed gradients: out_t = in_t * (*g) for up to 8 same-sized tensors in ONE launch
+// (autograd hands the fused-step Functions a device scalar: GradScaler factor x loss weight, backbone_train.py:101-125).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct ScaleArgs {
+  const void* in[8];
+  void* out[8];
+  int count;
+};
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+scale_grads_kernel(ScaleArgs a, int64_t n, const float* __restrict__ g) {
+  const float s = __ldg(g);
+  const TIn* src = reinterpret_cast<const TIn*>(a.in[blockIdx.y]);
+  TOut* dst = reinterpret_cast<TOut*>(a.out[blockIdx.y]);
+  const int64_t n8 = n / 8;
+  const bool vec = (((uintptr_t)src | (uintptr_t)dst) & 31u) == 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    for (int64_t i = t0; i < n8; i += stride) {
+      float v[8];
+      load8<TIn>(src + i * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= s;
+      store8<TOut>(dst + i * 8, v);
+    }
+    for (int64_t j = n8 * 8 + t0; j < n; j += stride) dst[j] = from_f32<TOut>(to_f32(src[j]) * s);
+  } else {
+    for (int64_t i = t0; i < n; i += stride) dst[i] = from_f32<TOut>(to_f32(src[i]) * s);
+  }
+}
+}  // namespace
+
 }  // namespace sm3
+
+extern "C" int sm3_scale_grads(const void* const* in_host_array, void* const* out_host_array, int count, int64_t numel,
+                               int in_dtype, int out_dtype, const float* g_device, void* stream) {
+  using namespace sm3;
+  SM3_REQUIRE(in_host_array && out_host_array && g_device, SM3_ERR_SHAPE, "scale_grads: null pointer");
+  SM3_REQUIRE(count >= 1 && count <= 8 && numel >= 0, SM3_ERR_SHAPE, "scale_grads: count=%d not in [1,8]", count);
+  SM3_REQUIRE(dtype_ok(in_dtype) && dtype_ok(out_dtype), SM3_ERR_DTYPE, "scale_grads: bad dtype");
+  if (numel == 0) return SM3_OK;
+  ScaleArgs a{};
+  a.count = count;
+  for (int t = 0; t < count; ++t) {
+    SM3_REQUIRE(in_host_array[t] && out_host_array[t], SM3_ERR_SHAPE, "scale_grads: tensor %d is null", t);
+    a.in[t] = in_host_array[t];
+    a.out[t] = out_host_array[t];
+  }
+  int64_t blocks = (numel / 8 + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8 / count + 1;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  SM3_DISPATCH_DTYPE(in_dtype, TIn, SM3_DISPATCH_DTYPE(out_dtype, TOut, {
+    scale_grads_kernel<TIn, TOut><<<dim3((unsigned)blocks, (unsigned)count), 256, 0, (cudaStream_t)stream>>>(a, numel, g_device);
+  }));
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}

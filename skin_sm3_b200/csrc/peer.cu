@@ -7,6 +7,8 @@
 // the reference's [all first views ; all second views] order on the concatenated batch (simclr.py:293,296-297).
 // A cross-rank barrier (symmetric-memory signal pads, issued from Python on the same stream) separates the stores
 // from the kernels that read the assembled buffers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sm3 {
@@ -77,20 +79,9 @@ __global__ void peer_signal_kernel(PeerPtrs flags, int rank, int channel, unsign
   unsigned* dst = reinterpret_cast<unsigned*>(flags.p[r]) + channel * 16 + rank;
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
 }
-__global__ void peer_wait_kernel(const unsigned* __restrict__ my_flags, int world, int channel, unsigned epoch) {
-  const int r = threadIdx.x;
-  if (r >= world) return;
-  const unsigned* src = my_flags + channel * 16 + r;
-  const long long t0 = clock64();
-  unsigned v;
-  do {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-    if ((int)(v - epoch) >= 0) break;
-    if (clock64() - t0 > 20000000000LL) {      // ~10 s: a missing peer must fail loudly, not hang the GPU
-      printf("sm3: peer wait timeout (channel %d, peer %d, have %u, want %u)\n", channel, r, v, epoch);
-      __trap();
-    }
-  } while (true);
+__global__ void peer_wait_kernel(const unsigned* __restrict__ my_flags, int world, int channel, unsigned epoch,
+                                 unsigned long long timeout_ns) {
+  if (threadIdx.x == 0) peer_flags_wait_all(my_flags, world, channel, epoch, timeout_ns);   // bounded, see common.cuh
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -191,7 +182,7 @@ __global__ void __launch_bounds__(256)
 loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, const float* __restrict__ pos, int n_local,
                           int pair_offset, int n_global, float inv_T, float scale, float* __restrict__ loss,
                           float* __restrict__ g_pos, float* __restrict__ g_lse, float* __restrict__ neg_sum,
-                          float* __restrict__ block_ws, PeerFused pf, int accumulate) {
+                          float* __restrict__ block_ws, PeerFused pf, int accumulate, float* __restrict__ a_local) {
   __shared__ float red[32];
   __shared__ bool is_last;
   const int rows = 2 * n_local;
@@ -210,6 +201,7 @@ loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, con
     g_pos[i] = -g;
     neg_sum[i] = s;
     const float a = s > 0.f ? g / s : 0.f;
+    if (a_local != nullptr) a_local[i] = a;          // single GPU: the backward's a_j (no separate prep launch)
     const size_t gr = (size_t)global_row(i, n_local, pair_offset, n_global);
     const size_t m_cols = (size_t)2 * n_global;
 #pragma unroll 4
@@ -245,6 +237,17 @@ loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, con
 
 }  // namespace
 
+unsigned long long peer_timeout_ns() {
+  static unsigned long long ns = 0;
+  if (ns == 0) {
+    const char* e = getenv("SM3_PEER_TIMEOUT_S");
+    double sec = e ? atof(e) : 1800.0;
+    if (!(sec > 0.0)) sec = 1800.0;
+    ns = (unsigned long long)(sec * 1e9);
+  }
+  return ns;
+}
+
 int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pair_offset, int n_global, int D, int p_dtype,
                           void* z_local, float* inv_norm, float eps, const PeerFused& pf, cudaStream_t st) {
   SM3_REQUIRE(D % 8 == 0 && D >= 8 && D <= 256, SM3_ERR_SHAPE, "l2norm_scatter: D=%d", D);
@@ -260,10 +263,11 @@ int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pai
 
 int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
                               int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
-                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate) {
+                              float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate,
+                              float* a_local) {
   const unsigned grid = (unsigned)((2 * (int64_t)n_local + 255) / 256);
   loss_stats_scatter_kernel<<<grid, 256, 0, st>>>(partial, n_partials, pos, n_local, pair_offset, n_global, inv_T, scale,
-                                                  loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate);
+                                                  loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate, a_local);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
@@ -274,7 +278,7 @@ int peer_signal_launch(const PeerPtrs& flags, int rank, int channel, unsigned ep
   return SM3_OK;
 }
 int peer_wait_launch(const unsigned* my_flags, int world, int channel, unsigned epoch, cudaStream_t st) {
-  peer_wait_kernel<<<1, 32, 0, st>>>(my_flags, world, channel, epoch);
+  peer_wait_kernel<<<1, 32, 0, st>>>(my_flags, world, channel, epoch, peer_timeout_ns());
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }

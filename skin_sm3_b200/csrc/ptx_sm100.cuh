@@ -42,15 +42,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must fail loudly (trap -> launch error), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug must fail loudly (trap -> launch error), never hang the GPU.  The bound is wall time
+// (%globaltimer): 2 s by default; kernels whose pipelines wait -- transitively -- for other ranks (fused exchange) pass
+// the cross-rank timeout on top of it, so a peer that is merely late does not look like a protocol bug.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long limit_ns = 2000000000ull) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("sm3: mbarrier wait timeout (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, bar, parity);
-      __trap();
+    if ((++spins & 0x3FFu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > limit_ns) {
+        printf("sm3: mbarrier wait timeout (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
@@ -65,6 +73,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst_smem), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// 1-D bulk copy global -> shared (16-byte aligned, size % 16 == 0), completes on `bar` like a tensor load
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"((uint64_t)src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 
 // ------------------------------------------------------------------ tcgen05: TMEM management

@@ -39,6 +39,23 @@ _EPS = 1e-12                             # F.normalize default
 # bench.py installs a callable(name) here that records a CUDA event on the current stream after each stage
 _PROFILE = None
 
+# Scratch of the one-call fused steps, reused across calls: keyed by (kind, device, stream, shape...).  All users of
+# one entry enqueue on the same stream, so consecutive steps are ordered and may share it (nothing in the scratch is
+# read after the call's last kernel: loss and gradients live in their own tensors).  Saves an allocation and a ctypes
+# size query per step on the launch-bound shapes.
+_SCRATCH = {}
+
+
+def _scratch(kind: str, dev: torch.device, key: tuple, nbytes_fn) -> torch.Tensor:
+    k = (kind, dev.index, torch.cuda.current_stream(dev).cuda_stream) + key
+    buf = _SCRATCH.get(k)
+    if buf is None:
+        if len(_SCRATCH) > 64:
+            _SCRATCH.clear()
+        buf = torch.empty(max(int(nbytes_fn()), 256), dtype=torch.uint8, device=dev)
+        _SCRATCH[k] = buf
+    return buf
+
 
 def _mark(name: str) -> None:
     if _PROFILE is not None:
@@ -237,6 +254,33 @@ def gather_global_order(t_local: torch.Tensor, group=None) -> torch.Tensor:
     return stage.transpose(0, 1).reshape((2 * n_local * w,) + tuple(t_local.shape[1:]))
 
 
+def _grad_safe(p: torch.Tensor) -> torch.Tensor:
+    """fp16 inputs (the reference's --amp dtype) are handed to the fused step as fp32: the step computes the backward
+    eagerly with upstream gradient 1, and d loss / d p ~ 1 / (2N) per element would land in fp16's subnormal / flush range
+    before ``backward()`` multiplies by the GradScaler factor.  fp32 storage keeps it exact; the cast back to fp16 happens
+    after that multiplication (as _MultiHeadCE / _BCEWithLogits do).  bf16 / fp32 inputs pass through untouched."""
+    return p.float() if p.dtype == torch.float16 else p
+
+
+def _scale_grads(dps, g: torch.Tensor, out_dtypes):
+    """dp * upstream for the eagerly computed gradients, all tensors in ONE launch (``sm3_scale_grads``); the cast to the
+    inputs' dtype (fp32 -> fp16 for --amp inputs) happens in the same kernel, after the multiplication."""
+    import ctypes as C
+    dps = [_contig(d) for d in dps]
+    g32 = g if (g.dtype == torch.float32 and g.dim() == 0) else g.reshape(()).float()
+    same = len(set(out_dtypes)) == 1 and len({d.numel() for d in dps}) == 1 and len({d.dtype for d in dps}) == 1
+    if not same or len(dps) > 8:
+        return tuple((d * g32.to(d.dtype)).to(o) for d, o in zip(dps, out_dtypes))
+    outs = [torch.empty(d.shape, dtype=out_dtypes[0], device=d.device) for d in dps]
+    k = len(dps)
+    with torch.cuda.device(dps[0].device):
+        check(lib().sm3_scale_grads((C.c_void_p * k)(*[d.data_ptr() for d in dps]),
+                                    (C.c_void_p * k)(*[o.data_ptr() for o in outs]), k, dps[0].numel(),
+                                    dtype_code(dps[0]), _lib._DTYPES[out_dtypes[0]], ptr(g32), stream_ptr()),
+              "sm3_scale_grads")
+    return tuple(outs)
+
+
 def _group_info(group):
     if group is None or not (dist.is_available() and dist.is_initialized()):
         return 1, 0
@@ -345,6 +389,8 @@ class _FusedInfoNCE(torch.autograd.Function):
         n_local = p1.shape[0]
         n_global = n_local * w
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        ctx.in_dtypes = (p1.dtype, p2.dtype)
+        p1, p2 = _grad_safe(p1), _grad_safe(p2)
         if w == 1 and _PROFILE is None:
             # single GPU: the whole step is enqueued by one C call (launch-bound shapes: ~8 launches, no Python
             # between them)
@@ -352,8 +398,8 @@ class _FusedInfoNCE(torch.autograd.Function):
             dev, d = p1c.device, p1c.shape[1]
             io = dtype_code(p1c)
             with torch.cuda.device(dev):
-                nbytes = lib().sm3_infonce_step_scratch_bytes(n_local, d, io, algo)
-                scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                scratch = _scratch("step", dev, (n_local, d, io, algo),
+                                   lambda: lib().sm3_infonce_step_scratch_bytes(n_local, d, io, algo))
                 loss = torch.empty((), dtype=torch.float32, device=dev)
                 dp1 = torch.empty_like(p1c) if need_grad else None
                 dp2 = torch.empty_like(p2c) if need_grad else None
@@ -386,8 +432,8 @@ class _FusedInfoNCE(torch.autograd.Function):
             dev, d = p1c.device, p1c.shape[1]
             main = torch.cuda.current_stream()
             with torch.cuda.device(dev):
-                nbytes = lib().sm3_infonce_step_peer_scratch_bytes(n_local, n_global, d)
-                scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                scratch = _scratch("peer", dev, (n_local, n_global, d),
+                                   lambda: lib().sm3_infonce_step_peer_scratch_bytes(n_local, n_global, d))
                 loss = torch.empty((), dtype=torch.float32, device=dev)
                 dp1 = torch.empty_like(p1c) if need_grad else None
                 dp2 = torch.empty_like(p2c) if need_grad else None
@@ -479,13 +525,7 @@ class _FusedInfoNCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        dp1, dp2 = ctx.saved_tensors
-        if dp1.numel() >= (1 << 22):
-            # large gradients: one vectorised multi-tensor launch (cfg4: ~15 us instead of 2 x 20 us of broadcast mul)
-            o1, o2 = torch._foreach_mul((dp1, dp2), g.to(dp1.dtype))
-        else:
-            # small ones: multi_tensor_apply's 64K-element chunks leave most SMs idle (cfg2: 18 us vs 2 x 2.5 us)
-            o1, o2 = dp1 * g.to(dp1.dtype), dp2 * g.to(dp2.dtype)
+        o1, o2 = _scale_grads(ctx.saved_tensors, g, ctx.in_dtypes)
         return o1, o2, None, None, None, None, None, None
 
 
@@ -514,15 +554,16 @@ class _FusedInfoNCEMulti(torch.autograd.Function):
     def forward(ctx, temperature, algo, weights, *ps):
         import ctypes as C
         t = len(ps) // 2
-        p1s = [_contig(p) for p in ps[:t]]
-        p2s = [_contig(p) for p in ps[t:]]
+        ctx.in_dtypes = tuple(p.dtype for p in ps)
+        p1s = [_contig(_grad_safe(p)) for p in ps[:t]]
+        p2s = [_contig(_grad_safe(p)) for p in ps[t:]]
         dev = require_cuda(*p1s, *p2s)
         n, d = p1s[0].shape
         io = dtype_code(p1s[0])
         need_grad = any(ctx.needs_input_grad[3:])
         with torch.cuda.device(dev):
-            nbytes = lib().sm3_infonce_step_multi_scratch_bytes(n, d, io, algo)
-            scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            scratch = _scratch("multi", dev, (n, d, io, algo),
+                               lambda: lib().sm3_infonce_step_multi_scratch_bytes(n, d, io, algo))
             loss = torch.empty((), dtype=torch.float32, device=dev)
             d1 = [torch.empty_like(p) for p in p1s] if need_grad else None
             d2 = [torch.empty_like(p) for p in p2s] if need_grad else None
@@ -537,11 +578,7 @@ class _FusedInfoNCEMulti(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        dps = ctx.saved_tensors
-        gg = g.to(dps[0].dtype)
-        if dps[0].numel() >= (1 << 22):
-            return (None, None, None) + tuple(torch._foreach_mul(dps, gg))
-        return (None, None, None) + tuple(dp * gg for dp in dps)
+        return (None, None, None) + _scale_grads(ctx.saved_tensors, g, ctx.in_dtypes)
 
 
 def fused_infonce_multi(pairs, temperature: float, weights: Optional[Sequence[float]] = None,

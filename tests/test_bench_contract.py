@@ -19,7 +19,8 @@ def test_reference_arm_prints_one_json_line():
               "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["steps"] == 1 and d["warmup"] == 0             # the arm runs exactly the steps it was asked for
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
 
@@ -32,7 +33,17 @@ def test_reference_arm_runs_the_reference_sized_case_in_full():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
     assert d["config"]["global_pairs"] == 64 and d["config"]["dim"] == 128
-    assert d["cpu_baseline"]["sample"].startswith("full step")
+    assert d["cpu_baseline"]["sample"].startswith("full step") and d["estimated"] is False
+    # the real reference (vendored by oracle/vendor_ref.py) is what runs when it is there
+    import os as _os
+    if _os.path.isdir(_os.path.join(ROOT, "oracle", "_ref", "skin_sm3")):
+        assert d["cpu_baseline"]["kind"] == "reference"
+    # same `config` object as our arm prints for this workload (the driver compares them)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", _os.path.join(ROOT, "bench.py"))
+    bm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bm)
+    assert d["config"] == bm.config_of(bm.WORKLOADS["cfg1"], 64, 128, 0.1, 1)
 
 
 def test_ours_arm_fails_loudly_without_cuda():

@@ -209,3 +209,24 @@ def test_kmeans_oracle_matches_reference_cluster_memory():
         # the initial indices are what torch.randperm gives for the recorded seed (how the product reproduces them)
         torch.manual_seed(int(g[f"{c}_seed"]))
         assert (torch.randperm(len(g[f"{c}_emb"]))[: len(g[f"{c}_init_idx"])].numpy() == g[f"{c}_init_idx"]).all()
+
+
+@pytest.mark.parametrize("name", ["infonce_n48_d128_T01_corr", "infonce_n200_d64_T02_corr", "infonce_n512_d256_T01"])
+def test_rowblock_oracle_pinned_to_reference(name):
+    """oracle.infonce_rowblock (the full-size checker used at cfg4 / cfg2 and by bench.py's parity block) against the
+    reference goldens: fp64 mode to 1e-12, fp32-GEMM mode (what runs at M = 65536) to 1e-6 (loss) / 1e-5 (gradients)."""
+    g = load(name)
+    T, n = float(g["temperature"]), int(g["n"])
+    if "dp1_f64" in g:
+        r = np.arange(n)
+        ref = np.concatenate([g["dp1_f64"], g["dp2_f64"]])
+    else:
+        r = g["grad_rows"]
+        ref = np.concatenate([g["dp1_rows_f64"], g["dp2_rows_f64"]])
+    rows = np.concatenate([r, n + r])
+    loss, dp, lse = O.infonce_rowblock(g["p1"], g["p2"], T, rows, chunk=77)
+    assert abs(loss - float(g["loss_f64"])) < 1e-12 * max(1.0, abs(loss))
+    np.testing.assert_allclose(dp, ref, rtol=0, atol=1e-14)
+    loss32, dp32, _ = O.infonce_rowblock(g["p1"], g["p2"], T, rows, chunk=77, matmul_dtype=np.float32, upstream=3.0)
+    assert abs(loss32 - float(g["loss_f64"])) < 1e-6 * abs(loss32)
+    assert np.abs(dp32 / 3.0 - ref).max() < 1e-5 * np.abs(ref).max()

@@ -1,0 +1,141 @@
+"""The reference's own training scripts, UNCHANGED, on the fused kernels (north_star: "tools/backbone_train.py and
+tools/mlc_train.py run unchanged").
+
+The scripts are the reference's files byte for byte: ``oracle/_ref/skin_sm3/tools/*.py`` (vendored by
+oracle/vendor_ref.py, git-ignored, travels to the GPU box) or the read-only checkout.  Each script is launched as
+``python tools/<script>.py ...`` with ``PYTHONPATH=skin_sm3_b200/dropin/_site`` -- nothing else -- so its ``mp.spawn``
+workers (tools/backbone_train.py:626-631) get the hook too.  The same command with ``SM3_DROPIN=0`` runs the STOCK
+reference modules (the hook then only supplies the synthetic dataset and the torchmetrics stand-in); the logged losses
+of the two runs must agree: same seed (src/utils/misc.py:193, fix_random_seeds) -> same initial weights (the drop-in
+builds its layers in the reference's order), same synthetic images, same augmentation draws.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SITE = os.path.join(ROOT, "skin_sm3_b200", "dropin", "_site")
+LOSS_RE = re.compile(r"Loss (\d+\.\d+) \((\d+\.\d+)\)")
+
+
+def ref_root():
+    for cand in (os.path.join(ROOT, "oracle", "_ref", "skin_sm3"), "/root/reference"):
+        if os.path.isfile(os.path.join(cand, "tools", "backbone_train.py")):
+            return cand
+    return None
+
+
+def run_script(script, args, log_dir, dropin, port, extra_env=None):
+    env = dict(os.environ)
+    env.update({"PYTHONPATH": SITE + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else ""),
+                "SM3_DROPIN": "1" if dropin else "0", "SM3_SHIMS": "1", "CUDA_VISIBLE_DEVICES": "0",
+                "SM3_SYNTH_LEN": "64", "SM3_SYNTH_SIDE": "96", "PYTHONHASHSEED": "0"})
+    env.update(extra_env or {})
+    cmd = [sys.executable, os.path.join(ref_root(), "tools", script), "--data-name", "SM3SyntheticPairs", "--data-path",
+           "none", "-a", "resnet18", "-b", "32", "--epochs", "1", "--img-sz", "64", "64", "-j", "0", "--print-freq", "1",
+           "--log-path", str(log_dir), "--port", str(port)] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=str(log_dir.parent))
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-4000:]
+    err = os.path.join(str(log_dir), "error.log")         # the scripts swallow exceptions into this file (:632-640)
+    assert not os.path.exists(err), open(err).read()[-4000:]
+    log = open(os.path.join(str(log_dir), "outputs.log")).read()
+    losses = [float(m.group(1)) for m in LOSS_RE.finditer(log)]
+    return losses, out, log
+
+
+@pytest.mark.gpu
+def test_backbone_train_and_mlc_train_run_unchanged(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    if ref_root() is None:
+        pytest.skip("no reference scripts (oracle/_ref not vendored and /root/reference absent)")
+    base = 29700 + (os.getpid() % 200)
+    pre = ["--arch-version", "v32", "--proj-dim", "128", "--temperature", "0.1", "-lr", "1e-3"]
+    # ---- tools/backbone_train.py: drop-in vs stock reference modules, fp32 ----
+    ours, out, _ = run_script("backbone_train.py", pre, tmp_path / "bt_ours", True, base)
+    assert "drop-in active: src.models.simclr" in out
+    assert len(ours) == 2, (ours, out[-2000:])            # 64 samples / batch 32
+    stock, out_s, _ = run_script("backbone_train.py", pre, tmp_path / "bt_stock", False, base + 1)
+    assert "drop-in active" not in out_s
+    assert len(stock) == 2
+    # iteration 0: same weights, same data -> the four InfoNCE terms agree to the log's 4 decimals (fp32 kernels);
+    # iteration 1 runs on weights updated with OUR gradients vs the reference's autograd: AdamW steps of lr 1e-3
+    assert abs(ours[0] - stock[0]) <= 2e-4 * max(1.0, abs(stock[0])), (ours, stock)
+    assert abs(ours[1] - stock[1]) <= 5e-3 * max(1.0, abs(stock[1])), (ours, stock)
+    ckpt = tmp_path / "bt_ours" / "checkpoint.pth.tar"
+    assert ckpt.exists()
+    sd = torch.load(str(ckpt), map_location="cpu")["state_dict"]
+    assert "cross_proj.0.6.weight" in sd and "derm_backbone.projector.0.weight" in sd       # reference key names
+    # ---- the same under --amp (fp16 autocast + GradScaler): bf16 tensor-core kernels ----
+    amp, out_a, _ = run_script("backbone_train.py", pre + ["--amp"], tmp_path / "bt_amp", True, base + 2)
+    assert len(amp) == 2 and abs(amp[0] - stock[0]) <= 2e-2 * abs(stock[0]), (amp, stock)
+    # ---- tools/mlc_train.py on that checkpoint: cluster_memory swapped by the hook, stock everything else ----
+    mlc = ["--extractor-weights", str(ckpt), "--extractor-proj-dim", "128", "--mlc-proj", "v4", "--mlc-proj-dim", "64",
+           "--sa-dim-ff", "64", "--sa-dropout", "0.0", "--temperature", "0.1", "-lr", "1e-3", "--save-freq", "1"]
+    m_ours, out_m, _ = run_script("mlc_train.py", mlc, tmp_path / "mlc_ours", True, base + 3)
+    assert "cluster_memory of the running script replaced" in out_m
+    m_stock, out_ms, _ = run_script("mlc_train.py", mlc, tmp_path / "mlc_stock", False, base + 4)
+    assert "cluster_memory of the running script replaced" not in out_ms
+    assert len(m_ours) == 2 and len(m_stock) == 2
+    # identical initial centroids (same randperm draw) and assignments unless a similarity is an fp32-vs-TF32 near tie
+    # (the script enables TF32, tools/mlc_train.py:294-295): the 8-head CE on the pseudo-labels agrees to ~1e-2
+    assert abs(m_ours[0] - m_stock[0]) <= 2e-2 * max(1.0, abs(m_stock[0])), (m_ours, m_stock)
+    assert (tmp_path / "mlc_ours" / "ckp_0.pth").exists()
+
+
+def test_hook_serves_shims_and_dataset_on_cpu(tmp_path):
+    """CPU part of the same contract: with only PYTHONPATH=dropin/_site the reference's script imports resolve
+    (torchmetrics stand-in, synthetic dataset registered where init_dataset looks, init_distributed_mode wrapped)."""
+    if ref_root() is None:
+        pytest.skip("no reference checkout")
+    code = r'''
+import sys, types
+sys.path.insert(0, %r)
+from torchmetrics.functional.classification import multiclass_auroc, multiclass_recall, multiclass_specificity, multiclass_precision
+import torch
+p = torch.tensor([[0.9, 0.05, 0.05], [0.1, 0.8, 0.1], [0.2, 0.2, 0.6], [0.6, 0.3, 0.1]]); t = torch.tensor([0, 1, 2, 1])
+assert torch.allclose(multiclass_recall(p, t, num_classes=3, average=None), torch.tensor([1.0, 0.5, 1.0]))
+assert torch.allclose(multiclass_precision(p, t, num_classes=3, average=None), torch.tensor([0.5, 1.0, 1.0]))
+assert torch.allclose(multiclass_specificity(p, t, num_classes=3, average=None), torch.tensor([2 / 3, 1.0, 1.0]))
+assert torch.allclose(multiclass_auroc(p, t, num_classes=3, average=None), torch.tensor([1.0, 1.0, 1.0]))
+from src.utils.data import datasets
+from src.utils.data.functional import NViewsTransform
+from torchvision import transforms as T
+cls = datasets.__dict__["SM3SyntheticPairs"]
+tr = NViewsTransform(T.Compose([T.RandomResizedCrop((32, 32)), T.ToTensor()]), 2)
+ds = cls(types.SimpleNamespace(seed=3407), data_trans=tr, mode="train")
+d, c, l = ds[5]
+assert len(d) == 2 and d[0].shape == (3, 32, 32) and l.shape == (8,) and len(ds) == 7
+i, (d1, c1, l1) = cls(types.SimpleNamespace(seed=3407), data_trans=tr.base_transform, mode="train", return_index=True)[5]
+assert i == 5 and d1.shape == (3, 32, 32) and torch.equal(l, l1)
+import src.utils.misc as misc
+assert getattr(misc.init_distributed_mode, "_sm3_wrapped", False)
+import src.models.simclr as sc
+assert sc.__file__.endswith("dropin/src/models/simclr.py"), sc.__file__
+print("HOOK_OK")
+''' % ref_root()
+    env = dict(os.environ, PYTHONPATH=SITE, SM3_SYNTH_LEN="7", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0 and "HOOK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "drop-in active" in r.stderr
+    # SM3_DROPIN=0: the stock module is served, the shims stay
+    code2 = "import sys; sys.path.insert(0, %r); import src.models.simclr as sc; import torchmetrics; print(sc.__file__)" % ref_root()
+    r = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=600,
+                       env=dict(env, SM3_DROPIN="0"), cwd=str(tmp_path))
+    assert r.returncode == 0 and "dropin" not in r.stdout and "drop-in active" not in r.stderr, r.stdout + r.stderr[-2000:]
+
+
+def test_sitecustomize_chains_to_the_next_one(tmp_path):
+    """putting dropin/_site first on PYTHONPATH must not swallow another sitecustomize further down the path."""
+    other = tmp_path / "other_site"
+    other.mkdir()
+    (other / "sitecustomize.py").write_text("import os\nos.environ['SM3_TEST_CHAINED'] = 'yes'\n")
+    env = dict(os.environ, PYTHONPATH=SITE + os.pathsep + str(other), SM3_DROPIN_QUIET="1")
+    r = subprocess.run([sys.executable, "-c", "import os; print(os.environ.get('SM3_TEST_CHAINED'))"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == "yes", r.stdout + r.stderr
