@@ -843,21 +843,24 @@ def small_shapes_probe(sm3):
 def tc_kernel_probe(sm3):
     """K2 / K3 launch times at cfg2 (4096 x 128: the D = 128 regime of every reference config) and at N = 8192 x 256 from the
     production path's stage events, for the kernel variants selectable at run time: backward form 1 (softmax warps split
-    the tile's columns) vs 2 (tile-alternating groups, a_j through shared memory), S/H stages, FMA-pipe exponentials in
-    the forward.  Microseconds per launch."""
-    knobs = ("SM3_TC_FWD_BM", "SM3_TC_POLY", "SM3_TC_BWD_NS", "SM3_TC_BWD_V")
+    the tile's columns) vs 2 (tile-alternating groups, a_j through shared memory) vs 3 (2 with 128-column tiles, D <= 128),
+    FMA-pipe exponentials in either kernel.  Microseconds per launch."""
+    knobs = ("SM3_TC_FWD_BM", "SM3_TC_POLY", "SM3_TC_BWD_NS", "SM3_TC_BWD_V", "SM3_TC_BWD_POLY")
     saved = {k: os.environ.get(k) for k in knobs}
     out = {}
     try:
         for n, d in ((4096, 128), (8192, 256)):
             p1, p2, _ = synth(n, d, 0, 1, seed=SEED + n)
             for name, cfg in (("default", {}), ("bwd_v1", {"SM3_TC_BWD_V": "1"}), ("bwd_v2", {"SM3_TC_BWD_V": "2"}),
-                              ("bwd_v2_ns2", {"SM3_TC_BWD_V": "2", "SM3_TC_BWD_NS": "2"}),
+                              ("bwd_v3_poly0", {"SM3_TC_BWD_V": "3", "SM3_TC_BWD_POLY": "0"}),
+                              ("bwd_v3_poly2", {"SM3_TC_BWD_V": "3", "SM3_TC_BWD_POLY": "2"}),
+                              ("bwd_v4_poly0", {"SM3_TC_BWD_V": "4", "SM3_TC_BWD_POLY": "0"}),
+                              ("bwd_v4_poly2", {"SM3_TC_BWD_V": "4", "SM3_TC_BWD_POLY": "2"}),
                               ("fwd_poly0", {"SM3_TC_POLY": "0"}), ("fwd_poly2", {"SM3_TC_POLY": "2"})):
                 for k in knobs:
                     os.environ.pop(k, None)
                 os.environ.update(cfg)
-                sm3.lib().sm3_debug_reload_env()
+                sm3.reload_env()
                 st = stage_times(sm3, p1, p2, 0.1, None, 1, 10, None)
                 out[f"n{n}_d{d}_{name}"] = {"fwd_us": round(st.get("infonce_fwd", 0) * 1e3, 1),
                                             "bwd_us": round(st.get("infonce_bwd", 0) * 1e3, 1)}
@@ -867,7 +870,7 @@ def tc_kernel_probe(sm3):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-        sm3.lib().sm3_debug_reload_env()
+        sm3.reload_env()
     return out
 
 

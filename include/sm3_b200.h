@@ -195,6 +195,26 @@ int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_dtype, const
 int sm3_sim_topk(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype, int k,
                  int64_t exclude_self_offset, float* vals, int64_t* idx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N4  DeepCluster spherical k-means of the memory bank    replaces the rank-0 loop of cluster_memory
+ *     tools/mlc_train.py:144-176 (torch.mm E step :153, .cpu().numpy() + scipy.sparse + Python loop M step :157-172,
+ *     F.normalize :175)
+ *   sm3_kmeans_assign : assign[i] = argmax_k <emb_i, centroid_k> (ties -> lower k); when sums/counts are given, also
+ *                       sums[k] = sum of the rows assigned to k, counts[k] = how many (fp32), in the SAME pass over the
+ *                       bank, deterministically (fixed-order folds, no float atomics).  emb fp32 [n, D], centroids [K, D].
+ *   sm3_kmeans_update : centroid_k = sums_k / counts_k where counts_k > 0 (else the old centroid, :173), then every
+ *                       centroid is L2-normalised (eps as F.normalize).  A multi-rank caller all-reduces sums / counts
+ *                       between the two calls and keeps its bank shard local.
+ *   Shapes: fp32, D % 128 == 0, D <= 512, K <= 8 (sm3_kmeans_supported() == 1); the Python front end falls back to
+ *   sm3_sim_topk + a one-hot GEMM otherwise.
+ * ---------------------------------------------------------------------------------------------- */
+int sm3_kmeans_supported(int D, int K, int dtype);
+size_t sm3_kmeans_workspace_bytes(int64_t n, int D, int K);
+int sm3_kmeans_assign(const float* emb, int64_t n, int D, const float* centroids, int K, int64_t* assign, float* sums,
+                      float* counts, void* workspace, size_t workspace_bytes, void* stream);
+int sm3_kmeans_update(const float* sums, const float* counts, const float* centroids_old, float* centroids_new, int D,
+                      int K, float eps, void* stream);
+
 /* Host-buffer convenience entry (the "plugin call" timed end to end by bench.py): copies p1/p2 from
  * HOST memory, runs normalise -> K2 -> loss -> K3 -> normalise-backward on `stream`, copies the loss
  * and both gradients back to HOST memory and synchronises the stream.  All device scratch comes from
@@ -284,6 +304,11 @@ void sm3_debug_reload_env(void);
  *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */
 int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,
                          void* stream);
+
+/* debug / bring-up microbenchmark (not a product path): dispatch rate of `count` back-to-back tcgen05.mma (M = 128, K = 16,
+ * bf16) of width n, A operand from shared memory (0) or TMEM (1), with `ldtm_warps` warps streaming tcgen05.ld meanwhile.
+ * out_host[16]: [0] cycles spent issuing, [1] cycles until all completed, [3..] tcgen05.ld round trips of the extra warps. */
+int sm3_debug_umma_rate(int n, int a_from_tmem, int count, int ldtm_warps, long long* out_host);
 
 #ifdef __cplusplus
 }

@@ -222,7 +222,9 @@ def gen_kmeans():
         mt = importlib.import_module("tools.mlc_train")
         args = types.SimpleNamespace(world_size=1, rank=0)
         out = {}
-        cases = [("a", 413, 64, 5, 0.35), ("b", 640, 256, 3, 0.6), ("c", 96, 16, 2, 0.5), ("d", 24, 8, 6, 0.05)]
+        # e / f: the shapes the fused k-means kernel takes (D % 128 == 0, K <= 8): Derm7pt bank size x mlc_proj_dim 512
+        cases = [("a", 413, 64, 5, 0.35), ("b", 640, 256, 3, 0.6), ("c", 96, 16, 2, 0.5), ("d", 24, 8, 6, 0.05),
+                 ("e", 413, 512, 5, 0.8), ("f", 1000, 128, 8, 0.7)]
         for tag, n, d, k, noise in cases:
             g = torch.Generator().manual_seed(SEED + n + d + k)
             true_c = nn.functional.normalize(torch.randn(k if tag != "d" else 3, d, generator=g), dim=1)

@@ -52,6 +52,10 @@ SIGNATURES = {
     "sm3_bce_workspace_bytes": (_sz, [_i64, _i]),
     "sm3_bce_logits": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp, _f, _vp, _sz, _vp]),
     "sm3_sim_topk": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _i64, _vp, _vp, _vp]),
+    "sm3_kmeans_supported": (_i, [_i, _i, _i]),
+    "sm3_kmeans_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "sm3_kmeans_assign": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sm3_kmeans_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "sm3_infonce_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "sm3_infonce_host": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "sm3_host_pipe_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
@@ -72,6 +76,7 @@ SIGNATURES = {
     "sm3_stage_timing_read": (_i, [_vp, _i]),
     "sm3_stage_timing_names": (C.c_char_p, []),
     "sm3_debug_reload_env": (None, []),
+    "sm3_debug_umma_rate": (_i, [_i, _i, _i, _i, _vp]),
     "sm3_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 

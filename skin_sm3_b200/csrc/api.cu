@@ -1,6 +1,7 @@
 // extern "C" surface of libsm3_b200.so (see include/sm3_b200.h).  Argument validation, algorithm choice
 // (tcgen05 vs fp32-FMA kernels -- both CUDA, there is no CPU path), and the host-buffer convenience entry.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -10,6 +11,15 @@
 namespace sm3 {
 
 static thread_local char g_err[512] = "";
+thread_local bool g_pdl = false;
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SM3_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -276,6 +286,9 @@ static int step_impl(const void* p1, const void* p2, int n_pairs, int D, int io_
   char* base = (char*)device_scratch;
   const int64_t n = n_pairs, m = 2 * n;
   const float inv_T = 1.0f / temperature;
+  unsigned* ticket = (unsigned*)(base + h.loss + 64);
+  if (h.algo == SM3_ALGO_TC) SM3_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));   // ahead of the kernel chain
+  PdlScope pdl(!g_stage_timing);          // event records between the kernels would break the chain anyway
   stage_begin(st, "normalize,infonce_fwd,loss,infonce_bwd,normalize_bwd");
   int rc = sm3_l2norm_fwd(p1, n, p2, n, D, io_dtype, base + h.z, h.z_dtype, (float*)(base + h.inv), 1e-12f, st);
   if (rc) return rc;
@@ -290,8 +303,6 @@ static int step_impl(const void* p1, const void* p2, int n_pairs, int D, int io_
                                       base + h.ws, h.ws_bytes, st);
     if (splits < 0) return splits;
     stage_mark(st);
-    unsigned* ticket = (unsigned*)(base + h.loss + 64);
-    SM3_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
     PeerFused none{};
     none.counter = ticket;
     // the same kernel also materialises a_j = g_lse_j / neg_sum_j where K3 expects it (behind the partial-gradient slabs:
@@ -478,6 +489,7 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
     SM3_REQUIRE(aligned16(p1) && aligned16(p2), SM3_ERR_SHAPE, "infonce_step_peer: fused mode needs 16-byte aligned rows");
     unsigned* counters = (unsigned*)flags_mine + 64;          // two local ticket words behind the 64 flag slots
     PeerFused pz{zp, fp, counters, rank, 0, epoch};
+    PdlScope pdl(!g_stage_timing);
     stage_begin(sm, "normalize_scatter,infonce_fwd,loss_scatter,infonce_bwd,normalize_bwd");
     rc = l2norm_scatter_launch(p1, p2, n_local, off, n_global, D, io_dtype, z, (float*)(base + h.inv), 1e-12f, pz, sm);
     if (rc) return rc;

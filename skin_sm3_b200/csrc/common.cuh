@@ -54,6 +54,36 @@ inline int resident_ctas(K kernel, int threads, size_t dyn_smem = 0) {
   return n;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// The fused steps enqueue 5 kernels back to back; at the reference's batch sizes each runs for a few microseconds, so the
+// launch latency and prologue (barrier init, TMEM allocation, tensor-map prefetch) of kernel k+1 are worth hiding behind
+// the tail of kernel k.  While a step is being enqueued `g_pdl` is set and every launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization; every kernel calls pdl_wait() before its first global-memory
+// access (it returns once the preceding kernel has completed and flushed) and pdl_launch() right after, which lets the
+// next kernel's CTAs become resident as soon as all of ours have started.  Without the attribute both are no-ops.
+// SM3_PDL=0 disables it.
+extern thread_local bool g_pdl;
+bool pdl_enabled();
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(g_pdl) { g_pdl = on && pdl_enabled(); }
+  ~PdlScope() { g_pdl = prev; }
+};
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (g_pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- scalar dtype conversion ------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

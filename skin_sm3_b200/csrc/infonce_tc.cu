@@ -33,7 +33,7 @@ constexpr float kLog2eTC = 1.4426950408889634f;
 // Optional pipeline trace (build with -DSM3_TRACE: `make TRACE=1` -> lib/libsm3_b200_trace.so).  CTA (0,0) stamps
 // clock64() at the hand-off points of the first tiles; tools/trace_tc.py prints the timeline.  Compiled out otherwise.
 #ifdef SM3_TRACE
-constexpr int kTraceTiles = 512, kTraceKinds = 8;
+constexpr int kTraceTiles = 512, kTraceKinds = 12;
 __device__ long long g_trace[kTraceTiles * kTraceKinds];
 #define SM3_TR(kind, it)                                                                 \
   do {                                                                                   \
@@ -153,6 +153,8 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();        // PDL: everything above overlapped the preceding kernel's tail; global memory from here on
+  pdl_launch();
   const uint32_t tmem_d = tmem, tmem_a = tmem + 256;
 
   if (threadIdx.x == 0) {
@@ -210,6 +212,62 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
   (void)lane;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bring-up microbenchmark: dispatch rate of tcgen05.mma (M = 128, K = 16) for a given N and operand source, on an
+// otherwise idle SM.  One thread issues `count` MMAs back to back into one accumulator; out[0] = cycles spent issuing,
+// out[1] = cycles until the commit fires (all done).  Operand contents are irrelevant (whatever smem / TMEM hold).
+// `ldtm_warps` > 0 adds that many warps streaming tcgen05.ld over the accumulator meanwhile (TMEM read contention).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(288, 1)
+umma_rate_kernel(int n, int a_tmem_mode, int count, int ldtm_warps, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + 16384, bars = sB + 65536;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 16);
+  __shared__ volatile int stop;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bars, 1); fence_barrier_init(); stop = 0; }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();        // PDL: everything above overlapped the preceding kernel's tail; global memory from here on
+  pdl_launch();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, n, 0, 0);
+    const uint64_t bdesc = make_smem_desc(sB, 16, 1024);
+    const uint64_t adesc = make_smem_desc(sA, 16, 1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < count; ++i) {
+      if (a_tmem_mode) umma_ts(tmem, tmem + 256 + (i & 3) * 8, bdesc, idesc, 1u);
+      else umma_ss(tmem, adesc, bdesc, idesc, 1u);
+    }
+    const long long t1 = clock64();
+    umma_commit(bars);
+    mbar_wait(bars, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+    stop = 1;
+  } else if (warp >= 1 && warp <= ldtm_warps) {
+    long long reads = 0;
+    uint32_t r[32];
+    while (!stop) {
+      tmem_ld_x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384, r);
+      tmem_ld_wait(r);
+      ++reads;
+      if (r[0] == 0x12345678u && reads < 0) break;    // keep the loads alive
+    }
+    if ((threadIdx.x & 31) == 0) out[2 + warp] = reads;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,6 +336,8 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();        // PDL: everything above overlapped the preceding kernel's tail; global memory from here on
+  pdl_launch();
 
   if (warp == 0) {
     // =========================== TMA producer (warp-uniform loop, one elected lane issues) ===========
@@ -465,6 +525,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);   // [2 row blocks][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SM3_TR(7, 0);                                      // trace: CTA start
   const unsigned long long bar_limit = 2000000000ull + p.wait_timeout_ns;   // + cross-rank bound in fused-exchange mode
   const int r0 = blockIdx.x * 256;
   const int split = blockIdx.y;
@@ -494,6 +555,8 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();        // PDL: everything above overlapped the preceding kernel's tail; global memory from here on
+  pdl_launch();
   constexpr uint32_t kColA1 = 128, kColS = 256;
 
   if (warp == 0) {
@@ -526,17 +589,20 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
     // =========================== MMA issuer ===========================
     mbar_wait(bar_aready, 0, bar_limit);
     tc_fence_after();
+    SM3_TR(7, 1);                                                          // trace: rows staged, first MMA
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t dhi = smem_desc_hi(1024);
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE;
       const uint32_t sph = (uint32_t)it & 1u;          // each S stage is used once per tile
       mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);
+      SM3_TR(0, it);
       const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
         mbar_wait(bar_sempty(rb), sph ^ 1u, bar_limit);
         tc_fence_after();
+        SM3_TR(8 + rb, it);                                                // trace: S stage rb free, issue starts
         const uint32_t d_tmem = tmem + kColS + (uint32_t)rb * 128u;
         const uint32_t a_tmem = tmem + (uint32_t)rb * kColA1;
         if (elect_one()) {
@@ -548,8 +614,10 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
           umma_commit(bar_sfull(rb));
         }
         __syncwarp();
+        SM3_TR(1 + rb, it);
       }
     }
+    SM3_TR(7, 2);
   } else {
     // =========================== softmax warps ===========================
     const int q = warp & 3;
@@ -604,6 +672,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
       for (int rb = 0; rb < 2; ++rb) {
         mbar_wait(bar_sfull(rb), sph, bar_limit);
         tc_fence_after();
+        if (warp == 2 && lane == 0) SM3_TR(3 + 2 * rb, it);
         const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)rb * 128u + (uint32_t)half * 64u;
         uint32_t a[32], b[32];
         tmem_ld_x32(taddr, a);
@@ -613,6 +682,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sempty(rb));
+        if (warp == 2 && lane == 0) SM3_TR(4 + 2 * rb, it);
         const bool need = (cb + 64 > p.m_cols) ||
                           (valid[rb] && ((unsigned)(g[rb] - cb) < 64u || (unsigned)(pj[rb] - cb) < 64u));
         if (!__any_sync(0xffffffffu, need)) {
@@ -652,6 +722,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SM3_TR(7, 4);                                      // trace: CTA end
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -741,6 +812,8 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();        // PDL: everything above overlapped the preceding kernel's tail; global memory from here on
+  pdl_launch();
   constexpr uint32_t kColS = C::kColS, kColDZ = C::kColDZ;
 
   if (warp == 0) {
@@ -953,24 +1026,30 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
 // TMEM: A [0, 32 DP) | S/H stage i [128 + 64 i, 192 + 64 i) | dZ [128 + 64 NS, 128 + 64 NS + 64 DP).  H (bf16 pairs)
 // overwrites the first 32 columns of the S stage it was computed from.
 // ------------------------------------------------------------------------------------------------
-template <int DP, int NS> struct Bwd2Cfg {
-  static constexpr int BN = 64;
-  static constexpr uint32_t PANEL = BN * 128;          // 8 KB: 64 rows x 64 bf16
+template <int DP, int NS, int BN_> struct Bwd2Cfg {
+  static constexpr int BN = BN_;                       // columns per tile: 64, or 128 (D <= 128: TMEM has the room)
+  static constexpr uint32_t PANEL = BN * 128;          // BN rows x 64 bf16
   static constexpr uint32_t STAGE = DP * PANEL;        // <= 32 KB
-  static constexpr uint32_t ACOL = BN * 4;             // 256 B: a_j of the tile's 64 columns
+  static constexpr uint32_t ACOL = BN * 4;             // a_j of the tile's columns
   static constexpr int NSTAGE = NS + 2;                // smem ring: tiles it .. it+NS are live, one more in flight
   static constexpr uint32_t SMEM = NSTAGE * (STAGE + ACOL) + 1024 + 256;
-  static constexpr uint32_t kColS = 128, kColDZ = 128 + 64 * NS;
+  static constexpr uint32_t kColS = 128, kColDZ = 128 + BN * NS;
+  static_assert(BN == 64 || BN == 128, "tile width");
   static_assert(32 * DP <= 128, "A operand region");
   static_assert(kColDZ + 64 * DP <= 512, "TMEM budget");
   static_assert(8 * (2 * NSTAGE + 2 * NS + 3) <= 256, "barrier block");
 };
 
-template <int DP, bool kWait, int NS>
+// COLSPLIT (needs BN = 128): every softmax warp works on EVERY tile and the two groups split its columns (group g owns
+// columns [64 g, 64 g + 64)), so one tile's exponentials occupy all four MUFU pipes while the tensor pipe runs the other
+// stage's dZ / S MMAs -- with only two 128-column stages in TMEM, tile-alternating groups cannot hide a tile's
+// ~2000-cycle softmax latency (measured: 1935 cycles per tile), the column split halves it.
+template <int DP, bool kWait, int NS, int BNT, int POLY, bool COLSPLIT>
 __global__ void __launch_bounds__(320, 1)
 infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
-  using C = Bwd2Cfg<DP, NS>;
-  static_assert(NS % 2 == 0, "each softmax group keeps its own S/H stages");
+  using C = Bwd2Cfg<DP, NS, BNT>;
+  static_assert(COLSPLIT || NS % 2 == 0, "each softmax group keeps its own S/H stages");
+  static_assert(!COLSPLIT || BNT == 128, "the column split is between two 64-column halves");
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
   constexpr int D = 64 * DP;
   extern __shared__ uint8_t smem_raw[];
@@ -990,6 +1069,7 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   const float* acol_smem = reinterpret_cast<const float*>(base_ptr + (sA - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SM3_TR(7, 0);                                      // trace: CTA start
   const unsigned long long bar_limit = 2000000000ull + p.wait_timeout_ns;   // + cross-rank bound in fused-exchange mode
   const int r0 = blockIdx.x * kBM;
   const int split = blockIdx.y;
@@ -1007,7 +1087,7 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
-    for (int i = 0; i < NS; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_hfull(i), 4); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_hfull(i), COLSPLIT ? 8 : 4); }
     mbar_init(bar_aready, 8);
     mbar_init(bar_dzfull, 1);
     fence_barrier_init();
@@ -1020,6 +1100,8 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();        // PDL: everything above overlapped the preceding kernel's tail; global memory from here on
+  pdl_launch();
   constexpr uint32_t kColS = C::kColS, kColDZ = C::kColDZ;
 
   if (warp == 0) {
@@ -1060,7 +1142,7 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
       const int s = it % NSTAGE, as = it % NS;
       mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);
       tc_fence_after();
-      const uint32_t d_tmem = tmem + kColS + (uint32_t)as * 64u;
+      const uint32_t d_tmem = tmem + kColS + (uint32_t)as * (uint32_t)BN;
       const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
       if (elect_one()) {
 #pragma unroll
@@ -1073,6 +1155,7 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
     };
     mbar_wait(bar_aready, 0, bar_limit);
     tc_fence_after();
+    SM3_TR(7, 1);                                                          // trace: rows staged, first MMA
 #pragma unroll
     for (int i = 0; i < NS; ++i)
       if (i < n_tiles) issue_s(i);
@@ -1081,7 +1164,7 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
       mbar_wait(bar_hfull(as), (uint32_t)(it / NS) & 1u, bar_limit);
       tc_fence_after();
       SM3_TR(0, it);
-      const uint32_t h_tmem = tmem + kColS + (uint32_t)as * 64u;     // 64 k-values packed in 32 columns
+      const uint32_t h_tmem = tmem + kColS + (uint32_t)as * (uint32_t)BN;   // BN k-values packed in BN / 2 columns
       const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, C::PANEL);   // MN-major: LBO = panel stride
       if (elect_one()) {
 #pragma unroll
@@ -1097,6 +1180,7 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
     }
     if (elect_one()) umma_commit(bar_dzfull);
     __syncwarp();
+    SM3_TR(7, 2);                                                          // trace: last MMA issued
   } else {
     // =========================== softmax / epilogue warps ===========================
     const int q = warp & 3;                    // TMEM lane quadrant
@@ -1139,70 +1223,80 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
     }
     const float c2 = p.c2;
 
-    for (int it = grp; it < n_tiles; it += 2) {
+    for (int it = COLSPLIT ? 0 : grp; it < n_tiles; it += COLSPLIT ? 1 : 2) {
       const int as = it % NS, s = it % NSTAGE;
       const int tile = tile_of(it);
       mbar_wait(bar_sfull(as), (uint32_t)(it / NS) & 1u, bar_limit);
       mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);   // completed long ago: makes the TMA-written a_j ours
       tc_fence_after();
-      if (warp == 2 && lane == 0) SM3_TR(3, it);
-      const uint32_t taddr = tmem + lane_addr + kColS + (uint32_t)as * 64u;
-      uint32_t v0[32], v1[32];
-      tmem_ld_x32(taddr, v0);
-      tmem_ld_x32(taddr + 32, v1);
-      tmem_ld_wait(v0);
-      tmem_ld_wait(v1);
-      if (warp == 2 && lane == 0) SM3_TR(4, it);
-      const int cb = tile * BN;
-      const bool need = (cb + BN > p.m_cols) ||
-                        (valid && ((unsigned)(g - cb) < (unsigned)BN || (unsigned)(pj - cb) < (unsigned)BN));
-      const float4* ap = reinterpret_cast<const float4*>(acol_smem + s * BN);
-      uint32_t h[32];
-      if (!__any_sync(0xffffffffu, need)) {
+      if ((warp == 2 || (!COLSPLIT && warp == 6)) && lane == 0) SM3_TR(3, it);
+      const uint32_t tbase = tmem + lane_addr + kColS + (uint32_t)as * (uint32_t)BN;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 aj = ap[i];                     // broadcast LDS.128
-          const uint32_t* v = i < 8 ? v0 : v1;
-          const int o = 4 * (i & 7);
-          const float e0 = ex2(fmaf(__uint_as_float(v[o]), c2, -c2)) * (a_i + aj.x);
-          const float e1 = ex2(fmaf(__uint_as_float(v[o + 1]), c2, -c2)) * (a_i + aj.y);
-          const float e2 = ex2(fmaf(__uint_as_float(v[o + 2]), c2, -c2)) * (a_i + aj.z);
-          const float e3 = ex2(fmaf(__uint_as_float(v[o + 3]), c2, -c2)) * (a_i + aj.w);
-          h[2 * i] = pack_bf16x2(e0, e1);
-          h[2 * i + 1] = pack_bf16x2(e2, e3);
-        }
-      } else {
-        const float* as_ = acol_smem + s * BN;
+      for (int hc0 = 0; hc0 < (COLSPLIT ? 1 : BN / 64); ++hc0) {   // 64 columns at a time
+        const int hc = COLSPLIT ? grp : hc0;
+        const uint32_t taddr = tbase + (uint32_t)hc * 64u;
+        uint32_t v0[32], v1[32];
+        tmem_ld_x32(taddr, v0);
+        tmem_ld_x32(taddr + 32, v1);
+        tmem_ld_wait(v0);
+        tmem_ld_wait(v1);
+        if (hc0 == 0 && (warp == 2 || (!COLSPLIT && warp == 6)) && lane == 0) SM3_TR(4, it);
+        const int cb = tile * BN + hc * 64;
+        const bool need = (cb + 64 > p.m_cols) ||
+                          (valid && ((unsigned)(g - cb) < 64u || (unsigned)(pj - cb) < 64u));
+        const float* as_ = acol_smem + s * BN + hc * 64;
+        const float4* ap = reinterpret_cast<const float4*>(as_);
+        uint32_t h[32];
+        if (!__any_sync(0xffffffffu, need)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c = 2 * i + u;
-            const int col = cb + c;
-            const float sv = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
-            float xv = 0.f;
-            if (valid && col < p.m_cols && col != g) {
-              if (col == pj) xv = gp_i + (kWait ? __ldcg(p.gpos_c + (size_t)col * p.cstride) : p.gpos_c[(size_t)col * p.cstride]);
-              else xv = ex2(fmaf(sv, c2, -c2)) * (a_i + as_[c]);
-            }
-            x[u] = xv;
+          for (int i = 0; i < 16; ++i) {
+            const float4 aj = ap[i];                     // broadcast LDS.128
+            const uint32_t* v = i < 8 ? v0 : v1;
+            const int o = 4 * (i & 7);
+            const float x0 = fmaf(__uint_as_float(v[o]), c2, -c2), x1 = fmaf(__uint_as_float(v[o + 1]), c2, -c2);
+            const float x2 = fmaf(__uint_as_float(v[o + 2]), c2, -c2), x3 = fmaf(__uint_as_float(v[o + 3]), c2, -c2);
+            // POLY of every 8 exponentials on the FMA pipes (i even: elements 0..3 of the group, i odd: 4..7)
+            const float e0 = ((i & 1) == 0 && 0 < POLY) || ((i & 1) == 1 && 4 < POLY) ? ex2_fma(x0) : ex2(x0);
+            const float e1 = ((i & 1) == 0 && 1 < POLY) || ((i & 1) == 1 && 5 < POLY) ? ex2_fma(x1) : ex2(x1);
+            const float e2 = ((i & 1) == 0 && 2 < POLY) || ((i & 1) == 1 && 6 < POLY) ? ex2_fma(x2) : ex2(x2);
+            const float e3 = ((i & 1) == 0 && 3 < POLY) || ((i & 1) == 1 && 7 < POLY) ? ex2_fma(x3) : ex2(x3);
+            h[2 * i] = pack_bf16x2(e0 * (a_i + aj.x), e1 * (a_i + aj.y));
+            h[2 * i + 1] = pack_bf16x2(e2 * (a_i + aj.z), e3 * (a_i + aj.w));
           }
-          h[i] = pack_bf16x2(x[0], x[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int c = 2 * i + u;
+              const int col = cb + c;
+              const float sv = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
+              float xv = 0.f;
+              if (valid && col < p.m_cols && col != g) {
+                if (col == pj) xv = gp_i + (kWait ? __ldcg(p.gpos_c + (size_t)col * p.cstride) : p.gpos_c[(size_t)col * p.cstride]);
+                else xv = ex2(fmaf(sv, c2, -c2)) * (a_i + as_[c]);
+              }
+              x[u] = xv;
+            }
+            h[i] = pack_bf16x2(x[0], x[1]);
+          }
         }
+        // H (packed bf16 pairs) goes to columns [32 hc, 32 hc + 32) of the stage: S columns this thread has consumed
+        tmem_st_x32(tbase + (uint32_t)hc * 32u, h);
       }
-      if (warp == 2 && lane == 0) SM3_TR(5, it);
-      tmem_st_x32(taddr, h);          // H overwrites the first 32 of this thread's own (already consumed) S columns
+      if ((warp == 2 || (!COLSPLIT && warp == 6)) && lane == 0) SM3_TR(5, it);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfull(as));
-      if (warp == 2 && lane == 0) SM3_TR(6, it);
+      if ((warp == 2 || (!COLSPLIT && warp == 6)) && lane == 0) SM3_TR(6, it);
     }
 
     // ---- epilogue: dZ (TMEM fp32) * 1/T -> global partial ----
     mbar_wait(bar_dzfull, 0, bar_limit);
     tc_fence_after();
+    if (warp == 2 && lane == 0) SM3_TR(7, 3);                              // trace: dZ complete, epilogue starts
     float* dst = p.dz_partial + ((size_t)split * p.m_rows + (valid ? l : 0)) * D;
 #pragma unroll
     for (int ch = 0; ch < 2 * DP; ++ch) {
@@ -1223,6 +1317,7 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SM3_TR(7, 4);                                      // trace: CTA end
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -1251,6 +1346,7 @@ struct TcPlan {
   int row_tiles, col_tiles, splits, tiles_per_split, bm;
 };
 // forward: 256-row CTAs (half the L2 traffic) once there are enough rows to fill the machine that way
+int tc_bwd_bn(int dp);      // backward column-tile width (defined with the other knobs below)
 int tc_fwd_rows_per_cta(int m_rows, int m_cols) {
   const char* e = getenv("SM3_TC_FWD_BM");
   if (e) return atoi(e) == 128 ? 128 : 256;
@@ -1260,7 +1356,7 @@ int tc_fwd_rows_per_cta(int m_rows, int m_cols) {
 TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
   TcPlan pl;
   const int m_rows = 2 * pb.n_local, m_cols = 2 * pb.n_global;
-  const int bn = bwd ? 64 : 128;
+  const int bn = bwd ? tc_bwd_bn(pb.D / 64) : 128;
   pl.bm = bwd ? kBM : tc_fwd_rows_per_cta(m_rows, m_cols);
   pl.row_tiles = (m_rows + pl.bm - 1) / pl.bm;
   pl.col_tiles = (m_cols + bn - 1) / bn;
@@ -1271,7 +1367,7 @@ TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
     const size_t cap = ((size_t)1 << 30) / (per ? per : 1);
     if ((size_t)max_splits > cap) max_splits = cap < 1 ? 1 : (int)cap;
   }
-  pl.splits = tc_pick_splits(pl.row_tiles, pl.col_tiles, bwd ? 6 : (pl.bm == 256 ? 3 : 4), max_splits);
+  pl.splits = tc_pick_splits(pl.row_tiles, pl.col_tiles, bwd ? (bn == 128 ? 4 : 6) : (pl.bm == 256 ? 3 : 4), max_splits);
   if (const char* e = getenv(bwd ? "SM3_TC_BWD_SPLITS" : "SM3_TC_FWD_SPLITS")) {     // tuning override (sweeps)
     const int want = atoi(e);
     if (want >= 1 && want <= max_splits && want <= pl.col_tiles) {
@@ -1341,7 +1437,7 @@ template <int DP, int NG, int POLY>
 int launch_fwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
   SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd_kernel<DP, NG, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)FwdCfg<DP>::SMEM));
-  infonce_tc_fwd_kernel<DP, NG, POLY><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, FwdCfg<DP>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(launch_k(infonce_tc_fwd_kernel<DP, NG, POLY>, dim3(pl.row_tiles, pl.splits), dim3(64 + 256 * NG), FwdCfg<DP>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
@@ -1349,7 +1445,7 @@ template <int DP, int POLY>
 int launch_fwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
   SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd2_kernel<DP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)FwdCfg<DP>::SMEM));
-  infonce_tc_fwd2_kernel<DP, POLY><<<dim3(pl.row_tiles, pl.splits), 320, FwdCfg<DP>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(launch_k(infonce_tc_fwd2_kernel<DP, POLY>, dim3(pl.row_tiles, pl.splits), dim3(320), FwdCfg<DP>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
@@ -1375,7 +1471,7 @@ template <int DP, int NG, bool kWait, int NS>
 int launch_bwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
   SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP, NG, kWait, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)BwdCfg<DP, NS>::SMEM));
-  infonce_tc_bwd_kernel<DP, NG, kWait, NS><<<dim3(pl.row_tiles, pl.splits), 64 + 256 * NG, BwdCfg<DP, NS>::SMEM, st>>>(tmap, p);
+  SM3_CHECK_CUDA(launch_k(infonce_tc_bwd_kernel<DP, NG, kWait, NS>, dim3(pl.row_tiles, pl.splits), dim3(64 + 256 * NG), BwdCfg<DP, NS>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
@@ -1389,33 +1485,68 @@ int tc_bwd_stages(int dp) {
   if (forced == 2 || dp > 2) return 2;
   return 4;
 }
-template <int DP, bool kWait, int NS>
+template <int DP, bool kWait, int NS, int BNT, int POLY, bool COLSPLIT = false>
 int launch_bwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd2_kernel<DP, kWait, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Bwd2Cfg<DP, NS>::SMEM));
-  infonce_tc_bwd2_kernel<DP, kWait, NS><<<dim3(pl.row_tiles, pl.splits), 320, Bwd2Cfg<DP, NS>::SMEM, st>>>(tmap, p);
+  using C = Bwd2Cfg<DP, NS, BNT>;
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd2_kernel<DP, kWait, NS, BNT, POLY, COLSPLIT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  SM3_CHECK_CUDA(launch_k(infonce_tc_bwd2_kernel<DP, kWait, NS, BNT, POLY, COLSPLIT>, dim3(pl.row_tiles, pl.splits), dim3(320), C::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
-// which backward kernel: 2 = tile-alternating softmax groups + a_j through shared memory (infonce_tc_bwd2_kernel),
-// 1 = the first form.  SM3_TC_BWD_V=1|2 overrides; default by embedding width (see tc_bwd_version()).
+// Which backward kernel (SM3_TC_BWD_V overrides; default by embedding width):
+//   1 = first form (softmax warps split each 64-column tile)              -- default for D > 128
+//   2 = tile-alternating groups + a_j through shared memory, 64-column tiles
+//   3 = the same with 128-COLUMN tiles (D <= 128 only: TMEM has room for two 128-column S/H stages)
+//   4 = 128-column tiles, all eight softmax warps on every tile, the two groups split its columns -- default for D <= 128.
+// Measured with the trace build on B200 (cfg2, D = 128): the thread that issues tcgen05.mma needs ~52 cycles per
+// instruction whatever its size, so the N = 64 S-MMAs of a 64-column tile (32 tensor cycles each) cannot keep the pipe
+// busy: 12 issues = ~940 cycles per tile against 512 cycles of tensor work.  128-column tiles halve the issues per column.
 int tc_bwd_version(int dp) {
   int& v = g_knob_bwd_v;
   if (v < 0) {
     const char* e = getenv("SM3_TC_BWD_V");
-    v = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    v = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 0;
   }
-  if (v != 0) return v;
-  return dp <= 2 ? 2 : 1;
+  int r = v != 0 ? v : (dp <= 2 ? 4 : 1);
+  if (r >= 3 && dp > 2) r = 2;
+  return r;
+}
+int tc_bwd_bn(int dp) { return tc_bwd_version(dp) >= 3 ? 128 : 64; }
+// exponentials per 8 on the FMA pipes in the 128-column backward (SM3_TC_BWD_POLY=0|2; default 2: at D <= 128 the
+// softmax side is MUFU-bound, 1024 MUFU cycles per 128 x 128 tile against 1024 tensor cycles)
+int g_knob_bwd_poly = -1;
+int tc_bwd_poly() {
+  int& v = g_knob_bwd_poly;
+  if (v < 0) {
+    const char* e = getenv("SM3_TC_BWD_POLY");
+    v = e ? (atoi(e) == 2 ? 2 : 0) : 2;
+  }
+  return v;
 }
 template <int DP>
 int launch_bwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  if (tc_bwd_version(DP) == 2) {
+  const int ver = tc_bwd_version(DP);
+  if constexpr (DP <= 2) {
+    if (ver == 3) {
+      const bool poly = tc_bwd_poly() == 2;
+      if (p.wait_flags != nullptr)
+        return poly ? launch_bwd2<DP, true, 2, 128, 2>(tmap, p, pl, st) : launch_bwd2<DP, true, 2, 128, 0>(tmap, p, pl, st);
+      return poly ? launch_bwd2<DP, false, 2, 128, 2>(tmap, p, pl, st) : launch_bwd2<DP, false, 2, 128, 0>(tmap, p, pl, st);
+    }
+    if (ver == 4) {
+      const bool poly = tc_bwd_poly() == 2;
+      if (p.wait_flags != nullptr)
+        return poly ? launch_bwd2<DP, true, 2, 128, 2, true>(tmap, p, pl, st) : launch_bwd2<DP, true, 2, 128, 0, true>(tmap, p, pl, st);
+      return poly ? launch_bwd2<DP, false, 2, 128, 2, true>(tmap, p, pl, st) : launch_bwd2<DP, false, 2, 128, 0, true>(tmap, p, pl, st);
+    }
+  }
+  if (ver >= 2) {
     constexpr int NS2 = DP <= 2 ? 4 : 2;
     const bool two = tc_bwd_stages(DP) == 2;
     if (p.wait_flags != nullptr)
-      return two ? launch_bwd2<DP, true, 2>(tmap, p, pl, st) : launch_bwd2<DP, true, NS2>(tmap, p, pl, st);
-    return two ? launch_bwd2<DP, false, 2>(tmap, p, pl, st) : launch_bwd2<DP, false, NS2>(tmap, p, pl, st);
+      return two ? launch_bwd2<DP, true, 2, 64, 0>(tmap, p, pl, st) : launch_bwd2<DP, true, NS2, 64, 0>(tmap, p, pl, st);
+    return two ? launch_bwd2<DP, false, 2, 64, 0>(tmap, p, pl, st) : launch_bwd2<DP, false, NS2, 64, 0>(tmap, p, pl, st);
   }
   // (the in-kernel-wait form of the multi-rank fused exchange stays on 2 stages until it has been run on >= 2 GPUs)
   if (p.wait_flags != nullptr) return launch_bwd_ng<DP, 1, true, 2>(tmap, p, pl, st);
@@ -1446,7 +1577,7 @@ size_t infonce_tc_workspace(const InfoNceProblem& pb, int backward) {
   if (pb.D % 64 != 0 || pb.D < 64 || pb.D > 256) return 0;
   const TcPlan pl = tc_plan(pb, backward != 0);
   if (!backward) return (size_t)pl.splits * 2 * pb.n_local * sizeof(float) + 256;
-  const size_t m_pad = ((size_t)2 * pb.n_global + 63) / 64 * 64 + 64;
+  const size_t m_pad = ((size_t)2 * pb.n_global + 127) / 128 * 128 + 128;   // whole 128-column tiles + one of slack
   return bwd_acol_offset(pb, pl) + m_pad * sizeof(float) + 256;
 }
 
@@ -1492,7 +1623,8 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
   SM3_REQUIRE(ws_bytes >= infonce_tc_workspace(pb, 1), SM3_ERR_WORKSPACE, "infonce(tc) bwd: workspace too small");
   const TcPlan pl = tc_plan(pb, true);
   TcParams p{};
-  fill_params(pb, pl, p, 64);
+  const int bn = tc_bwd_bn(pb.D / 64);
+  fill_params(pb, pl, p, bn);
   p.gpos_r = gpos_r; p.glse_r = glse_r; p.nsum_r = nsum_r; p.gpos_c = gpos_c; p.cstride = pb.col_stride;
   p.dz_partial = (float*)ws;
   SM3_REQUIRE(pb.wait_flags == nullptr || (pb.n_local % 128 == 0 && !pb.skip_local && pb.acol_direct != nullptr),
@@ -1502,12 +1634,12 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
   } else {
     float* acol = (float*)((char*)ws + bwd_acol_offset(pb, pl));
     p.acol = acol;
-    const int m_pad = (p.m_cols + 63) / 64 * 64 + 64;
+    const int m_pad = (p.m_cols + 127) / 128 * 128 + 128;
     tc_bwd_prep_kernel<<<(m_pad + 255) / 256, 256, 0, st>>>(glse_c, nsum_c, pb.col_stride, p.m_cols, m_pad, acol);
     SM3_CHECK_CUDA(cudaGetLastError());
   }
   CUtensorMap tmap;
-  int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 64);
+  int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, (uint32_t)bn);
   if (rc) return rc;
   switch (pb.D / 64) {
     case 1: rc = launch_bwd<1>(tmap, p, pl, st); break;
@@ -1526,6 +1658,7 @@ extern "C" void sm3_debug_reload_env(void) {
   sm3::g_knob_poly = -1;
   sm3::g_knob_bwd_ns = -1;
   sm3::g_knob_bwd_v = -1;
+  sm3::g_knob_bwd_poly = -1;
 }
 
 #ifdef SM3_TRACE
@@ -1569,5 +1702,24 @@ extern "C" int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, floa
   else SM3_PROBE(false, false);
 #undef SM3_PROBE
   SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+// debug microbenchmark (C ABI): see umma_rate_kernel.  out_host[0] = issue cycles, [1] = total cycles, [3..] = tcgen05.ld
+// round trips completed by the contending warps.
+extern "C" int sm3_debug_umma_rate(int n, int a_from_tmem, int count, int ldtm_warps, long long* out_host) {
+  using namespace sm3;
+  SM3_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && count >= 1 && count <= 4096 && ldtm_warps >= 0 && ldtm_warps <= 8 && out_host,
+              SM3_ERR_SHAPE, "umma_rate: bad arguments");
+  long long* dev = nullptr;
+  SM3_CHECK_CUDA(cudaMalloc(&dev, 16 * sizeof(long long)));
+  SM3_CHECK_CUDA(cudaMemset(dev, 0, 16 * sizeof(long long)));
+  const int smem = 16384 + 65536 + 1024 + 256;
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_kernel<<<1, 288, smem>>>(n, a_from_tmem, count, ldtm_warps, dev);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  SM3_REQUIRE(e == cudaSuccess, SM3_ERR_CUDA, "umma_rate: %s", cudaGetErrorString(e));
   return SM3_OK;
 }

@@ -44,6 +44,8 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_fwd_small_kernel(const TIn* __restrict__ pa, int64_t rows_a, const TIn* __restrict__ pb, int64_t rows_b, int D,
                         TOut* __restrict__ z, float* __restrict__ inv_norm, float eps) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int64_t rows = rows_a + rows_b;
   const bool have = lane < D / kChunk;
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_small_kernel(const float* __restrict__ dz, int n_partials, int64_t partial_stride, float scale,
                         const TZ* __restrict__ z, const float* __restrict__ inv_norm, float inv_eps,
                         TOut* __restrict__ dpa, int64_t rows_a, TOut* __restrict__ dpb, int64_t rows_b, int D) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   constexpr int R = 2;
   const int lane = threadIdx.x & 31;
   const int64_t rows = rows_a + rows_b;
@@ -187,6 +191,8 @@ template <typename TIn, typename TOut, bool kStream>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_fwd_persist_kernel(const TIn* __restrict__ pa, int64_t rows_a, const TIn* __restrict__ pb, int64_t rows_b, int D,
                           TOut* __restrict__ z, float* __restrict__ inv_norm, float eps) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int64_t rows = rows_a + rows_b;
   const bool have = lane < D / kChunk;
@@ -243,6 +249,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_persist_kernel(const float* __restrict__ dz, int n_partials, int64_t partial_stride, float scale,
                           const TZ* __restrict__ z, const float* __restrict__ inv_norm, float inv_eps,
                           TOut* __restrict__ dpa, int64_t rows_a, TOut* __restrict__ dpb, int64_t rows_b, int D) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   static_assert(sizeof(TZ) == 2, "16-bit z rows");
   constexpr int R = 2;
   const int lane = threadIdx.x & 31;
@@ -306,6 +314,8 @@ template <typename TIn, typename TOut, bool kVec>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_fwd_kernel(const TIn* __restrict__ pa, int64_t rows_a, const TIn* __restrict__ pb, int64_t rows_b, int D,
                   TOut* __restrict__ z, float* __restrict__ inv_norm, float eps) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows_a + rows_b) return;
@@ -352,6 +362,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_kernel(const float* __restrict__ dz, int n_partials, int64_t partial_stride, float scale,
                   const TZ* __restrict__ z, const float* __restrict__ inv_norm, float inv_eps,
                   TOut* __restrict__ dpa, int64_t rows_a, TOut* __restrict__ dpb, int64_t rows_b, int D) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows_a + rows_b) return;
@@ -439,12 +451,12 @@ int l2norm_fwd_launch(const void* p_a, int64_t rows_a, const void* p_b, int64_t 
         if (variant == 2) {
           static const int per_sm = resident_ctas(l2norm_fwd_persist_kernel<TIn, TOut, true>, kWarpsPerBlock * 32);
           const int64_t cap = (int64_t)num_sms() * per_sm;
-          l2norm_fwd_persist_kernel<TIn, TOut, true><<<(unsigned)(wantp < cap ? wantp : cap), kWarpsPerBlock * 32, 0, st>>>(
+          launch_k(l2norm_fwd_persist_kernel<TIn, TOut, true>, dim3((unsigned)(wantp < cap ? wantp : cap)), dim3(kWarpsPerBlock * 32), 0, st, 
               (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);
         } else {
           static const int per_sm = resident_ctas(l2norm_fwd_persist_kernel<TIn, TOut, false>, kWarpsPerBlock * 32);
           const int64_t cap = (int64_t)num_sms() * per_sm;
-          l2norm_fwd_persist_kernel<TIn, TOut, false><<<(unsigned)(wantp < cap ? wantp : cap), kWarpsPerBlock * 32, 0, st>>>(
+          launch_k(l2norm_fwd_persist_kernel<TIn, TOut, false>, dim3((unsigned)(wantp < cap ? wantp : cap)), dim3(kWarpsPerBlock * 32), 0, st, 
               (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);
         }
       }));
@@ -452,7 +464,7 @@ int l2norm_fwd_launch(const void* p_a, int64_t rows_a, const void* p_b, int64_t 
       return SM3_OK;
     }
     SM3_DISPATCH_DTYPE(p_dtype, TIn, SM3_DISPATCH_DTYPE(z_dtype, TOut, {
-      l2norm_fwd_small_kernel<TIn, TOut><<<g4, kWarpsPerBlock * 32, 0, st>>>(
+      launch_k(l2norm_fwd_small_kernel<TIn, TOut>, dim3(g4), dim3(kWarpsPerBlock * 32), 0, st, 
           (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);
     }));
     SM3_CHECK_CUDA(cudaGetLastError());
@@ -460,10 +472,10 @@ int l2norm_fwd_launch(const void* p_a, int64_t rows_a, const void* p_b, int64_t 
   }
   SM3_DISPATCH_DTYPE(p_dtype, TIn, SM3_DISPATCH_DTYPE(z_dtype, TOut, {
     if (vec)
-      l2norm_fwd_kernel<TIn, TOut, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+      launch_k(l2norm_fwd_kernel<TIn, TOut, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, st, 
           (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);
     else
-      l2norm_fwd_kernel<TIn, TOut, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+      launch_k(l2norm_fwd_kernel<TIn, TOut, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, st, 
           (const TIn*)p_a, rows_a, (const TIn*)p_b, rows_b, D, (TOut*)z, inv_norm, eps);
   }));
   SM3_CHECK_CUDA(cudaGetLastError());
@@ -488,7 +500,7 @@ int l2norm_bwd_launch(const float* dz_partials, int n_partials, float scale, con
       do {                                                                                                           \
         static const int per_sm = resident_ctas(l2norm_bwd_persist_kernel<TZ, TOut>, kWarpsPerBlock * 32);           \
         const int64_t cap = (int64_t)num_sms() * per_sm;                                                             \
-        l2norm_bwd_persist_kernel<TZ, TOut><<<(unsigned)(want2 < cap ? want2 : cap), kWarpsPerBlock * 32, 0, st>>>(  \
+        launch_k(l2norm_bwd_persist_kernel<TZ, TOut>, dim3((unsigned)(want2 < cap ? want2 : cap)), dim3(kWarpsPerBlock * 32), 0, st,   \
             dz_partials, n_partials, rows * (int64_t)D, scale, (const TZ*)z, inv_norm, inv_eps, (TOut*)dp_a, rows_a, \
             (TOut*)dp_b, rows_b, D);                                                                                 \
       } while (0)
@@ -499,7 +511,7 @@ int l2norm_bwd_launch(const float* dz_partials, int n_partials, float scale, con
       return SM3_OK;
     }
     SM3_DISPATCH_DTYPE(z_dtype, TZ, SM3_DISPATCH_DTYPE(dp_dtype, TOut, {
-      l2norm_bwd_small_kernel<TZ, TOut><<<g2, kWarpsPerBlock * 32, 0, st>>>(
+      launch_k(l2norm_bwd_small_kernel<TZ, TOut>, dim3(g2), dim3(kWarpsPerBlock * 32), 0, st, 
           dz_partials, n_partials, rows * (int64_t)D, scale, (const TZ*)z, inv_norm, inv_eps, (TOut*)dp_a, rows_a,
           (TOut*)dp_b, rows_b, D);
     }));
@@ -508,11 +520,11 @@ int l2norm_bwd_launch(const float* dz_partials, int n_partials, float scale, con
   }
   SM3_DISPATCH_DTYPE(z_dtype, TZ, SM3_DISPATCH_DTYPE(dp_dtype, TOut, {
     if (vec)
-      l2norm_bwd_kernel<TZ, TOut, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+      launch_k(l2norm_bwd_kernel<TZ, TOut, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, st, 
           dz_partials, n_partials, rows * (int64_t)D, scale, (const TZ*)z, inv_norm, inv_eps, (TOut*)dp_a, rows_a,
           (TOut*)dp_b, rows_b, D);
     else
-      l2norm_bwd_kernel<TZ, TOut, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+      launch_k(l2norm_bwd_kernel<TZ, TOut, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, st, 
           dz_partials, n_partials, rows * (int64_t)D, scale, (const TZ*)z, inv_norm, inv_eps, (TOut*)dp_a, rows_a,
           (TOut*)dp_b, rows_b, D);
   }));

@@ -118,6 +118,8 @@ template <typename TIn>
 __global__ void __launch_bounds__(256)
 l2norm_scatter_kernel(const TIn* __restrict__ pa, const TIn* __restrict__ pb, int n_local, int pair_offset, int n_global,
                       int D, __nv_bfloat16* __restrict__ z_local, float* __restrict__ inv_norm, float eps, PeerFused pf) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   __shared__ bool is_last;
   constexpr int kR = 4;
   const int lane = threadIdx.x & 31;
@@ -183,6 +185,8 @@ loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, con
                           int pair_offset, int n_global, float inv_T, float scale, float* __restrict__ loss,
                           float* __restrict__ g_pos, float* __restrict__ g_lse, float* __restrict__ neg_sum,
                           float* __restrict__ block_ws, PeerFused pf, int accumulate, float* __restrict__ a_local) {
+  pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
+  pdl_launch();
   __shared__ float red[32];
   __shared__ bool is_last;
   const int rows = 2 * n_local;
@@ -254,8 +258,8 @@ int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pai
   SM3_REQUIRE(aligned16(p_a) && aligned16(p_b) && aligned16(z_local), SM3_ERR_SHAPE, "l2norm_scatter: unaligned rows");
   const unsigned grid = (unsigned)((2 * (int64_t)n_local + 31) / 32);
   SM3_DISPATCH_DTYPE(p_dtype, TIn, {
-    l2norm_scatter_kernel<TIn><<<grid, 256, 0, st>>>((const TIn*)p_a, (const TIn*)p_b, n_local, pair_offset, n_global, D,
-                                                     (__nv_bfloat16*)z_local, inv_norm, eps, pf);
+    launch_k(l2norm_scatter_kernel<TIn>, dim3(grid), dim3(256), 0, st, (const TIn*)p_a, (const TIn*)p_b, n_local, pair_offset,
+             n_global, D, (__nv_bfloat16*)z_local, inv_norm, eps, pf);
   });
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
@@ -266,8 +270,8 @@ int loss_stats_scatter_launch(const float* partial, int n_partials, const float*
                               float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate,
                               float* a_local) {
   const unsigned grid = (unsigned)((2 * (int64_t)n_local + 255) / 256);
-  loss_stats_scatter_kernel<<<grid, 256, 0, st>>>(partial, n_partials, pos, n_local, pair_offset, n_global, inv_T, scale,
-                                                  loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate, a_local);
+  launch_k(loss_stats_scatter_kernel, dim3(grid), dim3(256), 0, st, partial, n_partials, pos, n_local, pair_offset, n_global,
+           inv_T, scale, loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate, a_local);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }

@@ -46,6 +46,13 @@ _PROFILE = None
 _SCRATCH = {}
 
 
+def reload_env() -> None:
+    """Re-read the SM3_TC_* tuning knobs (sweeps / tests that change them inside one process): drops the library's cached
+    values and the scratch cache, whose sizes depend on the kernel variant."""
+    lib().sm3_debug_reload_env()
+    _SCRATCH.clear()
+
+
 def _scratch(kind: str, dev: torch.device, key: tuple, nbytes_fn) -> torch.Tensor:
     k = (kind, dev.index, torch.cuda.current_stream(dev).cuda_stream) + key
     buf = _SCRATCH.get(k)
@@ -222,6 +229,25 @@ class core:
         return v[0] if n_partials == 1 else v.sum(0)
 
     @staticmethod
+    def scale_grads(dps, g: torch.Tensor, out_dtypes):
+        """out_t = dp_t * g for all tensors in ONE launch (``sm3_scale_grads``); the cast to the inputs' dtype (fp32 ->
+        fp16 for --amp inputs) happens in the same kernel, after the multiplication."""
+        import ctypes as C
+        dps = [_contig(d) for d in dps]
+        g32 = g if (g.dtype == torch.float32 and g.dim() == 0) else g.reshape(()).float()
+        same = len(set(out_dtypes)) == 1 and len({d.numel() for d in dps}) == 1 and len({d.dtype for d in dps}) == 1
+        if not same or len(dps) > 8:
+            return tuple((d * g32.to(d.dtype)).to(o) for d, o in zip(dps, out_dtypes))
+        outs = [torch.empty(d.shape, dtype=out_dtypes[0], device=d.device) for d in dps]
+        k = len(dps)
+        with torch.cuda.device(dps[0].device):
+            check(lib().sm3_scale_grads((C.c_void_p * k)(*[d.data_ptr() for d in dps]),
+                                        (C.c_void_p * k)(*[o.data_ptr() for o in outs]), k, dps[0].numel(),
+                                        dtype_code(dps[0]), _lib._DTYPES[out_dtypes[0]], ptr(g32), stream_ptr()),
+                  "sm3_scale_grads")
+        return tuple(outs)
+
+    @staticmethod
     def loss(pos, lse_neg, scale: float, out: Optional[torch.Tensor] = None, accumulate: bool = False,
              want_grads: bool = True):
         dev = require_cuda(pos, lse_neg)
@@ -263,22 +289,8 @@ def _grad_safe(p: torch.Tensor) -> torch.Tensor:
 
 
 def _scale_grads(dps, g: torch.Tensor, out_dtypes):
-    """dp * upstream for the eagerly computed gradients, all tensors in ONE launch (``sm3_scale_grads``); the cast to the
-    inputs' dtype (fp32 -> fp16 for --amp inputs) happens in the same kernel, after the multiplication."""
-    import ctypes as C
-    dps = [_contig(d) for d in dps]
-    g32 = g if (g.dtype == torch.float32 and g.dim() == 0) else g.reshape(()).float()
-    same = len(set(out_dtypes)) == 1 and len({d.numel() for d in dps}) == 1 and len({d.dtype for d in dps}) == 1
-    if not same or len(dps) > 8:
-        return tuple((d * g32.to(d.dtype)).to(o) for d, o in zip(dps, out_dtypes))
-    outs = [torch.empty(d.shape, dtype=out_dtypes[0], device=d.device) for d in dps]
-    k = len(dps)
-    with torch.cuda.device(dps[0].device):
-        check(lib().sm3_scale_grads((C.c_void_p * k)(*[d.data_ptr() for d in dps]),
-                                    (C.c_void_p * k)(*[o.data_ptr() for o in outs]), k, dps[0].numel(),
-                                    dtype_code(dps[0]), _lib._DTYPES[out_dtypes[0]], ptr(g32), stream_ptr()),
-              "sm3_scale_grads")
-    return tuple(outs)
+    """dp * upstream for the eagerly computed gradients (see core.scale_grads)."""
+    return core.scale_grads(dps, g, out_dtypes)
 
 
 def _group_info(group):
@@ -735,19 +747,72 @@ def knn_predict(query: torch.Tensor, bank: torch.Tensor, bank_labels: torch.Tens
 # ------------------------------------------------------------------------------------------------------
 # DeepCluster memory-bank clustering (N4)
 # ------------------------------------------------------------------------------------------------------
+class _kmeans_core:
+    """The two fused k-means kernels (csrc/kmeans.cu); tests/dist_worker.py swaps in a CPU stand-in for the gloo run."""
+
+    @staticmethod
+    def supported(d: int, k: int, emb: torch.Tensor) -> bool:
+        return emb.dtype == torch.float32 and bool(lib().sm3_kmeans_supported(d, k, _lib.F32))
+
+    @staticmethod
+    def assign(emb: torch.Tensor, cent: torch.Tensor, want_sums: bool):
+        """-> (assign int64 [n], packed [K*D + K] fp32 = cluster sums then counts, or None)"""
+        dev = require_cuda(emb, cent)
+        n, d = emb.shape
+        k = cent.shape[0]
+        assign = torch.empty(n, dtype=torch.int64, device=dev)
+        packed = torch.empty(k * d + k, dtype=torch.float32, device=dev) if want_sums else None
+        with torch.cuda.device(dev):
+            ws = _scratch("kmeans", dev, (n, d, k), lambda: lib().sm3_kmeans_workspace_bytes(n, d, k)) if want_sums else None
+            check(lib().sm3_kmeans_assign(ptr(emb), n, d, ptr(cent), k, ptr(assign), ptr(packed),
+                                          (packed.data_ptr() + 4 * k * d) if want_sums else None, ptr(ws),
+                                          ws.numel() if want_sums else 0, stream_ptr()), "sm3_kmeans_assign")
+        return assign, packed
+
+    @staticmethod
+    def update(packed: torch.Tensor, cent: torch.Tensor) -> torch.Tensor:
+        dev = require_cuda(packed, cent)
+        k, d = cent.shape
+        new = torch.empty_like(cent)
+        with torch.cuda.device(dev):
+            check(lib().sm3_kmeans_update(ptr(packed), packed.data_ptr() + 4 * k * d, ptr(cent), ptr(new), d, k, _EPS,
+                                          stream_ptr()), "sm3_kmeans_update")
+        return new
+
+
+kmeans_core = _kmeans_core
+
+
 @torch.no_grad()
-def spherical_kmeans(emb: torch.Tensor, init_idx: torch.Tensor, n_iters: int = 10):
+def spherical_kmeans(emb: torch.Tensor, init_idx: Optional[torch.Tensor], n_iters: int = 10, group=None,
+                     init_centroids: Optional[torch.Tensor] = None):
     """The rank-0 loop of ``cluster_memory`` (reference tools/mlc_train.py:144-176) without leaving the GPU: centroids
-    start at ``emb[init_idx]``; E step = ``sm3_sim_topk`` with k = 1 (argmax of ``emb @ centroids.T``, never
-    materialised, ties to the lower centroid); M step = per-cluster mean as a one-hot GEMM (deterministic, no
-    ``.cpu().numpy()`` / scipy.sparse / Python loop over clusters as at :161-172) for the non-empty clusters, then row
-    L2-normalisation of all centroids (K1).  Returns (assignments int64 [n], centroids fp32 [K, D])."""
-    require_cuda(emb, init_idx)
-    if emb.dim() != 2 or init_idx.dim() != 1:
-        raise ValueError("spherical_kmeans expects emb [n, D] and init_idx [K]")
+    start at ``emb[init_idx]`` (or ``init_centroids``); per iteration ONE pass over the bank does the E step (argmax of
+    ``emb @ centroids.T``, never materialised, ties to the lower centroid) and accumulates the M step's per-cluster sums
+    (``sm3_kmeans_assign``, deterministic), then ``sm3_kmeans_update`` takes the means of the non-empty clusters and
+    L2-normalises all centroids -- no ``.cpu().numpy()`` / scipy.sparse / Python loop over clusters as at :161-172.
+    With ``group`` the bank stays SHARDED: ``emb`` is this rank's shard, the [K*D + K] sums / counts are all-reduced
+    between the two kernels and every rank ends with identical centroids.  Shapes the fused kernels do not take
+    (D % 128 != 0, D > 512, K > 8) use ``sm3_sim_topk`` (k = 1) + a one-hot GEMM instead.
+    Returns (assignments int64 [n], centroids fp32 [K, D])."""
+    require_cuda(emb, init_idx, init_centroids)
+    if emb.dim() != 2:
+        raise ValueError("spherical_kmeans expects emb [n, D]")
     emb = _contig(emb.float())
-    cent = _contig(emb[init_idx.long()].clone())
-    k = cent.shape[0]
+    cent = _contig(init_centroids.float().clone()) if init_centroids is not None else _contig(emb[init_idx.long()].clone())
+    k, d = cent.shape
+    w, _ = _group_info(group)
+    if kmeans_core.supported(d, k, emb):
+        assign = None
+        for it in range(n_iters + 1):
+            last = it == n_iters
+            assign, packed = kmeans_core.assign(emb, cent, not last)
+            if last:
+                break
+            if w > 1:
+                dist.all_reduce(packed, group=group)
+            cent = kmeans_core.update(packed, cent)
+        return assign, cent
     assign = None
     tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False          # the cluster sums must be fp32 sums whatever the script set
@@ -760,6 +825,10 @@ def spherical_kmeans(emb: torch.Tensor, init_idx: torch.Tensor, n_iters: int = 1
             onehot = torch.nn.functional.one_hot(assign, k).to(emb.dtype)        # [n, K]
             counts = onehot.sum(0)                                               # exact in fp32 below 2^24 samples
             sums = onehot.t() @ emb                                              # [K, D]
+            if w > 1:
+                packed = torch.cat([sums.reshape(-1), counts])
+                dist.all_reduce(packed, group=group)
+                sums, counts = packed[: k * d].view(k, d), packed[k * d:]
             keep = (counts > 0).unsqueeze(1)
             cent = torch.where(keep, sums / counts.clamp(min=1.0).unsqueeze(1), cent)
             cent = l2_normalize(_contig(cent))
@@ -772,29 +841,41 @@ def spherical_kmeans(emb: torch.Tensor, init_idx: torch.Tensor, n_iters: int = 1
 def cluster_memory(args, prototypes, K: int, local_memory_index: torch.Tensor, local_memory_embeddings: torch.Tensor,
                    nmb_kmeans_iters: int = 10) -> torch.Tensor:
     """Drop-in for ``cluster_memory`` of tools/mlc_train.py:116-189 (same signature, same return value, same side
-    effect ``prototypes.weight.copy_(centroids)``).  Every rank all-gathers the bank and runs the identical
-    deterministic k-means on its own GPU instead of gathering to rank 0, looping in Python there and broadcasting the
-    result; only the K initial indices -- ``torch.randperm`` on rank 0's default generator, as at :144 -- are broadcast."""
+    effect ``prototypes.weight.copy_(centroids)``).  The bank stays sharded: every rank clusters its own
+    ``local_memory_embeddings`` against shared centroids and only [K*D + K] floats per iteration cross ranks
+    (all-reduce), instead of gathering the whole bank to rank 0, looping in Python there and broadcasting the result
+    (:137-143, :185-186).  The K initial centroids are the rows rank 0's ``torch.randperm`` picks out of the rank-major
+    concatenation of the shards, exactly as at :144-145."""
     dev = require_cuda(local_memory_embeddings)
-    index = local_memory_index.to(dev).long()
-    emb = _contig(local_memory_embeddings)
+    index = _contig(local_memory_index.to(dev).long())
+    emb = _contig(local_memory_embeddings.float())
     world = int(getattr(args, "world_size", 1))
-    if world > 1:
-        all_emb = torch.empty((world * emb.shape[0], emb.shape[1]), dtype=emb.dtype, device=dev)
-        all_idx = torch.empty(world * index.shape[0], dtype=index.dtype, device=dev)
-        dist.all_gather_into_tensor(all_emb, emb)
-        dist.all_gather_into_tensor(all_idx, _contig(index))
-    else:
-        all_emb, all_idx = emb, index
-    n = all_emb.shape[0]
+    rank = int(getattr(args, "rank", 0))
+    n_local, d = emb.shape
+    n = n_local * world
     if n < K:
         raise ValueError("please reduce the number of centroids")          # reference :146
-    init = torch.randperm(n)[:K].to(dev) if int(getattr(args, "rank", 0)) == 0 else torch.empty(K, dtype=torch.long, device=dev)
+    init = torch.randperm(n)[:K].to(dev) if rank == 0 else torch.empty(K, dtype=torch.long, device=dev)
+    group = None
     if world > 1:
         dist.broadcast(init, 0)
-    assign, centroids = spherical_kmeans(all_emb, init, nmb_kmeans_iters)
+        group = dist.group.WORLD
+        mine = (init >= rank * n_local) & (init < (rank + 1) * n_local)
+        cent0 = torch.zeros((K, d), dtype=torch.float32, device=dev)
+        cent0[mine] = emb[(init[mine] - rank * n_local)]
+        dist.all_reduce(cent0)                                              # each row has exactly one owner
+    else:
+        cent0 = emb[init]
+    assign, centroids = spherical_kmeans(emb, None, nmb_kmeans_iters, group=group, init_centroids=cent0)
+    if world > 1:
+        all_assign = torch.empty(n, dtype=assign.dtype, device=dev)
+        all_idx = torch.empty(n, dtype=index.dtype, device=dev)
+        dist.all_gather_into_tensor(all_assign, _contig(assign))
+        dist.all_gather_into_tensor(all_idx, index)
+    else:
+        all_assign, all_idx = assign, index
     assignments = torch.full((n,), -100, dtype=torch.long, device=dev)
-    assignments[all_idx] = assign
+    assignments[all_idx] = all_assign
     prototypes.weight.copy_(centroids.to(prototypes.weight.dtype))
     return assignments
 

@@ -48,6 +48,10 @@ class OracleCore:
         return val, (-scale * sig).float(), (scale * sig).float()
 
     @staticmethod
+    def scale_grads(dps, g, out_dtypes):
+        return tuple((d * g.to(d.dtype)).to(o) for d, o in zip(dps, out_dtypes))
+
+    @staticmethod
     def normalize_bwd(dz, n_partials, scale, z, inv, n1, n2, out_dtype, eps=1e-12):
         dp = O.normalize_bwd(dz.double().numpy() * scale, z.double().numpy(), inv.double().numpy())
         dp = torch.from_numpy(dp).to(out_dtype)
@@ -168,7 +172,30 @@ def main():
             return torch.gather(sim, 1, order).float(), order
         F3.sim_topk = cpu_topk
         F3.l2_normalize = lambda p, eps=1e-12, out_dtype=None: torch.nn.functional.normalize(p, dim=1, eps=eps)
-    for c in ("a", "c"):
+
+        class CpuKmeans:                      # stand-in for the fused k-means kernels (csrc/kmeans.cu), same contract
+            @staticmethod
+            def supported(d, k, emb):
+                return d % 128 == 0 and d <= 512 and k <= 8
+
+            @staticmethod
+            def assign(emb, cent, want_sums):
+                a = torch.argmax(emb @ cent.T, dim=1)
+                if not want_sums:
+                    return a, None
+                k, d = cent.shape
+                sums = torch.zeros(k, d).index_add_(0, a, emb)
+                counts = torch.bincount(a, minlength=k).float()
+                return a, torch.cat([sums.reshape(-1), counts])
+
+            @staticmethod
+            def update(packed, cent):
+                k, d = cent.shape
+                sums, counts = packed[: k * d].view(k, d), packed[k * d:]
+                new = torch.where((counts > 0).unsqueeze(1), sums / counts.clamp(min=1).unsqueeze(1), cent)
+                return torch.nn.functional.normalize(new, dim=1)
+        F3.kmeans_core = CpuKmeans
+    for c in ("a", "c", "b", "e"):            # a, c: generic path; b, e: the shapes the fused kernels take
         emb, index, init = gk[f"{c}_emb"], gk[f"{c}_index"], gk[f"{c}_init_idx"]
         n = (len(emb) // world) * world       # equal shards (DistributedSampler semantics)
         emb, index = emb[:n], index[:n]

@@ -133,17 +133,18 @@ def test_infonce_edge_cases_fp32(sm3):
             assert relerr(d2, g[k + "_dp2"]) < 1e-4, k
 
 
-@pytest.mark.parametrize("bwd_v", ["1", "2"])
+@pytest.mark.parametrize("bwd_v", ["1", "2", "3", "4"])
 @pytest.mark.parametrize("fwd_bm", ["128", "256"])
 @pytest.mark.parametrize("n,d,T", [(1024, 128, 0.1), (1000, 64, 0.5), (333, 192, 0.2), (1536, 256, 0.1),
                                    (64, 256, 0.1), (129, 128, 0.07)])
 def test_tensor_core_path_vs_oracle(sm3, monkeypatch, n, d, T, fwd_bm, bwd_v):
     """tcgen05 kernels (bf16 rows) vs the fp64 closed form on the same bf16-rounded inputs; ragged tile edges.
     fwd_bm selects the 128-row or the 256-row-per-CTA forward kernel (the latter is the default at cfg4 scale);
-    bwd_v the backward form (1: softmax warps split the tile's columns, 2: tile-alternating groups + a_j in smem)."""
+    bwd_v the backward form (1: softmax warps split the tile's columns, 2: tile-alternating groups + a_j in smem,
+    3: the same with 128-column tiles where D <= 128, 4: 128-column tiles with the groups splitting each tile's columns)."""
     monkeypatch.setenv("SM3_TC_FWD_BM", fwd_bm)
     monkeypatch.setenv("SM3_TC_BWD_V", bwd_v)
-    sm3.lib().sm3_debug_reload_env()
+    sm3.reload_env()
     g = torch.Generator().manual_seed(n + d)
     p1 = torch.randn(n, d, generator=g).bfloat16()
     p2 = (p1.float() + 0.5 * torch.randn(n, d, generator=g)).bfloat16()
@@ -163,10 +164,10 @@ def test_tensor_core_path_vs_oracle(sm3, monkeypatch, n, d, T, fwd_bm, bwd_v):
     assert abs(l2.item() - ref_loss) <= 2e-2 * max(abs(ref_loss), 1e-3)
     assert relerr(a.grad.float().cpu().numpy(), r1) < 2e-2 and relerr(b.grad.float().cpu().numpy(), r2) < 2e-2
     monkeypatch.undo()
-    sm3.lib().sm3_debug_reload_env()
+    sm3.reload_env()
 
 
-@pytest.mark.parametrize("bwd_v,ns", [("1", "4"), ("2", "4"), ("2", "2")])
+@pytest.mark.parametrize("bwd_v,ns", [("1", "4"), ("2", "4"), ("2", "2"), ("3", "2"), ("4", "2")])
 def test_backward_forms_agree(sm3, monkeypatch, bwd_v, ns):
     """Both backward kernels and both S/H stage counts produce the same partial-gradient sums (bf16 H, fp32 accumulation:
     differences are tile-order only) on a multi-split problem with ragged edges, against the FMA kernel."""
@@ -179,13 +180,13 @@ def test_backward_forms_agree(sm3, monkeypatch, bwd_v, ns):
     ref = sm3.core.sum_partials(ws, k, 2 * n, d).clone()
     monkeypatch.setenv("SM3_TC_BWD_V", bwd_v)
     monkeypatch.setenv("SM3_TC_BWD_NS", ns)
-    sm3.lib().sm3_debug_reload_env()
+    sm3.reload_env()
     try:
         ws, k = sm3.core.stats_bwd(z, z, n, 0, n, T, gp, gl, nsum, gp, gl, nsum, sm3.ALGO_TC)
         got = sm3.core.sum_partials(ws, k, 2 * n, d).clone()
     finally:
         monkeypatch.undo()
-        sm3.lib().sm3_debug_reload_env()
+        sm3.reload_env()
     assert relerr(got.cpu(), ref.cpu()) < 1.5e-2
 
 

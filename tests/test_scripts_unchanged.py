@@ -55,7 +55,11 @@ def test_backbone_train_and_mlc_train_run_unchanged(tmp_path):
     if ref_root() is None:
         pytest.skip("no reference scripts (oracle/_ref not vendored and /root/reference absent)")
     base = 29700 + (os.getpid() % 200)
-    pre = ["--arch-version", "v32", "--proj-dim", "128", "--temperature", "0.1", "-lr", "1e-3"]
+    # run.sh's own optimiser setting (lr 1e-6): AdamW's first step moves every weight by ~lr whatever the gradient's size,
+    # so with a large lr two fp32 implementations that differ in the last bits of a near-zero gradient diverge visibly
+    # after ONE step (measured: 1 % at lr 1e-3); the per-parameter gradients themselves are pinned against the real
+    # wrappers by test_dropin_model_matches_reference
+    pre = ["--arch-version", "v32", "--proj-dim", "128", "--temperature", "0.1", "-lr", "1e-6"]
     # ---- tools/backbone_train.py: drop-in vs stock reference modules, fp32 ----
     ours, out, _ = run_script("backbone_train.py", pre, tmp_path / "bt_ours", True, base)
     assert "drop-in active: src.models.simclr" in out
@@ -63,10 +67,9 @@ def test_backbone_train_and_mlc_train_run_unchanged(tmp_path):
     stock, out_s, _ = run_script("backbone_train.py", pre, tmp_path / "bt_stock", False, base + 1)
     assert "drop-in active" not in out_s
     assert len(stock) == 2
-    # iteration 0: same weights, same data -> the four InfoNCE terms agree to the log's 4 decimals (fp32 kernels);
-    # iteration 1 runs on weights updated with OUR gradients vs the reference's autograd: AdamW steps of lr 1e-3
+    # same weights, same data -> the four InfoNCE terms agree to the log's 4 decimals (fp32 kernels), both iterations
     assert abs(ours[0] - stock[0]) <= 2e-4 * max(1.0, abs(stock[0])), (ours, stock)
-    assert abs(ours[1] - stock[1]) <= 5e-3 * max(1.0, abs(stock[1])), (ours, stock)
+    assert abs(ours[1] - stock[1]) <= 5e-4 * max(1.0, abs(stock[1])), (ours, stock)
     ckpt = tmp_path / "bt_ours" / "checkpoint.pth.tar"
     assert ckpt.exists()
     sd = torch.load(str(ckpt), map_location="cpu")["state_dict"]
