@@ -272,6 +272,12 @@ int sm3_infonce_step_multi(int num_terms, const void* const* p1_host_array, cons
  *      inside the kernel, visiting this rank's own column tiles first (needs n_local % 128 == 0; flags buffers of
  *      >= 128 uint32, zero-initialised: words [64, 66) are local ticket counters; the stats buffer then holds the
  *      planes a_j = g_lse_j / neg_sum_j at [0, 2*n_global) and g_pos_j at [2*n_global, 4*n_global)).
+ *   3: as 2, but the rows are pushed from INSIDE K2: the normalise kernel only fills this rank's own rows, two extra
+ *      warps of K2's first-wave CTAs store the rows into the peers' z_cols destination by destination (rank+1 first) and
+ *      release one flag per destination, while the tensor-core warps visit the column tiles owner by owner (own columns,
+ *      then rank-1's, rank-2's, ...: the order the rows arrive) with one flag wait per source rank -- the whole scatter
+ *      hides behind compute.  Uses flag words [66, 85) as tickets; falls back to 2 for problems too small for the
+ *      256-row forward kernel.
  * D in {64,128,192,256}.
  * loss = weight * mean over this rank's rows (DDP convention).                                                     */
 size_t sm3_infonce_step_peer_scratch_bytes(int n_local, int n_global, int D);
@@ -304,6 +310,13 @@ void sm3_debug_reload_env(void);
  *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */
 int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,
                          void* stream);
+
+/* debug / single-GPU test of mode 3's forward (owner-ordered column tiles, one flag wait per source rank) with the caller
+ * standing in for the peers: z_cols complete, flags[0 .. world) of channel 0 already at `epoch`; nothing is pushed. */
+size_t sm3_debug_infonce_fwd_ordered_workspace(int n_local, int world, int D);
+int sm3_debug_infonce_fwd_ordered(const void* z_rows, const void* z_cols, int n_local, int rank, int world, int D, float inv_T,
+                                  const void* flags, unsigned epoch, float* pos, float* lse_neg, float* neg_sum,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* debug / bring-up microbenchmark (not a product path): dispatch rate of `count` back-to-back tcgen05.mma (M = 128, K = 16,
  * bf16) of width n, A operand from shared memory (0) or TMEM (1), with `ldtm_warps` warps streaming tcgen05.ld meanwhile.

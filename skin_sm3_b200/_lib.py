@@ -76,6 +76,8 @@ SIGNATURES = {
     "sm3_stage_timing_read": (_i, [_vp, _i]),
     "sm3_stage_timing_names": (C.c_char_p, []),
     "sm3_debug_reload_env": (None, []),
+    "sm3_debug_infonce_fwd_ordered_workspace": (_sz, [_i, _i, _i]),
+    "sm3_debug_infonce_fwd_ordered": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, C.c_uint, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sm3_debug_umma_rate": (_i, [_i, _i, _i, _i, _vp]),
     "sm3_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }

@@ -419,6 +419,12 @@ PeerPlan plan_peer(int n_local, int n_global, int D) {
   const size_t full_b = infonce_tc_workspace(full, 1), full_f = infonce_tc_workspace(full, 0);
   h.ws_b_bytes = split_b > full_b ? split_b : full_b;
   if (h.ws_b_bytes < full_f) h.ws_b_bytes = full_f;
+  if (n_local % 128 == 0 && n_global > n_local) {            // mode 3: the owner-ordered forward may use other split counts
+    InfoNceProblem fullp = full;
+    fullp.push_mode = 1;
+    const size_t f3 = infonce_tc_workspace(fullp, 0);
+    if (h.ws_b_bytes < f3) h.ws_b_bytes = f3;
+  }
   h.ws_b = take(h.ws_b_bytes);
   h.total = o;
   return h;
@@ -460,8 +466,8 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
   SM3_REQUIRE((dp1 == nullptr) == (dp2 == nullptr), SM3_ERR_SHAPE, "infonce_step_peer: dp1/dp2 must both be given or both NULL");
   SM3_REQUIRE(world >= 2 && rank >= 0 && rank < world && n_local >= 1, SM3_ERR_SHAPE,
               "infonce_step_peer: needs world >= 2 (got world=%d n_local=%d)", world, n_local);
-  SM3_REQUIRE(overlap >= 0 && overlap <= 2, SM3_ERR_SHAPE, "infonce_step_peer: mode %d not in {0,1,2}", overlap);
-  SM3_REQUIRE(!overlap || n_local % 128 == 0, SM3_ERR_SHAPE, "infonce_step_peer: modes 1 and 2 need n_local %% 128 == 0");
+  SM3_REQUIRE(overlap >= 0 && overlap <= 3, SM3_ERR_SHAPE, "infonce_step_peer: mode %d not in {0,1,2,3}", overlap);
+  SM3_REQUIRE(!overlap || n_local % 128 == 0, SM3_ERR_SHAPE, "infonce_step_peer: modes 1, 2 and 3 need n_local %% 128 == 0");
   SM3_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256 && dtype_ok(io_dtype) && temperature > 0.f, SM3_ERR_DTYPE,
               "infonce_step_peer: D must be in {64,128,192,256}");
   SM3_REQUIRE(overlap != 1 || stream_side != stream_main, SM3_ERR_SHAPE,
@@ -483,6 +489,50 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
   float *lse = (float*)(base + h.lse), *nsum = (float*)(base + h.nsum), *gpos = (float*)(base + h.gpos), *glse = (float*)(base + h.glse);
   void* z = base + h.z;
 
+  if (overlap == 3) {
+    // ---- fused exchange with the row push INSIDE K2 (5 launches): kernel 1 only normalises (local rows + this rank's
+    //      own rows of its column buffer); K2's two extra warps push the rows to the peers, destination rank+1 first,
+    //      while its tensor-core warps work through this rank's own column tiles, and it waits per source rank in the
+    //      order the rows arrive (rank-1, rank-2, ...).  Falls back to mode 2 where the 256-row kernel is not used. ----
+    InfoNceProblem probe{base + h.z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
+    if (!infonce_tc_push_supported(probe)) overlap = 2;
+  }
+  if (overlap == 3) {
+    SM3_REQUIRE(aligned16(p1) && aligned16(p2), SM3_ERR_SHAPE, "infonce_step_peer: fused mode needs 16-byte aligned rows");
+    unsigned* counters = (unsigned*)flags_mine + 64;          // [0,2) mode-2 tickets | [2,18) push tickets | [20] kernel 1
+    PeerFused own{};
+    own.data.world = 1; own.data.p[0] = z_cols_mine;          // only this rank's copy of the column buffer, no signal
+    own.flags.world = 0; own.counter = counters + 20; own.rank = rank; own.channel = 0; own.epoch = epoch;
+    PdlScope pdl(!g_stage_timing);
+    stage_begin(sm, "normalize,infonce_fwd_push,loss_scatter,infonce_bwd,normalize_bwd");
+    rc = l2norm_scatter_launch(p1, p2, n_local, off, n_global, D, io_dtype, z, (float*)(base + h.inv), 1e-12f, own, sm);
+    if (rc) return rc;
+    stage_mark(sm);
+    PeerFused pz{zp, fp, counters + 2, rank, 0, epoch};
+    InfoNceProblem pf{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
+    pf.wait_flags = (const unsigned*)flags_mine; pf.wait_world = world; pf.wait_channel = 0; pf.wait_epoch = epoch;
+    pf.no_finalize = 1;
+    pf.push_mode = 1; pf.push_src = z; pf.push = &pz;
+    const int splits = infonce_tc_fwd(pf, pos, lse, nsum, base + h.ws_b, h.ws_b_bytes, sm);
+    if (splits < 0) return splits;
+    stage_mark(sm);
+    PeerFused ps{sp, fp, counters + 1, rank, 1, epoch};
+    rc = loss_stats_scatter_launch((const float*)(base + h.ws_b), splits, pos, n_local, off, n_global, inv_T,
+                                   weight / (float)m, loss, gpos, glse, nsum, lse_l /* per-CTA loss sums */, ps, sm);
+    stage_mark(sm);
+    if (rc || !dp1) return rc;
+    InfoNceProblem pk{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
+    pk.wait_flags = (const unsigned*)flags_mine; pk.wait_world = world; pk.wait_channel = 1; pk.wait_epoch = epoch;
+    pk.acol_direct = (const float*)stats_mine;                 // planes written by the owners: a_j | g_pos_j
+    const float* gpos_cols = (const float*)stats_mine + (size_t)2 * n_global;
+    const int np = infonce_tc_bwd(pk, gpos, glse, nsum, gpos_cols, gpos_cols, gpos_cols, base + h.ws_b, h.ws_b_bytes, sm);
+    if (np < 0) return np;
+    stage_mark(sm);
+    rc = sm3_l2norm_bwd((const float*)(base + h.ws_b), np, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, dp1, n,
+                        dp2, n, D, io_dtype, sm);
+    stage_mark(sm);
+    return rc;
+  }
   if (overlap == 2) {
     // ---- fused exchange: 5 launches.  The producers publish + signal themselves, K2 / K3 wait inside the kernel and
     //      visit this rank's own column tiles first (see peer.cu, infonce_tc.cu). ----
@@ -575,6 +625,29 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
   if (np_r < 0) return np_r;
   return sm3_l2norm_bwd((const float*)(base + h.ws_b), np_l + np_r, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f,
                         dp1, n, dp2, n, D, io_dtype, sm);
+}
+
+// debug / single-GPU test of the owner-ordered forward (mode 3's tile mapping and per-source flag waits) without peers:
+// `flags` must already hold `epoch` in slots [0, world) of channel 0 (the caller plays the part of the other ranks and
+// has filled z_cols); no rows are pushed.  Same outputs as sm3_infonce_fwd.
+extern "C" int sm3_debug_infonce_fwd_ordered(const void* z_rows, const void* z_cols, int n_local, int rank, int world, int D,
+                                             float inv_T, const void* flags, unsigned epoch, float* pos, float* lse_neg,
+                                             float* neg_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  SM3_REQUIRE(z_rows && z_cols && flags && pos && lse_neg && neg_sum && workspace, SM3_ERR_SHAPE, "fwd_ordered: null pointer");
+  SM3_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world && n_local >= 128 && n_local % 128 == 0, SM3_ERR_SHAPE,
+              "fwd_ordered: needs 2 <= world <= 16 and n_local %% 128 == 0");
+  InfoNceProblem pb{z_rows, z_cols, n_local, rank * n_local, n_local * world, D, SM3_BF16, inv_T};
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  SM3_REQUIRE(infonce_tc_supported(pb), SM3_ERR_DTYPE, "fwd_ordered: tcgen05 path unavailable");
+  pb.wait_flags = (const unsigned*)flags; pb.wait_world = world; pb.wait_channel = 0; pb.wait_epoch = epoch;
+  pb.push_mode = 1;
+  return infonce_tc_fwd(pb, pos, lse_neg, neg_sum, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+extern "C" size_t sm3_debug_infonce_fwd_ordered_workspace(int n_local, int world, int D) {
+  InfoNceProblem pb{nullptr, nullptr, n_local, 0, n_local * world, D, SM3_BF16, 1.0f};
+  pb.push_mode = 1;
+  return infonce_tc_workspace(pb, 0);
 }
 
 extern "C" size_t sm3_infonce_host_scratch_bytes(int n_pairs, int D, int io_dtype, int algo) {

@@ -242,6 +242,12 @@ struct InfoNceProblem {
                                           // (written by the owners over NVLink) -> no prep kernel; g_pos_cols likewise
   int no_finalize = 0;                    // forward: leave the per-split partial sums in the workspace (the fused
                                           // loss kernel folds them)
+  // forward, multi-rank, 256-row tcgen05 kernel: column tiles visited owner by owner (own columns first, then the ranks
+  // whose rows arrive first) with one flag wait per source rank; when push_src is set the kernel itself stores this
+  // rank's rows into the peers' column buffers (two extra warps), see infonce_tc.cu
+  int push_mode = 0;
+  const void* push_src = nullptr;         // this rank's normalised rows, bf16 [2 n_local, D]
+  const struct PeerFused* push = nullptr; // destinations, flag buffers, [world] ticket words, rank, channel, epoch
 };
 struct PeerFused {          // what the fused exchange kernels need to publish to every rank
   PeerPtrs data;            // destination buffers (z_cols or stats), one per rank
@@ -265,6 +271,7 @@ int infonce_simt_bwd(const InfoNceProblem& pb, const float* gpos_r, const float*
                      const float* gpos_c, const float* glse_c, const float* nsum_c, void* ws, size_t ws_bytes,
                      cudaStream_t st);
 bool infonce_tc_supported(const InfoNceProblem& pb);
+bool infonce_tc_push_supported(const InfoNceProblem& pb);   // push_mode needs the 256-row forward kernel
 size_t infonce_tc_workspace(const InfoNceProblem& pb, int backward);
 int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* neg_sum, void* ws, size_t ws_bytes,
                    cudaStream_t st);

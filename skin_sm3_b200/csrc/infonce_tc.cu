@@ -63,6 +63,15 @@ struct TcParams {
   unsigned wait_epoch;
   unsigned long long wait_timeout_ns;
   int loc_a, loc_b, loc_len;
+  // owner-ordered tiles + in-kernel row push (multi-rank forward, see infonce_tc_fwd2_kernel): tiles are visited owner by
+  // owner -- this rank's own columns, then rank-1's, rank-2's, ... -- and split s takes every own_S-th tile of an
+  // owner's two ranges (own_L tiles each); the kernel's two extra warps store this rank's rows into the peers' column
+  // buffers destination by destination in the order rank+1, rank+2, ... and release a per-destination flag.
+  int own_order, own_L, own_S;
+  const uint4* push_src;         // this rank's normalised rows [m_rows, D] (nullptr = no pushing)
+  int push_vpr, push_ctas;       // 16-byte vectors per row; how many CTAs (the first wave) share the copy
+  PeerPtrs push_dst, push_flags;
+  unsigned* push_counter;        // [world] zero-initialised tickets, reset by the last CTA
 };
 
 // Per-CTA starting rotation of the column-tile order.  Default: pseudo-random (decorrelates the CTAs of a wave, see the
@@ -82,6 +91,24 @@ __device__ __forceinline__ int tile_rotation(const TcParams& p, int t_begin, int
 }
 __device__ __forceinline__ bool tile_is_local(const TcParams& p, int t) {
   return (unsigned)(t - p.loc_a) < (unsigned)p.loc_len || (unsigned)(t - p.loc_b) < (unsigned)p.loc_len;
+}
+// owner-ordered tile of visiting position `it` for split `split` (see TcParams::own_order); *owner = rank that owns it
+__device__ __forceinline__ int owner_tile(const TcParams& p, int it, int split, int rot, int* owner) {
+  const int per = p.own_L / p.own_S;           // tiles of one owner range that one split visits
+  const int j = it / (2 * per);                // owner's position in the visiting order
+  const int r = it - j * 2 * per;
+  const int half = r >= per ? 1 : 0;
+  int q = r - half * per + rot;                // per-CTA rotation inside the range (decorrelates the CTAs' L2 accesses)
+  if (q >= per) q -= per;
+  int o = p.wait_world > 0 ? (p.pair_offset / p.n_local) - j : 0;
+  if (o < 0) o += p.wait_world;
+  *owner = o;
+  return half * (p.wait_world * p.own_L) + o * p.own_L + split + q * p.own_S;
+}
+// one source rank's flag (channel * 16 + src) instead of all of them
+__device__ __forceinline__ void peer_flag_wait_one(const unsigned* flags, int channel, int src, unsigned epoch,
+                                                   unsigned long long timeout_ns) {
+  peer_flags_wait_all(flags + src, 1, channel, epoch, timeout_ns);
 }
 // generic-proxy acquire of the peers' flags -> async-proxy (TMA) reads of the rows they published
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -504,8 +531,10 @@ infonce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
 // TMEM: A0 [0,128) | A1 [128,256) | S(row block 0) [256,384) | S(row block 1) [384,512); the two S stages ping-pong
 // between the MMA warp and the 8 softmax warps exactly like FA-style two-Q-tile kernels.
 // ------------------------------------------------------------------------------------------------
-template <int DP, int POLY>
-__global__ void __launch_bounds__(320, 1)
+// kPush: two extra warps (10, 11) push this rank's rows to the peers while the first column tiles -- this rank's own --
+// are being computed (multi-rank fused exchange, owner-ordered tiles; see TcParams).
+template <int DP, int POLY, bool kPush>
+__global__ void __launch_bounds__(kPush ? 384 : 320, 1)
 infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
   using C = FwdCfg<DP>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
@@ -532,8 +561,11 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(p.col_tiles, t_begin + p.tiles_per_split);
   const int n_tiles = t_end - t_begin;
-  const int rot = tile_rotation(p, t_begin, n_tiles);
+  const int own_per = p.own_order ? p.own_L / p.own_S : 1;
+  const int rot = p.own_order ? (int)((blockIdx.x * 37u + blockIdx.y * 11u) % (unsigned)own_per)
+                              : tile_rotation(p, t_begin, n_tiles);
   auto tile_of = [&](int it) {
+    if (p.own_order) { int o; return owner_tile(p, it, split, rot, &o); }
     int t = it + rot;
     t = t_begin + (t >= n_tiles ? t - n_tiles : t);
     if (t >= p.skip_a) t += p.skip_len;        // skip mode: hop over the column tiles owned by this rank
@@ -563,11 +595,24 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
     // =========================== TMA producer ===========================
     if (elect_one()) prefetch_tensormap(&tmap_cols);
     bool remote_ready = (p.wait_flags == nullptr);
+    int ready_pos = 0;                                    // owner-ordered mode: owners [0, ready_pos] have landed
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % NSTAGE;
       const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
       const int tile = tile_of(it);
-      if (!remote_ready && !tile_is_local(p, tile)) {     // fused exchange: the peers' rows must have landed
+      if (p.own_order) {
+        const int pos = it / (2 * own_per);
+        if (pos > ready_pos) {                            // first tile of the next owner: its rows must have landed
+          int o;
+          owner_tile(p, it, split, rot, &o);
+          if (elect_one()) {
+            peer_flag_wait_one(p.wait_flags, p.wait_channel, o, p.wait_epoch, p.wait_timeout_ns);
+            fence_proxy_async_global();
+          }
+          __syncwarp();
+          ready_pos = pos;
+        }
+      } else if (!remote_ready && !tile_is_local(p, tile)) {     // fused exchange: the peers' rows must have landed
         if (elect_one()) {
           peer_flags_wait_all(p.wait_flags, p.wait_world, p.wait_channel, p.wait_epoch, p.wait_timeout_ns);
           fence_proxy_async_global();
@@ -618,6 +663,37 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
       }
     }
     SM3_TR(7, 2);
+  } else if (kPush && warp >= 10) {
+    // =========================== row pushers (first-wave CTAs only) ===========================
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (p.push_src != nullptr && cta < (unsigned)p.push_ctas) {
+      const int t = (int)threadIdx.x - 320;
+      const long total = (long)p.m_rows * p.push_vpr;
+      const long per_cta = (total + p.push_ctas - 1) / p.push_ctas;
+      const long begin = (long)cta * per_cta, end = min(total, begin + per_cta);
+      const int me = p.pair_offset / p.n_local;
+      for (int j = 1; j < p.wait_world; ++j) {
+        const int dst = (me + j) % p.wait_world;          // rank+1 first: it visits OUR columns first after its own
+        uint4* out = reinterpret_cast<uint4*>(p.push_dst.p[dst]);
+        for (long i = begin + t; i < end; i += 64) {
+          const int lrow = (int)(i / p.push_vpr);
+          const int v = (int)(i - (long)lrow * p.push_vpr);
+          const int grow = global_row(lrow, p.n_local, p.pair_offset, p.n_global);
+          out[(long)grow * p.push_vpr + v] = __ldg(p.push_src + i);
+        }
+        named_bar_sync(2, 64);                            // all 64 pushers' stores precede thread 0's fence + ticket
+        if (t == 0) {
+          __threadfence_system();
+          const unsigned k = atomicAdd(p.push_counter + dst, 1u);
+          if (k == (unsigned)p.push_ctas - 1u) {          // every slice of this destination is visible: release its flag
+            p.push_counter[dst] = 0u;
+            __threadfence_system();
+            unsigned* f = reinterpret_cast<unsigned*>(p.push_flags.p[dst]) + p.wait_channel * 16 + me;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(p.wait_epoch) : "memory");
+          }
+        }
+      }
+    }
   } else {
     // =========================== softmax warps ===========================
     const int q = warp & 3;
@@ -1368,6 +1444,24 @@ TcPlan tc_plan(const InfoNceProblem& pb, bool bwd) {
     if ((size_t)max_splits > cap) max_splits = cap < 1 ? 1 : (int)cap;
   }
   pl.splits = tc_pick_splits(pl.row_tiles, pl.col_tiles, bwd ? (bn == 128 ? 4 : 6) : (pl.bm == 256 ? 3 : 4), max_splits);
+  if (!bwd && pb.push_mode) {
+    // owner-ordered tiles: every split takes every S-th tile of each owner's range, so S must divide the range length
+    pl.bm = 256;
+    pl.row_tiles = (m_rows + 255) / 256;
+    const int L = pb.n_local / 128;
+    const int sms = num_sms();
+    int best = 1;
+    double best_cost = 1e30;
+    for (int sdiv = 1; sdiv <= L && sdiv <= max_splits; ++sdiv) {
+      if (L % sdiv) continue;
+      const long waves = ((long)pl.row_tiles * sdiv + sms - 1) / sms;
+      const double cost = (double)waves * (pl.col_tiles / sdiv + 3) + 0.01 * sdiv;
+      if (cost < best_cost) { best_cost = cost; best = sdiv; }
+    }
+    pl.splits = best;
+    pl.tiles_per_split = pl.col_tiles / best;
+    return pl;
+  }
   if (const char* e = getenv(bwd ? "SM3_TC_BWD_SPLITS" : "SM3_TC_FWD_SPLITS")) {     // tuning override (sweeps)
     const int want = atoi(e);
     if (want >= 1 && want <= max_splits && want <= pl.col_tiles) {
@@ -1399,6 +1493,8 @@ void fill_params(const InfoNceProblem& pb, const TcPlan& pl, TcParams& p, int bn
   p.inv_T = pb.inv_T; p.c2 = pb.inv_T * kLog2eTC;
   p.tiles_per_split = pl.tiles_per_split; p.col_tiles = pl.col_tiles;
   p.z_rows = (const __nv_bfloat16*)pb.z_rows;
+  p.own_order = 0; p.own_L = 1; p.own_S = 1; p.push_src = nullptr; p.push_vpr = 0; p.push_ctas = 0; p.push_counter = nullptr;
+  p.push_dst.world = 0; p.push_flags.world = 0;
 }
 
 // number of softmax warp groups (8 warps each): tuning knob, SM3_TC_GROUPS=1|2.  Measured on B200 (cfg4): one group
@@ -1443,9 +1539,15 @@ int launch_fwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, 
 }
 template <int DP, int POLY>
 int launch_fwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd2_kernel<DP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (p.push_src != nullptr) {
+    SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd2_kernel<DP, POLY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)FwdCfg<DP>::SMEM));
+    SM3_CHECK_CUDA(launch_k(infonce_tc_fwd2_kernel<DP, POLY, true>, dim3(pl.row_tiles, pl.splits), dim3(384), FwdCfg<DP>::SMEM, st, tmap, p));
+    return SM3_OK;
+  }
+  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd2_kernel<DP, POLY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)FwdCfg<DP>::SMEM));
-  SM3_CHECK_CUDA(launch_k(infonce_tc_fwd2_kernel<DP, POLY>, dim3(pl.row_tiles, pl.splits), dim3(320), FwdCfg<DP>::SMEM, st, tmap, p));
+  SM3_CHECK_CUDA(launch_k(infonce_tc_fwd2_kernel<DP, POLY, false>, dim3(pl.row_tiles, pl.splits), dim3(320), FwdCfg<DP>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
@@ -1566,6 +1668,11 @@ size_t bwd_acol_offset(const InfoNceProblem& pb, const TcPlan& pl) {
 
 size_t infonce_tc_acol_offset(const InfoNceProblem& pb) { return bwd_acol_offset(pb, tc_plan(pb, true)); }
 
+bool infonce_tc_push_supported(const InfoNceProblem& pb) {
+  return infonce_tc_supported(pb) && pb.n_local % 128 == 0 && pb.n_global > pb.n_local &&
+         tc_fwd_rows_per_cta(2 * pb.n_local, 2 * pb.n_global) == 256;
+}
+
 bool infonce_tc_supported(const InfoNceProblem& pb) {
   static int sm100 = -1;
   if (sm100 < 0) sm100 = sm3_device_supported() == 1 ? 1 : 0;
@@ -1597,6 +1704,20 @@ int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* 
   fill_params(pb, pl, p, 128);
   p.pos = pos;
   p.partial = (float*)ws;
+  if (pb.push_mode) {
+    SM3_REQUIRE(pb.wait_flags != nullptr && pb.n_local % 128 == 0 && pl.bm == 256 && !pb.skip_local, SM3_ERR_SHAPE,
+                "infonce(tc): push mode needs the fused exchange, n_local %% 128 == 0 and the 256-row kernel");
+    p.own_order = 1; p.own_L = pb.n_local / 128; p.own_S = pl.splits;
+    if (pb.push_src != nullptr) {
+      SM3_REQUIRE(pb.push != nullptr && pb.push->counter != nullptr && pb.push->data.world == pb.wait_world &&
+                      pb.push->flags.world == pb.wait_world, SM3_ERR_SHAPE, "infonce(tc): push mode without destinations");
+      p.push_src = (const uint4*)pb.push_src;
+      p.push_vpr = pb.D * 2 / 16;
+      const int ctas = pl.row_tiles * pl.splits;
+      p.push_ctas = ctas < num_sms() ? ctas : num_sms();
+      p.push_dst = pb.push->data; p.push_flags = pb.push->flags; p.push_counter = pb.push->counter;
+    }
+  }
   CUtensorMap tmap;
   int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 128);
   if (rc) return rc;

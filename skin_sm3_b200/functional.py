@@ -450,15 +450,17 @@ class _FusedInfoNCE(torch.autograd.Function):
                 dp1 = torch.empty_like(p1c) if need_grad else None
                 dp2 = torch.empty_like(p2c) if need_grad else None
                 scratch.record_stream(pbuf.side)
+                # mode 3 = fused exchange with the row push inside K2 (SM3_PEER_PUSH=0 -> mode 2: push in the normalise kernel)
+                mode = (3 if os.environ.get("SM3_PEER_PUSH", "1") != "0" else 2) if fused else int(overlap)
                 check(lib().sm3_infonce_step_peer(ptr(p1c), ptr(p2c), n_local, rank, w, d, dtype_code(p1c), temperature,
                                                   weight, ptr(loss), ptr(dp1), ptr(dp2), ptr(pbuf.z[slot]),
                                                   pbuf.zp[slot], ptr(pbuf.st[slot]), pbuf.stp[slot], ptr(pbuf.flags),
-                                                  pbuf.fp, pbuf.step & 0x7FFFFFFF, 2 if fused else int(overlap), ptr(scratch),
+                                                  pbuf.fp, pbuf.step & 0x7FFFFFFF, mode, ptr(scratch),
                                                   scratch.numel(), main.cuda_stream, pbuf.side.cuda_stream),
                       "sm3_infonce_step_peer")
             if need_grad:
                 ctx.save_for_backward(dp1, dp2)
-            ctx.comm_used = "peer-fused" if fused else ("peer-overlap" if overlap else "peer")
+            ctx.comm_used = ("peer-fused-push" if mode == 3 else "peer-fused") if fused else ("peer-overlap" if overlap else "peer")
             return loss
         if overlap:
             # ---- exchange on a side stream, local column block on the main stream, then the remote blocks ----

@@ -147,8 +147,15 @@ def main():
                 p1 = torch.randn(n_local, d, generator=g).bfloat16()
                 p2 = (p1.float() + 0.5 * torch.randn(n_local, d, generator=g)).bfloat16()
                 outs = []
-                for fused in ("0", "1"):
+                # nccl reference, fused exchange with the push in the normalise kernel (mode 2), fused exchange with the
+                # push inside K2 + owner-ordered tiles (mode 3; the 256-row forward kernel is forced for these small shapes)
+                for fused, push in (("0", "0"), ("1", "0"), ("1", "1")):
                     os.environ["SM3_PEER_FUSED"] = fused
+                    os.environ["SM3_PEER_PUSH"] = push
+                    if push == "1":
+                        os.environ["SM3_TC_FWD_BM"] = "256"
+                    else:
+                        os.environ.pop("SM3_TC_FWD_BM", None)
                     a4 = p1.to(dev).requires_grad_(True)
                     b4 = p2.to(dev).requires_grad_(True)
                     l4 = sm3.fused_infonce(a4, b4, T, precision="bf16", group=dist.group.WORLD,
@@ -156,11 +163,13 @@ def main():
                     l4.backward()
                     outs.append((l4.item(), a4.grad.double(), b4.grad.double()))
                 os.environ["SM3_PEER_FUSED"] = "0"
-                (l_n, ga_n, gb_n), (l_f, ga_f, gb_f) = outs
-                assert abs(l_f - l_n) <= 2e-6 * abs(l_n), ("fused loss", step, l_f, l_n)
-                ea = (ga_f - ga_n).abs().max().item() / ga_n.abs().max().item()
-                eb = (gb_f - gb_n).abs().max().item() / gb_n.abs().max().item()
-                assert ea <= 1e-2 and eb <= 1e-2, ("fused grads", n_local, step, ea, eb)
+                os.environ.pop("SM3_TC_FWD_BM", None)
+                (l_n, ga_n, gb_n) = outs[0]
+                for which, (l_f, ga_f, gb_f) in zip(("fused", "fused+push"), outs[1:]):
+                    assert abs(l_f - l_n) <= 2e-6 * abs(l_n), (which, "loss", step, l_f, l_n)
+                    ea = (ga_f - ga_n).abs().max().item() / ga_n.abs().max().item()
+                    eb = (gb_f - gb_n).abs().max().item() / gb_n.abs().max().item()
+                    assert ea <= 1e-2 and eb <= 1e-2, (which, "grads", n_local, step, ea, eb)
         results["fused"] = "ok"
     # ---- N4: the DeepCluster clustering drop-in across ranks (bank sharded by rank, identical result everywhere) ----
     import types

@@ -293,6 +293,33 @@ def test_row_block_sharding_reproduces_single_block(sm3):
             assert relerr(dzr.cpu(), dz[rows].cpu()) < 1e-4
 
 
+@pytest.mark.parametrize("n_local,d,world", [(512, 128, 4), (1024, 256, 2), (256, 64, 8)])
+def test_owner_ordered_forward_matches_plain_forward(sm3, monkeypatch, n_local, d, world):
+    """Mode 3 of the multi-rank step visits the column tiles owner by owner (own columns, then rank-1's, ...), every split
+    taking every S-th tile of an owner's range, and waits for one flag per source rank.  Emulated on one GPU: the test
+    plays the peers (complete column buffer, flags pre-set), every rank's row block must reproduce the plain kernel."""
+    monkeypatch.setenv("SM3_TC_FWD_BM", "256")
+    T = 0.1
+    n = n_local * world
+    g = torch.Generator().manual_seed(n + d)
+    z, _ = sm3.core.normalize_pair(torch.randn(2 * n, d, generator=g).cuda(), None, torch.bfloat16)
+    pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
+    flags = torch.full((128,), 7, dtype=torch.int32, device="cuda")
+    lib = sm3.lib()
+    for r in range(world):
+        rows = torch.from_numpy(O.global_row_index(n_local, r * n_local, n)).cuda()
+        zr = z[rows].contiguous()
+        out = torch.empty((3, 2 * n_local), dtype=torch.float32, device="cuda")
+        ws = torch.empty(int(lib.sm3_debug_infonce_fwd_ordered_workspace(n_local, world, d)) + 256, dtype=torch.uint8, device="cuda")
+        rc = lib.sm3_debug_infonce_fwd_ordered(zr.data_ptr(), z.data_ptr(), n_local, r, world, d, 1.0 / T, flags.data_ptr(), 7,
+                                               out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), ws.data_ptr(),
+                                               ws.numel(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, sm3._lib.last_error()
+        assert relerr(out[0].cpu(), pos[rows].cpu()) < 1e-5, ("pos", r)
+        assert relerr(out[2].cpu(), nsum[rows].cpu()) < 1e-5, ("neg_sum", r)       # same tiles, another summation order
+        assert relerr(out[1].cpu(), lse[rows].cpu()) < 1e-5, ("lse", r)
+
+
 def test_fused_scalar_loss_and_grad_scaling(sm3):
     """fused_infonce == CE(cal_logits) incl. an upstream scale (GradScaler x loss weight, backbone_train.py:101-125)."""
     g = load("infonce_n64_d128_T01")
