@@ -286,14 +286,25 @@ def time_e2e(sm3, p1, p2, T, group, world, steps, warmup, depth=2):
         barrier(world)
         return max_over_ranks(max(e0.elapsed_time(e1), wall_ms), world)     # host clock: the copies run on other streams
 
+    pipe = None
     if world == 1:
         host = sm3.HostInfoNCE(n_local, d, torch.bfloat16, sm3.ALGO_AUTO)             # sm3_infonce_host: synchronises
         pipe = sm3.HostInfoNCEPipeline(n_local, d, torch.bfloat16, sm3.ALGO_AUTO, depth)  # sm3_host_pipe_*
+    elif COMM != "nccl":
+        try:        # peer mode of the same C pipeline: sm3_host_pipe_submit_peer runs the multi-rank fused step
+            pipe = sm3.HostInfoNCEPipeline(n_local, d, torch.bfloat16, sm3.ALGO_AUTO, depth, group=group)
+        except Exception as e:
+            print(f"[bench] peer host pipeline unavailable ({e!r}); e2e falls back to the Python-driven loop", file=sys.stderr)
+            pipe = None
+    if pipe is not None:
         sink = []
 
         def run_sync(k=steps):
             for _ in range(k):
-                host(hp1, hp2, T)
+                if world == 1:
+                    host(hp1, hp2, T)
+                else:
+                    sink.append(float(pipe.wait(pipe.submit(hp1, hp2, T))[0][0]))
 
         def run_pipe(k=steps):
             tickets = []
@@ -700,8 +711,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-E2E_MULTI_API = ("skin_sm3_b200.fused_infonce(group=WORLD) fed from / drained to pinned host memory on two copy "
-                 "streams, 2 slots; sync_value = drained after every step")
+E2E_MULTI_API = ("sm3_host_pipe_submit_peer/wait (C ABI, pinned host buffers, 2-slot copy/compute pipeline around "
+                 "sm3_infonce_step_peer); sync_value = waited for after every submit.  (SM3_COMM=nccl: the public op fed "
+                 "from / drained to pinned host memory by two copy streams in Python)")
 
 
 def cfg2_block(sm3, pk, args, flush):

@@ -241,6 +241,19 @@ int64_t sm3_host_pipe_submit(sm3_host_pipe* pipe, const void* p1_host, const voi
 int sm3_host_pipe_wait(sm3_host_pipe* pipe, int64_t ticket);
 int sm3_host_pipe_destroy(sm3_host_pipe* pipe);
 
+/* Peer mode of the pipeline (multi-rank jobs): the handle is created for this rank's n_local pairs of a job with n_global
+ * pairs, and every submit runs sm3_infonce_step_peer (exchange mode 0, 2 or 3, see below) between the copies, with the
+ * symmetric buffers of the slot and the epoch the caller chose for that step (they must follow the same sequence on every
+ * rank).  wait / destroy are the ordinary ones.  Gradients are those of sm3_infonce_step_peer (sum over ranks of the
+ * per-rank mean losses). */
+size_t sm3_host_pipe_peer_scratch_bytes(int n_local, int n_global, int D, int io_dtype, int depth);
+int sm3_host_pipe_create_peer(sm3_host_pipe** out, int n_local, int n_global, int D, int io_dtype, int depth,
+                              void* device_scratch, size_t scratch_bytes);
+int64_t sm3_host_pipe_submit_peer(sm3_host_pipe* pipe, const void* p1_host, const void* p2_host, float temperature,
+                                  float* loss_host, void* dp1_host, void* dp2_host, int rank, int world, void* z_cols_mine,
+                                  void* const* z_peers_host, void* stats_mine, void* const* stats_peers_host,
+                                  void* flags_mine, void* const* flags_peers_host, unsigned epoch, int mode);
+
 /* Device-pointer form of the same fused step: ONE call enqueues normalise -> K2 -> loss -> K3 -> normalise-backward on
  * `stream` (no copies, no synchronisation).  loss = weight * mean-CE (device scalar); dp1/dp2 may both be NULL
  * (forward only).  precision follows `algo` (AUTO = tcgen05 on bf16 rows when D allows, else the fp32 FMA kernels). */

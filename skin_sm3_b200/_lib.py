@@ -63,6 +63,10 @@ SIGNATURES = {
     "sm3_host_pipe_submit": (_i64, [_vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "sm3_host_pipe_wait": (_i, [_vp, _i64]),
     "sm3_host_pipe_destroy": (_i, [_vp]),
+    "sm3_host_pipe_peer_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sm3_host_pipe_create_peer": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _sz]),
+    "sm3_host_pipe_submit_peer": (_i64, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp, C.POINTER(_vp), _vp, C.POINTER(_vp),
+                                         _vp, C.POINTER(_vp), C.c_uint, _i]),
     "sm3_infonce_step_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "sm3_infonce_step": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "sm3_infonce_step_multi_scratch_bytes": (_sz, [_i, _i, _i, _i]),

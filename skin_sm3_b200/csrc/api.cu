@@ -689,6 +689,7 @@ extern "C" int sm3_infonce_host(const void* p1_host, const void* p2_host, int n_
 // ---------------------------------------------------------------------------------------------------
 struct sm3_host_pipe {
   int n_pairs, D, io_dtype, algo, depth, device;
+  int n_global;                 // > n_pairs: peer mode (n_pairs = this rank's pairs), steps go through sm3_infonce_step_peer
   size_t in_bytes, io_stride, step_bytes, total;
   char* base;
   cudaStream_t s_h2d, s_run, s_d2h;
@@ -720,7 +721,7 @@ extern "C" int sm3_host_pipe_create(sm3_host_pipe** out, int n_pairs, int D, int
   SM3_REQUIRE(aligned16(device_scratch), SM3_ERR_SHAPE, "host_pipe_create: scratch must be 16-byte aligned");
   sm3_host_pipe* hp = new (std::nothrow) sm3_host_pipe();
   SM3_REQUIRE(hp != nullptr, SM3_ERR_CUDA, "host_pipe_create: out of host memory");
-  hp->n_pairs = n_pairs; hp->D = D; hp->io_dtype = io_dtype; hp->algo = algo; hp->depth = depth;
+  hp->n_pairs = n_pairs; hp->D = D; hp->io_dtype = io_dtype; hp->algo = algo; hp->depth = depth; hp->n_global = n_pairs;
   hp->in_bytes = (size_t)n_pairs * D * dtype_size(io_dtype);
   hp->io_stride = pipe_io_stride(hp->in_bytes);
   hp->step_bytes = align_up(plan_host(n_pairs, D, io_dtype, algo).total);
@@ -815,4 +816,82 @@ extern "C" int sm3_host_pipe_wait(sm3_host_pipe* hp, int64_t ticket) {
   if (ticket + hp->depth < hp->next_ticket) return SM3_OK;
   SM3_CHECK_CUDA(cudaEventSynchronize(hp->ev_out[ticket % hp->depth]));
   return SM3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// peer mode of the pipelined host-buffer entry: the same three-stream pipeline around sm3_infonce_step_peer, so that a
+// multi-rank job's host-to-host throughput is not bounded by Python between 0.6 ms steps.  The caller passes the
+// symmetric buffers of the slot it wants used and the step's epoch with every submit (skin_sm3_b200.peer owns both).
+// ---------------------------------------------------------------------------------------------------
+extern "C" size_t sm3_host_pipe_peer_scratch_bytes(int n_local, int n_global, int D, int io_dtype, int depth) {
+  if (n_local < 1 || n_global < n_local || !dtype_ok(io_dtype) || depth < 1 || depth > SM3_PIPE_MAX_DEPTH) return 0;
+  const size_t step = sm3_infonce_step_peer_scratch_bytes(n_local, n_global, D);
+  if (step == 0) return 0;
+  const size_t in_bytes = (size_t)n_local * D * dtype_size(io_dtype);
+  return align_up(step) + (size_t)depth * pipe_io_stride(in_bytes);
+}
+
+extern "C" int sm3_host_pipe_create_peer(sm3_host_pipe** out, int n_local, int n_global, int D, int io_dtype, int depth,
+                                         void* device_scratch, size_t scratch_bytes) {
+  SM3_REQUIRE(out != nullptr && device_scratch != nullptr, SM3_ERR_SHAPE, "host_pipe_create_peer: null pointer");
+  *out = nullptr;
+  const size_t need = sm3_host_pipe_peer_scratch_bytes(n_local, n_global, D, io_dtype, depth);
+  SM3_REQUIRE(need != 0, SM3_ERR_SHAPE, "host_pipe_create_peer: bad shape / dtype / depth");
+  SM3_REQUIRE(scratch_bytes >= need, SM3_ERR_WORKSPACE, "host_pipe_create_peer: scratch %zu < %zu", scratch_bytes, need);
+  // build an ordinary handle for a shape whose single-GPU plan is certainly smaller, then re-point it at the peer plan
+  sm3_host_pipe* hp = nullptr;
+  int rc = sm3_host_pipe_create(&hp, 1, D, io_dtype, SM3_ALGO_AUTO, depth, device_scratch, scratch_bytes);
+  if (rc) return rc;
+  hp->n_pairs = n_local; hp->n_global = n_global;
+  hp->in_bytes = (size_t)n_local * D * dtype_size(io_dtype);
+  hp->io_stride = pipe_io_stride(hp->in_bytes);
+  hp->step_bytes = align_up(sm3_infonce_step_peer_scratch_bytes(n_local, n_global, D));
+  hp->total = need;
+  *out = hp;
+  return SM3_OK;
+}
+
+extern "C" int64_t sm3_host_pipe_submit_peer(sm3_host_pipe* hp, const void* p1_host, const void* p2_host, float temperature,
+                                             float* loss_host, void* dp1_host, void* dp2_host, int rank, int world,
+                                             void* z_cols_mine, void* const* z_peers_host, void* stats_mine,
+                                             void* const* stats_peers_host, void* flags_mine,
+                                             void* const* flags_peers_host, unsigned epoch, int mode) {
+  SM3_REQUIRE(hp && p1_host && p2_host && loss_host, SM3_ERR_SHAPE, "host_pipe_submit_peer: null pointer");
+  SM3_REQUIRE(hp->n_global > hp->n_pairs && hp->n_global == hp->n_pairs * world, SM3_ERR_SHAPE,
+              "host_pipe_submit_peer: handle was not created for %d ranks", world);
+  SM3_REQUIRE((dp1_host == nullptr) == (dp2_host == nullptr), SM3_ERR_SHAPE,
+              "host_pipe_submit_peer: dp1_host/dp2_host must both be given or both NULL");
+  SM3_REQUIRE(mode == 0 || mode == 2 || mode == 3, SM3_ERR_SHAPE, "host_pipe_submit_peer: exchange mode must be 0, 2 or 3");
+  int dev = -1;
+  SM3_CHECK_CUDA(cudaGetDevice(&dev));
+  SM3_REQUIRE(dev == hp->device, SM3_ERR_SHAPE, "host_pipe_submit_peer: handle belongs to device %d, current device is %d",
+              hp->device, dev);
+  const int64_t ticket = hp->next_ticket;
+  const int s = (int)(ticket % hp->depth);
+  if (hp->busy[s]) SM3_CHECK_CUDA(cudaEventSynchronize(hp->ev_out[s]));
+  char* io = hp->base + hp->step_bytes + (size_t)s * hp->io_stride;
+  const size_t a = align_up(hp->in_bytes);
+  char *p1 = io, *p2 = io + a, *dp1 = io + 2 * a, *dp2 = io + 3 * a;
+  float* loss = (float*)(io + 4 * a);
+  if (hp->busy[s]) SM3_CHECK_CUDA(cudaStreamWaitEvent(hp->s_h2d, hp->ev_run[s], 0));
+  SM3_CHECK_CUDA(cudaMemcpyAsync(p1, p1_host, hp->in_bytes, cudaMemcpyHostToDevice, hp->s_h2d));
+  SM3_CHECK_CUDA(cudaMemcpyAsync(p2, p2_host, hp->in_bytes, cudaMemcpyHostToDevice, hp->s_h2d));
+  SM3_CHECK_CUDA(cudaEventRecord(hp->ev_in[s], hp->s_h2d));
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(hp->s_run, hp->ev_in[s], 0));
+  const int rc = sm3_infonce_step_peer(p1, p2, hp->n_pairs, rank, world, hp->D, hp->io_dtype, temperature, 1.0f, loss,
+                                       dp1_host ? dp1 : nullptr, dp1_host ? dp2 : nullptr, z_cols_mine, z_peers_host,
+                                       stats_mine, stats_peers_host, flags_mine, flags_peers_host, epoch, mode, hp->base,
+                                       hp->step_bytes, hp->s_run, hp->s_run);
+  if (rc) return rc;
+  SM3_CHECK_CUDA(cudaEventRecord(hp->ev_run[s], hp->s_run));
+  SM3_CHECK_CUDA(cudaStreamWaitEvent(hp->s_d2h, hp->ev_run[s], 0));
+  SM3_CHECK_CUDA(cudaMemcpyAsync(loss_host, loss, 4, cudaMemcpyDeviceToHost, hp->s_d2h));
+  if (dp1_host) {
+    SM3_CHECK_CUDA(cudaMemcpyAsync(dp1_host, dp1, hp->in_bytes, cudaMemcpyDeviceToHost, hp->s_d2h));
+    SM3_CHECK_CUDA(cudaMemcpyAsync(dp2_host, dp2, hp->in_bytes, cudaMemcpyDeviceToHost, hp->s_d2h));
+  }
+  SM3_CHECK_CUDA(cudaEventRecord(hp->ev_out[s], hp->s_d2h));
+  hp->busy[s] = 1;
+  hp->next_ticket = ticket + 1;
+  return ticket;
 }

@@ -921,20 +921,34 @@ class HostInfoNCEPipeline:
     neighbouring steps overlap the kernels, so host-to-host throughput approaches the device-resident rate."""
 
     def __init__(self, n_pairs: int, d: int, dtype: torch.dtype = torch.bfloat16, algo: int = ALGO_AUTO, depth: int = 2,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, group=None):
+        """``group`` (torch.distributed process group, > 1 rank): peer mode -- ``n_pairs`` is this rank's share, every
+        submit runs the multi-rank fused step (NVLink peer-memory exchange) between the copies; all ranks must submit the
+        same number of steps in the same order."""
         import ctypes as C
         self.n, self.d, self.dtype, self.depth = n_pairs, d, dtype, depth
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         code = _lib._DTYPES[dtype]
+        self.world, self.rank = _group_info(group)
+        self.pbuf = None
         with torch.cuda.device(self.device):
-            nbytes = lib().sm3_host_pipe_scratch_bytes(n_pairs, d, code, algo, depth)
+            if self.world > 1:
+                from . import peer
+                self.pbuf = peer.get_peer_buffers(group, n_pairs * self.world, d, self.device)
+                nbytes = lib().sm3_host_pipe_peer_scratch_bytes(n_pairs, n_pairs * self.world, d, code, depth)
+            else:
+                nbytes = lib().sm3_host_pipe_scratch_bytes(n_pairs, d, code, algo, depth)
             if nbytes == 0:
                 raise ValueError("bad shape / depth for HostInfoNCEPipeline")
             self.scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             torch.cuda.synchronize(self.device)       # the handle's streams do not order against torch's allocator
             h = C.c_void_p()
-            check(lib().sm3_host_pipe_create(C.byref(h), n_pairs, d, code, algo, depth, ptr(self.scratch),
-                                             self.scratch.numel()), "sm3_host_pipe_create")
+            if self.world > 1:
+                check(lib().sm3_host_pipe_create_peer(C.byref(h), n_pairs, n_pairs * self.world, d, code, depth,
+                                                      ptr(self.scratch), self.scratch.numel()), "sm3_host_pipe_create_peer")
+            else:
+                check(lib().sm3_host_pipe_create(C.byref(h), n_pairs, d, code, algo, depth, ptr(self.scratch),
+                                                 self.scratch.numel()), "sm3_host_pipe_create")
         self._h = h
         self._next = 0
         self.out = [(torch.empty(1, dtype=torch.float32).pin_memory(), torch.empty((n_pairs, d), dtype=dtype).pin_memory(),
@@ -947,8 +961,19 @@ class HostInfoNCEPipeline:
         assert not p2_host.is_cuda and p2_host.dtype == self.dtype and tuple(p2_host.shape) == (self.n, self.d)
         with torch.cuda.device(self.device):
             loss, dp1, dp2 = self.out[self._next % self.depth]
-            t = check(lib().sm3_host_pipe_submit(self._h, p1_host.data_ptr(), p2_host.data_ptr(), temperature,
-                                                 loss.data_ptr(), dp1.data_ptr(), dp2.data_ptr()), "sm3_host_pipe_submit")
+            if self.pbuf is not None:
+                pb = self.pbuf
+                slot = pb.next_slot()
+                fused = self.n % 128 == 0 and os.environ.get("SM3_PEER_FUSED", "1") != "0"
+                mode = (3 if os.environ.get("SM3_PEER_PUSH", "1") != "0" else 2) if fused else 0
+                t = check(lib().sm3_host_pipe_submit_peer(self._h, p1_host.data_ptr(), p2_host.data_ptr(), temperature,
+                                                          loss.data_ptr(), dp1.data_ptr(), dp2.data_ptr(), self.rank,
+                                                          self.world, ptr(pb.z[slot]), pb.zp[slot], ptr(pb.st[slot]),
+                                                          pb.stp[slot], ptr(pb.flags), pb.fp, pb.step & 0x7FFFFFFF, mode),
+                          "sm3_host_pipe_submit_peer")
+            else:
+                t = check(lib().sm3_host_pipe_submit(self._h, p1_host.data_ptr(), p2_host.data_ptr(), temperature,
+                                                     loss.data_ptr(), dp1.data_ptr(), dp2.data_ptr()), "sm3_host_pipe_submit")
         self._next = t + 1
         return t
 

@@ -171,6 +171,33 @@ def main():
                     eb = (gb_f - gb_n).abs().max().item() / gb_n.abs().max().item()
                     assert ea <= 1e-2 and eb <= 1e-2, (which, "grads", n_local, step, ea, eb)
         results["fused"] = "ok"
+        # peer mode of the pipelined host-buffer entry (sm3_host_pipe_submit_peer): several steps in flight, results
+        # against the NCCL path on the same batches
+        n_local, d, T = 512, 128, 0.1
+        os.environ["SM3_PEER_FUSED"] = "1"
+        pipe = sm3.HostInfoNCEPipeline(n_local, d, torch.bfloat16, depth=2, group=dist.group.WORLD)
+        batches, tickets, got = [], [], []
+        for step in range(5):
+            g = torch.Generator().manual_seed(500 + step + 100 * rank)
+            p1 = torch.randn(n_local, d, generator=g).bfloat16().pin_memory()
+            p2 = (p1.float() + 0.5 * torch.randn(n_local, d, generator=g)).bfloat16().pin_memory()
+            batches.append((p1, p2))
+            tickets.append(pipe.submit(p1, p2, T))
+            if len(tickets) == 2:
+                got.append(tuple(t.clone() for t in pipe.wait(tickets.pop(0))))
+        for t in tickets:
+            got.append(tuple(x.clone() for x in pipe.wait(t)))
+        pipe.close()
+        os.environ["SM3_PEER_FUSED"] = "0"
+        for (p1, p2), (l_p, d1_p, d2_p) in zip(batches, got):
+            a5 = p1.to(dev).requires_grad_(True)
+            b5 = p2.to(dev).requires_grad_(True)
+            l5 = sm3.fused_infonce(a5, b5, T, precision="bf16", group=dist.group.WORLD, comm="nccl")
+            l5.backward()
+            assert abs(float(l_p) - l5.item()) <= 2e-6 * abs(l5.item()), ("pipe loss", float(l_p), l5.item())
+            e6 = (d1_p.double() - a5.grad.double().cpu()).abs().max().item() / a5.grad.double().abs().max().item()
+            assert e6 <= 1e-2, ("pipe grads", e6)
+        results["pipe"] = "ok"
     # ---- N4: the DeepCluster clustering drop-in across ranks (bank sharded by rank, identical result everywhere) ----
     import types
     gk = np.load(os.path.join(ROOT, "tests", "golden", "kmeans.npz"))
