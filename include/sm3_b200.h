@@ -215,6 +215,34 @@ int sm3_kmeans_assign(const float* emb, int64_t n, int D, const float* centroids
 int sm3_kmeans_update(const float* sums, const float* counts, const float* centroids_old, float* centroids_new, int D,
                       int K, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N2  fused projector tail    replaces the last two layers of make_projector -- nn.Linear(in_dim, proj_dim, bias=False)
+ *     and nn.BatchNorm1d(proj_dim, affine=False), src/models/simclr.py:25-26 -- together with the F.normalize that
+ *     follows them (:62, :138, :294), and their autograd backward.
+ *   sm3_proj_tail_gemm  : Y [R, D] fp32 = H [R, K] W[D, K]^T on the tensor cores (fp16 / bf16 operands, fp32
+ *                         accumulation) and totals[2 D] = per-column (sum Y, sum Y^2) from the same epilogue
+ *   (SyncBatchNorm, tools/backbone_train.py:510: the caller all-reduces totals and the row count between the two calls)
+ *   sm3_proj_tail_bn_l2 : y^ = (Y - mean) rstd (batch statistics + running-stat update in training mode, running
+ *                         statistics in eval mode), z = y^ / max(|y^|, l2_eps) as bf16, inv_norm, mean / rstd saved
+ *   sm3_proj_tail_bwd1  : dy^ = inv_norm (dz - z <z, dz>) with dz = sum of K3's partial slabs; totals2[2 D] = column sums
+ *                         of dy^ and dy^ * y^        (all-reduced by the caller under SyncBatchNorm)
+ *   sm3_proj_tail_bwd2  : dY = rstd (dy^ - totals2[0] / count - y^ totals2[1] / count) in H's dtype; dW = dY^T H and
+ *                         dH = dY W are plain GEMMs left to the caller (cuBLAS).
+ *   Shapes: K % 64 == 0, D in {64, 128, 192, 256}, 16-byte aligned rows (sm3_proj_tail_supported() == 1).
+ * ---------------------------------------------------------------------------------------------- */
+int sm3_proj_tail_supported(int K, int D, int dtype);
+size_t sm3_proj_tail_workspace_bytes(int64_t R, int D);
+int sm3_proj_tail_gemm(const void* h, const void* w, int64_t R, int K, int D, int dtype, float* y, float* totals,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int sm3_proj_tail_bn_l2(const float* y, int64_t R, int D, const float* totals, float count, float bn_eps, float l2_eps,
+                        int training, float momentum, float* running_mean, float* running_var, float* mean_out,
+                        float* rstd_out, void* z_bf16, float* inv_norm, void* stream);
+int sm3_proj_tail_bwd1(const float* dz_partials, int n_partials, int64_t partial_stride, const void* z_bf16,
+                       const float* inv_norm, float l2_eps, const float* y, const float* mean, const float* rstd, int64_t R,
+                       int D, float* dyhat, float* totals2, void* workspace, size_t workspace_bytes, void* stream);
+int sm3_proj_tail_bwd2(const float* dyhat, const float* y, const float* mean, const float* rstd, const float* totals2,
+                       float count, int training, int64_t R, int D, void* dy, int dy_dtype, void* stream);
+
 /* Host-buffer convenience entry (the "plugin call" timed end to end by bench.py): copies p1/p2 from
  * HOST memory, runs normalise -> K2 -> loss -> K3 -> normalise-backward on `stream`, copies the loss
  * and both gradients back to HOST memory and synchronises the stream.  All device scratch comes from

@@ -254,6 +254,57 @@ def gen_kmeans():
             dist.destroy_process_group()
 
 
+def gen_projtail():
+    """The REAL make_projector (src/models/simclr.py:17-27): its last two layers in train mode, then F.normalize as in
+    _cal_logits (:294), a random linear functional as the loss; values and autograd gradients in fp64, inputs rounded to
+    bf16 so the CUDA path sees identical numbers.  Also the complete term: _cal_logits with two real projectors + CE."""
+    from src.models import simclr
+    torch.manual_seed(SEED)              # make_projector draws its weights from the default generator
+    out = {}
+    cases = [("a", 96, 128, 64), ("b", 136, 192, 128), ("c", 160, 64, 256)]
+    for tag, r, k, d in cases:
+        g = torch.Generator().manual_seed(SEED + r + k + d)
+        proj = simclr.make_projector(k, d).double()
+        lin, bn = proj[6], proj[7]
+        with torch.no_grad():
+            lin.weight.copy_(lin.weight.bfloat16().double())
+            bn.running_mean.copy_(torch.randn(d, generator=g).double() * 0.1)
+            bn.running_var.copy_(1 + 0.2 * torch.rand(d, generator=g).double())
+        h = torch.relu(torch.randn(r, k, generator=g)).bfloat16().double().requires_grad_(True)
+        gz = torch.randn(r, d, generator=g).double()
+        out[f"{tag}_rm0"], out[f"{tag}_rv0"] = _np(bn.running_mean).copy(), _np(bn.running_var).copy()   # before the update
+        proj.train()
+        z = nn.functional.normalize(bn(lin(h)), dim=1)
+        (z * gz).sum().backward()
+        out.update({f"{tag}_h": _np(h).astype(np.float32), f"{tag}_w": _np(lin.weight).astype(np.float32),   # bf16 values: exact
+                    f"{tag}_gz": _np(gz), f"{tag}_z": _np(z),
+                    f"{tag}_dh": _np(h.grad), f"{tag}_dw": _np(lin.weight.grad), f"{tag}_rm1": _np(bn.running_mean),
+                    f"{tag}_rv1": _np(bn.running_var)})
+        proj.eval()
+        out[f"{tag}_z_eval"] = _np(nn.functional.normalize(bn(lin(h.detach())), dim=1))
+    # the whole cross-modal term through two real projector tails (V32: one projector per modality, :405-410)
+    n, k, d, T = 128, 64, 64, 0.1
+    g = torch.Generator().manual_seed(SEED + 777)
+    p1, p2 = simclr.make_projector(k, d).double().train(), simclr.make_projector(k, d).double().train()
+    tails = [nn.Sequential(p[6], p[7]) for p in (p1, p2)]
+    with torch.no_grad():
+        for t in tails:
+            t[0].weight.copy_(t[0].weight.bfloat16().double())
+    f1 = torch.relu(torch.randn(n, k, generator=g)).bfloat16().double().requires_grad_(True)
+    f2 = (f1.detach() + 0.3 * torch.relu(torch.randn(n, k, generator=g))).bfloat16().double().requires_grad_(True)
+    logits, labels = simclr.SimCLRSkinV3._cal_logits(None, f1, f2, tails[0], tails[1], T)
+    loss = nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    out.update({"term_f1": _np(f1).astype(np.float32), "term_f2": _np(f2).astype(np.float32),
+                "term_w1": _np(tails[0][0].weight).astype(np.float32), "term_w2": _np(tails[1][0].weight).astype(np.float32),
+                "term_loss": _np(loss), "term_df1": _np(f1.grad), "term_df2": _np(f2.grad),
+                "term_dw1": _np(tails[0][0].weight.grad), "term_dw2": _np(tails[1][0].weight.grad),
+                "term_T": np.float64(T), "term_n": np.int64(n)})
+    out["cases"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(OUT, "projtail.npz"), **out)
+    print("projtail.npz", float(loss))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -267,11 +318,15 @@ def main():
     gen_knn()
     gen_model()
     gen_kmeans()
+    gen_projtail()
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "kmeans":      # regenerate one fixture without touching the others
         os.makedirs(OUT, exist_ok=True)
         gen_kmeans()
+    elif len(sys.argv) > 1 and sys.argv[1] == "projtail":
+        os.makedirs(OUT, exist_ok=True)
+        gen_projtail()
     else:
         main()

@@ -18,6 +18,8 @@ What it restates (all citations relative to the reference checkout):
 * ``bce_with_logits``      -> (no reference counterpart: PARITY UNPINNED; restates
                               torch.nn.functional.binary_cross_entropy_with_logits)
 * ``knn_topk`` / ``knn_predict`` -> KNNOnlineEvaluator.predict         src/models/evaluator.py:43-83
+* ``projector_tail`` (+``_bwd``) -> last Linear + BatchNorm1d(affine=False) of make_projector + F.normalize
+                              src/models/simclr.py:25-26, :62, :294
 
 Pinning: ``oracle/make_golden.py`` runs the *real* reference functions (imported from
 /root/reference) on seeded inputs and stores inputs + outputs under ``tests/golden/``;
@@ -50,6 +52,47 @@ def normalize_bwd(dz: np.ndarray, z: np.ndarray, inv: np.ndarray, clamped=None):
     if clamped is not None:
         dp = np.where(clamped[:, None], dz * inv[:, None], dp)
     return dp
+
+
+# --------------------------------------------------------------------------------------
+# N2: projector tail = last Linear (no bias) -> BatchNorm1d(affine=False) -> F.normalize   (simclr.py:25-26 then :62/:294)
+# --------------------------------------------------------------------------------------
+def projector_tail(h: np.ndarray, w: np.ndarray, bn_eps: float = 1e-5, l2_eps: float = 1e-12, running=None,
+                   momentum: float = 0.1, training: bool = True):
+    """z = normalize(batchnorm(h @ w.T)) in float64.  Training mode uses the batch statistics (biased variance) and returns
+    the updated running statistics (unbiased variance, momentum) as nn.BatchNorm1d does; eval mode uses `running`.
+    Returns dict(y, mean, rstd, yhat, z, inv, running_mean, running_var)."""
+    h = np.asarray(h, np.float64)
+    w = np.asarray(w, np.float64)
+    y = h @ w.T
+    r = y.shape[0]
+    if training:
+        mean = y.mean(axis=0)
+        var = y.var(axis=0)
+        rm = rv = None
+        if running is not None:
+            rm = (1 - momentum) * np.asarray(running[0], np.float64) + momentum * mean
+            rv = (1 - momentum) * np.asarray(running[1], np.float64) + momentum * var * r / max(r - 1, 1)
+    else:
+        mean, var = np.asarray(running[0], np.float64), np.asarray(running[1], np.float64)
+        rm, rv = mean, var
+    rstd = 1.0 / np.sqrt(var + bn_eps)
+    yhat = (y - mean) * rstd
+    z, inv = normalize(yhat, l2_eps)
+    return dict(y=y, mean=mean, rstd=rstd, yhat=yhat, z=z, inv=inv, running_mean=rm, running_var=rv)
+
+
+def projector_tail_bwd(h, w, fwd: dict, dz: np.ndarray, training: bool = True, l2_eps: float = 1e-12):
+    """Gradients of sum(z * dz) w.r.t. h and w through normalize -> batchnorm -> linear (float64)."""
+    h = np.asarray(h, np.float64)
+    w = np.asarray(w, np.float64)
+    clamped = (1.0 / fwd["inv"]) <= l2_eps
+    dyhat = normalize_bwd(dz, fwd["z"], fwd["inv"], clamped)
+    if training:
+        dy = fwd["rstd"] * (dyhat - dyhat.mean(axis=0) - fwd["yhat"] * (dyhat * fwd["yhat"]).mean(axis=0))
+    else:
+        dy = fwd["rstd"] * dyhat
+    return dy @ w, dy.T @ h, dy
 
 
 # --------------------------------------------------------------------------------------

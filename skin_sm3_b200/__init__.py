@@ -6,6 +6,6 @@ Public surface (all CUDA-only, backed by libsm3_b200.so; no CPU fallback):
 """
 from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, LIB_PATH, build, lib  # noqa: F401
 from .functional import (GraphedInfoNCE, cluster_memory, spherical_kmeans, HostInfoNCE, HostInfoNCEPipeline, NUM_CLASSES, bce_with_logits, cal_logits, core, fused_infonce, fused_infonce_multi,  # noqa: F401
-                         gather_global_order, knn_predict, l2_normalize, multihead_ce, pick_precision, reload_env, sim_topk)
+                         gather_global_order, knn_predict, l2_normalize, multihead_ce, pick_precision, reload_env, sim_topk, TailSpec, tail_cal_logits, tail_supported)
 
 __version__ = "0.1.0"

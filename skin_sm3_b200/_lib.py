@@ -56,6 +56,12 @@ SIGNATURES = {
     "sm3_kmeans_workspace_bytes": (_sz, [_i64, _i, _i]),
     "sm3_kmeans_assign": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sm3_kmeans_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "sm3_proj_tail_supported": (_i, [_i, _i, _i]),
+    "sm3_proj_tail_workspace_bytes": (_sz, [_i64, _i]),
+    "sm3_proj_tail_gemm": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "sm3_proj_tail_bn_l2": (_i, [_vp, _i64, _i, _vp, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sm3_proj_tail_bwd1": (_i, [_vp, _i, _i64, _vp, _vp, _f, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
+    "sm3_proj_tail_bwd2": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i64, _i, _vp, _i, _vp]),
     "sm3_infonce_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "sm3_infonce_host": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "sm3_host_pipe_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),

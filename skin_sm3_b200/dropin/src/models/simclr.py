@@ -10,6 +10,9 @@ reference loss, value and gradient.
 Runtime switches (environment, read at call time so unchanged scripts can opt in):
   SM3_PRECISION         auto | bf16 | fp32     (default auto: fp32 inputs outside autocast stay exact fp32)
   SM3_GLOBAL_NEGATIVES  1 -> all-gather the normalised embeddings over the default process group
+  SM3_FUSED_TAIL        0 -> keep the projector's last Linear + BatchNorm on stock kernels (default 1: under autocast the
+                        last two layers of make_projector and the F.normalize after them run as the fused tail,
+                        skin_sm3_b200.tail_cal_logits; fp32 inputs always take the stock layers)
 """
 import os
 from copy import deepcopy
@@ -45,6 +48,37 @@ def _pair_logits(feats_a, feats_b, temperature):
     return F3.cal_logits(feats_a, feats_b, temperature, precision, group)
 
 
+def _projected_logits(groups, temperature):
+    """groups: [(x, projector)] -- one entry holding all 2N rows (both views through one projector, reference :61) or two
+    entries of N rows (one projector per half, reference :293).  Under autocast the projector's last Linear + affine-free
+    BatchNorm + the F.normalize that follows go through the fused tail; otherwise the stock layers + cal_logits."""
+    precision, group = _runtime()
+    fused = os.environ.get("SM3_FUSED_TAIL", "1") != "0" and precision != "fp32"
+    tails = []
+    if fused:
+        for x, proj in groups:
+            if not (isinstance(proj, nn.Sequential) and len(proj) == 8):
+                fused = False
+                break
+            h = proj[:6](x)
+            if not F3.tail_supported(h, proj[6], proj[7]):
+                tails.append((None, proj[6:](h)))          # the body has run; finish this group on the stock layers
+                fused = False
+            else:
+                tails.append((F3.TailSpec(h, proj[6].weight.to(h.dtype), proj[7]), None))
+        if fused:
+            return F3.tail_cal_logits([t for t, _ in tails], temperature, group)
+        # mixed / unsupported: fall through with what has been computed so far
+        outs = [p if p is not None else t.bn(torch.nn.functional.linear(t.h, t.w)) for t, p in tails]
+        outs += [proj(x) for x, proj in groups[len(tails):]]
+    else:
+        outs = [proj(x) for x, proj in groups]
+    if len(outs) == 1:
+        n = outs[0].shape[0] // 2
+        return F3.cal_logits(outs[0][:n], outs[0][n:], temperature, precision, group)
+    return F3.cal_logits(outs[0], outs[1], temperature, precision, group)
+
+
 class SimCLR(nn.Module):
     """One modality: encoder + projector, intra-modal InfoNCE between two augmented views (reference :31-96)."""
 
@@ -63,8 +97,7 @@ class SimCLR(nn.Module):
         f1 = self.encoder(x1)
         f2 = self.encoder(x2)
         # one projector pass over both views: its BatchNorm sees all 2N rows jointly (reference :61)
-        proj = self.projector(torch.cat([f1, f2], dim=0))
-        out = _pair_logits(proj[:n], proj[n:], self.temperature)
+        out = _projected_logits([(torch.cat([f1, f2], dim=0), self.projector)], self.temperature)
         return (out, (f1, f2)) if self.return_feats else out
 
     def extract(self, imgs):
@@ -173,7 +206,7 @@ class SimCLRSkinV3(_TwoBranch):
 
     def _cal_logits(self, f1, f2, projector1, projector2, temperature):
         # each modality goes through its projector separately: BatchNorm statistics per N rows (reference :293)
-        return _pair_logits(projector1(f1), projector2(f2), temperature)
+        return _projected_logits([(f1, projector1), (f2, projector2)], temperature)
 
     def _projectors(self):
         return self.cross_proj, self.cross_proj

@@ -53,8 +53,13 @@ def reload_env() -> None:
     _SCRATCH.clear()
 
 
+_PLAN_KNOBS = ("SM3_TC_FWD_BM", "SM3_TC_BWD_V", "SM3_TC_BWD_NS", "SM3_TC_FWD_SPLITS", "SM3_TC_BWD_SPLITS")
+
+
 def _scratch(kind: str, dev: torch.device, key: tuple, nbytes_fn) -> torch.Tensor:
-    k = (kind, dev.index, torch.cuda.current_stream(dev).cuda_stream) + key
+    # the launch plans (hence the sizes) depend on the tuning knobs that are read from the environment at every call
+    env = os.environ
+    k = (kind, dev.index, torch.cuda.current_stream(dev).cuda_stream) + key + tuple(env.get(n) for n in _PLAN_KNOBS)
     buf = _SCRATCH.get(k)
     if buf is None:
         if len(_SCRATCH) > 64:
@@ -373,6 +378,149 @@ def cal_logits(p1: torch.Tensor, p2: torch.Tensor, temperature: float, precision
         raise ValueError("temperature must be > 0")
     z_dtype, algo = pick_precision(p1, precision)
     logits = _InfoNCELogits.apply(p1, p2, float(temperature), z_dtype, algo, group)
+    labels = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)
+    return logits, labels
+
+
+# ------------------------------------------------------------------------------------------------------
+# N2: fused projector tail (last Linear + affine-free BatchNorm + F.normalize) feeding K2 / K3 directly
+# ------------------------------------------------------------------------------------------------------
+class TailSpec:
+    """One application of a projector's last two layers: rows ``h`` [R, K], the Linear's weight cast to h's dtype, and
+    the BatchNorm module (statistics source + running-stat side effect)."""
+    __slots__ = ("h", "w", "bn")
+
+    def __init__(self, h, w, bn):
+        self.h, self.w, self.bn = h, w, bn
+
+
+def tail_supported(h: torch.Tensor, linear, bn) -> bool:
+    """Can ``bn(linear(h))`` followed by F.normalize go through the fused tail?  16-bit CUDA rows (autocast), a plain
+    bias-free nn.Linear, an affine-free BatchNorm1d / SyncBatchNorm, K % 64 == 0, D in {64, 128, 192, 256}."""
+    import torch.nn as nn
+    if not (h.is_cuda and h.dim() == 2 and h.dtype in (torch.float16, torch.bfloat16)):
+        return False
+    if type(linear) is not nn.Linear or linear.bias is not None:
+        return False
+    if not isinstance(bn, (nn.BatchNorm1d, nn.SyncBatchNorm)) or bn.affine:
+        return False
+    if bn.training and h.shape[0] < 2:
+        return False
+    return bool(lib().sm3_proj_tail_supported(h.shape[1], linear.weight.shape[0], dtype_code(h)))
+
+
+def _bn_sync_group(bn):
+    import torch.nn as nn
+    if isinstance(bn, nn.SyncBatchNorm) and bn.training and dist.is_available() and dist.is_initialized():
+        g = bn.process_group if bn.process_group is not None else dist.group.WORLD
+        if dist.get_world_size(g) > 1:
+            return g
+    return None
+
+
+class _TailInfoNCELogits(torch.autograd.Function):
+    """[Linear -> BatchNorm(affine=False) -> normalise] for one (2N rows) or two (N rows each) row groups, then the K2
+    statistics; backward = K3 -> normalise / BatchNorm backward kernels -> two cuBLAS GEMMs per group."""
+
+    @staticmethod
+    def forward(ctx, temperature, group, bns, *hw):
+        k = len(bns)
+        hs = [_contig(t) for t in hw[:k]]
+        ws = [_contig(t) for t in hw[k:]]
+        dev = require_cuda(*hs, *ws)
+        d = ws[0].shape[0]
+        rows = [h.shape[0] for h in hs]
+        m = sum(rows)
+        n_local = m // 2
+        w_, rank = _group_info(group)
+        z = torch.empty((m, d), dtype=torch.bfloat16, device=dev)
+        inv = torch.empty(m, dtype=torch.float32, device=dev)
+        saved, meta = [], []
+        off = 0
+        with torch.cuda.device(dev):
+            for h, w, bn, r in zip(hs, ws, bns, rows):
+                kdim = h.shape[1]
+                y = torch.empty((r, d), dtype=torch.float32, device=dev)
+                totals = torch.empty(2 * d, dtype=torch.float32, device=dev)
+                wsb = torch.empty(int(lib().sm3_proj_tail_workspace_bytes(r, d)), dtype=torch.uint8, device=dev)
+                training = bn.training or not bn.track_running_stats
+                count = float(r)
+                sync = _bn_sync_group(bn)
+                check(lib().sm3_proj_tail_gemm(ptr(h), ptr(w), r, kdim, d, dtype_code(h), ptr(y), ptr(totals), ptr(wsb),
+                                               wsb.numel(), stream_ptr()), "sm3_proj_tail_gemm")
+                if training and sync is not None:              # SyncBatchNorm: global statistics (backbone_train.py:510)
+                    dist.all_reduce(totals, group=sync)        # equal shards per rank (DistributedSampler, misc.py:400)
+                    count = float(r * dist.get_world_size(sync))
+                mom = 0.0
+                rm = rv = None
+                if bn.track_running_stats:
+                    rm, rv = bn.running_mean, bn.running_var
+                    if bn.training:
+                        bn.num_batches_tracked += 1
+                        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                mean = torch.empty(d, dtype=torch.float32, device=dev)
+                rstd = torch.empty(d, dtype=torch.float32, device=dev)
+                upd = bool(bn.training and bn.track_running_stats)
+                check(lib().sm3_proj_tail_bn_l2(ptr(y), r, d, ptr(totals), count, bn.eps, _EPS, int(training), mom,
+                                                ptr(rm) if (upd or not training) else None,
+                                                ptr(rv) if (upd or not training) else None, ptr(mean), ptr(rstd),
+                                                z.data_ptr() + off * d * 2, inv.data_ptr() + off * 4, stream_ptr()),
+                      "sm3_proj_tail_bn_l2")
+                saved += [h, w, y, mean, rstd]
+                meta.append((off, r, count, training, sync, h.dtype))
+                off += r
+        z_cols = gather_global_order(z, group) if w_ > 1 else z
+        pos, lse, nsum = core.stats_fwd(z, z_cols, n_local, rank * n_local, n_local * w_, temperature, ALGO_TC)
+        ctx.save_for_backward(z, inv, z_cols, nsum, *saved)
+        ctx.meta = (temperature, group, w_, rank, n_local, d, meta)
+        return torch.stack((pos, lse), dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, inv, z_cols, nsum, *saved = ctx.saved_tensors
+        temperature, group, w_, rank, n_local, d, meta = ctx.meta
+        dev = z.device
+        g = g.float()
+        g_pos, g_lse = _contig(g[:, 0]), _contig(g[:, 1])
+        if w_ > 1:
+            packed = gather_global_order(torch.stack((g_pos, g_lse, nsum), dim=1), group)
+            gp_c, gl_c, ns_c = (_contig(packed[:, k]) for k in range(3))
+        else:
+            gp_c, gl_c, ns_c = g_pos, g_lse, nsum
+        ws, npart = core.stats_bwd(z, z_cols, n_local, rank * n_local, n_local * w_, temperature, g_pos, g_lse, nsum,
+                                   gp_c, gl_c, ns_c, ALGO_TC)
+        m = 2 * n_local
+        dhs, dws = [], []
+        with torch.cuda.device(dev):
+            for gi, (off, r, count, training, sync, h_dtype) in enumerate(meta):
+                h, w, y, mean, rstd = saved[5 * gi: 5 * gi + 5]
+                dyhat = torch.empty((r, d), dtype=torch.float32, device=dev)
+                totals2 = torch.empty(2 * d, dtype=torch.float32, device=dev)
+                wsb = torch.empty(int(lib().sm3_proj_tail_workspace_bytes(r, d)), dtype=torch.uint8, device=dev)
+                check(lib().sm3_proj_tail_bwd1(ws.data_ptr() + off * d * 4, npart, m * d, z.data_ptr() + off * d * 2,
+                                               inv.data_ptr() + off * 4, _EPS, ptr(y), ptr(mean), ptr(rstd), r, d, ptr(dyhat),
+                                               ptr(totals2), ptr(wsb), wsb.numel(), stream_ptr()), "sm3_proj_tail_bwd1")
+                if sync is not None:
+                    dist.all_reduce(totals2, group=sync)
+                dy = torch.empty((r, d), dtype=h_dtype, device=dev)
+                check(lib().sm3_proj_tail_bwd2(ptr(dyhat), ptr(y), ptr(mean), ptr(rstd), ptr(totals2), count, int(training), r,
+                                               d, ptr(dy), dtype_code(dy), stream_ptr()), "sm3_proj_tail_bwd2")
+                dhs.append(dy @ w)                     # [R, D] x [D, K]   (cuBLAS)
+                dws.append(dy.t() @ h)                 # [D, R] x [R, K]
+        return (None, None, None) + tuple(dhs) + tuple(dws)
+
+
+def tail_cal_logits(tails: Sequence[TailSpec], temperature: float, group=None):
+    """``cal_logits`` with the projector tails fused in: ``tails`` is one TailSpec over all 2N rows (SimCLR.forward,
+    simclr.py:61: BatchNorm over both views jointly) or two over N rows each (_cal_logits, :293: one BatchNorm pass per
+    modality).  Returns ``(logits [2N, 2], zeros [2N])`` like ``cal_logits``; gradients flow to every ``h`` and ``w``."""
+    if len(tails) not in (1, 2):
+        raise ValueError("tail_cal_logits takes one (2N rows) or two (N rows each) row groups")
+    rows = [t.h.shape[0] for t in tails]
+    if (len(tails) == 1 and rows[0] % 2) or (len(tails) == 2 and rows[0] != rows[1]):
+        raise ValueError("the row groups must split into two halves of N rows")
+    logits = _TailInfoNCELogits.apply(float(temperature), group, tuple(t.bn for t in tails), *[t.h for t in tails],
+                                      *[t.w for t in tails])
     labels = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)
     return logits, labels
 

@@ -527,6 +527,110 @@ def test_cfg2_full_parity(sm3):
 
 
 # ---------------------------------------------------------------------------------------------------
+# N2: fused projector tail (last Linear + affine-free BatchNorm + F.normalize) against the real make_projector goldens
+# ---------------------------------------------------------------------------------------------------
+def _tail_modules(w, rm, rv, dtype):
+    d, k = w.shape
+    lin = torch.nn.Linear(k, d, bias=False).cuda()
+    bn = torch.nn.BatchNorm1d(d, affine=False).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(w))
+        bn.running_mean.copy_(torch.from_numpy(rm)); bn.running_var.copy_(torch.from_numpy(rv))
+    return lin, bn
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_projector_tail_kernels_vs_reference_golden(sm3, dtype):
+    """sm3_proj_tail_gemm / _bn_l2 / _bwd1 / _bwd2 one by one: z, the running statistics and d/dh, d/dW of sum(z * G)
+    against values recorded from the real layers (fp64); eval mode too."""
+    import ctypes as C
+    lib = sm3.lib()
+    g = load("projtail")
+    code = {torch.bfloat16: 2, torch.float16: 1}[dtype]
+    st = torch.cuda.current_stream().cuda_stream
+    for c in g["cases"]:
+        h32, w32, gz = g[f"{c}_h"], g[f"{c}_w"], g[f"{c}_gz"]
+        r, k = h32.shape
+        d = w32.shape[0]
+        h, w = cuda(h32, dtype), cuda(w32, dtype)                     # bf16-representable values: exact in fp16 too? (no:
+        href, wref = h.float().cpu().numpy().astype(np.float64), w.float().cpu().numpy().astype(np.float64)   # re-read)
+        f = O.projector_tail(href, wref, running=(g[f"{c}_rm0"], g[f"{c}_rv0"]))
+        y = torch.empty((r, d), dtype=torch.float32, device="cuda")
+        totals = torch.empty(2 * d, dtype=torch.float32, device="cuda")
+        ws = torch.empty(int(lib.sm3_proj_tail_workspace_bytes(r, d)), dtype=torch.uint8, device="cuda")
+        assert lib.sm3_proj_tail_gemm(h.data_ptr(), w.data_ptr(), r, k, d, code, y.data_ptr(), totals.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), st) == 0, sm3._lib.last_error()
+        assert relerr(y.cpu().numpy(), f["y"]) < 1e-5                  # fp32 accumulation of exact 16-bit products
+        assert relerr(totals[:d].cpu().numpy(), f["y"].sum(0)) < 1e-4 and relerr(totals[d:].cpu().numpy(), (f["y"] ** 2).sum(0)) < 1e-4
+        rm, rv = cuda(g[f"{c}_rm0"]), cuda(g[f"{c}_rv0"])
+        mean, rstd = torch.empty(d, device="cuda"), torch.empty(d, device="cuda")
+        z = torch.empty((r, d), dtype=torch.bfloat16, device="cuda")
+        inv = torch.empty(r, dtype=torch.float32, device="cuda")
+        assert lib.sm3_proj_tail_bn_l2(y.data_ptr(), r, d, totals.data_ptr(), float(r), 1e-5, 1e-12, 1, 0.1, rm.data_ptr(),
+                                       rv.data_ptr(), mean.data_ptr(), rstd.data_ptr(), z.data_ptr(), inv.data_ptr(), st) == 0
+        assert relerr(z.float().cpu().numpy(), f["z"]) < 8e-3          # bf16 output
+        assert relerr(inv.cpu().numpy(), f["inv"]) < 1e-4
+        assert relerr(rm.cpu().numpy(), f["running_mean"]) < 1e-5 and relerr(rv.cpu().numpy(), f["running_var"]) < 1e-4
+        # backward through the same kernels: upstream dz = G in one "partial slab"
+        dz = cuda(gz)
+        dyhat = torch.empty((r, d), dtype=torch.float32, device="cuda")
+        totals2 = torch.empty(2 * d, dtype=torch.float32, device="cuda")
+        assert lib.sm3_proj_tail_bwd1(dz.data_ptr(), 1, r * d, z.data_ptr(), inv.data_ptr(), 1e-12, y.data_ptr(), mean.data_ptr(),
+                                      rstd.data_ptr(), r, d, dyhat.data_ptr(), totals2.data_ptr(), ws.data_ptr(), ws.numel(), st) == 0
+        dy = torch.empty((r, d), dtype=torch.float32, device="cuda")
+        assert lib.sm3_proj_tail_bwd2(dyhat.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), totals2.data_ptr(),
+                                      float(r), 1, r, d, dy.data_ptr(), 0, st) == 0
+        dh_ref, dw_ref, dy_ref = O.projector_tail_bwd(href, wref, f, gz)
+        assert relerr(dy.cpu().numpy(), dy_ref) < 2e-2                 # z is bf16
+        assert relerr((dy.double() @ w.double()).cpu().numpy(), dh_ref) < 2e-2
+        assert relerr((dy.double().t() @ h.double()).cpu().numpy(), dw_ref) < 2e-2
+        # eval mode: running statistics
+        rm1, rv1 = cuda(g[f"{c}_rm1"]), cuda(g[f"{c}_rv1"])
+        assert lib.sm3_proj_tail_bn_l2(y.data_ptr(), r, d, None, float(r), 1e-5, 1e-12, 0, 0.0, rm1.data_ptr(), rv1.data_ptr(),
+                                       mean.data_ptr(), rstd.data_ptr(), z.data_ptr(), inv.data_ptr(), st) == 0
+        fe = O.projector_tail(href, wref, running=(g[f"{c}_rm1"], g[f"{c}_rv1"]), training=False)
+        assert relerr(z.float().cpu().numpy(), fe["z"]) < 8e-3
+
+
+def test_tail_cal_logits_matches_reference_term(sm3):
+    """Two real projector tails -> _cal_logits -> CE (golden): loss and gradients w.r.t. both inputs and both weights
+    through skin_sm3_b200.tail_cal_logits + the script's own criterion, and the one-group form against cal_logits."""
+    g = load("projtail")
+    n, T = int(g["term_n"]), float(g["term_T"])
+    tails, leaves = [], []
+    for i in (1, 2):
+        lin, bn = _tail_modules(g[f"term_w{i}"], np.zeros(g[f"term_w{i}"].shape[0]), np.ones(g[f"term_w{i}"].shape[0]), torch.bfloat16)
+        h = cuda(g[f"term_f{i}"], torch.bfloat16).requires_grad_(True)
+        assert sm3.tail_supported(h, lin, bn)
+        tails.append(sm3.TailSpec(h, lin.weight.to(torch.bfloat16), bn))
+        leaves.append((h, lin, bn))
+    logits, labels = sm3.tail_cal_logits(tails, T)
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    ref = float(g["term_loss"])
+    assert abs(loss.item() - ref) <= 2e-2 * abs(ref), (loss.item(), ref)
+    for i, (h, lin, bn) in enumerate(leaves, 1):
+        assert relerr(h.grad.float().cpu().numpy(), g[f"term_df{i}"]) < 2e-2, i
+        assert relerr(lin.weight.grad.float().cpu().numpy(), g[f"term_dw{i}"]) < 2e-2, i
+        assert int(bn.num_batches_tracked) == 1
+    # one group of 2N rows == the stock layers + cal_logits on the same rows (SimCLR.forward's joint BatchNorm)
+    c = "b"
+    lin, bn = _tail_modules(g[f"{c}_w"], g[f"{c}_rm0"], g[f"{c}_rv0"], torch.bfloat16)
+    lin2, bn2 = _tail_modules(g[f"{c}_w"], g[f"{c}_rm0"], g[f"{c}_rv0"], torch.bfloat16)
+    h = cuda(g[f"{c}_h"], torch.bfloat16).requires_grad_(True)
+    h2 = cuda(g[f"{c}_h"], torch.bfloat16).requires_grad_(True)
+    la, _ = sm3.tail_cal_logits([sm3.TailSpec(h, lin.weight.to(torch.bfloat16), bn)], T)
+    p = bn2(F.linear(h2.float(), lin2.weight))
+    half = p.shape[0] // 2
+    lb, _ = sm3.cal_logits(p[:half], p[half:], T, precision="bf16")
+    F.cross_entropy(la, torch.zeros(len(la), dtype=torch.long, device="cuda")).backward()
+    F.cross_entropy(lb, torch.zeros(len(lb), dtype=torch.long, device="cuda")).backward()
+    assert relerr(la[:, 1].detach().cpu(), lb[:, 1].detach().cpu()) < 2e-2
+    assert relerr(h.grad.float().cpu(), h2.grad.float().cpu()) < 3e-2
+    assert relerr(bn.running_var.cpu(), bn2.running_var.cpu()) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------
 # heads
 # ---------------------------------------------------------------------------------------------------
 def test_multihead_ce_matches_reference_loops(sm3):

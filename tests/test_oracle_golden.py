@@ -230,3 +230,32 @@ def test_rowblock_oracle_pinned_to_reference(name):
     loss32, dp32, _ = O.infonce_rowblock(g["p1"], g["p2"], T, rows, chunk=77, matmul_dtype=np.float32, upstream=3.0)
     assert abs(loss32 - float(g["loss_f64"])) < 1e-6 * abs(loss32)
     assert np.abs(dp32 / 3.0 - ref).max() < 1e-5 * np.abs(ref).max()
+
+
+def test_projector_tail_oracle_pinned_to_reference():
+    """oracle.projector_tail / projector_tail_bwd against the REAL make_projector's last two layers (train and eval mode)
+    + F.normalize, values and autograd gradients recorded in fp64 (tests/golden/projtail.npz)."""
+    g = load("projtail")
+    for c in g["cases"]:
+        h, w, gz = g[f"{c}_h"].astype(np.float64), g[f"{c}_w"].astype(np.float64), g[f"{c}_gz"]
+        f = O.projector_tail(h, w, running=(g[f"{c}_rm0"], g[f"{c}_rv0"]))
+        np.testing.assert_allclose(f["z"], g[f"{c}_z"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(f["running_mean"], g[f"{c}_rm1"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(f["running_var"], g[f"{c}_rv1"], rtol=0, atol=1e-13)
+        dh, dw, _ = O.projector_tail_bwd(h, w, f, gz)
+        np.testing.assert_allclose(dh, g[f"{c}_dh"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(dw, g[f"{c}_dw"], rtol=0, atol=1e-11)
+        fe = O.projector_tail(h, w, running=(g[f"{c}_rm1"], g[f"{c}_rv1"]), training=False)
+        np.testing.assert_allclose(fe["z"], g[f"{c}_z_eval"], rtol=0, atol=1e-12)
+    # the whole term: two tails -> _cal_logits -> CE, gradients down to the tails' inputs and weights
+    n, T = int(g["term_n"]), float(g["term_T"])
+    f1, f2 = g["term_f1"].astype(np.float64), g["term_f2"].astype(np.float64)
+    w1, w2 = g["term_w1"].astype(np.float64), g["term_w2"].astype(np.float64)
+    t1, t2 = O.projector_tail(f1, w1), O.projector_tail(f2, w2)
+    loss, dp1, dp2 = O.infonce_closed_form(t1["yhat"], t2["yhat"], T)
+    assert abs(loss - float(g["term_loss"])) < 1e-12
+    # infonce_closed_form returns d loss / d (un-normalised rows); push it through the BatchNorm + Linear backward
+    for t, dp, f, w, df, dw in ((t1, dp1, f1, w1, "term_df1", "term_dw1"), (t2, dp2, f2, w2, "term_df2", "term_dw2")):
+        dy = t["rstd"] * (dp - dp.mean(axis=0) - t["yhat"] * (dp * t["yhat"]).mean(axis=0))
+        np.testing.assert_allclose(dy @ w, g[df], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(dy.T @ f, g[dw], rtol=0, atol=1e-12)
