@@ -1020,13 +1020,60 @@ def retrieval_probe(sm3):
     return out
 
 
+def projector_tail_probe(sm3):
+    """N2: the last Linear(2048 -> D, no bias) + BatchNorm1d(D, affine=False) + F.normalize of make_projector
+    (src/models/simclr.py:25-26, :294) at the cfg2 row count, bf16: stock torch layers + K1 against the fused tail
+    (tcgen05 GEMM with the statistics in its epilogue, then BatchNorm + L2 in one pass), forward and forward + backward."""
+    import ctypes as C
+    pk = peaks()
+    out = {}
+    for r, k, d in ((8192, 2048, 128), (65536, 2048, 256)):
+        h = torch.relu(torch.randn(r, k, device="cuda")).bfloat16().requires_grad_(True)
+        lin = torch.nn.Linear(k, d, bias=False).cuda()
+        bn = torch.nn.BatchNorm1d(d, affine=False).cuda()
+        w16 = lin.weight.detach().bfloat16().requires_grad_(True)
+        gz = torch.randn(r, d, device="cuda")
+
+        def stock_fwd():
+            return sm3.l2_normalize(bn(torch.nn.functional.linear(h, w16)).float(), out_dtype=torch.bfloat16)
+
+        lib = sm3.lib()
+        y = torch.empty((r, d), dtype=torch.float32, device="cuda")
+        totals = torch.empty(2 * d, dtype=torch.float32, device="cuda")
+        ws = torch.empty(int(lib.sm3_proj_tail_workspace_bytes(r, d)), dtype=torch.uint8, device="cuda")
+        mean, rstd = torch.empty(d, device="cuda"), torch.empty(d, device="cuda")
+        z = torch.empty((r, d), dtype=torch.bfloat16, device="cuda")
+        inv = torch.empty(r, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+
+        def gemm():
+            lib.sm3_proj_tail_gemm(h.data_ptr(), w16.data_ptr(), r, k, d, 2, y.data_ptr(), totals.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), st)
+
+        def fused_fwd():
+            gemm()
+            lib.sm3_proj_tail_bn_l2(y.data_ptr(), r, d, totals.data_ptr(), float(r), 1e-5, 1e-12, 1, 0.1,
+                                    bn.running_mean.data_ptr(), bn.running_var.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    z.data_ptr(), inv.data_ptr(), st)
+
+        t_gemm = _ev_us(gemm, reps=20)
+        t_cublas = _ev_us(lambda: torch.nn.functional.linear(h, w16), reps=20)
+        nbytes = r * k * 2 + d * k * 2 + r * d * 4
+        out[f"r{r}_k{k}_d{d}"] = {
+            "stock_fwd_us": round(_ev_us(stock_fwd, reps=20), 1), "fused_fwd_us": round(_ev_us(fused_fwd, reps=20), 1),
+            "tail_gemm_us": round(t_gemm, 1), "cublas_linear_us": round(t_cublas, 1),
+            "tail_gemm_GBps": round(nbytes / t_gemm / 1e3, 1), "tail_gemm_frac_hbm": round(nbytes / t_gemm / 1e3 / pk["hbm"], 3),
+            "tail_gemm_TFLOPs": round(2.0 * r * k * d / t_gemm / 1e6, 1)}
+    return out
+
+
 def run_extras_child():
     """Child of the default bench run (see run_ours): probes whose failure must not reach the parent."""
     import skin_sm3_b200 as sm3
     torch.cuda.set_device(0)
     out = {}
     for key, probe in (("small_shapes", small_shapes_probe), ("tc_kernels_cfg2", tc_kernel_probe),
-                       ("kmeans", kmeans_probe), ("retrieval", retrieval_probe)):
+                       ("kmeans", kmeans_probe), ("retrieval", retrieval_probe), ("projector_tail", projector_tail_probe)):
         try:
             out[key] = probe(sm3)
         except Exception as e:
