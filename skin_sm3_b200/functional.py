@@ -598,8 +598,11 @@ class _FusedInfoNCE(torch.autograd.Function):
                 dp1 = torch.empty_like(p1c) if need_grad else None
                 dp2 = torch.empty_like(p2c) if need_grad else None
                 scratch.record_stream(pbuf.side)
-                # mode 3 = fused exchange with the row push inside K2 (SM3_PEER_PUSH=0 -> mode 2: push in the normalise kernel)
-                mode = (3 if os.environ.get("SM3_PEER_PUSH", "1") != "0" else 2) if fused else int(overlap)
+                # mode 2 = fused exchange, rows pushed by the normalise kernel (default); SM3_PEER_PUSH=1 -> mode 3: rows
+                # pushed from inside K2 with owner-ordered tiles.  Measured on 8 x B200 (cfg4, profiles/r02_scale8_*.json):
+                # mode 3 shortens the kernels (stage sum 0.69-0.72 vs 0.81 ms) but not the free-running step (0.70-0.74
+                # vs 0.74 ms) and is 7 % slower at 2 ranks, so it stays opt-in.
+                mode = (3 if os.environ.get("SM3_PEER_PUSH", "0") == "1" else 2) if fused else int(overlap)
                 check(lib().sm3_infonce_step_peer(ptr(p1c), ptr(p2c), n_local, rank, w, d, dtype_code(p1c), temperature,
                                                   weight, ptr(loss), ptr(dp1), ptr(dp2), ptr(pbuf.z[slot]),
                                                   pbuf.zp[slot], ptr(pbuf.st[slot]), pbuf.stp[slot], ptr(pbuf.flags),
@@ -1113,7 +1116,7 @@ class HostInfoNCEPipeline:
                 pb = self.pbuf
                 slot = pb.next_slot()
                 fused = self.n % 128 == 0 and os.environ.get("SM3_PEER_FUSED", "1") != "0"
-                mode = (3 if os.environ.get("SM3_PEER_PUSH", "1") != "0" else 2) if fused else 0
+                mode = (3 if os.environ.get("SM3_PEER_PUSH", "0") == "1" else 2) if fused else 0
                 t = check(lib().sm3_host_pipe_submit_peer(self._h, p1_host.data_ptr(), p2_host.data_ptr(), temperature,
                                                           loss.data_ptr(), dp1.data_ptr(), dp2.data_ptr(), self.rank,
                                                           self.world, ptr(pb.z[slot]), pb.zp[slot], ptr(pb.st[slot]),
