@@ -134,7 +134,24 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // row-major bf16 matrix [rows, cols]; box = 64 columns (128 B, one swizzle row) x box_rows rows
+int make_tmap_bf16_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+struct TmapKey { const void* base; uint64_t rows, cols; uint32_t box_rows; };
 int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  // the encoded descriptor depends only on (pointer, shape, box): steps that reuse their scratch hit this cache
+  // (cuTensorMapEncodeTiled is ~3 us of host time, twice per step)
+  static thread_local TmapKey keys[8];
+  static thread_local CUtensorMap vals[8];
+  static thread_local int next = 0;
+  for (int i = 0; i < 8; ++i)
+    if (keys[i].base == base && keys[i].rows == rows && keys[i].cols == cols && keys[i].box_rows == box_rows && base != nullptr) {
+      *map = vals[i];
+      return SM3_OK;
+    }
+  const int rc = make_tmap_bf16_uncached(map, base, rows, cols, box_rows);
+  if (rc == SM3_OK) { keys[next] = TmapKey{base, rows, cols, box_rows}; vals[next] = *map; next = (next + 1) & 7; }
+  return rc;
+}
+int make_tmap_bf16_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   SM3_REQUIRE(fn != nullptr, SM3_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[2] = {cols, rows};
@@ -148,6 +165,19 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t c
               (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows);
   return SM3_OK;
 }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instantiation and device: the launch-bound shapes pay
+// ~3 us of host time for every redundant call (5 kernels per step)
+#define SM3_SMEM_ATTR_ONCE(kernel, bytes)                                                                    \
+  do {                                                                                                       \
+    static int done_dev[16] = {0};                                                                           \
+    int dev_ = 0;                                                                                            \
+    cudaGetDevice(&dev_);                                                                                    \
+    if (dev_ < 0 || dev_ >= 16 || !done_dev[dev_]) {                                                         \
+      SM3_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (dev_ >= 0 && dev_ < 16) done_dev[dev_] = 1;                                                        \
+    }                                                                                                        \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // bring-up probe: one 128 x n x k MMA chain, every operand source/layout combination the real kernels use
@@ -1531,8 +1561,7 @@ int tc_poly(int dp) {
 
 template <int DP, int NG, int POLY>
 int launch_fwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd_kernel<DP, NG, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)FwdCfg<DP>::SMEM));
+  SM3_SMEM_ATTR_ONCE((infonce_tc_fwd_kernel<DP, NG, POLY>), FwdCfg<DP>::SMEM);
   SM3_CHECK_CUDA(launch_k(infonce_tc_fwd_kernel<DP, NG, POLY>, dim3(pl.row_tiles, pl.splits), dim3(64 + 256 * NG), FwdCfg<DP>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
@@ -1540,13 +1569,11 @@ int launch_fwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, 
 template <int DP, int POLY>
 int launch_fwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
   if (p.push_src != nullptr) {
-    SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd2_kernel<DP, POLY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)FwdCfg<DP>::SMEM));
+    SM3_SMEM_ATTR_ONCE((infonce_tc_fwd2_kernel<DP, POLY, true>), FwdCfg<DP>::SMEM);
     SM3_CHECK_CUDA(launch_k(infonce_tc_fwd2_kernel<DP, POLY, true>, dim3(pl.row_tiles, pl.splits), dim3(384), FwdCfg<DP>::SMEM, st, tmap, p));
     return SM3_OK;
   }
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_fwd2_kernel<DP, POLY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)FwdCfg<DP>::SMEM));
+  SM3_SMEM_ATTR_ONCE((infonce_tc_fwd2_kernel<DP, POLY, false>), FwdCfg<DP>::SMEM);
   SM3_CHECK_CUDA(launch_k(infonce_tc_fwd2_kernel<DP, POLY, false>, dim3(pl.row_tiles, pl.splits), dim3(320), FwdCfg<DP>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
@@ -1571,8 +1598,7 @@ int launch_fwd(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cud
 }
 template <int DP, int NG, bool kWait, int NS>
 int launch_bwd_ng(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd_kernel<DP, NG, kWait, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BwdCfg<DP, NS>::SMEM));
+  SM3_SMEM_ATTR_ONCE((infonce_tc_bwd_kernel<DP, NG, kWait, NS>), (BwdCfg<DP, NS>::SMEM));
   SM3_CHECK_CUDA(launch_k(infonce_tc_bwd_kernel<DP, NG, kWait, NS>, dim3(pl.row_tiles, pl.splits), dim3(64 + 256 * NG), BwdCfg<DP, NS>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
@@ -1590,8 +1616,7 @@ int tc_bwd_stages(int dp) {
 template <int DP, bool kWait, int NS, int BNT, int POLY, bool COLSPLIT = false>
 int launch_bwd2(const CUtensorMap& tmap, const TcParams& p, const TcPlan& pl, cudaStream_t st) {
   using C = Bwd2Cfg<DP, NS, BNT>;
-  SM3_CHECK_CUDA(cudaFuncSetAttribute(infonce_tc_bwd2_kernel<DP, kWait, NS, BNT, POLY, COLSPLIT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  SM3_SMEM_ATTR_ONCE((infonce_tc_bwd2_kernel<DP, kWait, NS, BNT, POLY, COLSPLIT>), (C::SMEM));
   SM3_CHECK_CUDA(launch_k(infonce_tc_bwd2_kernel<DP, kWait, NS, BNT, POLY, COLSPLIT>, dim3(pl.row_tiles, pl.splits), dim3(320), C::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
