@@ -656,8 +656,13 @@ def run_ours(args):
         r = line["roofline"]
         if t_fwd:
             achf = flops_fwd / (t_fwd * 1e-3) / 1e12
-            r["fwd"] = {"kernel": "infonce_tc_fwd2_kernel (K2)" + (", incl. in-kernel waits for the peers' rows" if world > 1 else ""),
+            sym, ex_fl = fwd_symmetric(sm3, n, d) if world == 1 else (False, flops_fwd)
+            r["fwd"] = {"kernel": ("infonce_tc_fwdsym_kernel (K2, upper-triangular tiles)" if sym else "infonce_tc_fwd2_kernel (K2)") +
+                                  (", incl. in-kernel waits for the peers' rows" if world > 1 else ""),
                         "achieved": achf, "frac": achf / pk["tflops"], "launch_ms": t_fwd, "flops_per_launch": flops_fwd,
+                        "executed_flops_per_launch": ex_fl,
+                        "note": ("algorithmic 2 M^2 D as SURVEY 8d defines it; the symmetric kernel EXECUTES about half of it, "
+                                 "so frac can exceed what the tensor pipe did") if sym else None,
                         "traffic": (tr.get(args.workload, {}).get("fwd_dram_bytes_per_launch") if world == 1 else None)}
         r["step"] = {"achieved": (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12,
                      "frac": (flops_fwd + flops_bwd) / (ms_step * 1e-3) / 1e12 / pk["tflops"],
@@ -716,6 +721,15 @@ E2E_MULTI_API = ("sm3_host_pipe_submit_peer/wait (C ABI, pinned host buffers, 2-
                  "from / drained to pinned host memory by two copy streams in Python)")
 
 
+def fwd_symmetric(sm3, n, d):
+    """(does the single-rank forward of this shape run the symmetric kernel, FLOPs it executes per launch)."""
+    import ctypes as C
+    from skin_sm3_b200 import _lib
+    tiles = C.c_longlong(0)
+    on = bool(_lib.lib().sm3_infonce_fwd_symmetric(int(n), int(d), C.byref(tiles)))
+    return on, float(tiles.value) * 2.0 * 128 * 128 * d
+
+
 def cfg2_block(sm3, pk, args, flush):
     """BASELINE configs[1] (4096 x 128): production step (eager op), CUDA-graph replay, e2e, per-kernel rooflines from the
     production path's stage events, full-size parity against the fp64 closed form, the reference on the host cores and
@@ -747,6 +761,8 @@ def cfg2_block(sm3, pk, args, flush):
             ach = fl / (st2[nm] * 1e-3) / 1e12
             blk[key] = {"launch_us": round(st2[nm] * 1e3, 2), "achieved": ach, "frac": ach / pk["tflops"], "unit": "TFLOP/s",
                         "flops_per_launch": fl, "traffic": tr.get(key + "_dram_bytes_per_launch")}
+            if key == "fwd":
+                blk[key]["symmetric"], blk[key]["executed_flops_per_launch"] = fwd_symmetric(sm3, n2, d2)
     # parity at this size: every gradient element against the fp64 closed form (the checker, outside all timing)
     from oracle import sm3_oracle as O
     a, b = q1.cuda().requires_grad_(True), q2.cuda().requires_grad_(True)

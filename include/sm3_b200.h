@@ -151,6 +151,12 @@ int sm3_infonce_bwd_remote_packed(const void* z_rows, const void* z_cols, int n_
                                   const float* neg_sum_rows, const float* stats_cols, void* workspace,
                                   size_t workspace_bytes, void* stream);
 
+/* 1 when sm3_infonce_fwd / sm3_infonce_step run the SYMMETRIC forward for this single-rank shape (rows == columns, bf16,
+ * 2 n_pairs % 256 == 0, enough tiles to fill the GPU; SM3_TC_FWD_SYM=0 disables): S = Z Z^T is symmetric, so only the
+ * upper-triangular 128 x 128 tiles are computed and a tile's column sums stand in for the transposed tile's row sums --
+ * about half the executed MMAs and exponentials for the same result.  *executed_tiles (may be NULL) = S tiles computed. */
+int sm3_infonce_fwd_symmetric(int n_pairs, int D, long long* executed_tiles);
+
 /* loss half of nn.CrossEntropyLoss()(logits, 0) on the sufficient statistics, fused with its own
  * gradient (tools/backbone_train.py:101-121):
  *   loss   = scale * sum_i softplus(lse_neg_i - pos_i)             (scale = weight / M_global)
@@ -194,6 +200,13 @@ int sm3_bce_logits(const void* x, int x_dtype, const void* t, int t_dtype, const
  * ---------------------------------------------------------------------------------------------- */
 int sm3_sim_topk(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype, int k,
                  int64_t exclude_self_offset, float* vals, int64_t* idx, void* stream);
+/* Tiled form of the same search (the one the Python front end uses): register-tiled FP32 contraction, threshold-filtered
+ * candidate buffers, the bank split across CTAs and a merge kernel; needs a caller-owned 8-byte-aligned workspace of
+ * sm3_sim_topk_workspace_bytes().  Identical results (exact top-k, ties -> lower bank index). */
+size_t sm3_sim_topk_workspace_bytes(int64_t n_query, int64_t n_bank, int k);
+int sm3_sim_topk_ws(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype, int k,
+                    int64_t exclude_self_offset, float* vals, int64_t* idx, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * N4  DeepCluster spherical k-means of the memory bank    replaces the rank-0 loop of cluster_memory

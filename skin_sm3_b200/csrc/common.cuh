@@ -167,6 +167,48 @@ __device__ __forceinline__ int positive_of(int g, int n_global) {
   return g < n_global ? g + n_global : g - n_global;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Symmetric forward (single rank, rows == columns; infonce_tc_fwdsym_kernel): only the column tiles J >= 2R of every
+// 256-row pair R are visited, and a tile with J > 2R + 1 contributes its ROW sums to rows R and its COLUMN sums to the
+// rows of tile J.  The (R, J) work items form one flat list -- row pairs in the folded order 0, P-1, 1, P-2, ... so that
+// every folded pair holds T + 2 tiles -- cut into pieces of `tpc` tiles, one per CTA.  Workspace layout (floats):
+//   [maxseg][M]  row sums of the k-th CTA that worked on the row pair (k < nseg(R))
+//   [P][M]       column sums: slab R' holds what row pair R' contributed to each later row (valid for R' < R(row))
+// The folds recognise the layout by kSymFlag in n_partials (low bits = tpc); everything is summed in a fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSymFlag = 0x40000000;
+__host__ __device__ inline long sym_flat_start(int R, int T, int P) {
+  const int i = R < P - 1 - R ? R : P - 1 - R;
+  long f = (long)i * (T + 2);
+  if (R != i) f += T - 2 * i;
+  return f;
+}
+__host__ __device__ inline int sym_maxseg(int T, int tpc) { return (T - 1) / tpc + 2; }
+__device__ __forceinline__ float fold_row_partials(const float* __restrict__ partial, int n_partials, int64_t rows,
+                                                   int64_t i) {
+  float s = 0.f;
+  if (!(n_partials & kSymFlag)) {
+    for (int k = 0; k < n_partials; ++k) s += partial[(int64_t)k * rows + i];
+    return s;
+  }
+  const int tpc = n_partials & (kSymFlag - 1);
+  const int T = (int)(rows / 128), P = T / 2, R = (int)(i / 256);
+  const long f = sym_flat_start(R, T, P);
+  const int nseg = (int)((f + (T - 2 * R) - 1) / tpc - f / tpc) + 1;
+  for (int k = 0; k < nseg; ++k) s += partial[(int64_t)k * rows + i];
+  const float* col = partial + (int64_t)sym_maxseg(T, tpc) * rows + i;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  int r = 0;
+  for (; r + 4 <= R; r += 4) {
+    c0 += col[(int64_t)r * rows];
+    c1 += col[(int64_t)(r + 1) * rows];
+    c2 += col[(int64_t)(r + 2) * rows];
+    c3 += col[(int64_t)(r + 3) * rows];
+  }
+  for (; r < R; ++r) c0 += col[(int64_t)r * rows];
+  return s + ((c0 + c1) + (c2 + c3));
+}
+
 // Cross-rank flag wait used INSIDE kernels (fused exchange): one thread spins until every peer has published `epoch`
 // on `channel` of this rank's flag buffer (slot layout: flags[channel * 16 + source_rank], epochs only grow).  The
 // acquire at system scope orders this thread's later reads after the peers' stores.  A peer may legitimately be late

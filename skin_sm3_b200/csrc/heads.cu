@@ -674,8 +674,7 @@ __global__ void infonce_finalize_kernel(const float* __restrict__ partial, int n
                                         const float* __restrict__ extra) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
-  float s = extra ? extra[i] : 0.f;
-  for (int k = 0; k < n_partials; ++k) s += partial[(int64_t)k * rows + i];
+  const float s = (extra ? extra[i] : 0.f) + fold_row_partials(partial, n_partials, rows, i);
   neg_sum[i] = s;
   lse_neg[i] = inv_T + logf(s);     // s == 0 (no negatives, N == 1) -> -inf, CE([pos,-inf],0) = 0
 }

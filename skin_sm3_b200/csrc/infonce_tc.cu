@@ -72,6 +72,9 @@ struct TcParams {
   int push_vpr, push_ctas;       // 16-byte vectors per row; how many CTAs (the first wave) share the copy
   PeerPtrs push_dst, push_flags;
   unsigned* push_counter;        // [world] zero-initialised tickets, reset by the last CTA
+  // symmetric forward (single rank): column tiles per side, tiles per CTA, row-sum slabs, flat work-list length
+  int sym_T, sym_tpc, sym_maxseg;
+  long sym_W;
 };
 
 // Per-CTA starting rotation of the column-tile order.  Default: pseudo-random (decorrelates the CTAs of a wave, see the
@@ -829,6 +832,322 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) SM3_TR(7, 4);                                      // trace: CTA end
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// symmetric forward (single rank, rows == columns): S = Z Z^T is symmetric, so only the column tiles J >= 2R of every
+// 256-row pair R are computed; a tile with J > 2R + 1 gives its row sums to the rows of R and its COLUMN sums to the rows
+// of tile J (what the transposed tile would have produced): half the MMAs and half the exponentials of the kernel above.
+// Work list, workspace layout and the fold: see kSymFlag in common.cuh.  Same warp roles / TMEM / smem ring as the
+// 256-row kernel; differences:
+//   * a CTA walks a contiguous piece of the flat (R, J) list and re-stages its A rows when R changes;
+//   * the softmax warps read S in the 16x256b fragment layout (thread = 4 rows x 16 columns of its 32 x 64 slice), add
+//     their rows per column while they accumulate the row sums (1 extra FADD per logit), finish the column sums with a
+//     3-step butterfly over the 8 lanes that share a column (14 shuffles per tile), fold the four lane quadrants through
+//     shared memory in a fixed order and write 128 floats per tile;
+//   * the row sums need their 2-step cross-lane reduction only once per (CTA, R) segment.
+// ------------------------------------------------------------------------------------------------
+template <int DP> struct SymCfg {
+  static constexpr uint32_t SMEM = FwdCfg<DP>::NSTAGE * FwdCfg<DP>::STAGE + 1024 /*align*/ + 256 /*barriers*/ +
+                                   1024 /*xsum [2][128]*/ + 4096 /*cbuf [2][8][64]*/;
+};
+__device__ __forceinline__ void sym_decode(long f, int T, int P, int& R, int& off) {
+  const int i = (int)(f / (T + 2));
+  const int rem = (int)(f - (long)i * (T + 2));
+  const int len_i = T - 2 * i;
+  if (rem < len_i) { R = i; off = rem; } else { R = P - 1 - i; off = rem - len_i; }
+}
+
+template <int DP, int POLY>
+__global__ void __launch_bounds__(320, 1)
+infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
+  using C = FwdCfg<DP>;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
+  constexpr int D = 64 * DP;
+  const int T = p.sym_T, P = T >> 1;
+  const long f0 = (long)blockIdx.x * p.sym_tpc;
+  const long f1 = min(p.sym_W, f0 + p.sym_tpc);
+  if (f0 >= f1) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sB = base;
+  const uint32_t bars = sB + NSTAGE * C::STAGE;
+  auto bar_full = [&](int i) { return bars + 8u * i; };
+  auto bar_empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
+  auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
+  auto bar_sempty = [&](int i) { return bars + 8u * (2 * NSTAGE + 2 + i); };
+  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 5));
+  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);          // [2 row blocks][128]
+  float* cbuf = xsum + 256;                                                         // [2 tile parities][8 warps][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long bar_limit = 2000000000ull;
+  if (threadIdx.x == 0) SM3_TR(7, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_sempty(i), 8); }
+    mbar_init(bar_aready, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_launch();
+  constexpr uint32_t kColA1 = 128, kColS = 256;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) prefetch_tensormap(&tmap_cols);
+    int it = 0;
+    for (long f = f0; f < f1;) {
+      int R, off;
+      sym_decode(f, T, P, R, off);
+      const int cnt = (int)min((long)(T - 2 * R - off), f1 - f);
+      for (int t = 0; t < cnt; ++t, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+        mbar_wait(bar_empty(s), ph ^ 1u, bar_limit);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full(s), C::STAGE);
+          const int row = (2 * R + off + t) * BN;
+#pragma unroll
+          for (int pnl = 0; pnl < DP; ++pnl)
+            tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
+        }
+        __syncwarp();
+      }
+      f += cnt;
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    int it = 0, seg = 0;
+    for (long f = f0; f < f1; ++seg) {
+      int R, off;
+      sym_decode(f, T, P, R, off);
+      const int cnt = (int)min((long)(T - 2 * R - off), f1 - f);
+      mbar_wait(bar_aready, (uint32_t)seg & 1u, bar_limit);      // this row pair's A operands are in TMEM
+      tc_fence_after();
+      for (int t = 0; t < cnt; ++t, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t sph = (uint32_t)it & 1u;
+        mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);
+        if (it == 0) SM3_TR(7, 1);
+        SM3_TR(0, it);
+        const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          mbar_wait(bar_sempty(rb), sph ^ 1u, bar_limit);
+          tc_fence_after();
+          SM3_TR(8 + rb, it);
+          const uint32_t d_tmem = tmem + kColS + (uint32_t)rb * 128u;
+          const uint32_t a_tmem = tmem + (uint32_t)rb * kColA1;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4 * DP; ++ks)
+              umma_ts(d_tmem, a_tmem + ks * 8, desc64(lo0 + (((ks >> 2) * C::PANEL + (ks & 3) * 32) >> 4), dhi), idesc,
+                      ks > 0);
+            if (rb == 1) umma_commit(bar_empty(s));
+            umma_commit(bar_sfull(rb));
+          }
+          __syncwarp();
+          SM3_TR(1 + rb, it);
+        }
+      }
+      f += cnt;
+    }
+    SM3_TR(7, 2);
+  } else {
+    // =========================== softmax warps ===========================
+    const int q = warp & 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int t0 = lane & 3, t1 = lane >> 2;
+    const int row_in_tile = q * 32 + lane;                       // staging view: thread <-> TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t lane_hi = (uint32_t)(q * 32 + 16) << 16;
+    const float c2 = p.c2;
+    const int64_t M = p.m_rows;
+    float* colpart = p.partial + (int64_t)p.sym_maxseg * M;
+    int it = 0;
+    for (long f = f0; f < f1;) {
+      int R, off;
+      sym_decode(f, T, P, R, off);
+      const int cnt = (int)min((long)(T - 2 * R - off), f1 - f);
+      const int r0 = R * 256;
+      // ---- stage this row pair into TMEM as A operands (all S-MMAs of the previous segment have completed: every
+      //      softmax warp has waited for the last S tile) ----
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+        for (int ch = 0; ch < DP; ++ch) {
+          if ((ch & 1) == half) {
+            uint32_t r[32];
+            const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)(r0 + rb * 128 + row_in_tile) * D + ch * 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 v = __ldg(src + i);
+              r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+            }
+            tmem_st_x32(tmem + lane_addr + rb * kColA1 + ch * 32, r);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_aready);
+
+      float sum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int t = 0; t < cnt; ++t, ++it) {
+        const int J = 2 * R + off + t;
+        const uint32_t sph = (uint32_t)it & 1u;
+        const bool do_col = J > 2 * R + 1;
+        float colacc[16];
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          mbar_wait(bar_sfull(rb), sph, bar_limit);
+          tc_fence_after();
+          if (warp == 2 && lane == 0) SM3_TR(3 + 2 * rb, it);
+          const uint32_t taddr = tmem + kColS + (uint32_t)rb * 128u + (uint32_t)half * 64u;
+          uint32_t va[32], vb[32];
+          tmem_ld_16x256b_x8(taddr + lane_addr, va);
+          tmem_ld_16x256b_x8(taddr + lane_hi, vb);
+          tmem_ld_wait(va);
+          tmem_ld_wait(vb);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sempty(rb));
+          if (warp == 2 && lane == 0) SM3_TR(4 + 2 * rb, it);
+          int Jp = 2 * R + rb + P;                               // the tile that holds these rows' positives
+          if (Jp >= T) Jp -= T;
+          if (J != 2 * R + rb && J != Jp) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const int e = 2 * k + b;
+                const float x0 = fmaf(__uint_as_float(va[4 * k + b]), c2, -c2);
+                const float x1 = fmaf(__uint_as_float(va[4 * k + 2 + b]), c2, -c2);
+                const float x2 = fmaf(__uint_as_float(vb[4 * k + b]), c2, -c2);
+                const float x3 = fmaf(__uint_as_float(vb[4 * k + 2 + b]), c2, -c2);
+                const float e0 = (((4 * e) & 7) < POLY) ? ex2_fma(x0) : ex2(x0);
+                const float e1 = (((4 * e + 1) & 7) < POLY) ? ex2_fma(x1) : ex2(x1);
+                const float e2 = (((4 * e + 2) & 7) < POLY) ? ex2_fma(x2) : ex2(x2);
+                const float e3 = (((4 * e + 3) & 7) < POLY) ? ex2_fma(x3) : ex2(x3);
+                sum[rb][0] += e0; sum[rb][1] += e1; sum[rb][2] += e2; sum[rb][3] += e3;
+                const float cs = (e0 + e1) + (e2 + e3);
+                if (rb == 0) colacc[e] = cs; else colacc[e] += cs;
+              }
+            }
+          } else {
+            // the tile holds the diagonal or the positives of these rows: mask per element
+            const int rbase = r0 + rb * 128 + q * 32 + t1;
+            const int cbase = J * BN + half * 64 + 2 * t0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const int e = 2 * k + b;
+                const int col = cbase + 8 * k + b;
+                float cs = 0.f;
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                  const int row = rbase + 8 * (sl & 1) + 16 * (sl >> 1);
+                  const uint32_t raw_v = sl < 2 ? va[4 * k + 2 * sl + b] : vb[4 * k + 2 * (sl - 2) + b];
+                  const float sv = __uint_as_float(raw_v);
+                  const int pj = positive_of(row, p.n_global);
+                  const bool is_pos = (col == pj);
+                  if (is_pos && pj > row) {                      // S is symmetric: one read serves both rows of the pair
+                    const float pv = sv * p.inv_T;
+                    p.pos[row] = pv;
+                    p.pos[pj] = pv;
+                  }
+                  const float ev = (is_pos || col == row) ? 0.f : ex2(fmaf(sv, c2, -c2));
+                  sum[rb][sl] += ev;
+                  cs += ev;
+                }
+                if (rb == 0) colacc[e] = cs; else colacc[e] += cs;
+              }
+            }
+          }
+        }
+        if (warp == 2 && lane == 0) SM3_TR(10, it);
+        if (do_col) {
+          // column sums over this warp's 32 rows x 2 row blocks: butterfly over the lanes t1 = lane / 4 that share a
+          // column; lane ends up with columns 2 * lane + {0, 1} of its 64-column half
+          const bool h4 = (lane & 16) != 0, h2 = (lane & 8) != 0, h1 = (lane & 4) != 0;
+          float c8[8], c4[4], cf[2];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float lo = colacc[j], hi = colacc[j + 8];
+            c8[j] = (h4 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h4 ? lo : hi, 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float lo = c8[j], hi = c8[j + 4];
+            c4[j] = (h2 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h2 ? lo : hi, 8);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float lo = c4[j], hi = c4[j + 2];
+            cf[j] = (h1 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h1 ? lo : hi, 4);
+          }
+          float* cb = cbuf + (it & 1) * 512;
+          *reinterpret_cast<float2*>(cb + (half * 4 + q) * 64 + 2 * lane) = make_float2(cf[0], cf[1]);
+          named_bar_sync(1, 256);
+          if (lane < 16) {                                       // 8 warps x 16 columns: fold the four lane quadrants
+            const int c = (half * 4 + q) * 16 + lane;
+            const float* src = cb + (c >> 6) * 256 + (c & 63);
+            colpart[(int64_t)R * M + (int64_t)J * BN + c] = (src[0] + src[64]) + (src[128] + src[192]);
+          }
+        }
+        if (warp == 2 && lane == 0) SM3_TR(11, it);
+      }
+      // ---- row sums of this (CTA, row pair) segment ----
+      const int kseg = (int)blockIdx.x - (int)(sym_flat_start(R, T, P) / p.sym_tpc);
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          float v = sum[rb][sl];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          sum[rb][sl] = v;
+          if (half == 1 && t0 == 0) xsum[rb * 128 + q * 32 + t1 + 8 * (sl & 1) + 16 * (sl >> 1)] = v;
+        }
+      }
+      named_bar_sync(1, 256);
+      if (half == 0 && t0 == 0) {
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            const int rl = rb * 128 + q * 32 + t1 + 8 * (sl & 1) + 16 * (sl >> 1);
+            p.partial[(int64_t)kseg * M + r0 + rl] = sum[rb][sl] + xsum[rl];
+          }
+        }
+      }
+      named_bar_sync(1, 256);
+      f += cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) SM3_TR(7, 4);
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -1689,6 +2008,53 @@ size_t bwd_acol_offset(const InfoNceProblem& pb, const TcPlan& pl) {
   return (dz + 255) & ~(size_t)255;
 }
 
+
+// symmetric forward: when it applies and how the flat tile list is cut (see kSymFlag in common.cuh).  SM3_TC_FWD_SYM=0
+// keeps the full-matrix kernel, 2 uses the symmetric one at every size it supports.
+int g_knob_sym = -1;
+struct SymPlan {
+  bool on;
+  int T, P, tpc, nctas, maxseg;
+  long W;
+  size_t ws;
+};
+SymPlan tc_sym_plan(const InfoNceProblem& pb) {
+  SymPlan sp{};
+  if (g_knob_sym < 0) {
+    const char* e = getenv("SM3_TC_FWD_SYM");
+    g_knob_sym = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;      // 2: also below the size threshold (tests)
+  }
+  if (!g_knob_sym || pb.n_local != pb.n_global || pb.pair_offset != 0 || pb.skip_local || pb.wait_flags != nullptr ||
+      pb.push_mode || pb.extra_neg_sum != nullptr || pb.z_rows != pb.z_cols)
+    return sp;
+  const long M = 2L * pb.n_global;
+  if (M % 256 != 0) return sp;
+  sp.T = (int)(M / 128);
+  sp.P = sp.T / 2;
+  sp.W = (long)sp.P * (sp.P + 1);
+  const int sms = num_sms();
+  if (g_knob_sym != 2 && sp.W < 2L * sms) return sp;   // too few tiles to fill the machine with half of them
+  sp.tpc = (int)((sp.W + sms - 1) / sms);
+  sp.nctas = (int)((sp.W + sp.tpc - 1) / sp.tpc);
+  sp.maxseg = sym_maxseg(sp.T, sp.tpc);
+  sp.ws = (size_t)(sp.maxseg + sp.P) * (size_t)M * sizeof(float) + 256;
+  // in the fused step the loss kernel reads these sums while it writes a_j behind the backward's partial-gradient slabs
+  if (sp.ws > bwd_acol_offset(pb, tc_plan(pb, true))) return sp;
+  sp.on = true;
+  return sp;
+}
+template <int DP, int POLY>
+int launch_fwdsym_p(const CUtensorMap& tmap, const TcParams& p, const SymPlan& sp, cudaStream_t st) {
+  SM3_SMEM_ATTR_ONCE((infonce_tc_fwdsym_kernel<DP, POLY>), SymCfg<DP>::SMEM);
+  SM3_CHECK_CUDA(launch_k(infonce_tc_fwdsym_kernel<DP, POLY>, dim3(sp.nctas), dim3(320), SymCfg<DP>::SMEM, st, tmap, p));
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+template <int DP>
+int launch_fwdsym(const CUtensorMap& tmap, const TcParams& p, const SymPlan& sp, cudaStream_t st) {
+  return tc_poly(DP) == 2 ? launch_fwdsym_p<DP, 2>(tmap, p, sp, st) : launch_fwdsym_p<DP, 0>(tmap, p, sp, st);
+}
+
 }  // namespace
 
 size_t infonce_tc_acol_offset(const InfoNceProblem& pb) { return bwd_acol_offset(pb, tc_plan(pb, true)); }
@@ -1708,7 +2074,11 @@ bool infonce_tc_supported(const InfoNceProblem& pb) {
 size_t infonce_tc_workspace(const InfoNceProblem& pb, int backward) {
   if (pb.D % 64 != 0 || pb.D < 64 || pb.D > 256) return 0;
   const TcPlan pl = tc_plan(pb, backward != 0);
-  if (!backward) return (size_t)pl.splits * 2 * pb.n_local * sizeof(float) + 256;
+  if (!backward) {
+    const size_t full = (size_t)pl.splits * 2 * pb.n_local * sizeof(float) + 256;
+    const SymPlan sp = tc_sym_plan(pb);
+    return sp.on && sp.ws > full ? sp.ws : full;
+  }
   const size_t m_pad = ((size_t)2 * pb.n_global + 127) / 128 * 128 + 128;   // whole 128-column tiles + one of slack
   return bwd_acol_offset(pb, pl) + m_pad * sizeof(float) + 256;
 }
@@ -1746,6 +2116,20 @@ int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* 
   CUtensorMap tmap;
   int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 128);
   if (rc) return rc;
+  const SymPlan sp = tc_sym_plan(pb);
+  if (sp.on) {
+    p.sym_T = sp.T; p.sym_tpc = sp.tpc; p.sym_maxseg = sp.maxseg; p.sym_W = sp.W;
+    switch (pb.D / 64) {
+      case 1: rc = launch_fwdsym<1>(tmap, p, sp, st); break;
+      case 2: rc = launch_fwdsym<2>(tmap, p, sp, st); break;
+      case 3: rc = launch_fwdsym<3>(tmap, p, sp, st); break;
+      default: rc = launch_fwdsym<4>(tmap, p, sp, st); break;
+    }
+    if (rc) return rc;
+    const int enc = kSymFlag | sp.tpc;
+    if (pb.no_finalize) return enc;
+    return infonce_finalize_launch(p.partial, enc, p.m_rows, pb.inv_T, neg_sum, lse_neg, st, nullptr);
+  }
   switch (pb.D / 64) {
     case 1: rc = launch_fwd<1>(tmap, p, pl, st); break;
     case 2: rc = launch_fwd<2>(tmap, p, pl, st); break;
@@ -1799,12 +2183,24 @@ int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* g
 
 }  // namespace sm3
 
+// 1 when the single-rank tcgen05 forward of this shape runs the symmetric kernel; *executed_tiles (optional) receives the
+// number of 128 x 128 S tiles it computes (the full-matrix kernel computes (2 n_pairs / 128)^2)
+extern "C" int sm3_infonce_fwd_symmetric(int n_pairs, int D, long long* executed_tiles) {
+  using namespace sm3;
+  if (n_pairs < 1 || D % 64 != 0 || D < 64 || D > 256) return 0;
+  InfoNceProblem pb{nullptr, nullptr, n_pairs, 0, n_pairs, D, SM3_BF16, 1.0f};
+  const SymPlan sp = tc_sym_plan(pb);
+  if (executed_tiles) *executed_tiles = sp.on ? 2 * sp.W : (long long)((2L * n_pairs + 127) / 128) * ((2L * n_pairs + 127) / 128);
+  return sp.on ? 1 : 0;
+}
+
 extern "C" void sm3_debug_reload_env(void) {
   sm3::g_knob_groups = 0;
   sm3::g_knob_poly = -1;
   sm3::g_knob_bwd_ns = -1;
   sm3::g_knob_bwd_v = -1;
   sm3::g_knob_bwd_poly = -1;
+  sm3::g_knob_sym = -1;
 }
 
 #ifdef SM3_TRACE

@@ -193,8 +193,7 @@ loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, con
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float term = 0.f;
   if (i < rows) {
-    float s = 0.f;
-    for (int k = 0; k < n_partials; ++k) s += partial[(size_t)k * rows + i];
+    const float s = fold_row_partials(partial, n_partials, rows, i);
     const float lse = inv_T + logf(s);               // s == 0 (a single pair: no negatives) -> -inf, term = 0
     const float x = lse - pos[i];
     const float e = __expf(-fabsf(x));

@@ -183,6 +183,22 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16x256b shape (the accumulator-fragment layout): the warp reads 16 TMEM lanes starting at the lane field of taddr
+// (32 * (warp_id % 4) or that + 16) x 64 columns; with t = lane id, register 4k + 2a + b holds TMEM lane
+// (t / 4 + 8a), column base + 8k + 2 (t % 4) + b.  Every thread thus owns 2 rows x 16 columns: a column lives in 8
+// threads (3 butterfly steps reduce it) instead of 32, which is what the symmetric forward's column sums need.
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 // tcgen05.ld is asynchronous: the destination registers are only defined after tcgen05.wait::ld.  The
 // registers are threaded through the wait as "+r" operands so the compiler cannot hoist their uses above it.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {

@@ -137,6 +137,225 @@ sim_topk_kernel(const T* __restrict__ query, const T* __restrict__ bank, int64_t
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled form (sm3_sim_topk_ws): the dot products are a register-tiled FP32 contraction (32 queries x 128 bank rows per
+// CTA step, 4 x 4 outputs per thread, operands staged k-major in shared memory) instead of one warp per bank row, and the
+// selection is threshold-filtered: a value only enters a query's candidate buffer if its key beats the query's current
+// K-th best, and a buffer is sorted + merged into the running list (by one warp) only when it may overflow -- after the
+// first few tiles that is rare (expected candidates per query ~ K (1 + ln(rows / K))).  The bank is split across CTAs so
+// that few queries still fill the machine; a second kernel merges the per-split lists.  Same 64-bit keys as above, so the
+// result is the exact top-k with ties resolved to the lower bank index.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kQ2 = 32, kB2 = 128, kKC = 32, kT2 = 256, kCap = 256;
+
+__device__ void warp_bitonic_sort_desc(unsigned long long* a, int n, int lane) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < n / 2; t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncwarp();
+}
+__device__ void warp_bitonic_merge_desc(unsigned long long* a, int n, int lane) {
+  for (int stride = n >> 1; stride > 0; stride >>= 1) {
+    __syncwarp();
+    for (int t = lane; t < n / 2; t += 32) {
+      const int lo = 2 * t - (t & (stride - 1));
+      const int hi = lo + stride;
+      const unsigned long long x = a[lo], y = a[hi];
+      if (x < y) { a[lo] = y; a[hi] = x; }
+    }
+  }
+  __syncwarp();
+}
+// run[0..K) (sorted descending) <- top-K of run U cand[0..c); one warp; cand is clobbered
+__device__ void warp_merge_candidates(unsigned long long* run, unsigned long long* cand, int c, int K, int lane) {
+  int n = 32;
+  while (n < c) n <<= 1;
+  for (int i = c + lane; i < n; i += 32) cand[i] = 0ull;
+  warp_bitonic_sort_desc(cand, n, lane);
+  for (int i = lane; i < K; i += 32) {
+    const unsigned long long a = run[i], b = (K - 1 - i) < n ? cand[K - 1 - i] : 0ull;
+    run[i] = a > b ? a : b;
+  }
+  warp_bitonic_merge_desc(run, K, lane);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT2)
+sim_topk_tile_kernel(const T* __restrict__ query, const T* __restrict__ bank, int64_t n_query, int64_t n_bank, int D,
+                     int K, int64_t exclude_self_offset, int64_t rows_per_split, int vec,
+                     unsigned long long* __restrict__ lists) {
+  extern __shared__ unsigned char smem_raw[];
+  float* Qs = reinterpret_cast<float*>(smem_raw);                         // [kKC][kQ2]
+  float* Bs = Qs + kKC * kQ2;                                             // [kKC][kB2]
+  unsigned long long* run = reinterpret_cast<unsigned long long*>(Bs + kKC * kB2);   // [kQ2][K]
+  unsigned long long* cand = run + kQ2 * K;                               // [kQ2][kCap]
+  unsigned long long* tau = cand + kQ2 * kCap;                            // [kQ2]
+  int* cnt = reinterpret_cast<int*>(tau + kQ2);                           // [kQ2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = lane, ty = warp;                                         // 4 bank columns tx + 32 j | 4 queries 4 ty + i
+  const int64_t q0 = (int64_t)blockIdx.x * kQ2;
+  const int64_t b_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t b_end = min(n_bank, b_begin + rows_per_split);
+  constexpr int V = VecIO<T>::N;
+
+  for (int i = tid; i < kQ2 * K; i += kT2) run[i] = 0ull;
+  if (tid < kQ2) { tau[tid] = 0ull; cnt[tid] = 0; }
+  __syncthreads();
+
+  for (int64_t b0 = b_begin; b0 < b_end; b0 += kB2) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += kKC) {
+      // ---- stage the operand tiles k-major (zero padded) ----
+      if (vec) {
+        for (int v = tid; v < kQ2 * (kKC / V); v += kT2) {
+          const int r = v % kQ2, kv = v / kQ2;
+          float o[V];
+          if (q0 + r < n_query && k0 + kv * V < D) VecIO<T>::load(query + (q0 + r) * D + k0 + kv * V, o);
+          else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) o[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < V; ++e) Qs[(kv * V + e) * kQ2 + r] = o[e];
+        }
+        for (int v = tid; v < kB2 * (kKC / V); v += kT2) {
+          const int r = v % kB2, kv = v / kB2;
+          float o[V];
+          if (b0 + r < b_end && k0 + kv * V < D) VecIO<T>::load(bank + (b0 + r) * D + k0 + kv * V, o);
+          else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) o[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < V; ++e) Bs[(kv * V + e) * kB2 + r] = o[e];
+        }
+      } else {
+        for (int v = tid; v < kQ2 * kKC; v += kT2) {
+          const int r = v % kQ2, k = v / kQ2;
+          Qs[k * kQ2 + r] = (q0 + r < n_query && k0 + k < D) ? to_f32(query[(q0 + r) * D + k0 + k]) : 0.f;
+        }
+        for (int v = tid; v < kB2 * kKC; v += kT2) {
+          const int r = v % kB2, k = v / kB2;
+          Bs[k * kB2 + r] = (b0 + r < b_end && k0 + k < D) ? to_f32(bank[(b0 + r) * D + k0 + k]) : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < kKC; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(Qs + k * kQ2 + 4 * ty);
+        const float b[4] = {Bs[k * kB2 + tx], Bs[k * kB2 + tx + 32], Bs[k * kB2 + tx + 64], Bs[k * kB2 + tx + 96]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+          acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+          acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+          acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- threshold filter into the candidate buffers ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = 4 * ty + i;
+      if (q0 + q >= n_query) continue;
+      const unsigned long long tk = tau[q];
+      const int64_t self = exclude_self_offset >= 0 ? exclude_self_offset + q0 + q : -1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t col = b0 + tx + 32 * j;
+        if (col < b_end && col != self) {
+          const unsigned long long key = make_key(acc[i][j], (unsigned)col);
+          if (key > tk) cand[q * kCap + atomicAdd(&cnt[q], 1)] = key;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- merge the buffers that could overflow on the next tile (warp w owns queries 4 w .. 4 w + 3) ----
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const int q = 4 * warp + i;
+      const int c = cnt[q];
+      if (c > kCap - kB2) {
+        warp_merge_candidates(run + q * K, cand + q * kCap, c, K, lane);
+        if (lane == 0) { cnt[q] = 0; tau[q] = run[q * K + K - 1]; }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const int q = 4 * warp + i;
+    const int c = cnt[q];
+    if (c > 0) warp_merge_candidates(run + q * K, cand + q * kCap, c, K, lane);
+    __syncwarp();
+    if (q0 + q < n_query) {
+      unsigned long long* dst = lists + ((int64_t)blockIdx.y * n_query + q0 + q) * K;
+      for (int r = lane; r < K; r += 32) dst[r] = run[q * K + r];
+    }
+  }
+}
+
+// per query: merge the per-split lists (each sorted descending), emit values and indices; one warp per query
+__global__ void __launch_bounds__(128)
+sim_topk_merge_kernel(const unsigned long long* __restrict__ lists, int splits, int64_t n_query, int K, int k,
+                      float* __restrict__ vals, int64_t* __restrict__ idx) {
+  __shared__ unsigned long long res_all[4 * kMaxK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+  if (q >= n_query) return;
+  unsigned long long* res = res_all + warp * kMaxK;
+  for (int i = lane; i < K; i += 32) res[i] = lists[q * K + i];
+  for (int s = 1; s < splits; ++s) {
+    __syncwarp();
+    const unsigned long long* l = lists + ((int64_t)s * n_query + q) * K;
+    for (int i = lane; i < K; i += 32) {
+      const unsigned long long a = res[i], b = l[K - 1 - i];
+      res[i] = a > b ? a : b;
+    }
+    warp_bitonic_merge_desc(res, K, lane);
+  }
+  __syncwarp();
+  for (int r = lane; r < k; r += 32) {
+    const unsigned long long key = res[r];
+    const bool ok = key != 0ull;
+    vals[q * k + r] = ok ? key_value(key) : -INFINITY;
+    idx[q * k + r] = ok ? (int64_t)(~(unsigned)(key & 0xFFFFFFFFull)) : -1;
+  }
+}
+
+struct Topk2Plan { int K, splits; int64_t rows_per_split; size_t smem, ws; };
+Topk2Plan topk2_plan(int64_t n_query, int64_t n_bank, int k) {
+  Topk2Plan p{};
+  p.K = 8;
+  while (p.K < k) p.K <<= 1;
+  const int64_t qt = (n_query + kQ2 - 1) / kQ2;
+  int64_t want = num_sms() / qt;
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  int64_t rps = (n_bank + want - 1) / want;
+  rps = (rps + kB2 - 1) / kB2 * kB2;
+  p.rows_per_split = rps;
+  p.splits = (int)((n_bank + rps - 1) / rps);
+  p.smem = (size_t)(kKC * kQ2 + kKC * kB2) * 4 + (size_t)kQ2 * p.K * 8 + (size_t)kQ2 * kCap * 8 + kQ2 * 8 + kQ2 * 4;
+  p.ws = (size_t)p.splits * n_query * p.K * 8;
+  return p;
+}
+
 }  // namespace
 }  // namespace sm3
 
@@ -160,6 +379,38 @@ extern "C" int sm3_sim_topk(const void* query, const void* bank, int64_t n_query
     sim_topk_kernel<T><<<grid, kTopkThreads, smem, st>>>((const T*)query, (const T*)bank, n_query, n_bank, D, k, K,
                                                          exclude_self_offset, vals, idx);
   });
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+extern "C" size_t sm3_sim_topk_workspace_bytes(int64_t n_query, int64_t n_bank, int k) {
+  if (n_query < 1 || n_bank < 1 || k < 1 || k > kMaxK) return 0;
+  return topk2_plan(n_query, n_bank, k).ws;
+}
+
+extern "C" int sm3_sim_topk_ws(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype,
+                               int k, int64_t exclude_self_offset, float* vals, int64_t* idx, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(query && bank && vals && idx && workspace, SM3_ERR_SHAPE, "sim_topk_ws: null pointer");
+  SM3_REQUIRE(dtype_ok(dtype), SM3_ERR_DTYPE, "sim_topk_ws: bad dtype %d", dtype);
+  SM3_REQUIRE(n_query >= 1 && n_bank >= 1 && D >= 1, SM3_ERR_SHAPE, "sim_topk_ws: bad shape");
+  SM3_REQUIRE(n_bank < ((int64_t)1 << 32) - 1, SM3_ERR_SHAPE, "sim_topk_ws: bank too large");
+  SM3_REQUIRE(k >= 1 && k <= kMaxK && k <= n_bank, SM3_ERR_SHAPE, "sim_topk_ws: need 1 <= k <= min(%d, n_bank), got %d",
+              kMaxK, k);
+  const Topk2Plan pl = topk2_plan(n_query, n_bank, k);
+  SM3_REQUIRE(workspace_bytes >= pl.ws, SM3_ERR_WORKSPACE, "sim_topk_ws: workspace %zu < %zu", workspace_bytes, pl.ws);
+  SM3_REQUIRE((((uintptr_t)workspace) & 7u) == 0, SM3_ERR_SHAPE, "sim_topk_ws: workspace must be 8-byte aligned");
+  unsigned long long* lists = (unsigned long long*)workspace;
+  const dim3 grid((unsigned)((n_query + kQ2 - 1) / kQ2), (unsigned)pl.splits);
+  SM3_DISPATCH_DTYPE(dtype, T, {
+    const int vec = (D % VecIO<T>::N == 0) && ((((uintptr_t)bank) & 15u) == 0) && ((((uintptr_t)query) & 15u) == 0);
+    SM3_CHECK_CUDA(cudaFuncSetAttribute(sim_topk_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    sim_topk_tile_kernel<T><<<grid, kT2, pl.smem, st>>>((const T*)query, (const T*)bank, n_query, n_bank, D, pl.K,
+                                                        exclude_self_offset, pl.rows_per_split, vec, lists);
+  });
+  SM3_CHECK_CUDA(cudaGetLastError());
+  sim_topk_merge_kernel<<<(unsigned)((n_query + 3) / 4), 128, 0, st>>>(lists, pl.splits, n_query, pl.K, k, vals, idx);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }

@@ -53,7 +53,8 @@ def reload_env() -> None:
     _SCRATCH.clear()
 
 
-_PLAN_KNOBS = ("SM3_TC_FWD_BM", "SM3_TC_BWD_V", "SM3_TC_BWD_NS", "SM3_TC_FWD_SPLITS", "SM3_TC_BWD_SPLITS")
+_PLAN_KNOBS = ("SM3_TC_FWD_BM", "SM3_TC_BWD_V", "SM3_TC_BWD_NS", "SM3_TC_FWD_SPLITS", "SM3_TC_BWD_SPLITS",
+               "SM3_TC_FWD_SYM")
 
 
 def _scratch(kind: str, dev: torch.device, key: tuple, nbytes_fn) -> torch.Tensor:
@@ -880,8 +881,15 @@ def sim_topk(query: torch.Tensor, bank: torch.Tensor, k: int, exclude_self_offse
     vals = torch.empty((b, k), dtype=torch.float32, device=dev)
     idx = torch.empty((b, k), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        check(lib().sm3_sim_topk(ptr(query), ptr(bank), b, bank.shape[0], d, dtype_code(query), int(k),
-                                 int(exclude_self_offset), ptr(vals), ptr(idx), stream_ptr()), "sm3_sim_topk")
+        if os.environ.get("SM3_TOPK_TILED", "1") != "0":
+            nbytes = int(lib().sm3_sim_topk_workspace_bytes(b, bank.shape[0], int(k)))
+            ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+            check(lib().sm3_sim_topk_ws(ptr(query), ptr(bank), b, bank.shape[0], d, dtype_code(query), int(k),
+                                        int(exclude_self_offset), ptr(vals), ptr(idx), ptr(ws), ws.numel(),
+                                        stream_ptr()), "sm3_sim_topk_ws")
+        else:                                       # single-pass form (no workspace), kept for comparison
+            check(lib().sm3_sim_topk(ptr(query), ptr(bank), b, bank.shape[0], d, dtype_code(query), int(k),
+                                     int(exclude_self_offset), ptr(vals), ptr(idx), stream_ptr()), "sm3_sim_topk")
     return vals, idx
 
 

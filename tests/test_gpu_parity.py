@@ -167,6 +167,45 @@ def test_tensor_core_path_vs_oracle(sm3, monkeypatch, n, d, T, fwd_bm, bwd_v):
     sm3.reload_env()
 
 
+@pytest.mark.parametrize("n,d", [(128, 128), (384, 64), (640, 256), (1152, 128), (2304, 128), (2432, 192), (4096, 256)])
+def test_symmetric_forward_matches_full_forward(sm3, monkeypatch, n, d):
+    """The symmetric forward (upper-triangular tiles only, column sums standing in for the transposed tiles) gives the
+    same row statistics as the full-matrix kernel and as the fp64 closed form, at sizes that cover an odd and an even
+    number of row pairs, one tile per CTA (forced below the size threshold) and several, and every embedding width.
+    Also through the fused step (loss kernel folding the triangular workspace) and deterministic run to run."""
+    T = 0.1
+    g = torch.Generator().manual_seed(29 + n)
+    p1 = torch.randn(n, d, generator=g)
+    p2 = p1 + 0.5 * torch.randn(n, d, generator=g)
+    z, _ = sm3.core.normalize_pair(p1.cuda(), p2.cuda(), torch.bfloat16)
+    out = {}
+    try:
+        for mode in ("0", "2"):
+            monkeypatch.setenv("SM3_TC_FWD_SYM", mode)
+            sm3.reload_env()
+            pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
+            a, b = p1.bfloat16().cuda().requires_grad_(True), p2.bfloat16().cuda().requires_grad_(True)
+            loss = sm3.fused_infonce(a, b, T, precision="bf16")
+            loss.backward()
+            out[mode] = (pos.clone(), lse.clone(), nsum.clone(), loss.item(), a.grad.clone())
+            if mode == "2":
+                pos2, lse2, nsum2 = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
+                assert torch.equal(nsum2, out[mode][2]) and torch.equal(pos2, out[mode][0])
+    finally:
+        monkeypatch.undo()
+        sm3.reload_env()
+    full, sym = out["0"], out["2"]
+    assert torch.equal(full[0], sym[0]) or (full[0] - sym[0]).abs().max().item() < 1e-5          # positives
+    assert ((full[2] - sym[2]).abs() / full[2].abs()).max().item() < 2e-5                          # neg_sum, every row
+    assert (full[1] - sym[1]).abs().max().item() < 2e-5                                            # lse
+    assert abs(full[3] - sym[3]) <= 2e-6 * abs(full[3])
+    assert relerr(sym[4].float().cpu(), full[4].float().cpu()) < 8e-3          # bf16 gradients: one rounding step apart
+    zf = z.float().cpu().numpy().astype(np.float64)
+    ref_pos, ref_lse = O.infonce_stats(zf, n, T)                 # fp64 on the same bf16 rows the kernels read
+    assert np.abs(sym[0].cpu().numpy() - ref_pos).max() < 1e-4
+    assert np.abs(sym[1].cpu().numpy() - ref_lse).max() < 1e-4
+
+
 @pytest.mark.parametrize("bwd_v,ns", [("1", "4"), ("2", "4"), ("2", "2"), ("3", "2"), ("4", "2")])
 def test_backward_forms_agree(sm3, monkeypatch, bwd_v, ns):
     """Both backward kernels and both S/H stage counts produce the same partial-gradient sums (bf16 H, fp32 accumulation:
@@ -778,6 +817,35 @@ def test_sim_topk_vs_oracle(sm3, dtype, bq, nb, d, k):
         assert np.abs(sim[r, i[r][bad]] - sim[r, ri[r][bad]]).max() < 1e-4 * np.abs(sim[r]).max(), (r, bad)
     both = np.sort(i, axis=1)
     assert (both[:, 1:] != both[:, :-1]).all()                    # no duplicates
+
+
+@pytest.mark.parametrize("bq,nb,d,k,self_off", [(512, 16384, 128, 200, -1), (1000, 3000, 96, 5, 0), (40, 70000, 64, 17, -1)])
+def test_sim_topk_tiled_equals_single_pass(sm3, monkeypatch, bq, nb, d, k, self_off):
+    """The tiled, threshold-filtered search (bank split across CTAs + merge kernel) and the single-pass kernel return the
+    same top-k set: same 64-bit keys, so any difference can only come from fp32 accumulation order of near-ties."""
+    g = torch.Generator().manual_seed(bq + k)
+    q = torch.randn(bq, d, generator=g).cuda()
+    bank = torch.randn(nb, d, generator=g).cuda()
+    v1, i1 = sm3.sim_topk(q, bank, k, exclude_self_offset=self_off)
+    monkeypatch.setenv("SM3_TOPK_TILED", "0")
+    v0, i0 = sm3.sim_topk(q, bank, k, exclude_self_offset=self_off)
+    monkeypatch.undo()
+    assert (v1[:, :-1] >= v1[:, 1:]).all()                                   # sorted descending
+    assert (i1 >= 0).all() and (i1 < nb).all()
+    if self_off >= 0:
+        assert (i1 != (torch.arange(bq, device=i1.device) + self_off)[:, None]).all()
+    agree = (i1 == i0).float().mean().item()
+    assert agree > 0.999, agree
+    assert relerr(v1.cpu().numpy(), v0.cpu().numpy()) < 1e-5
+    s1 = torch.sort(i1, dim=1).values
+    assert (s1[:, 1:] != s1[:, :-1]).all()                                   # no duplicates
+    # against the library formulation on the same GPU
+    sim = q @ bank.T
+    if self_off >= 0:
+        sim[torch.arange(bq), torch.arange(bq) + self_off] = -float("inf")
+    rv, ri = sim.topk(k, dim=1)
+    assert (ri == i1).float().mean().item() > 0.995
+    assert relerr(v1.cpu().numpy(), rv.cpu().numpy()) < 1e-5
 
 
 def test_in_batch_retrieval_top1_is_the_positive(sm3):

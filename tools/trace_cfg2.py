@@ -65,11 +65,12 @@ ph = t[:5, 7] - t0
 nt = int((t[:, 0] > 0).sum())
 print(f"\n=== forward (fwd2 if 256-row CTAs)  n={n} d={d}: {nt} tiles in CTA (0,0)")
 print(f"CTA phases: first MMA {ph[1]}, last MMA issued {ph[2]}, CTA end {ph[4]}")
-print("tile   Bland S0free  S0iss S1free  S1iss | S0rdy S0reg S1rdy S1reg | period  ld0   exp0(S0reg->S1rdy-ish)  ld1")
-for it in list(range(0, min(nt, 12))):
+print("tile   Bland S0free  S0iss S1free  S1iss | S0rdy S0reg S1rdy S1reg | period  ld0   exp0(S0reg->S1rdy-ish)  ld1 | (symmetric kernel) exp1  colsum")
+for it in list(range(0, min(nt, 16))):
     r = t[it] - t0
     prev = t[it - 1] - t0 if it else r
     print(f"{it:4d} {int(r[0]):7d} {int(r[8]):6d} {int(r[1]):6d} {int(r[9]):6d} {int(r[2]):6d} | {int(r[3]):6d} {int(r[4]):6d} {int(r[5]):6d} {int(r[6]):6d} | "
-          f"{int(r[3] - prev[3]):6d} {int(r[4] - r[3]):5d} {int(r[5] - r[4]):6d} {int(r[6] - r[5]):5d}")
+          f"{int(r[3] - prev[3]):6d} {int(r[4] - r[3]):5d} {int(r[5] - r[4]):6d} {int(r[6] - r[5]):5d}" +
+          (f" | {int(r[10] - r[6]):6d} {int(r[11] - r[10]):6d}" if t[it, 10] > 0 else ""))
 nf = int((t[:, 3] > 0).sum())
 print("tiles traced in the forward CTA:", nf)
