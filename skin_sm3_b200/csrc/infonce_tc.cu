@@ -850,7 +850,7 @@ infonce_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
 // ------------------------------------------------------------------------------------------------
 template <int DP> struct SymCfg {
   static constexpr uint32_t SMEM = FwdCfg<DP>::NSTAGE * FwdCfg<DP>::STAGE + 1024 /*align*/ + 256 /*barriers*/ +
-                                   1024 /*xsum [2][128]*/ + 4096 /*cbuf [2][8][64]*/;
+                                   3072 /*xsum [3][2][128]*/ + 6144 /*cbuf [3][512]*/;
 };
 __device__ __forceinline__ void sym_decode(long f, int T, int P, int& R, int& off) {
   const int i = (int)(f / (T + 2));
@@ -859,12 +859,17 @@ __device__ __forceinline__ void sym_decode(long f, int T, int P, int& R, int& of
   if (rem < len_i) { R = i; off = rem; } else { R = P - 1 - i; off = rem - len_i; }
 }
 
-template <int DP, int POLY>
-__global__ void __launch_bounds__(320, 1)
+// NQ = softmax warps per lane quadrant (2 or 4): each owns 128 / NQ columns of every S tile.  4 (16 softmax warps, 576
+// threads, <= 112 registers) doubles the warps that hide each other's MUFU / TMEM / shuffle latencies.
+template <int DP, int POLY, int NQ>
+__global__ void __launch_bounds__(64 + 128 * NQ, 1)
 infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
   using C = FwdCfg<DP>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
   constexpr int D = 64 * DP;
+  constexpr int NW = 4 * NQ;             // softmax warps
+  constexpr int CW = 128 / NQ;           // S-tile columns per softmax warp
+  constexpr int KS = CW / 8;             // 8-column groups per warp: registers 4 k .. 4 k + 3 of a 16x256b load
   const int T = p.sym_T, P = T >> 1;
   const long f0 = (long)blockIdx.x * p.sym_tpc;
   const long f1 = min(p.sym_W, f0 + p.sym_tpc);
@@ -881,9 +886,10 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
   auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
   auto bar_sempty = [&](int i) { return bars + 8u * (2 * NSTAGE + 2 + i); };
   const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 5));
-  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);          // [2 row blocks][128]
-  float* cbuf = xsum + 256;                                                         // [2 tile parities][8 warps][64]
+  auto bar_col = [&](int i) { return bars + 8u * (2 * NSTAGE + 5 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 8));
+  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);          // [NQ - 1][2 row blocks][128]
+  float* cbuf = xsum + 768;                                                         // [3 ring slots][NW warps][CW]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned long long bar_limit = 2000000000ull;
@@ -891,8 +897,9 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_sempty(i), 8); }
-    mbar_init(bar_aready, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_sempty(i), NW); }
+    mbar_init(bar_aready, NW);
+    for (int i = 0; i < 3; ++i) mbar_init(bar_col(i), NW);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -973,15 +980,31 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
   } else {
     // =========================== softmax warps ===========================
     const int q = warp & 3;
-    const int half = ((warp - 2) >> 2) & 1;
+    const int cg = (warp - 2) >> 2;                              // column group of this warp: columns [cg * CW, +CW)
     const int t0 = lane & 3, t1 = lane >> 2;
     const int row_in_tile = q * 32 + lane;                       // staging view: thread <-> TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t lane_hi = (uint32_t)(q * 32 + 16) << 16;
     const float c2 = p.c2;
+    const uint64_t c2p = f2_pack(c2, c2), nc2p = f2_pack(-c2, -c2);
+    const bool clamp = 2.0f * c2 > 125.0f;
     const int64_t M = p.m_rows;
     float* colpart = p.partial + (int64_t)p.sym_maxseg * M;
     int it = 0;
+    // column sums are folded across the four lane quadrants one tile LATE (no CTA-wide rendezvous per tile): ring of 3
+    // buffers, one mbarrier each (NW warp arrivals); pend_* describe the tile whose fold is outstanding
+    int ncol = 0, pend_R = -1, pend_J = 0;
+    auto fold_pending = [&]() {
+      if (pend_R < 0) return;
+      const int ci = (ncol - 1) % 3;
+      mbar_wait(bar_col(ci), (uint32_t)((ncol - 1) / 3) & 1u, bar_limit);
+      if (lane < 128 / NW) {                                     // NW warps x 128 / NW columns, quadrants in a fixed order
+        const int c = (warp - 2) * (128 / NW) + lane;
+        const float* src = cbuf + ci * 512 + (c / CW) * (4 * CW) + (c % CW);
+        colpart[(int64_t)pend_R * M + (int64_t)pend_J * BN + c] = (src[0] + src[CW]) + (src[2 * CW] + src[3 * CW]);
+      }
+      pend_R = -1;
+    };
     for (long f = f0; f < f1;) {
       int R, off;
       sym_decode(f, T, P, R, off);
@@ -993,7 +1016,7 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
       for (int rb = 0; rb < 2; ++rb) {
 #pragma unroll
         for (int ch = 0; ch < DP; ++ch) {
-          if ((ch & 1) == half) {
+          if ((ch % NQ) == cg) {
             uint32_t r[32];
             const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)(r0 + rb * 128 + row_in_tile) * D + ch * 64);
 #pragma unroll
@@ -1010,139 +1033,161 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_aready);
 
-      float sum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      // packed (column b = 0 | b = 1) running row sums of the thread's 4 rows per row block
+      uint64_t sum2[2][4];
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) sum2[rb][sl] = 0ull;
       for (int t = 0; t < cnt; ++t, ++it) {
         const int J = 2 * R + off + t;
         const uint32_t sph = (uint32_t)it & 1u;
         const bool do_col = J > 2 * R + 1;
-        float colacc[16];
+        uint64_t col2[KS];                                       // packed column sums: columns 8 k + 2 t0 + {0, 1}
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
           mbar_wait(bar_sfull(rb), sph, bar_limit);
           tc_fence_after();
           if (warp == 2 && lane == 0) SM3_TR(3 + 2 * rb, it);
-          const uint32_t taddr = tmem + kColS + (uint32_t)rb * 128u + (uint32_t)half * 64u;
-          uint32_t va[32], vb[32];
-          tmem_ld_16x256b_x8(taddr + lane_addr, va);
-          tmem_ld_16x256b_x8(taddr + lane_hi, vb);
+          const uint32_t taddr = tmem + kColS + (uint32_t)rb * 128u + (uint32_t)(cg * CW);
+          uint32_t va[4 * KS], vb[4 * KS];
+          tmem_ld_16x256b(taddr + lane_addr, va);                // rows t1, t1 + 8 of the quadrant
           tmem_ld_wait(va);
-          tmem_ld_wait(vb);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_sempty(rb));
-          if (warp == 2 && lane == 0) SM3_TR(4 + 2 * rb, it);
+          tmem_ld_16x256b(taddr + lane_hi, vb);                  // rows t1 + 16, t1 + 24: in flight during the first half
           int Jp = 2 * R + rb + P;                               // the tile that holds these rows' positives
           if (Jp >= T) Jp -= T;
-          if (J != 2 * R + rb && J != Jp) {
+          const bool special = (J == 2 * R + rb) || (J == Jp);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-#pragma unroll
-              for (int b = 0; b < 2; ++b) {
-                const int e = 2 * k + b;
-                const float x0 = fmaf(__uint_as_float(va[4 * k + b]), c2, -c2);
-                const float x1 = fmaf(__uint_as_float(va[4 * k + 2 + b]), c2, -c2);
-                const float x2 = fmaf(__uint_as_float(vb[4 * k + b]), c2, -c2);
-                const float x3 = fmaf(__uint_as_float(vb[4 * k + 2 + b]), c2, -c2);
-                const float e0 = (((4 * e) & 7) < POLY) ? ex2_fma(x0) : ex2(x0);
-                const float e1 = (((4 * e + 1) & 7) < POLY) ? ex2_fma(x1) : ex2(x1);
-                const float e2 = (((4 * e + 2) & 7) < POLY) ? ex2_fma(x2) : ex2(x2);
-                const float e3 = (((4 * e + 3) & 7) < POLY) ? ex2_fma(x3) : ex2(x3);
-                sum[rb][0] += e0; sum[rb][1] += e1; sum[rb][2] += e2; sum[rb][3] += e3;
-                const float cs = (e0 + e1) + (e2 + e3);
-                if (rb == 0) colacc[e] = cs; else colacc[e] += cs;
-              }
+          for (int hv = 0; hv < 2; ++hv) {
+            if (hv == 1) {
+              tmem_ld_wait(vb);
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_sempty(rb));        // S stage free (the MMA warp runs a tile ahead anyway)
+              if (warp == 2 && lane == 0) SM3_TR(4 + 2 * rb, it);
             }
-          } else {
-            // the tile holds the diagonal or the positives of these rows: mask per element
-            const int rbase = r0 + rb * 128 + q * 32 + t1;
-            const int cbase = J * BN + half * 64 + 2 * t0;
+            const uint32_t* v = hv == 0 ? va : vb;
+            if (!special) {
+              uint64_t e[2 * KS];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+              for (int k = 0; k < KS; ++k) {
+                e[2 * k] = f2_fma(f2_pack_u(v[4 * k], v[4 * k + 1]), c2p, nc2p);
+                e[2 * k + 1] = f2_fma(f2_pack_u(v[4 * k + 2], v[4 * k + 3]), c2p, nc2p);
+              }
+              // POLY of every 8 exponentials on the FMA pipes: whole pairs (4: every other pair; 2: every fourth pair)
 #pragma unroll
-              for (int b = 0; b < 2; ++b) {
-                const int e = 2 * k + b;
-                const int col = cbase + 8 * k + b;
-                float cs = 0.f;
+              for (int i = 0; i < 2 * KS; ++i)
+                e[i] = ((POLY >= 4 && (i & 1) == 0) || (POLY >= 2 && POLY < 4 && (i & 3) == 0)) ? f2_ex2_fma(e[i], clamp) : f2_ex2(e[i]);
 #pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                  const int row = rbase + 8 * (sl & 1) + 16 * (sl >> 1);
-                  const uint32_t raw_v = sl < 2 ? va[4 * k + 2 * sl + b] : vb[4 * k + 2 * (sl - 2) + b];
-                  const float sv = __uint_as_float(raw_v);
+              for (int k = 0; k < KS; ++k) {
+                sum2[rb][2 * hv] = f2_add(sum2[rb][2 * hv], e[2 * k]);
+                sum2[rb][2 * hv + 1] = f2_add(sum2[rb][2 * hv + 1], e[2 * k + 1]);
+                const uint64_t cs = f2_add(e[2 * k], e[2 * k + 1]);
+                col2[k] = (rb == 0 && hv == 0) ? cs : f2_add(col2[k], cs);
+              }
+            } else {
+              // the tile holds the diagonal or the positives of these rows: mask per element
+              const int rbase = r0 + rb * 128 + q * 32 + t1 + 16 * hv;
+              const int cbase = J * BN + cg * CW + 2 * t0;
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                uint64_t cs = 0ull;
+#pragma unroll
+                for (int a8 = 0; a8 < 2; ++a8) {
+                  const int row = rbase + 8 * a8;
                   const int pj = positive_of(row, p.n_global);
-                  const bool is_pos = (col == pj);
-                  if (is_pos && pj > row) {                      // S is symmetric: one read serves both rows of the pair
-                    const float pv = sv * p.inv_T;
-                    p.pos[row] = pv;
-                    p.pos[pj] = pv;
+                  float ev[2];
+#pragma unroll
+                  for (int bb = 0; bb < 2; ++bb) {
+                    const int col = cbase + 8 * k + bb;
+                    const float sv = __uint_as_float(v[4 * k + 2 * a8 + bb]);
+                    const bool is_pos = (col == pj);
+                    if (is_pos && pj > row) {                    // S is symmetric: one read serves both rows of the pair
+                      const float pv = sv * p.inv_T;
+                      p.pos[row] = pv;
+                      p.pos[pj] = pv;
+                    }
+                    ev[bb] = (is_pos || col == row) ? 0.f : ex2(fmaf(sv, c2, -c2));
                   }
-                  const float ev = (is_pos || col == row) ? 0.f : ex2(fmaf(sv, c2, -c2));
-                  sum[rb][sl] += ev;
-                  cs += ev;
+                  const uint64_t e = f2_pack(ev[0], ev[1]);
+                  sum2[rb][2 * hv + a8] = f2_add(sum2[rb][2 * hv + a8], e);
+                  cs = f2_add(cs, e);
                 }
-                if (rb == 0) colacc[e] = cs; else colacc[e] += cs;
+                col2[k] = (rb == 0 && hv == 0) ? cs : f2_add(col2[k], cs);
               }
             }
           }
         }
         if (warp == 2 && lane == 0) SM3_TR(10, it);
+        fold_pending();                                          // the previous column-sum tile: every warp arrived long ago
         if (do_col) {
           // column sums over this warp's 32 rows x 2 row blocks: butterfly over the lanes t1 = lane / 4 that share a
-          // column; lane ends up with columns 2 * lane + {0, 1} of its 64-column half
+          // column (lane bit 4 <-> k bit 2 or 1, ...); each step halves the values a lane carries
+          float ca[2 * KS];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) f2_unpack(col2[k], ca[2 * k], ca[2 * k + 1]);
           const bool h4 = (lane & 16) != 0, h2 = (lane & 8) != 0, h1 = (lane & 4) != 0;
-          float c8[8], c4[4], cf[2];
+          float* cb = cbuf + (ncol % 3) * 512 + (cg * 4 + q) * CW;
+          if constexpr (KS == 8) {
+            float c8[8], c4[4], cf[2];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float lo = colacc[j], hi = colacc[j + 8];
-            c8[j] = (h4 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h4 ? lo : hi, 16);
-          }
+            for (int j = 0; j < 8; ++j) c8[j] = (h4 ? ca[j + 8] : ca[j]) + __shfl_xor_sync(0xffffffffu, h4 ? ca[j] : ca[j + 8], 16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float lo = c8[j], hi = c8[j + 4];
-            c4[j] = (h2 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h2 ? lo : hi, 8);
-          }
+            for (int j = 0; j < 4; ++j) c4[j] = (h2 ? c8[j + 4] : c8[j]) + __shfl_xor_sync(0xffffffffu, h2 ? c8[j] : c8[j + 4], 8);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float lo = c4[j], hi = c4[j + 2];
-            cf[j] = (h1 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h1 ? lo : hi, 4);
+            for (int j = 0; j < 2; ++j) cf[j] = (h1 ? c4[j + 2] : c4[j]) + __shfl_xor_sync(0xffffffffu, h1 ? c4[j] : c4[j + 2], 4);
+            *reinterpret_cast<float2*>(cb + 2 * lane) = make_float2(cf[0], cf[1]);       // columns 2 lane + {0, 1}
+          } else {
+            float c4[4], c2v[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c4[j] = (h4 ? ca[j + 4] : ca[j]) + __shfl_xor_sync(0xffffffffu, h4 ? ca[j] : ca[j + 4], 16);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) c2v[j] = (h2 ? c4[j + 2] : c4[j]) + __shfl_xor_sync(0xffffffffu, h2 ? c4[j] : c4[j + 2], 8);
+            const float cf = (h1 ? c2v[1] : c2v[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c2v[0] : c2v[1], 4);
+            // k = 2 * bit4 + bit3, b = bit2  ->  column 8 k + 2 t0 + b
+            cb[8 * (2 * (int)h4 + (int)h2) + 2 * t0 + (int)h1] = cf;
           }
-          float* cb = cbuf + (it & 1) * 512;
-          *reinterpret_cast<float2*>(cb + (half * 4 + q) * 64 + 2 * lane) = make_float2(cf[0], cf[1]);
-          named_bar_sync(1, 256);
-          if (lane < 16) {                                       // 8 warps x 16 columns: fold the four lane quadrants
-            const int c = (half * 4 + q) * 16 + lane;
-            const float* src = cb + (c >> 6) * 256 + (c & 63);
-            colpart[(int64_t)R * M + (int64_t)J * BN + c] = (src[0] + src[64]) + (src[128] + src[192]);
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_col(ncol % 3));
+          pend_R = R; pend_J = J;
+          ++ncol;
         }
         if (warp == 2 && lane == 0) SM3_TR(11, it);
       }
-      // ---- row sums of this (CTA, row pair) segment ----
+      // ---- row sums of this (CTA, row pair) segment: fold the NQ column groups in a fixed order ----
       const int kseg = (int)blockIdx.x - (int)(sym_flat_start(R, T, P) / p.sym_tpc);
+      float rs[2][4];
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
-          float v = sum[rb][sl];
+          float lo, hi;
+          f2_unpack(sum2[rb][sl], lo, hi);
+          float v = lo + hi;
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
-          sum[rb][sl] = v;
-          if (half == 1 && t0 == 0) xsum[rb * 128 + q * 32 + t1 + 8 * (sl & 1) + 16 * (sl >> 1)] = v;
+          rs[rb][sl] = v;
+          if (cg > 0 && t0 == 0) xsum[(cg - 1) * 256 + rb * 128 + q * 32 + t1 + 8 * (sl & 1) + 16 * (sl >> 1)] = v;
         }
       }
-      named_bar_sync(1, 256);
-      if (half == 0 && t0 == 0) {
+      named_bar_sync(1, 32 * NW);
+      if (cg == 0 && t0 == 0) {
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl) {
             const int rl = rb * 128 + q * 32 + t1 + 8 * (sl & 1) + 16 * (sl >> 1);
-            p.partial[(int64_t)kseg * M + r0 + rl] = sum[rb][sl] + xsum[rl];
+            float v = rs[rb][sl];
+#pragma unroll
+            for (int g = 1; g < NQ; ++g) v += xsum[(g - 1) * 256 + rl];
+            p.partial[(int64_t)kseg * M + r0 + rl] = v;
           }
         }
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 32 * NW);
       f += cnt;
     }
+    fold_pending();
   }
 
   tc_fence_before();
@@ -2043,16 +2088,37 @@ SymPlan tc_sym_plan(const InfoNceProblem& pb) {
   sp.on = true;
   return sp;
 }
-template <int DP, int POLY>
-int launch_fwdsym_p(const CUtensorMap& tmap, const TcParams& p, const SymPlan& sp, cudaStream_t st) {
-  SM3_SMEM_ATTR_ONCE((infonce_tc_fwdsym_kernel<DP, POLY>), SymCfg<DP>::SMEM);
-  SM3_CHECK_CUDA(launch_k(infonce_tc_fwdsym_kernel<DP, POLY>, dim3(sp.nctas), dim3(320), SymCfg<DP>::SMEM, st, tmap, p));
+int g_knob_sym_nq = -1;
+template <int DP, int POLY, int NQ>
+int launch_fwdsym_q(const CUtensorMap& tmap, const TcParams& p, const SymPlan& sp, cudaStream_t st) {
+  SM3_SMEM_ATTR_ONCE((infonce_tc_fwdsym_kernel<DP, POLY, NQ>), SymCfg<DP>::SMEM);
+  SM3_CHECK_CUDA(launch_k(infonce_tc_fwdsym_kernel<DP, POLY, NQ>, dim3(sp.nctas), dim3(64 + 128 * NQ), SymCfg<DP>::SMEM, st, tmap, p));
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }
+// softmax warps per lane quadrant: SM3_TC_SYM_NQ = 2 | 4.  Sixteen softmax warps (4) do not beat eight (2): 1.05-1.23 ms
+// against 1.00-1.05 ms at cfg4, 32.7-36.1 against 34.6-35.7 us at cfg2 (the 16x256b TMEM loads queue behind each other
+// and the per-warp fixed work -- barrier waits, butterfly, fold -- doubles), so 2 is the default.
+template <int DP, int POLY>
+int launch_fwdsym_p(const CUtensorMap& tmap, const TcParams& p, const SymPlan& sp, cudaStream_t st) {
+  if (g_knob_sym_nq < 0) {
+    const char* e = getenv("SM3_TC_SYM_NQ");
+    g_knob_sym_nq = (e && e[0] == '4') ? 4 : 2;
+  }
+  return g_knob_sym_nq == 2 ? launch_fwdsym_q<DP, POLY, 2>(tmap, p, sp, st) : launch_fwdsym_q<DP, POLY, 4>(tmap, p, sp, st);
+}
+// SM3_TC_POLY = 0 | 2 | 4 of every 8 exponentials of the symmetric kernel leave the MUFU pipe for the FMA pipes (packed
+// FFMA2 / FADD2 form, ~5.5 issue slots per exponential).  Measured on B200 (profiles/r02_sym_variants.txt): cfg4
+// 1.05 / 1.00 / 1.13 ms and cfg2 34.6 / 35.7 / 35.6 us for 0 / 2 / 4 -- within run-to-run noise of each other, because
+// the kernel is bound by neither pipe (MUFU 24-50 % busy, issue slots ~40 %) but by the latency of its per-tile chain
+// S ready -> tcgen05.ld -> exp -> column butterfly with only two softmax warps per sub-partition.  Default 2.
 template <int DP>
 int launch_fwdsym(const CUtensorMap& tmap, const TcParams& p, const SymPlan& sp, cudaStream_t st) {
-  return tc_poly(DP) == 2 ? launch_fwdsym_p<DP, 2>(tmap, p, sp, st) : launch_fwdsym_p<DP, 0>(tmap, p, sp, st);
+  (void)tc_poly(DP);                        // reads SM3_TC_POLY into g_knob_poly (-2 = not set)
+  const int poly = g_knob_poly == -2 ? 2 : g_knob_poly;
+  if (poly >= 3) return launch_fwdsym_p<DP, 4>(tmap, p, sp, st);
+  if (poly >= 1) return launch_fwdsym_p<DP, 2>(tmap, p, sp, st);
+  return launch_fwdsym_p<DP, 0>(tmap, p, sp, st);
 }
 
 }  // namespace
@@ -2201,6 +2267,7 @@ extern "C" void sm3_debug_reload_env(void) {
   sm3::g_knob_bwd_v = -1;
   sm3::g_knob_bwd_poly = -1;
   sm3::g_knob_sym = -1;
+  sm3::g_knob_sym_nq = -1;
 }
 
 #ifdef SM3_TRACE

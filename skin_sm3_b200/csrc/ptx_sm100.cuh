@@ -199,6 +199,25 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_16x256b_x8(taddr, r); }
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_16x256b_x4(taddr, r); }
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+        "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+      :
+      : "memory");
+}
 // tcgen05.ld is asynchronous: the destination registers are only defined after tcgen05.wait::ld.  The
 // registers are threaded through the wait as "+r" operands so the compiler cannot hoist their uses above it.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
@@ -252,6 +271,57 @@ __device__ __forceinline__ float ex2_fma(float x) {
   p = fmaf(p, f, 0.693121970f);
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot) ----
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_pack_u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x of both halves on the MUFU pipe / on the FMA pipes (ex2_fma above, packed: 3 FADD2 + 4 FFMA2 + 2 integer ops per
+// PAIR instead of ~10 operations per element).  clamp: only needed when x can fall below -125 (1/T > 43).
+__device__ __forceinline__ uint64_t f2_ex2(uint64_t x) {
+  float a, b;
+  f2_unpack(x, a, b);
+  return f2_pack(ex2(a), ex2(b));
+}
+__device__ __forceinline__ uint64_t f2_ex2_fma(uint64_t x, bool clamp) {
+  if (clamp) {
+    float a, b;
+    f2_unpack(x, a, b);
+    x = f2_pack(fmaxf(a, -125.0f), fmaxf(b, -125.0f));
+  }
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f), nmagic = f2_pack(-12582912.0f, -12582912.0f);
+  const uint64_t r = f2_add(x, magic);
+  const uint64_t n = f2_add(r, nmagic);
+  const uint64_t f = f2_fma(n, f2_pack(-1.0f, -1.0f), x);
+  uint64_t p = f2_fma(f, f2_pack(0.00960039534f, 0.00960039534f), f2_pack(0.0559168942f, 0.0559168942f));
+  p = f2_fma(p, f, f2_pack(0.240237191f, 0.240237191f));
+  p = f2_fma(p, f, f2_pack(0.693121970f, 0.693121970f));
+  p = f2_fma(p, f, f2_pack(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(r, r0, r1);
+  return f2_pack(__int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23)),
+                 __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

@@ -212,37 +212,63 @@ sim_topk_tile_kernel(const T* __restrict__ query, const T* __restrict__ bank, in
   if (tid < kQ2) { tau[tid] = 0ull; cnt[tid] = 0; }
   __syncthreads();
 
+  // operand tiles travel global -> registers -> shared memory: the loads of the NEXT k-chunk are issued before the FMAs
+  // of the current one, so their latency is covered by compute (vector path; the scalar path stages directly)
+  constexpr int NQV = (kQ2 * (kKC / V) + kT2 - 1) / kT2, NBV = kB2 * (kKC / V) / kT2;
+  float qreg[NQV][V], breg[NBV][V];
+  auto g_load = [&](int64_t b0, int k0) {
+#pragma unroll
+    for (int i = 0; i < NQV; ++i) {
+      const int v = tid + i * kT2;
+      const int r = v % kQ2, kv = v / kQ2;
+      if (v < kQ2 * (kKC / V) && q0 + r < n_query && k0 + kv * V < D) VecIO<T>::load(query + (q0 + r) * D + k0 + kv * V, qreg[i]);
+      else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) qreg[i][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) {
+      const int v = tid + i * kT2;
+      const int r = v % kB2, kv = v / kB2;
+      if (b0 + r < b_end && k0 + kv * V < D) VecIO<T>::load(bank + (b0 + r) * D + k0 + kv * V, breg[i]);
+      else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) breg[i][e] = 0.f;
+      }
+    }
+  };
+  auto s_store = [&]() {
+#pragma unroll
+    for (int i = 0; i < NQV; ++i) {
+      const int v = tid + i * kT2;
+      const int r = v % kQ2, kv = v / kQ2;
+      if (v < kQ2 * (kKC / V)) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) Qs[(kv * V + e) * kQ2 + r] = qreg[i][e];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) {
+      const int v = tid + i * kT2;
+      const int r = v % kB2, kv = v / kB2;
+#pragma unroll
+      for (int e = 0; e < V; ++e) Bs[(kv * V + e) * kB2 + r] = breg[i][e];
+    }
+  };
+  const int nchunk = (D + kKC - 1) / kKC;
+  if (vec) g_load(b_begin, 0);
   for (int64_t b0 = b_begin; b0 < b_end; b0 += kB2) {
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < D; k0 += kKC) {
+    for (int kc = 0; kc < nchunk; ++kc) {
+      const int k0 = kc * kKC;
       // ---- stage the operand tiles k-major (zero padded) ----
       if (vec) {
-        for (int v = tid; v < kQ2 * (kKC / V); v += kT2) {
-          const int r = v % kQ2, kv = v / kQ2;
-          float o[V];
-          if (q0 + r < n_query && k0 + kv * V < D) VecIO<T>::load(query + (q0 + r) * D + k0 + kv * V, o);
-          else {
-#pragma unroll
-            for (int e = 0; e < V; ++e) o[e] = 0.f;
-          }
-#pragma unroll
-          for (int e = 0; e < V; ++e) Qs[(kv * V + e) * kQ2 + r] = o[e];
-        }
-        for (int v = tid; v < kB2 * (kKC / V); v += kT2) {
-          const int r = v % kB2, kv = v / kB2;
-          float o[V];
-          if (b0 + r < b_end && k0 + kv * V < D) VecIO<T>::load(bank + (b0 + r) * D + k0 + kv * V, o);
-          else {
-#pragma unroll
-            for (int e = 0; e < V; ++e) o[e] = 0.f;
-          }
-#pragma unroll
-          for (int e = 0; e < V; ++e) Bs[(kv * V + e) * kB2 + r] = o[e];
-        }
+        s_store();
       } else {
         for (int v = tid; v < kQ2 * kKC; v += kT2) {
           const int r = v % kQ2, k = v / kQ2;
@@ -254,6 +280,10 @@ sim_topk_tile_kernel(const T* __restrict__ query, const T* __restrict__ bank, in
         }
       }
       __syncthreads();
+      if (vec) {
+        if (kc + 1 < nchunk) g_load(b0, k0 + kKC);
+        else if (b0 + kB2 < b_end) g_load(b0 + kB2, 0);
+      }
 #pragma unroll 8
       for (int k = 0; k < kKC; ++k) {
         const float4 a = *reinterpret_cast<const float4*>(Qs + k * kQ2 + 4 * ty);

@@ -167,8 +167,9 @@ def test_tensor_core_path_vs_oracle(sm3, monkeypatch, n, d, T, fwd_bm, bwd_v):
     sm3.reload_env()
 
 
+@pytest.mark.parametrize("nq", ["4", "2"])
 @pytest.mark.parametrize("n,d", [(128, 128), (384, 64), (640, 256), (1152, 128), (2304, 128), (2432, 192), (4096, 256)])
-def test_symmetric_forward_matches_full_forward(sm3, monkeypatch, n, d):
+def test_symmetric_forward_matches_full_forward(sm3, monkeypatch, n, d, nq):
     """The symmetric forward (upper-triangular tiles only, column sums standing in for the transposed tiles) gives the
     same row statistics as the full-matrix kernel and as the fp64 closed form, at sizes that cover an odd and an even
     number of row pairs, one tile per CTA (forced below the size threshold) and several, and every embedding width.
@@ -182,6 +183,7 @@ def test_symmetric_forward_matches_full_forward(sm3, monkeypatch, n, d):
     try:
         for mode in ("0", "2"):
             monkeypatch.setenv("SM3_TC_FWD_SYM", mode)
+            monkeypatch.setenv("SM3_TC_SYM_NQ", nq)              # softmax warps per lane quadrant of the symmetric kernel
             sm3.reload_env()
             pos, lse, nsum = sm3.core.stats_fwd(z, z, n, 0, n, T, sm3.ALGO_TC)
             a, b = p1.bfloat16().cuda().requires_grad_(True), p2.bfloat16().cuda().requires_grad_(True)
