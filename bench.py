@@ -920,6 +920,42 @@ def kmeans_probe(sm3):
     return out
 
 
+def head_block_probe(sm3):
+    """N3 tail at the run.sh shape (B = 256 per GPU, 8 feature slots x 512, 24 prototype rows, DeepCluster CE with
+    ignore_index): fused normalise + prototype heads + 8-head CE, forward + backward, against the reference's op sequence
+    (tools/mlc_train.py:81-87 and :255-261 -- 8 normalise + 8 Linear + 8 CE and their backward) on the same GPU.
+    Microseconds per step, back-to-back launches; plus a bandwidth-sized batch against the HBM roofline."""
+    import torch.nn.functional as F
+    counts = [5, 3, 2, 3, 3, 3, 3, 2]
+    out = {}
+    for b in (256, 65536):
+        g = torch.Generator().manual_seed(SEED + b)
+        sa = torch.randn(8, b, 512, generator=g).cuda().requires_grad_(True)
+        ws = [torch.randn(n, 512, generator=g).mul_(0.05).cuda().requires_grad_(True) for n in counts]
+        tg = torch.stack([torch.randint(0, n, (b,), generator=g) for n in counts], dim=1).cuda()
+        tg[::7, 3] = -100
+        crit = torch.nn.CrossEntropyLoss(ignore_index=-100)
+
+        def ours():
+            _, lg = sm3.proto_heads(sa, ws, True)
+            sm3.multihead_ce(lg, tg, temperature=0.5, ignore_index=-100, class_counts=counts).backward()
+
+        def ref():
+            z = [F.normalize(sa[i], dim=-1, p=2) for i in range(8)]
+            loss = 0
+            for i in range(8):
+                loss = loss + crit((z[i] @ ws[i].t()) / 0.5, tg[:, i])
+            (loss / 8).backward()
+
+        t_o, t_r = _ev_us(ours, reps=20), _ev_us(ref, reps=20)
+        key = f"b{b}"
+        out[key] = {"fused_us": round(t_o, 1), "reference_ops_us": round(t_r, 1)}
+        if b > 10000:      # forward reads + writes the features, backward reads z and writes d feats
+            byts = 4.0 * 8 * b * 512 * 4
+            out[key]["fused_GBps"] = round(byts / (t_o * 1e-6) / 1e9, 1)
+    return out
+
+
 def run_cfg3(args):
     """the pretraining step of tools/backbone_train.py:95-130 (style 0) on synthetic 224 x 224 pairs,
     256 pairs per GPU, dual ResNet-50 branches (stock torchvision / cuDNN, out of scope) + the drop-in SimCLRSkinV32 whose
@@ -1089,7 +1125,8 @@ def run_extras_child():
     torch.cuda.set_device(0)
     out = {}
     for key, probe in (("small_shapes", small_shapes_probe), ("tc_kernels_cfg2", tc_kernel_probe),
-                       ("kmeans", kmeans_probe), ("retrieval", retrieval_probe), ("projector_tail", projector_tail_probe)):
+                       ("kmeans", kmeans_probe), ("retrieval", retrieval_probe), ("projector_tail", projector_tail_probe),
+                       ("head_block", head_block_probe)):
         try:
             out[key] = probe(sm3)
         except Exception as e:

@@ -209,6 +209,25 @@ int sm3_sim_topk_ws(const void* query, const void* bank, int64_t n_query, int64_
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N3  prototype heads of the multi-label block    replaces tools/mlc_train.py:81-87 (Model.forward)
+ *       for i: sa_feats[i] = F.normalize(sa_feats[i], dim=-1)                     (when l2_norm)
+ *       preds = [prototypes[i](sa_feats[i % len(sa_feats)]) for i in range(8)]    (bias-free Linears)
+ *   feats [Hf, B, D] (Hf = len(sa_feats): 8, or 1 with Identity projectors), W_cat [C, D] fp32 = the prototype weights
+ *   concatenated in head order (C = 24), class_slot_host[c] = feature slot class c reads (head(c) % Hf).
+ *   fwd: z_out = normalised rows (feats' dtype; untouched when !l2_norm), inv_norm [Hf*B], logits [B, C] fp32 in the
+ *        layout sm3_multihead_ce consumes.   bwd: d_feats = d(loss)/d(feats) from dlogits [B, C] (+ d_extra, the gradient
+ *        that reached the returned sa_feats, may be NULL); dW_cat = dlogits^T z is a plain GEMM the caller runs.
+ *   Shapes: D % 128 == 0 (fp32) / % 256 (16-bit), D <= 512 / 1024, C <= 64 (sm3_proto_heads_supported() == 1).
+ * ---------------------------------------------------------------------------------------------- */
+int sm3_proto_heads_supported(int D, int C, int dtype);
+int sm3_proto_heads_fwd(const void* feats, int dtype, int Hf, int64_t B, int D, const float* W_cat, int C,
+                        const int* class_slot_host, int l2_norm, float eps, void* z_out, float* inv_norm, float* logits,
+                        void* stream);
+int sm3_proto_heads_bwd(const void* z_or_feats, int dtype, int Hf, int64_t B, int D, const float* W_cat, int C,
+                        const int* class_slot_host, int l2_norm, const float* inv_norm, const float* dlogits,
+                        const void* d_extra, void* d_feats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * N4  DeepCluster spherical k-means of the memory bank    replaces the rank-0 loop of cluster_memory
  *     tools/mlc_train.py:144-176 (torch.mm E step :153, .cpu().numpy() + scipy.sparse + Python loop M step :157-172,
  *     F.normalize :175)

@@ -305,6 +305,85 @@ def gen_projtail():
     print("projtail.npz", float(loss))
 
 
+def gen_mlchead():
+    """The REAL multi-label ``Model`` (tools/mlc_train.py:58-89) with a stub extractor, MultiLabelProjector4 (run.sh's
+    ``--mlc-proj v4``) or Identity projectors, its own TransformerEncoderLayer and prototypes, followed by the DeepCluster
+    loss loop of :255-261 (``CE(pred / T, pseudo-label, ignore_index=-100)``, mean over the 8 heads).  Recorded: the
+    self-attention output (input of the fused tail, captured by a forward hook), the returned features and predictions,
+    the loss, and the gradients that reach the self-attention output and the prototype weights."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_mlc_train", os.path.join(REF, "tools", "mlc_train.py"))
+    mt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mt)
+    from src.models.projector import MultiLabelProjector4
+
+    class StubExtractor(nn.Module):
+        def extract(self, a, b):
+            return [a, b]
+
+    out = {}
+    cases = [("v4", 24, 48, 128, True, 8), ("v4raw", 20, 32, 256, False, 8), ("ident", 16, 64, 128, True, 1)]
+    for tag, b, half, d, l2, hf in cases:
+        torch.manual_seed(SEED + b + d)
+        feat_dim = 2 * half
+        proj = MultiLabelProjector4(feat_dim, d, 8) if hf == 8 else nn.Identity()
+        model = mt.Model(StubExtractor(), proj, d if hf == 8 else feat_dim, l2, 1, 64, 0.0).double()
+        model.train()
+        g = torch.Generator().manual_seed(SEED + 7 * b)
+        xa = torch.randn(b, half, generator=g, dtype=torch.float64)
+        xb = torch.randn(b, half, generator=g, dtype=torch.float64)
+        grabbed = {}
+
+        def grab(_m, _inp, res):
+            if res.requires_grad:
+                res.retain_grad()
+            grabbed["sa"] = res
+            grabbed["sa_value"] = res.detach().clone()      # the reference normalises this tensor in place afterwards
+
+        h = model.mlc_sa.register_forward_hook(grab)
+        T = 0.7
+        targets = torch.stack([torch.randint(0, n, (b,), generator=g) for n in mt.NUM_CLASSES], dim=1)
+        targets[::5, 2] = -100
+        crit = nn.CrossEntropyLoss(ignore_index=-100)
+
+        def deepcluster_loss(preds):
+            loss = 0
+            for pred, tgt in zip(preds, targets.t()):
+                loss = loss + crit(pred / T, tgt)
+            return loss / len(preds)
+
+        if not l2:
+            sa_out, preds = model(xa, xb)
+            loss = deepcluster_loss(preds)
+            loss.backward()
+            d_sa, dw = grabbed["sa"].grad, torch.cat([p.weight.grad for p in model.prototypes], dim=0)
+        else:
+            # With l2_norm the reference normalises `sa_feats[i]` IN PLACE (tools/mlc_train.py:81-83), which autograd
+            # rejects in backward ("modified by an inplace operation"), so that path only ever runs under no_grad
+            # (init_memory, :96-108).  Forward values from the real Model; gradients from the same arithmetic written
+            # out of place on the captured self-attention output.
+            with torch.no_grad():
+                sa_out, preds = model(xa, xb)
+            loss = deepcluster_loss(preds)
+            sa_in = grabbed["sa_value"].clone().requires_grad_(True)
+            zn = nn.functional.normalize(sa_in, dim=-1, p=2)
+            preds2 = [model.prototypes[i](zn[i % len(zn)]) for i in range(len(model.prototypes))]
+            assert all(torch.equal(a, b_) for a, b_ in zip(preds, preds2))
+            loss2 = deepcluster_loss(preds2)
+            loss2.backward()
+            d_sa, dw = sa_in.grad, torch.cat([p.weight.grad for p in model.prototypes], dim=0)
+        h.remove()
+        f32 = lambda t: _np(t).astype(np.float32)           # noqa: E731  (fixture size; compared at 1e-5)
+        out.update({f"{tag}_sa_in": f32(grabbed["sa_value"]), f"{tag}_sa_out": f32(sa_out),
+                    f"{tag}_logits": _np(torch.cat(preds, dim=1)), f"{tag}_loss": _np(loss),
+                    f"{tag}_targets": targets.numpy().astype(np.int64), f"{tag}_T": np.float64(T),
+                    f"{tag}_l2": np.int64(int(l2)), f"{tag}_d_sa_in": f32(d_sa),
+                    f"{tag}_w": _np(torch.cat([p.weight for p in model.prototypes], dim=0)), f"{tag}_dw": _np(dw)})
+    out["cases"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(OUT, "mlchead.npz"), **out)
+    print("mlchead.npz", float(loss))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -319,6 +398,7 @@ def main():
     gen_model()
     gen_kmeans()
     gen_projtail()
+    gen_mlchead()
 
 
 if __name__ == "__main__":
@@ -328,5 +408,8 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "projtail":
         os.makedirs(OUT, exist_ok=True)
         gen_projtail()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mlchead":
+        os.makedirs(OUT, exist_ok=True)
+        gen_mlchead()
     else:
         main()

@@ -292,6 +292,38 @@ def stats_backward(z, n_pairs, temperature, g_pos, g_lse, rows=None, chunk: int 
 # --------------------------------------------------------------------------------------
 # H1: multi-head softmax cross-entropy
 # --------------------------------------------------------------------------------------
+def proto_heads(sa_feats: np.ndarray, w_cat: np.ndarray, class_counts, l2_norm: bool, eps: float = 1e-12):
+    """Tail of the multi-label Model.forward (reference tools/mlc_train.py:81-87): optional row normalisation of every
+    feature slot, then ``preds[h] = sa[h % Hf] @ W_h^T`` for the bias-free prototype Linears; logits concatenated [B, C]."""
+    sa = np.asarray(sa_feats, np.float64)
+    hf = sa.shape[0]
+    if l2_norm:
+        sa = sa / np.maximum(np.linalg.norm(sa, axis=-1, keepdims=True), eps)
+    outs, off = [], 0
+    for h, n in enumerate(class_counts):
+        outs.append(sa[h % hf] @ np.asarray(w_cat[off:off + n], np.float64).T)
+        off += n
+    return sa, np.concatenate(outs, axis=1)
+
+
+def proto_heads_bwd(sa_feats, w_cat, class_counts, l2_norm: bool, dlogits, eps: float = 1e-12):
+    """Gradients of ``proto_heads`` w.r.t. the (un-normalised) features and the concatenated prototype weights."""
+    x = np.asarray(sa_feats, np.float64)
+    hf = x.shape[0]
+    nrm = np.maximum(np.linalg.norm(x, axis=-1, keepdims=True), eps)
+    z = x / nrm if l2_norm else x
+    dz = np.zeros_like(x)
+    dw = np.zeros_like(np.asarray(w_cat, np.float64))
+    off = 0
+    for h, n in enumerate(class_counts):
+        g = np.asarray(dlogits[:, off:off + n], np.float64)
+        dz[h % hf] += g @ np.asarray(w_cat[off:off + n], np.float64)
+        dw[off:off + n] = g.T @ z[h % hf]
+        off += n
+    dx = (dz - z * (z * dz).sum(-1, keepdims=True)) / nrm if l2_norm else dz
+    return dx, dw
+
+
 def multihead_ce(logits: np.ndarray, labels: np.ndarray, weights=None, inv_temperature: float = 1.0,
                  ignore_index: int = -100, num_classes=NUM_CLASSES):
     """loss = sum_h w_h * CE(logits_h * inv_T, labels[:, h]) / H  with per-head mean reduction.

@@ -10,7 +10,9 @@ What it installs (each switchable by environment, read at install time):
     import four of its names at module level (tools/backbone_train.py:32-37)                (SM3_SHIMS=0 disables);
   * after ``src.utils.misc`` has been imported, ``init_distributed_mode`` (called first thing by every script's
     ``main``, e.g. tools/mlc_train.py:303) is wrapped: on return it replaces the running script's module-level
-    ``cluster_memory`` (tools/mlc_train.py:116-189) by ``skin_sm3_b200.cluster_memory``     (SM3_DROPIN_KMEANS=0 disables).
+    ``cluster_memory`` (tools/mlc_train.py:116-189) by ``skin_sm3_b200.cluster_memory``     (SM3_DROPIN_KMEANS=0 disables)
+    and gives the script's own ``Model`` class (tools/mlc_train.py:58-89) the fused normalise + prototype-heads tail
+    (``skin_sm3_b200.mlc_model_forward``)                                                   (SM3_DROPIN_HEADS=0 disables).
 The first time the shadow module is served a one-line notice goes to stderr (SM3_DROPIN_QUIET=1 silences it), so a
 run whose hook silently did not install (e.g. another sitecustomize earlier on the path) is easy to spot.
 """
@@ -61,10 +63,19 @@ def _wrap_init_distributed(mod) -> None:
         out = orig(args)
         main = sys.modules.get("__main__")
         cm = getattr(main, "cluster_memory", None)
-        if callable(cm) and getattr(cm, "__module__", "") in ("__main__", "__mp_main__"):
+        if (os.environ.get("SM3_DROPIN_KMEANS", "1") == "1" and callable(cm)
+                and getattr(cm, "__module__", "") in ("__main__", "__mp_main__")):
             from skin_sm3_b200.functional import cluster_memory
             main.cluster_memory = cluster_memory
             _note("drop-in active: cluster_memory of the running script replaced by skin_sm3_b200.cluster_memory")
+        # the multi-label script defines its `Model` itself (tools/mlc_train.py:58-89): give it the fused prototype tail
+        model_cls = getattr(main, "Model", None)
+        if (os.environ.get("SM3_DROPIN_HEADS", "1") == "1" and isinstance(model_cls, type)
+                and getattr(model_cls, "__module__", "") in ("__main__", "__mp_main__")
+                and {"mlc_sa", "prototypes", "projectors", "extractor"} <= set(model_cls.__init__.__code__.co_names)):
+            from skin_sm3_b200.functional import mlc_model_forward
+            model_cls.forward = mlc_model_forward
+            _note("drop-in active: Model.forward of the running script uses the fused prototype heads")
         return out
 
     init_distributed_mode._sm3_wrapped = True
@@ -124,7 +135,8 @@ def install_hook() -> None:
         patches["src.utils.data.datasets"] = _register_synthetic_dataset
         if SHIMS not in sys.path:
             sys.path.append(SHIMS)            # END of the path: an installed torchmetrics is found first
-    if os.environ.get("SM3_DROPIN", "1") == "1" and os.environ.get("SM3_DROPIN_KMEANS", "1") == "1":
+    if os.environ.get("SM3_DROPIN", "1") == "1" and (os.environ.get("SM3_DROPIN_KMEANS", "1") == "1" or
+                                                   os.environ.get("SM3_DROPIN_HEADS", "1") == "1"):
         patches["src.utils.misc"] = _wrap_init_distributed
     if patches and not any(isinstance(f, _PostImportFinder) for f in sys.meta_path):
         sys.meta_path.insert(0, _PostImportFinder(patches))

@@ -906,6 +906,100 @@ def knn_predict(query: torch.Tensor, bank: torch.Tensor, bank_labels: torch.Tens
 
 
 # ------------------------------------------------------------------------------------------------------
+# N3: prototype heads of the multi-label block (tail of Model.forward, reference tools/mlc_train.py:70-89)
+# ------------------------------------------------------------------------------------------------------
+class _ProtoHeads(torch.autograd.Function):
+    """(normalised feats, [B, C] logits) from sm3_proto_heads_fwd; backward = sm3_proto_heads_bwd + one GEMM for dW."""
+
+    @staticmethod
+    def forward(ctx, feats, w_cat, slots, l2_norm):
+        import ctypes as C
+        dev = require_cuda(feats, w_cat)
+        hf, b, d = feats.shape
+        c = w_cat.shape[0]
+        feats = _contig(feats)
+        w32 = _contig(w_cat.float())
+        logits = torch.empty((b, c), dtype=torch.float32, device=dev)
+        z = torch.empty_like(feats) if l2_norm else feats
+        inv = torch.empty(hf * b, dtype=torch.float32, device=dev) if l2_norm else None
+        slot_arr = (C.c_int * c)(*slots)
+        with torch.cuda.device(dev):
+            check(lib().sm3_proto_heads_fwd(ptr(feats), dtype_code(feats), hf, b, d, ptr(w32), c, slot_arr, int(l2_norm),
+                                            1e-12, ptr(z) if l2_norm else None, ptr(inv), ptr(logits), stream_ptr()),
+                  "sm3_proto_heads_fwd")
+        ctx.save_for_backward(z, w32, inv if inv is not None else torch.empty(0, device=dev))
+        ctx.slots, ctx.l2_norm, ctx.w_dtype = tuple(slots), bool(l2_norm), w_cat.dtype
+        ctx.set_materialize_grads(False)          # the returned features usually carry no gradient (memory bank only)
+        return z, logits
+
+    @staticmethod
+    def backward(ctx, dz_extra, dlogits):
+        import ctypes as C
+        z, w32, inv = ctx.saved_tensors
+        hf, b, d = z.shape
+        c = w32.shape[0]
+        dlogits = torch.zeros((b, c), dtype=torch.float32, device=z.device) if dlogits is None else _contig(dlogits.float())
+        d_feats = dw = None
+        slot_arr = (C.c_int * c)(*ctx.slots)
+        if ctx.needs_input_grad[0]:
+            d_feats = torch.empty_like(z)
+            extra = _contig(dz_extra.to(z.dtype)) if dz_extra is not None else None
+            with torch.cuda.device(z.device):
+                check(lib().sm3_proto_heads_bwd(ptr(z), dtype_code(z), hf, b, d, ptr(w32), c, slot_arr, int(ctx.l2_norm),
+                                                ptr(inv) if ctx.l2_norm else None, ptr(dlogits), ptr(extra), ptr(d_feats),
+                                                stream_ptr()), "sm3_proto_heads_bwd")
+        if ctx.needs_input_grad[1]:
+            # dW[c] = sum_b dlogit[b, c] * z[slot(c), b, :]: one GEMM per feature slot that is read (1 or Hf of them)
+            dw = torch.empty_like(w32)
+            slots = torch.tensor(ctx.slots, device=z.device)
+            for s_ in sorted(set(ctx.slots)):
+                cols = (slots == s_).nonzero(as_tuple=True)[0]
+                dw[cols] = dlogits[:, cols].t() @ z[s_].float()
+            dw = dw.to(ctx.w_dtype)
+        return d_feats, dw, None, None
+
+
+def proto_heads_supported(feats: torch.Tensor, n_classes_total: int) -> bool:
+    return feats.is_cuda and feats.dim() == 3 and feats.dtype in (torch.float32, torch.float16, torch.bfloat16) and \
+        bool(lib().sm3_proto_heads_supported(int(feats.shape[2]), int(n_classes_total), dtype_code(feats)))
+
+
+def proto_heads(sa_feats: torch.Tensor, prototype_weights: Sequence[torch.Tensor], l2_norm: bool = False):
+    """The tail of the multi-label ``Model.forward`` (reference tools/mlc_train.py:81-87) in one launch: optional
+    ``F.normalize(sa_feats[i], dim=-1)`` of every feature slot and ``preds[i] = prototypes[i](sa_feats[i % len(sa_feats)])``.
+    ``sa_feats`` [Hf, B, D]; ``prototype_weights`` = the H bias-free Linear weights ``[n_i, D]``.  Returns
+    ``(sa_feats_out [Hf, B, D], logits [B, sum n_i] fp32)``: ``logits.split(n_i, 1)`` are the reference's ``preds`` and the
+    tensor is what ``multihead_ce(logits, targets, class_counts=n_i, ...)`` consumes without a ``torch.cat``."""
+    hf = sa_feats.shape[0]
+    counts = [int(w.shape[0]) for w in prototype_weights]
+    slots = [h % hf for h, n in enumerate(counts) for _ in range(n)]
+    w_cat = torch.cat(list(prototype_weights), dim=0)
+    return _ProtoHeads.apply(sa_feats, w_cat, slots, bool(l2_norm))
+
+
+def mlc_model_forward(self, derm_imgs, clinic_imgs):
+    """Drop-in body for ``Model.forward`` of tools/mlc_train.py:70-89 (same attributes, same return structure
+    ``(sa_feats, preds)``): everything up to the self-attention layer is the reference's own sequence, the normalise +
+    eight prototype Linears run as the fused kernel.  Falls back to the stock tail for shapes the kernel does not take."""
+    feats = self.extractor.extract(derm_imgs, clinic_imgs)
+    feats = torch.cat(feats, dim=1)
+    proj_feats = self.projectors(feats)
+    if not isinstance(proj_feats, list):
+        proj_feats = [proj_feats]
+    proj_feats = torch.stack(proj_feats, dim=0)
+    sa_feats = self.mlc_sa(proj_feats)
+    weights = [p.weight for p in self.prototypes]
+    total = sum(int(w.shape[0]) for w in weights)
+    if not proto_heads_supported(sa_feats, total):
+        if self.l2_norm:
+            sa_feats = torch.nn.functional.normalize(sa_feats, dim=-1, p=2)
+        return sa_feats, [p(sa_feats[i % len(sa_feats)]) for i, p in enumerate(self.prototypes)]
+    sa_out, logits = proto_heads(sa_feats, weights, self.l2_norm)
+    preds = list(torch.split(logits.to(sa_feats.dtype), [int(w.shape[0]) for w in weights], dim=1))
+    return sa_out, preds
+
+
+# ------------------------------------------------------------------------------------------------------
 # DeepCluster memory-bank clustering (N4)
 # ------------------------------------------------------------------------------------------------------
 class _kmeans_core:

@@ -863,6 +863,52 @@ def test_in_batch_retrieval_top1_is_the_positive(sm3):
 
 
 # ---------------------------------------------------------------------------------------------------
+# N3: fused prototype heads against the reference's multi-label Model (golden from tools/mlc_train.py:58-89, 255-261)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_proto_heads_match_reference_model(sm3, dtype):
+    g = load("mlchead")
+    counts = [5, 3, 2, 3, 3, 3, 3, 2]
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    for tag in g["cases"]:
+        l2, T = bool(g[f"{tag}_l2"]), float(g[f"{tag}_T"])
+        if dtype != torch.float32 and g[f"{tag}_sa_in"].shape[2] % 256:
+            continue                                              # 16-bit rows need D % 256 == 0
+        sa = cuda(g[f"{tag}_sa_in"], dtype).requires_grad_(True)
+        w = cuda(g[f"{tag}_w"])
+        ws = [t.clone().requires_grad_(True) for t in torch.split(w, counts, dim=0)]
+        assert sm3.proto_heads_supported(sa, 24)
+        sa_out, logits = sm3.proto_heads(sa, ws, l2)
+        assert logits.shape == (sa.shape[1], 24) and logits.dtype == torch.float32 and sa_out.shape == sa.shape
+        ref_sa = g[f"{tag}_sa_out"] if dtype == torch.float32 else O.proto_heads(sa.detach().float().cpu().numpy(), g[f"{tag}_w"], counts, l2)[0]
+        ref_logits = g[f"{tag}_logits"] if dtype == torch.float32 else O.proto_heads(sa.detach().float().cpu().numpy(), g[f"{tag}_w"], counts, l2)[1]
+        assert relerr(sa_out.detach().float().cpu().numpy(), ref_sa) < tol, tag
+        assert relerr(logits.detach().cpu().numpy(), ref_logits) < tol, tag
+        # DeepCluster loss through the fused 8-head CE (the [B, 24] layout needs no torch.cat) and backward through both
+        loss = sm3.multihead_ce(logits, cuda(g[f"{tag}_targets"], torch.long), temperature=T, ignore_index=-100,
+                                class_counts=counts)
+        loss.backward()
+        if dtype == torch.float32:
+            assert abs(loss.item() - float(g[f"{tag}_loss"])) < 2e-5, tag
+            assert relerr(sa.grad.cpu().numpy(), g[f"{tag}_d_sa_in"]) < 1e-4, tag
+            assert relerr(torch.cat([t.grad for t in ws]).cpu().numpy(), g[f"{tag}_dw"]) < 1e-4, tag
+        else:
+            _, dl = O.multihead_ce(ref_logits, g[f"{tag}_targets"], None, 1.0 / T, ignore_index=-100)
+            dx, dw = O.proto_heads_bwd(sa.detach().float().cpu().numpy(), g[f"{tag}_w"], counts, l2, dl)
+            assert relerr(sa.grad.float().cpu().numpy(), dx) < 3e-2, tag
+            assert relerr(torch.cat([t.grad for t in ws]).cpu().numpy(), dw) < 3e-2, tag
+        # a gradient arriving at the returned features (not the reference's use, but legal) is added in
+        sa2 = cuda(g[f"{tag}_sa_in"], dtype).requires_grad_(True)
+        so2, lg2 = sm3.proto_heads(sa2, [t.detach() for t in ws], l2)
+        (so2.float().sum() + lg2.sum()).backward()
+        xs = cuda(g[f"{tag}_sa_in"], dtype).float().requires_grad_(True)
+        zz = torch.nn.functional.normalize(xs, dim=-1) if l2 else xs
+        ref = zz.sum() + sum((zz[h % zz.shape[0]] @ t.detach().t()).sum() for h, t in enumerate(ws))
+        ref.backward()
+        assert relerr(sa2.grad.float().cpu().numpy(), xs.grad.cpu().numpy()) < (1e-4 if dtype == torch.float32 else 3e-2), tag
+
+
+# ---------------------------------------------------------------------------------------------------
 # N4: DeepCluster memory-bank k-means against the reference's cluster_memory (golden)
 # ---------------------------------------------------------------------------------------------------
 def test_cluster_memory_matches_reference(sm3):

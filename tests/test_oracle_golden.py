@@ -259,3 +259,20 @@ def test_projector_tail_oracle_pinned_to_reference():
         dy = t["rstd"] * (dp - dp.mean(axis=0) - t["yhat"] * (dp * t["yhat"]).mean(axis=0))
         np.testing.assert_allclose(dy @ w, g[df], rtol=0, atol=1e-12)
         np.testing.assert_allclose(dy.T @ f, g[dw], rtol=0, atol=1e-12)
+
+
+def test_proto_heads_oracle_pinned_to_reference_model():
+    """oracle.proto_heads / proto_heads_bwd against the REAL multi-label Model (tools/mlc_train.py:58-89) + the DeepCluster
+    loss loop (:255-261): returned features, predictions, loss through the 8-head CE oracle, and both gradients."""
+    g = np.load(os.path.join(GOLDEN, "mlchead.npz"), allow_pickle=False)
+    counts = [5, 3, 2, 3, 3, 3, 3, 2]
+    for tag in g["cases"]:
+        sa_in, w, l2 = g[f"{tag}_sa_in"], g[f"{tag}_w"], bool(g[f"{tag}_l2"])
+        sa_out, logits = O.proto_heads(sa_in, w, counts, l2)
+        assert np.abs(sa_out - g[f"{tag}_sa_out"]).max() < 2e-6, tag          # fixture stores the features in fp32
+        assert np.abs(logits - g[f"{tag}_logits"]).max() < 2e-6, tag
+        loss, dlogits = O.multihead_ce(logits, g[f"{tag}_targets"], None, 1.0 / float(g[f"{tag}_T"]), ignore_index=-100)
+        assert abs(loss - float(g[f"{tag}_loss"])) < 1e-6, tag
+        dx, dw = O.proto_heads_bwd(sa_in, w, counts, l2, dlogits)
+        assert np.abs(dx - g[f"{tag}_d_sa_in"]).max() < 1e-6 * max(1.0, np.abs(g[f"{tag}_d_sa_in"]).max() * 1e3), tag
+        assert np.abs(dw - g[f"{tag}_dw"]).max() < 1e-6, tag

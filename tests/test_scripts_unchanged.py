@@ -77,11 +77,13 @@ def test_backbone_train_and_mlc_train_run_unchanged(tmp_path):
     # ---- the same under --amp (fp16 autocast + GradScaler): bf16 tensor-core kernels ----
     amp, out_a, _ = run_script("backbone_train.py", pre + ["--amp"], tmp_path / "bt_amp", True, base + 2)
     assert len(amp) == 2 and abs(amp[0] - stock[0]) <= 2e-2 * abs(stock[0]), (amp, stock)
-    # ---- tools/mlc_train.py on that checkpoint: cluster_memory swapped by the hook, stock everything else ----
-    mlc = ["--extractor-weights", str(ckpt), "--extractor-proj-dim", "128", "--mlc-proj", "v4", "--mlc-proj-dim", "64",
+    # ---- tools/mlc_train.py on that checkpoint: cluster_memory and the prototype-heads tail of its Model swapped by
+    #      the hook (fused k-means and fused heads at D = 128), stock everything else ----
+    mlc = ["--extractor-weights", str(ckpt), "--extractor-proj-dim", "128", "--mlc-proj", "v4", "--mlc-proj-dim", "128",
            "--sa-dim-ff", "64", "--sa-dropout", "0.0", "--temperature", "0.1", "-lr", "1e-3", "--save-freq", "1"]
     m_ours, out_m, _ = run_script("mlc_train.py", mlc, tmp_path / "mlc_ours", True, base + 3)
     assert "cluster_memory of the running script replaced" in out_m
+    assert "Model.forward of the running script uses the fused prototype heads" in out_m      # N3 tail, D = 128: kernel path
     m_stock, out_ms, _ = run_script("mlc_train.py", mlc, tmp_path / "mlc_stock", False, base + 4)
     assert "cluster_memory of the running script replaced" not in out_ms
     assert len(m_ours) == 2 and len(m_stock) == 2
