@@ -351,6 +351,12 @@ int sm3_infonce_step_multi(int num_terms, const void* const* p1_host_array, cons
  *      then rank-1's, rank-2's, ...: the order the rows arrive) with one flag wait per source rank -- the whole scatter
  *      hides behind compute.  Uses flag words [66, 85) as tickets; falls back to 2 for problems too small for the
  *      256-row forward kernel.
+ *   4: as 2, with the SYMMETRIC forward across ranks (6 launches): S is symmetric, so of the blocks (rows of r, columns
+ *      of q) and (rows of q, columns of r) only one is computed.  Rank r takes its own block (upper-triangular tiles), the
+ *      full blocks against ranks r+1 ... r+(world-1)/2 and, for even world, half of the block against rank r+world/2 --
+ *      world/2 of the world column blocks, the same on every rank --, keeps the row sums and ships the COLUMN sums of the
+ *      foreign blocks to their owners (plane 2 of the statistics buffer, [source rank][2*n_local], flag channel 2, ticket
+ *      word 88); the loss kernel adds what it received in a fixed order.  Falls back to 2 when n_local % 128 != 0.
  * D in {64,128,192,256}.
  * loss = weight * mean over this rank's rows (DDP convention).                                                     */
 size_t sm3_infonce_step_peer_scratch_bytes(int n_local, int n_global, int D);
@@ -383,6 +389,18 @@ void sm3_debug_reload_env(void);
  *   C[128, n] (fp32) = A[128, k] * B   with the operand sources / layouts selected by `variant`.   */
 int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,
                          void* stream);
+
+/* debug / single-GPU test of mode 4 (symmetric forward across ranks): the caller plays every rank on one device.
+ * _forward = rank `rank`'s K2 (flags_mine must hold `epoch` in channel 0 for all sources) + its column-sum push into the
+ * per-rank statistics / flag buffers; _fold = that rank's loss kernel without publishing (neg_sum, gradients of the
+ * statistics, loss = mean over its rows), to be enqueued after every rank's _forward. */
+size_t sm3_debug_mr_workspace(int n_local, int world, int rank);
+int sm3_debug_mr_forward(const void* z_local, const void* z_all, int n_local, int world, int rank, int D, float inv_T,
+                         void* flags_mine, void* const* stats_peers_host, void* const* flags_peers_host, unsigned epoch,
+                         float* pos, void* workspace, size_t workspace_bytes, void* stream);
+int sm3_debug_mr_fold(const void* workspace, int n_local, int world, int rank, float inv_T, const float* pos,
+                      const void* stats_mine, void* flags_mine, unsigned epoch, float* loss, float* neg_sum, float* g_pos,
+                      float* g_lse, float* block_ws, void* stream);
 
 /* debug / single-GPU test of mode 3's forward (owner-ordered column tiles, one flag wait per source rank) with the caller
  * standing in for the peers: z_cols complete, flags[0 .. world) of channel 0 already at `epoch`; nothing is pushed. */

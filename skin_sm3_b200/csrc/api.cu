@@ -466,8 +466,8 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
   SM3_REQUIRE((dp1 == nullptr) == (dp2 == nullptr), SM3_ERR_SHAPE, "infonce_step_peer: dp1/dp2 must both be given or both NULL");
   SM3_REQUIRE(world >= 2 && rank >= 0 && rank < world && n_local >= 1, SM3_ERR_SHAPE,
               "infonce_step_peer: needs world >= 2 (got world=%d n_local=%d)", world, n_local);
-  SM3_REQUIRE(overlap >= 0 && overlap <= 3, SM3_ERR_SHAPE, "infonce_step_peer: mode %d not in {0,1,2,3}", overlap);
-  SM3_REQUIRE(!overlap || n_local % 128 == 0, SM3_ERR_SHAPE, "infonce_step_peer: modes 1, 2 and 3 need n_local %% 128 == 0");
+  SM3_REQUIRE(overlap >= 0 && overlap <= 4, SM3_ERR_SHAPE, "infonce_step_peer: mode %d not in {0,1,2,3,4}", overlap);
+  SM3_REQUIRE(!overlap || n_local % 128 == 0, SM3_ERR_SHAPE, "infonce_step_peer: modes 1 to 4 need n_local %% 128 == 0");
   SM3_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256 && dtype_ok(io_dtype) && temperature > 0.f, SM3_ERR_DTYPE,
               "infonce_step_peer: D must be in {64,128,192,256}");
   SM3_REQUIRE(overlap != 1 || stream_side != stream_main, SM3_ERR_SHAPE,
@@ -519,6 +519,53 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
     PeerFused ps{sp, fp, counters + 1, rank, 1, epoch};
     rc = loss_stats_scatter_launch((const float*)(base + h.ws_b), splits, pos, n_local, off, n_global, inv_T,
                                    weight / (float)m, loss, gpos, glse, nsum, lse_l /* per-CTA loss sums */, ps, sm);
+    stage_mark(sm);
+    if (rc || !dp1) return rc;
+    InfoNceProblem pk{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
+    pk.wait_flags = (const unsigned*)flags_mine; pk.wait_world = world; pk.wait_channel = 1; pk.wait_epoch = epoch;
+    pk.acol_direct = (const float*)stats_mine;                 // planes written by the owners: a_j | g_pos_j
+    const float* gpos_cols = (const float*)stats_mine + (size_t)2 * n_global;
+    const int np = infonce_tc_bwd(pk, gpos, glse, nsum, gpos_cols, gpos_cols, gpos_cols, base + h.ws_b, h.ws_b_bytes, sm);
+    if (np < 0) return np;
+    stage_mark(sm);
+    rc = sm3_l2norm_bwd((const float*)(base + h.ws_b), np, 1.0f, z, SM3_BF16, (float*)(base + h.inv), 1e-12f, dp1, n,
+                        dp2, n, D, io_dtype, sm);
+    stage_mark(sm);
+    return rc;
+  }
+  if (overlap == 4) {
+    // ---- fused exchange + SYMMETRIC forward across ranks (6 launches): every rank computes W / 2 of the W column blocks
+    //      of its row block (own block upper-triangular, the next (W-1)/2 ranks' blocks, half of the antipodal one) and
+    //      sends the column sums of the foreign blocks to their owners (see MrPlan, common.cuh).  Falls back to mode 2
+    //      when the plan does not apply (n_local %% 128, workspace). ----
+    const MrPlan mp = infonce_tc_mr_plan(n_local, world, rank);
+    if (!mp.on || infonce_tc_mr_workspace(mp) > h.ws_b_bytes) overlap = 2;
+  }
+  if (overlap == 4) {
+    SM3_REQUIRE(aligned16(p1) && aligned16(p2), SM3_ERR_SHAPE, "infonce_step_peer: fused mode needs 16-byte aligned rows");
+    const MrPlan mp = infonce_tc_mr_plan(n_local, world, rank);
+    unsigned* counters = (unsigned*)flags_mine + 64;          // [0,2) tickets of modes 2 / 4 | [24] column-sum push
+    PeerFused pz{zp, fp, counters, rank, 0, epoch};
+    PdlScope pdl(!g_stage_timing);
+    stage_begin(sm, "normalize_scatter,infonce_fwd_sym,colsum_push,loss_scatter,infonce_bwd,normalize_bwd");
+    rc = l2norm_scatter_launch(p1, p2, n_local, off, n_global, D, io_dtype, z, (float*)(base + h.inv), 1e-12f, pz, sm);
+    if (rc) return rc;
+    stage_mark(sm);
+    InfoNceProblem pf{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
+    pf.wait_flags = (const unsigned*)flags_mine; pf.wait_world = world; pf.wait_channel = 0; pf.wait_epoch = epoch;
+    SM3_REQUIRE(infonce_tc_supported(pf), SM3_ERR_DTYPE, "infonce_step_peer: tcgen05 path unavailable");
+    rc = infonce_tc_fwd_mr(pf, mp, pos, base + h.ws_b, h.ws_b_bytes, sm);
+    if (rc) return rc;
+    stage_mark(sm);
+    const float* slabs = (const float*)(base + h.ws_b) + (size_t)(mp.maxseg + mp.P_l) * (size_t)m;
+    rc = colsum_push_launch(slabs, mp, n_local, sp, fp, counters + 24, epoch, sm);
+    if (rc) return rc;
+    stage_mark(sm);
+    PeerFused ps{sp, fp, counters + 1, rank, 1, epoch};
+    MrFold mf{mp, (const float*)stats_mine + (size_t)4 * n_global, (const unsigned*)flags_mine, epoch, peer_timeout_ns()};
+    rc = loss_stats_scatter_launch((const float*)(base + h.ws_b), 0, pos, n_local, off, n_global, inv_T,
+                                   weight / (float)m, loss, gpos, glse, nsum, lse_l /* per-CTA loss sums */, ps, sm, 0,
+                                   nullptr, &mf);
     stage_mark(sm);
     if (rc || !dp1) return rc;
     InfoNceProblem pk{z, z_cols_mine, n_local, off, n_global, D, SM3_BF16, inv_T};
@@ -648,6 +695,49 @@ extern "C" size_t sm3_debug_infonce_fwd_ordered_workspace(int n_local, int world
   InfoNceProblem pb{nullptr, nullptr, n_local, 0, n_local * world, D, SM3_BF16, 1.0f};
   pb.push_mode = 1;
   return infonce_tc_workspace(pb, 0);
+}
+
+// debug / single-GPU test of mode 4 (symmetric forward across ranks) without peers: the caller plays all ranks on one
+// device, one after the other.  _forward runs rank `rank`'s K2 (its flags must already hold `epoch` in channel 0 for every
+// source) and the column-sum push into the given per-rank statistics / flag buffers; _fold runs rank `rank`'s loss kernel
+// (nothing published) once every rank's _forward has been enqueued, and leaves neg_sum / lse_neg / loss.
+extern "C" size_t sm3_debug_mr_workspace(int n_local, int world, int rank) {
+  const MrPlan mp = infonce_tc_mr_plan(n_local, world, rank);
+  return mp.on ? infonce_tc_mr_workspace(mp) : 0;
+}
+extern "C" int sm3_debug_mr_forward(const void* z_local, const void* z_all, int n_local, int world, int rank, int D,
+                                    float inv_T, void* flags_mine, void* const* stats_peers_host,
+                                    void* const* flags_peers_host, unsigned epoch, float* pos, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(z_local && z_all && flags_mine && pos && workspace, SM3_ERR_SHAPE, "debug_mr_forward: null pointer");
+  const MrPlan mp = infonce_tc_mr_plan(n_local, world, rank);
+  SM3_REQUIRE(mp.on, SM3_ERR_SHAPE, "debug_mr_forward: no plan for n_local=%d world=%d", n_local, world);
+  PeerPtrs sp, fp;
+  int rc = fill_peer_ptrs(sp, stats_peers_host, world);
+  if (rc) return rc;
+  if ((rc = fill_peer_ptrs(fp, flags_peers_host, world))) return rc;
+  InfoNceProblem pf{z_local, z_all, n_local, rank * n_local, n_local * world, D, SM3_BF16, inv_T};
+  pf.wait_flags = (const unsigned*)flags_mine; pf.wait_world = world; pf.wait_channel = 0; pf.wait_epoch = epoch;
+  SM3_REQUIRE(infonce_tc_supported(pf), SM3_ERR_DTYPE, "debug_mr_forward: tcgen05 path unavailable");
+  rc = infonce_tc_fwd_mr(pf, mp, pos, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  const float* slabs = (const float*)workspace + (size_t)(mp.maxseg + mp.P_l) * (size_t)(2 * n_local);
+  return colsum_push_launch(slabs, mp, n_local, sp, fp, (unsigned*)flags_mine + 64 + 24, epoch, st);
+}
+extern "C" int sm3_debug_mr_fold(const void* workspace, int n_local, int world, int rank, float inv_T, const float* pos,
+                                 const void* stats_mine, void* flags_mine, unsigned epoch, float* loss, float* neg_sum,
+                                 float* g_pos, float* g_lse, float* block_ws, void* stream) {
+  SM3_REQUIRE(workspace && pos && stats_mine && flags_mine && loss && neg_sum && g_pos && g_lse && block_ws, SM3_ERR_SHAPE,
+              "debug_mr_fold: null pointer");
+  const MrPlan mp = infonce_tc_mr_plan(n_local, world, rank);
+  SM3_REQUIRE(mp.on, SM3_ERR_SHAPE, "debug_mr_fold: no plan");
+  PeerFused none{};
+  none.counter = (unsigned*)flags_mine + 64 + 1;
+  MrFold mf{mp, (const float*)stats_mine + (size_t)4 * n_local * world, (const unsigned*)flags_mine, epoch, peer_timeout_ns()};
+  return loss_stats_scatter_launch((const float*)workspace, 0, pos, n_local, rank * n_local, n_local * world, inv_T,
+                                   1.0f / (2.0f * n_local), loss, g_pos, g_lse, neg_sum, block_ws, none, (cudaStream_t)stream,
+                                   0, nullptr, &mf);
 }
 
 extern "C" size_t sm3_infonce_host_scratch_bytes(int n_pairs, int D, int io_dtype, int algo) {

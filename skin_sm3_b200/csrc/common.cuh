@@ -209,6 +209,61 @@ __device__ __forceinline__ float fold_row_partials(const float* __restrict__ par
   return s + ((c0 + c1) + (c2 + c3));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Symmetric forward ACROSS ranks (sm3_infonce_step_peer mode 4; infonce_tc_fwdsym_mr_kernel).  S is symmetric, so of the
+// two blocks (rows of rank r, columns of rank q) and (rows of q, columns of r) only one has to be computed: its row sums
+// belong to the row owner and its COLUMN sums to the column owner.  Circulant assignment: rank r computes
+//   * its own block (a single-rank problem of n_local pairs in local coordinates: upper-triangular tiles, as above),
+//   * the full blocks against the H = (W - 1) / 2 ranks r + 1 ... r + H (mod W),
+//   * for even W half of the block against the antipodal rank r + W / 2: ranks r < W / 2 take that rank's first
+//     Ja = 2 (P_l / 2) column tiles for all their row pairs (anti = 1), ranks r >= W / 2 take all of its column tiles for
+//     their row pairs R >= P_l / 2, i.e. their rows from Ja * 128 on (anti = 2),
+// i.e. W / 2 blocks instead of W, the same on every rank.  Per row pair R the tiles are visited own block first, then
+// partner by partner (the order their rows arrive); the flat list over R is cut into pieces of tpc tiles per CTA.
+// Workspace (floats, M_l = 2 n_local): [maxseg][M_l] row sums | [P_l][M_l] own-block column sums | [np][P_l][M_l] column
+// sums for the partners' rows.  A second small kernel folds the partner slabs and stores one [M_l] vector per partner
+// into the partner's statistics buffer (plane 2, slot = source rank); the loss kernel adds what it received.
+// ---------------------------------------------------------------------------------------------------------------
+struct MrPlan {
+  int on, W, rank, H, anti, np;      // np = H + (anti != 0)
+  int T_l, P_l, tpc, maxseg, nctas;
+  long flat;                         // tiles in this rank's flat list
+};
+__host__ __device__ inline int mr_count(const MrPlan& m, int R) {
+  int c = (m.T_l - 2 * R) + m.H * m.T_l;
+  if (m.anti == 1) c += 2 * (m.P_l / 2);
+  else if (m.anti == 2 && R >= m.P_l / 2) c += m.T_l;
+  return c;
+}
+__host__ __device__ inline long mr_prefix(const MrPlan& m, int R) {      // tiles of the row pairs before R
+  long f = (long)R * m.T_l - (long)R * (R - 1) + (long)m.H * m.T_l * R;
+  if (m.anti == 1) f += (long)R * (2 * (m.P_l / 2));
+  else if (m.anti == 2 && R > m.P_l / 2) f += (long)(R - m.P_l / 2) * m.T_l;
+  return f;
+}
+// which rank's rows partner slot ps (0 .. np - 1) reads, and the global 128-column tile of its local tile j_l
+__host__ __device__ inline int mr_partner_rank(const MrPlan& m, int ps) {
+  return ps < m.H ? (m.rank + 1 + ps) % m.W : (m.rank + m.W / 2) % m.W;
+}
+__host__ __device__ inline int mr_global_tile(const MrPlan& m, int owner, int j_l) {
+  const int half = m.T_l / 2;
+  return j_l < half ? owner * half + j_l : m.W * half + owner * half + (j_l - half);
+}
+__device__ __forceinline__ float fold_row_partials_mr(const float* __restrict__ partial, const MrPlan& m, int64_t i) {
+  const int64_t rows = (int64_t)m.T_l * 128;
+  const int R = (int)(i / 256);
+  const long f = mr_prefix(m, R);
+  const int nseg = (int)((f + mr_count(m, R) - 1) / m.tpc - f / m.tpc) + 1;
+  float s = 0.f;
+  for (int k = 0; k < nseg; ++k) s += partial[(int64_t)k * rows + i];
+  const float* col = partial + (int64_t)m.maxseg * rows + i;
+  float c0 = 0.f, c1 = 0.f;
+  int r = 0;
+  for (; r + 2 <= R; r += 2) { c0 += col[(int64_t)r * rows]; c1 += col[(int64_t)(r + 1) * rows]; }
+  if (r < R) c0 += col[(int64_t)r * rows];
+  return s + (c0 + c1);
+}
+
 // Cross-rank flag wait used INSIDE kernels (fused exchange): one thread spins until every peer has published `epoch`
 // on `channel` of this rank's flag buffer (slot layout: flags[channel * 16 + source_rank], epochs only grow).  The
 // acquire at system scope orders this thread's later reads after the peers' stores.  A peer may legitimately be late
@@ -300,10 +355,26 @@ struct PeerFused {          // what the fused exchange kernels need to publish t
 };
 int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pair_offset, int n_global, int D, int p_dtype,
                           void* z_local, float* inv_norm, float eps, const PeerFused& pf, cudaStream_t st);
+// mr (optional): the forward was the cross-rank symmetric kernel -- fold its workspace, wait for the column sums the
+// contributing ranks stored into `colsum_in` (this rank's statistics buffer, plane 2: [source rank][M_l]) and add them
+struct MrFold {
+  MrPlan plan;
+  const float* colsum_in;
+  const unsigned* flags;       // this rank's flag buffer; contributors signal channel 2
+  unsigned epoch;
+  unsigned long long timeout_ns;
+};
 int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
                               int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
                               float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate = 0,
-                              float* a_local = nullptr);
+                              float* a_local = nullptr, const MrFold* mr = nullptr);
+// folds the partner column-sum slabs of the cross-rank symmetric forward and stores one vector per partner into the
+// partner's statistics buffer (plane 2, slot = this rank), then releases flag channel 2 on the partners
+int colsum_push_launch(const float* partner_slabs, const MrPlan& plan, int n_local, const PeerPtrs& stats,
+                       const PeerPtrs& flags, unsigned* ticket, unsigned epoch, cudaStream_t st);
+MrPlan infonce_tc_mr_plan(int n_local, int world, int rank);
+size_t infonce_tc_mr_workspace(const MrPlan& m);
+int infonce_tc_fwd_mr(const InfoNceProblem& pb, const MrPlan& m, float* pos, void* ws, size_t ws_bytes, cudaStream_t st);
 // byte offset of the a_j array (padded to a multiple of 64 columns + 64) inside the tcgen05 backward workspace
 size_t infonce_tc_acol_offset(const InfoNceProblem& pb);
 size_t infonce_simt_workspace(const InfoNceProblem& pb, int backward);

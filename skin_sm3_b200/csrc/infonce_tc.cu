@@ -75,6 +75,7 @@ struct TcParams {
   // symmetric forward (single rank): column tiles per side, tiles per CTA, row-sum slabs, flat work-list length
   int sym_T, sym_tpc, sym_maxseg;
   long sym_W;
+  MrPlan mr;            // cross-rank symmetric forward (infonce_tc_fwdsym_mr_kernel)
 };
 
 // Per-CTA starting rotation of the column-tile order.  Default: pseudo-random (decorrelates the CTAs of a wave, see the
@@ -1197,6 +1198,382 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// symmetric forward ACROSS ranks (see MrPlan in common.cuh): the kernel above with (a) the per-row-pair tile sequence
+// "own block (upper-triangular, local coordinates) | partner blocks | antipodal half block", (b) one flag wait per source
+// rank in the TMA warp before the first tile of that rank's rows, (c) the column sums of partner tiles going to
+// per-partner slabs (they are pushed to the owners by colsum_push_kernel).  Diagonal / positive masks only occur in the
+// own block, in local row / column indices.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mr_decode(const MrPlan& m, long f, int& R, int& off) {
+  int lo = 0, hi = m.P_l - 1;                       // largest R with mr_prefix(R) <= f
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (mr_prefix(m, mid) <= f) lo = mid; else hi = mid - 1;
+  }
+  R = lo;
+  off = (int)(f - mr_prefix(m, lo));
+}
+// t-th tile of row pair R: partner slot (-1 = own block) and the tile index in the owner's local tile order
+__device__ __forceinline__ void mr_tile(const MrPlan& m, int R, int t, int& ps, int& j_l) {
+  const int own = m.T_l - 2 * R;
+  if (t < own) { ps = -1; j_l = 2 * R + t; return; }
+  t -= own;
+  const int q = t / m.T_l;
+  if (q < m.H) { ps = q; j_l = t - q * m.T_l; return; }
+  ps = m.H;
+  j_l = t - m.H * m.T_l;                            // antipodal: [0, 2 (P_l / 2)) for anti == 1, [0, T_l) for anti == 2
+}
+
+template <int DP, int POLY, int NQ>
+__global__ void __launch_bounds__(64 + 128 * NQ, 1)
+infonce_tc_fwdsym_mr_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p) {
+  using C = FwdCfg<DP>;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
+  constexpr int D = 64 * DP;
+  constexpr int NW = 4 * NQ;             // softmax warps
+  constexpr int CW = 128 / NQ;           // S-tile columns per softmax warp
+  constexpr int KS = CW / 8;             // 8-column groups per warp: registers 4 k .. 4 k + 3 of a 16x256b load
+  const MrPlan& mr = p.mr;
+  const int T = mr.T_l, P = mr.P_l;                 // LOCAL column tiles / row pairs
+  const long f0 = (long)blockIdx.x * mr.tpc;
+  const long f1 = min(mr.flat, f0 + mr.tpc);
+  if (f0 >= f1) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sB = base;
+  const uint32_t bars = sB + NSTAGE * C::STAGE;
+  auto bar_full = [&](int i) { return bars + 8u * i; };
+  auto bar_empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
+  auto bar_sfull = [&](int i) { return bars + 8u * (2 * NSTAGE + i); };
+  auto bar_sempty = [&](int i) { return bars + 8u * (2 * NSTAGE + 2 + i); };
+  const uint32_t bar_aready = bars + 8u * (2 * NSTAGE + 4);
+  auto bar_col = [&](int i) { return bars + 8u * (2 * NSTAGE + 5 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (2 * NSTAGE + 8));
+  float* xsum = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);          // [NQ - 1][2 row blocks][128]
+  float* cbuf = xsum + 768;                                                         // [3 ring slots][NW warps][CW]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long bar_limit = 2000000000ull + p.wait_timeout_ns;
+  if (threadIdx.x == 0) SM3_TR(7, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_sfull(i), 1); mbar_init(bar_sempty(i), NW); }
+    mbar_init(bar_aready, NW);
+    for (int i = 0; i < 3; ++i) mbar_init(bar_col(i), NW);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_launch();
+  constexpr uint32_t kColA1 = 128, kColS = 256;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) prefetch_tensormap(&tmap_cols);
+    int it = 0;
+    unsigned seen = 0u;                                          // partner slots whose rows are known to have landed
+    for (long f = f0; f < f1;) {
+      int R, off;
+      mr_decode(mr, f, R, off);
+      const int cnt = (int)min((long)(mr_count(mr, R) - off), f1 - f);
+      for (int t = 0; t < cnt; ++t, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+        int ps, j_l;
+        mr_tile(mr, R, off + t, ps, j_l);
+        const int owner = ps < 0 ? mr.rank : mr_partner_rank(mr, ps);
+        if (ps >= 0 && !((seen >> ps) & 1u)) {                   // first tile of this partner's rows: they must have landed
+          if (elect_one()) {
+            peer_flag_wait_one(p.wait_flags, p.wait_channel, owner, p.wait_epoch, p.wait_timeout_ns);
+            fence_proxy_async_global();
+          }
+          __syncwarp();
+          seen |= 1u << ps;
+        }
+        mbar_wait(bar_empty(s), ph ^ 1u, bar_limit);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full(s), C::STAGE);
+          const int row = mr_global_tile(mr, owner, j_l) * BN;
+#pragma unroll
+          for (int pnl = 0; pnl < DP; ++pnl)
+            tma_load_2d(sB + s * C::STAGE + pnl * C::PANEL, &tmap_cols, bar_full(s), pnl * 64, row);
+        }
+        __syncwarp();
+      }
+      f += cnt;
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t dhi = smem_desc_hi(1024);
+    int it = 0, seg = 0;
+    for (long f = f0; f < f1; ++seg) {
+      int R, off;
+      mr_decode(mr, f, R, off);
+      const int cnt = (int)min((long)(mr_count(mr, R) - off), f1 - f);
+      mbar_wait(bar_aready, (uint32_t)seg & 1u, bar_limit);      // this row pair's A operands are in TMEM
+      tc_fence_after();
+      for (int t = 0; t < cnt; ++t, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t sph = (uint32_t)it & 1u;
+        mbar_wait(bar_full(s), (uint32_t)(it / NSTAGE) & 1u, bar_limit);
+        if (it == 0) SM3_TR(7, 1);
+        SM3_TR(0, it);
+        const uint32_t lo0 = smem_desc_lo(sB + s * C::STAGE, 16);
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          mbar_wait(bar_sempty(rb), sph ^ 1u, bar_limit);
+          tc_fence_after();
+          SM3_TR(8 + rb, it);
+          const uint32_t d_tmem = tmem + kColS + (uint32_t)rb * 128u;
+          const uint32_t a_tmem = tmem + (uint32_t)rb * kColA1;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4 * DP; ++ks)
+              umma_ts(d_tmem, a_tmem + ks * 8, desc64(lo0 + (((ks >> 2) * C::PANEL + (ks & 3) * 32) >> 4), dhi), idesc,
+                      ks > 0);
+            if (rb == 1) umma_commit(bar_empty(s));
+            umma_commit(bar_sfull(rb));
+          }
+          __syncwarp();
+          SM3_TR(1 + rb, it);
+        }
+      }
+      f += cnt;
+    }
+    SM3_TR(7, 2);
+  } else {
+    // =========================== softmax warps ===========================
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;                              // column group of this warp: columns [cg * CW, +CW)
+    const int t0 = lane & 3, t1 = lane >> 2;
+    const int row_in_tile = q * 32 + lane;                       // staging view: thread <-> TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t lane_hi = (uint32_t)(q * 32 + 16) << 16;
+    const float c2 = p.c2;
+    const uint64_t c2p = f2_pack(c2, c2), nc2p = f2_pack(-c2, -c2);
+    const bool clamp = 2.0f * c2 > 125.0f;
+    const int64_t M = p.m_rows;                                  // local rows
+    float* colpart = p.partial + (int64_t)mr.maxseg * M;         // own block: [P][M]; partner slot ps: [(1 + ps) P ...][M]
+    int it = 0;
+    // column sums are folded across the four lane quadrants one tile LATE (no CTA-wide rendezvous per tile): ring of 3
+    // buffers, one mbarrier each (NW warp arrivals); pend_* describe the tile whose fold is outstanding
+    int ncol = 0, pend_R = -1, pend_J = 0;                        // pend_R: slab row (own: R, partner ps: (1 + ps) P + R)
+    auto fold_pending = [&]() {
+      if (pend_R < 0) return;
+      const int ci = (ncol - 1) % 3;
+      mbar_wait(bar_col(ci), (uint32_t)((ncol - 1) / 3) & 1u, bar_limit);
+      if (lane < 128 / NW) {                                     // NW warps x 128 / NW columns, quadrants in a fixed order
+        const int c = (warp - 2) * (128 / NW) + lane;
+        const float* src = cbuf + ci * 512 + (c / CW) * (4 * CW) + (c % CW);
+        colpart[(int64_t)pend_R * M + (int64_t)pend_J * BN + c] = (src[0] + src[CW]) + (src[2 * CW] + src[3 * CW]);
+      }
+      pend_R = -1;
+    };
+    for (long f = f0; f < f1;) {
+      int R, off;
+      mr_decode(mr, f, R, off);
+      const int cnt = (int)min((long)(mr_count(mr, R) - off), f1 - f);
+      const int r0 = R * 256;
+      // ---- stage this row pair into TMEM as A operands (all S-MMAs of the previous segment have completed: every
+      //      softmax warp has waited for the last S tile) ----
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+        for (int ch = 0; ch < DP; ++ch) {
+          if ((ch % NQ) == cg) {
+            uint32_t r[32];
+            const uint4* src = reinterpret_cast<const uint4*>(p.z_rows + (size_t)(r0 + rb * 128 + row_in_tile) * D + ch * 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 v = __ldg(src + i);
+              r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+            }
+            tmem_st_x32(tmem + lane_addr + rb * kColA1 + ch * 32, r);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_aready);
+
+      // packed (column b = 0 | b = 1) running row sums of the thread's 4 rows per row block
+      uint64_t sum2[2][4];
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) sum2[rb][sl] = 0ull;
+      for (int t = 0; t < cnt; ++t, ++it) {
+        int ps, J;                                             // J: tile index in the column owner's LOCAL order
+        mr_tile(mr, R, off + t, ps, J);
+        const uint32_t sph = (uint32_t)it & 1u;
+        const bool do_col = ps >= 0 || J > 2 * R + 1;
+        uint64_t col2[KS];                                       // packed column sums: columns 8 k + 2 t0 + {0, 1}
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          mbar_wait(bar_sfull(rb), sph, bar_limit);
+          tc_fence_after();
+          if (warp == 2 && lane == 0) SM3_TR(3 + 2 * rb, it);
+          const uint32_t taddr = tmem + kColS + (uint32_t)rb * 128u + (uint32_t)(cg * CW);
+          uint32_t va[4 * KS], vb[4 * KS];
+          tmem_ld_16x256b(taddr + lane_addr, va);                // rows t1, t1 + 8 of the quadrant
+          tmem_ld_wait(va);
+          tmem_ld_16x256b(taddr + lane_hi, vb);                  // rows t1 + 16, t1 + 24: in flight during the first half
+          int Jp = 2 * R + rb + P;                               // the tile that holds these rows' positives
+          if (Jp >= T) Jp -= T;
+          const bool special = ps < 0 && ((J == 2 * R + rb) || (J == Jp));
+#pragma unroll
+          for (int hv = 0; hv < 2; ++hv) {
+            if (hv == 1) {
+              tmem_ld_wait(vb);
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_sempty(rb));        // S stage free (the MMA warp runs a tile ahead anyway)
+              if (warp == 2 && lane == 0) SM3_TR(4 + 2 * rb, it);
+            }
+            const uint32_t* v = hv == 0 ? va : vb;
+            if (!special) {
+              uint64_t e[2 * KS];
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                e[2 * k] = f2_fma(f2_pack_u(v[4 * k], v[4 * k + 1]), c2p, nc2p);
+                e[2 * k + 1] = f2_fma(f2_pack_u(v[4 * k + 2], v[4 * k + 3]), c2p, nc2p);
+              }
+              // POLY of every 8 exponentials on the FMA pipes: whole pairs (4: every other pair; 2: every fourth pair)
+#pragma unroll
+              for (int i = 0; i < 2 * KS; ++i)
+                e[i] = ((POLY >= 4 && (i & 1) == 0) || (POLY >= 2 && POLY < 4 && (i & 3) == 0)) ? f2_ex2_fma(e[i], clamp) : f2_ex2(e[i]);
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                sum2[rb][2 * hv] = f2_add(sum2[rb][2 * hv], e[2 * k]);
+                sum2[rb][2 * hv + 1] = f2_add(sum2[rb][2 * hv + 1], e[2 * k + 1]);
+                const uint64_t cs = f2_add(e[2 * k], e[2 * k + 1]);
+                col2[k] = (rb == 0 && hv == 0) ? cs : f2_add(col2[k], cs);
+              }
+            } else {
+              // the tile holds the diagonal or the positives of these rows: mask per element
+              const int rbase = r0 + rb * 128 + q * 32 + t1 + 16 * hv;
+              const int cbase = J * BN + cg * CW + 2 * t0;
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                uint64_t cs = 0ull;
+#pragma unroll
+                for (int a8 = 0; a8 < 2; ++a8) {
+                  const int row = rbase + 8 * a8;
+                  const int pj = positive_of(row, p.n_local);    // local coordinates: the own block is an n_local problem
+                  float ev[2];
+#pragma unroll
+                  for (int bb = 0; bb < 2; ++bb) {
+                    const int col = cbase + 8 * k + bb;
+                    const float sv = __uint_as_float(v[4 * k + 2 * a8 + bb]);
+                    const bool is_pos = (col == pj);
+                    if (is_pos && pj > row) {                    // S is symmetric: one read serves both rows of the pair
+                      const float pv = sv * p.inv_T;
+                      p.pos[row] = pv;
+                      p.pos[pj] = pv;
+                    }
+                    ev[bb] = (is_pos || col == row) ? 0.f : ex2(fmaf(sv, c2, -c2));
+                  }
+                  const uint64_t e = f2_pack(ev[0], ev[1]);
+                  sum2[rb][2 * hv + a8] = f2_add(sum2[rb][2 * hv + a8], e);
+                  cs = f2_add(cs, e);
+                }
+                col2[k] = (rb == 0 && hv == 0) ? cs : f2_add(col2[k], cs);
+              }
+            }
+          }
+        }
+        if (warp == 2 && lane == 0) SM3_TR(10, it);
+        fold_pending();                                          // the previous column-sum tile: every warp arrived long ago
+        if (do_col) {
+          // column sums over this warp's 32 rows x 2 row blocks: butterfly over the lanes t1 = lane / 4 that share a
+          // column (lane bit 4 <-> k bit 2 or 1, ...); each step halves the values a lane carries
+          float ca[2 * KS];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) f2_unpack(col2[k], ca[2 * k], ca[2 * k + 1]);
+          const bool h4 = (lane & 16) != 0, h2 = (lane & 8) != 0, h1 = (lane & 4) != 0;
+          float* cb = cbuf + (ncol % 3) * 512 + (cg * 4 + q) * CW;
+          if constexpr (KS == 8) {
+            float c8[8], c4[4], cf[2];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c8[j] = (h4 ? ca[j + 8] : ca[j]) + __shfl_xor_sync(0xffffffffu, h4 ? ca[j] : ca[j + 8], 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c4[j] = (h2 ? c8[j + 4] : c8[j]) + __shfl_xor_sync(0xffffffffu, h2 ? c8[j] : c8[j + 4], 8);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) cf[j] = (h1 ? c4[j + 2] : c4[j]) + __shfl_xor_sync(0xffffffffu, h1 ? c4[j] : c4[j + 2], 4);
+            *reinterpret_cast<float2*>(cb + 2 * lane) = make_float2(cf[0], cf[1]);       // columns 2 lane + {0, 1}
+          } else {
+            float c4[4], c2v[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c4[j] = (h4 ? ca[j + 4] : ca[j]) + __shfl_xor_sync(0xffffffffu, h4 ? ca[j] : ca[j + 4], 16);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) c2v[j] = (h2 ? c4[j + 2] : c4[j]) + __shfl_xor_sync(0xffffffffu, h2 ? c4[j] : c4[j + 2], 8);
+            const float cf = (h1 ? c2v[1] : c2v[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c2v[0] : c2v[1], 4);
+            // k = 2 * bit4 + bit3, b = bit2  ->  column 8 k + 2 t0 + b
+            cb[8 * (2 * (int)h4 + (int)h2) + 2 * t0 + (int)h1] = cf;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_col(ncol % 3));
+          pend_R = (ps < 0 ? 0 : (1 + ps) * P) + R; pend_J = J;
+          ++ncol;
+        }
+        if (warp == 2 && lane == 0) SM3_TR(11, it);
+      }
+      // ---- row sums of this (CTA, row pair) segment: fold the NQ column groups in a fixed order ----
+      const int kseg = (int)blockIdx.x - (int)(mr_prefix(mr, R) / mr.tpc);
+      float rs[2][4];
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          float lo, hi;
+          f2_unpack(sum2[rb][sl], lo, hi);
+          float v = lo + hi;
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          rs[rb][sl] = v;
+          if (cg > 0 && t0 == 0) xsum[(cg - 1) * 256 + rb * 128 + q * 32 + t1 + 8 * (sl & 1) + 16 * (sl >> 1)] = v;
+        }
+      }
+      named_bar_sync(1, 32 * NW);
+      if (cg == 0 && t0 == 0) {
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            const int rl = rb * 128 + q * 32 + t1 + 8 * (sl & 1) + 16 * (sl >> 1);
+            float v = rs[rb][sl];
+#pragma unroll
+            for (int g = 1; g < NQ; ++g) v += xsum[(g - 1) * 256 + rl];
+            p.partial[(int64_t)kseg * M + r0 + rl] = v;
+          }
+        }
+      }
+      named_bar_sync(1, 32 * NW);
+      f += cnt;
+    }
+    fold_pending();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) SM3_TR(7, 4);
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 // NS = S/H stages in TMEM.  2 at D = 256 (all 512 columns in use).  At D <= 128 TMEM has room for 4, which keeps four
@@ -2205,6 +2582,69 @@ int infonce_tc_fwd(const InfoNceProblem& pb, float* pos, float* lse_neg, float* 
   if (rc) return rc;
   if (pb.no_finalize) return pl.splits;             // the caller folds the [splits][m_rows] partial sums itself
   return infonce_finalize_launch(p.partial, pl.splits, p.m_rows, pb.inv_T, neg_sum, lse_neg, st, pb.extra_neg_sum);
+}
+
+// ---- cross-rank symmetric forward: plan, workspace, launch (see MrPlan in common.cuh) ----
+MrPlan infonce_tc_mr_plan(int n_local, int world, int rank) {
+  MrPlan m{};
+  if (world < 2 || world > 16 || n_local % 128 != 0 || n_local < 128) return m;
+  m.W = world; m.rank = rank;
+  m.H = (world - 1) / 2;
+  m.anti = (world % 2 == 0) ? (rank < world / 2 ? 1 : 2) : 0;
+  m.np = m.H + (m.anti ? 1 : 0);
+  m.T_l = 2 * n_local / 128;
+  m.P_l = m.T_l / 2;
+  m.flat = mr_prefix(m, m.P_l);
+  const int sms = num_sms();
+  m.tpc = (int)((m.flat + sms - 1) / sms);
+  if (m.tpc < 1) m.tpc = 1;
+  m.nctas = (int)((m.flat + m.tpc - 1) / m.tpc);
+  int cmax = 0;
+  for (int R = 0; R < m.P_l; ++R) cmax = mr_count(m, R) > cmax ? mr_count(m, R) : cmax;
+  m.maxseg = (cmax - 1) / m.tpc + 2;
+  m.on = 1;
+  return m;
+}
+size_t infonce_tc_mr_workspace(const MrPlan& m) {
+  return (size_t)(m.maxseg + (1 + m.np) * m.P_l) * (size_t)m.T_l * 128 * sizeof(float) + 256;
+}
+namespace {
+template <int DP>
+int launch_fwdsym_mr(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {
+  (void)tc_poly(DP);
+  const int poly = g_knob_poly == -2 ? 2 : g_knob_poly;
+  if (poly >= 1) {
+    SM3_SMEM_ATTR_ONCE((infonce_tc_fwdsym_mr_kernel<DP, 2, 2>), SymCfg<DP>::SMEM);
+    SM3_CHECK_CUDA(launch_k(infonce_tc_fwdsym_mr_kernel<DP, 2, 2>, dim3(p.mr.nctas), dim3(320), SymCfg<DP>::SMEM, st, tmap, p));
+  } else {
+    SM3_SMEM_ATTR_ONCE((infonce_tc_fwdsym_mr_kernel<DP, 0, 2>), SymCfg<DP>::SMEM);
+    SM3_CHECK_CUDA(launch_k(infonce_tc_fwdsym_mr_kernel<DP, 0, 2>, dim3(p.mr.nctas), dim3(320), SymCfg<DP>::SMEM, st, tmap, p));
+  }
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+}  // namespace
+// pb: this rank's row block against the all-gathered columns (wait_flags etc. as for the fused exchange).  Leaves the row
+// sums / own-block column sums / partner column slabs in ws (infonce_tc_mr_workspace bytes) and the positives in pos.
+int infonce_tc_fwd_mr(const InfoNceProblem& pb, const MrPlan& m, float* pos, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SM3_REQUIRE(m.on && pb.wait_flags != nullptr && pb.n_local % 128 == 0 && pb.n_global == pb.n_local * m.W &&
+                  pb.pair_offset == m.rank * pb.n_local, SM3_ERR_SHAPE, "infonce(tc) symmetric exchange: bad plan");
+  SM3_REQUIRE(ws_bytes >= infonce_tc_mr_workspace(m), SM3_ERR_WORKSPACE, "infonce(tc) symmetric exchange: workspace too small");
+  const TcPlan pl = tc_plan(pb, false);
+  TcParams p{};
+  fill_params(pb, pl, p, 128);
+  p.pos = pos;
+  p.partial = (float*)ws;
+  p.mr = m;
+  CUtensorMap tmap;
+  int rc = make_tmap_bf16(&tmap, pb.z_cols, (uint64_t)p.m_cols, (uint64_t)pb.D, 128);
+  if (rc) return rc;
+  switch (pb.D / 64) {
+    case 1: return launch_fwdsym_mr<1>(tmap, p, st);
+    case 2: return launch_fwdsym_mr<2>(tmap, p, st);
+    case 3: return launch_fwdsym_mr<3>(tmap, p, st);
+    default: return launch_fwdsym_mr<4>(tmap, p, st);
+  }
 }
 
 int infonce_tc_bwd(const InfoNceProblem& pb, const float* gpos_r, const float* glse_r, const float* nsum_r,

@@ -184,16 +184,39 @@ __global__ void __launch_bounds__(256)
 loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, const float* __restrict__ pos, int n_local,
                           int pair_offset, int n_global, float inv_T, float scale, float* __restrict__ loss,
                           float* __restrict__ g_pos, float* __restrict__ g_lse, float* __restrict__ neg_sum,
-                          float* __restrict__ block_ws, PeerFused pf, int accumulate, float* __restrict__ a_local) {
+                          float* __restrict__ block_ws, PeerFused pf, int accumulate, float* __restrict__ a_local,
+                          MrFold mr) {
   pdl_wait();        // PDL: the preceding kernel of the fused step has completed (no-op otherwise)
   pdl_launch();
   __shared__ float red[32];
   __shared__ bool is_last;
   const int rows = 2 * n_local;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mr.plan.on) {
+    // cross-rank symmetric forward: the column sums of the blocks other ranks computed for us arrive in plane 2 of this
+    // rank's statistics buffer, one [rows] vector per contributing rank; wait for their channel-2 flags (one thread)
+    if (threadIdx.x == 0) {
+      const MrPlan& m = mr.plan;
+      for (int c = 0; c < m.np; ++c) {
+        const int src = c < m.H ? (m.rank - 1 - c + 2 * m.W) % m.W : (m.rank + m.W / 2) % m.W;
+        peer_flags_wait_all(mr.flags + src, 1, 2, mr.epoch, mr.timeout_ns);
+      }
+    }
+    __syncthreads();
+  }
   float term = 0.f;
   if (i < rows) {
-    const float s = fold_row_partials(partial, n_partials, rows, i);
+    float s;
+    if (mr.plan.on) {
+      const MrPlan& m = mr.plan;
+      s = fold_row_partials_mr(partial, m, i);
+      for (int c = 0; c < m.np; ++c) {                 // fixed order: rank-1, rank-2, ..., antipodal
+        const int src = c < m.H ? (m.rank - 1 - c + 2 * m.W) % m.W : (m.rank + m.W / 2) % m.W;
+        s += __ldcg(mr.colsum_in + (size_t)src * rows + i);
+      }
+    } else {
+      s = fold_row_partials(partial, n_partials, rows, i);
+    }
     const float lse = inv_T + logf(s);               // s == 0 (a single pair: no negatives) -> -inf, term = 0
     const float x = lse - pos[i];
     const float e = __expf(-fabsf(x));
@@ -238,6 +261,53 @@ loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, con
   }
 }
 
+
+// Cross-rank symmetric forward: column sums this rank computed for its partners' rows.  Partner slot ps holds [P_l][M_l]
+// slabs (one per local row pair); the vector sum over the row pairs that visited the partner (all of them, or only the
+// row pairs R >= P_l / 2 for anti == 2; only the partner's first 256 (P_l / 2) rows for anti == 1) goes to plane 2 of the partner's
+// statistics buffer at [this rank][row]; the last CTA releases channel 2 on every partner.
+__global__ void __launch_bounds__(256)
+colsum_push_kernel(const float* __restrict__ slabs, MrPlan m, int n_local, PeerPtrs stats, PeerPtrs flags,
+                   unsigned* __restrict__ ticket, unsigned epoch) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ bool is_last;
+  const int64_t rows = 2 * (int64_t)n_local;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ps = blockIdx.y;
+  if (i < rows) {
+    const bool anti = ps >= m.H;
+    const int r_begin = (anti && m.anti == 2) ? m.P_l / 2 : 0;
+    const bool covered = !(anti && m.anti == 1) || i < (int64_t)256 * (m.P_l / 2);
+    float c0 = 0.f, c1 = 0.f;
+    if (covered) {
+      const float* col = slabs + ((int64_t)ps * m.P_l) * rows + i;
+      int r = r_begin;
+      for (; r + 2 <= m.P_l; r += 2) { c0 += col[(int64_t)r * rows]; c1 += col[(int64_t)(r + 1) * rows]; }
+      if (r < m.P_l) c0 += col[(int64_t)r * rows];
+    }
+    const int dst = mr_partner_rank(m, ps);
+    float* out = reinterpret_cast<float*>(stats.p[dst]) + (size_t)4 * n_local * m.W /* planes 0, 1 */ +
+                 (size_t)m.rank * rows + i;
+    *out = c0 + c1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x == 0) *ticket = 0u;
+    if ((int)threadIdx.x < m.np) {
+      __threadfence_system();
+      unsigned* dst = reinterpret_cast<unsigned*>(flags.p[mr_partner_rank(m, (int)threadIdx.x)]) + 2 * 16 + m.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+    }
+  }
+}
+
 }  // namespace
 
 unsigned long long peer_timeout_ns() {
@@ -267,10 +337,21 @@ int l2norm_scatter_launch(const void* p_a, const void* p_b, int n_local, int pai
 int loss_stats_scatter_launch(const float* partial, int n_partials, const float* pos, int n_local, int pair_offset,
                               int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
                               float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate,
-                              float* a_local) {
+                              float* a_local, const MrFold* mr) {
   const unsigned grid = (unsigned)((2 * (int64_t)n_local + 255) / 256);
+  MrFold mf{};
+  if (mr != nullptr) mf = *mr;
   launch_k(loss_stats_scatter_kernel, dim3(grid), dim3(256), 0, st, partial, n_partials, pos, n_local, pair_offset, n_global,
-           inv_T, scale, loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate, a_local);
+           inv_T, scale, loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate, a_local, mf);
+  SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+int colsum_push_launch(const float* partner_slabs, const MrPlan& plan, int n_local, const PeerPtrs& stats,
+                       const PeerPtrs& flags, unsigned* ticket, unsigned epoch, cudaStream_t st) {
+  if (plan.np < 1) return SM3_OK;
+  const dim3 grid((unsigned)((2 * (int64_t)n_local + 255) / 256), (unsigned)plan.np);
+  launch_k(colsum_push_kernel, grid, dim3(256), 0, st, partner_slabs, plan, n_local, stats, flags, ticket, epoch);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;
 }

@@ -541,6 +541,15 @@ def _resolve_comm(comm: str, w: int, z_dtype, n_global: int, d: int, device, gro
         return None
 
 
+def _fused_mode() -> int:
+    """Exchange mode of sm3_infonce_step_peer for the fused path: 4 = symmetric forward across ranks (every rank computes
+    half of its row block's column blocks and ships the column sums of the rest to their owners; SM3_PEER_SYM=0 disables),
+    3 = rows pushed from inside K2 (SM3_PEER_PUSH=1), 2 = rows pushed by the normalise kernel."""
+    if os.environ.get("SM3_PEER_PUSH", "0") == "1":
+        return 3
+    return 4 if os.environ.get("SM3_PEER_SYM", "1") != "0" else 2
+
+
 class _FusedInfoNCE(torch.autograd.Function):
     """Scalar loss with the backward computed eagerly in forward (one pass: fwd + bwd kernels back to back)."""
 
@@ -603,7 +612,7 @@ class _FusedInfoNCE(torch.autograd.Function):
                 # pushed from inside K2 with owner-ordered tiles.  Measured on 8 x B200 (cfg4, profiles/r02_scale8_*.json):
                 # mode 3 shortens the kernels (stage sum 0.69-0.72 vs 0.81 ms) but not the free-running step (0.70-0.74
                 # vs 0.74 ms) and is 7 % slower at 2 ranks, so it stays opt-in.
-                mode = (3 if os.environ.get("SM3_PEER_PUSH", "0") == "1" else 2) if fused else int(overlap)
+                mode = _fused_mode() if fused else int(overlap)
                 check(lib().sm3_infonce_step_peer(ptr(p1c), ptr(p2c), n_local, rank, w, d, dtype_code(p1c), temperature,
                                                   weight, ptr(loss), ptr(dp1), ptr(dp2), ptr(pbuf.z[slot]),
                                                   pbuf.zp[slot], ptr(pbuf.st[slot]), pbuf.stp[slot], ptr(pbuf.flags),
@@ -612,7 +621,7 @@ class _FusedInfoNCE(torch.autograd.Function):
                       "sm3_infonce_step_peer")
             if need_grad:
                 ctx.save_for_backward(dp1, dp2)
-            ctx.comm_used = ("peer-fused-push" if mode == 3 else "peer-fused") if fused else ("peer-overlap" if overlap else "peer")
+            ctx.comm_used = ({3: "peer-fused-push", 4: "peer-fused-sym"}.get(mode, "peer-fused")) if fused else ("peer-overlap" if overlap else "peer")
             return loss
         if overlap:
             # ---- exchange on a side stream, local column block on the main stream, then the remote blocks ----
@@ -908,6 +917,27 @@ def knn_predict(query: torch.Tensor, bank: torch.Tensor, bank_labels: torch.Tens
 # ------------------------------------------------------------------------------------------------------
 # N3: prototype heads of the multi-label block (tail of Model.forward, reference tools/mlc_train.py:70-89)
 # ------------------------------------------------------------------------------------------------------
+_PROTO_INDEX = {}
+
+
+def _proto_index(slots, hf: int, dev: torch.device):
+    """Cached index tensors for the batched dW GEMM of the prototype heads: `gather` picks, per feature slot, the logit
+    columns that read it (padded with the index of an appended zero column), `scatter` maps the [hf * width] result rows
+    back to class order."""
+    key = (tuple(slots), hf, dev.index)
+    hit = _PROTO_INDEX.get(key)
+    if hit is None:
+        per = [[c for c, s_ in enumerate(slots) if s_ == slot] for slot in range(hf)]
+        width = max(len(p) for p in per)
+        c_total = len(slots)
+        gather = [c for p in per for c in (p + [c_total] * (width - len(p)))]
+        where = {c: i for i, c in enumerate(gather) if c < c_total}
+        scatter = [where[c] for c in range(c_total)]
+        hit = (torch.tensor(gather, device=dev), torch.tensor(scatter, device=dev), width)
+        _PROTO_INDEX[key] = hit
+    return hit
+
+
 class _ProtoHeads(torch.autograd.Function):
     """(normalised feats, [B, C] logits) from sm3_proto_heads_fwd; backward = sm3_proto_heads_bwd + one GEMM for dW."""
 
@@ -949,12 +979,14 @@ class _ProtoHeads(torch.autograd.Function):
                                                 ptr(inv) if ctx.l2_norm else None, ptr(dlogits), ptr(extra), ptr(d_feats),
                                                 stream_ptr()), "sm3_proto_heads_bwd")
         if ctx.needs_input_grad[1]:
-            # dW[c] = sum_b dlogit[b, c] * z[slot(c), b, :]: one GEMM per feature slot that is read (1 or Hf of them)
-            dw = torch.empty_like(w32)
-            slots = torch.tensor(ctx.slots, device=z.device)
-            for s_ in sorted(set(ctx.slots)):
-                cols = (slots == s_).nonzero(as_tuple=True)[0]
-                dw[cols] = dlogits[:, cols].t() @ z[s_].float()
+            # dW[c] = sum_b dlogit[b, c] * z[slot(c), b, :]  (no host synchronisation: index tensors are cached)
+            if hf == 1:
+                dw = dlogits.t() @ z[0].float()
+            else:
+                gather, scatter, width = _proto_index(ctx.slots, hf, z.device)
+                dl = torch.cat([dlogits, dlogits.new_zeros(b, 1)], dim=1)[:, gather].view(b, hf, width)
+                per_slot = torch.bmm(dl.permute(1, 2, 0), z.float())                  # [hf, width, d]
+                dw = per_slot.reshape(hf * width, d)[scatter]
             dw = dw.to(ctx.w_dtype)
         return d_feats, dw, None, None
 
@@ -1218,7 +1250,7 @@ class HostInfoNCEPipeline:
                 pb = self.pbuf
                 slot = pb.next_slot()
                 fused = self.n % 128 == 0 and os.environ.get("SM3_PEER_FUSED", "1") != "0"
-                mode = (3 if os.environ.get("SM3_PEER_PUSH", "0") == "1" else 2) if fused else 0
+                mode = _fused_mode() if fused else 0
                 t = check(lib().sm3_host_pipe_submit_peer(self._h, p1_host.data_ptr(), p2_host.data_ptr(), temperature,
                                                           loss.data_ptr(), dp1.data_ptr(), dp2.data_ptr(), self.rank,
                                                           self.world, ptr(pb.z[slot]), pb.zp[slot], ptr(pb.st[slot]),

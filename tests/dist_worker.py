@@ -149,9 +149,11 @@ def main():
                 outs = []
                 # nccl reference, fused exchange with the push in the normalise kernel (mode 2), fused exchange with the
                 # push inside K2 + owner-ordered tiles (mode 3; the 256-row forward kernel is forced for these small shapes)
-                for fused, push in (("0", "0"), ("1", "0"), ("1", "1")):
+                # ... and the fused exchange with the symmetric forward across ranks (mode 4)
+                for fused, push, sym in (("0", "0", "0"), ("1", "0", "0"), ("1", "1", "0"), ("1", "0", "1")):
                     os.environ["SM3_PEER_FUSED"] = fused
                     os.environ["SM3_PEER_PUSH"] = push
+                    os.environ["SM3_PEER_SYM"] = sym
                     if push == "1":
                         os.environ["SM3_TC_FWD_BM"] = "256"
                     else:
@@ -163,9 +165,10 @@ def main():
                     l4.backward()
                     outs.append((l4.item(), a4.grad.double(), b4.grad.double()))
                 os.environ["SM3_PEER_FUSED"] = "0"
+                os.environ.pop("SM3_PEER_SYM", None)
                 os.environ.pop("SM3_TC_FWD_BM", None)
                 (l_n, ga_n, gb_n) = outs[0]
-                for which, (l_f, ga_f, gb_f) in zip(("fused", "fused+push"), outs[1:]):
+                for which, (l_f, ga_f, gb_f) in zip(("fused", "fused+push", "fused+sym"), outs[1:]):
                     assert abs(l_f - l_n) <= 2e-6 * abs(l_n), (which, "loss", step, l_f, l_n)
                     ea = (ga_f - ga_n).abs().max().item() / ga_n.abs().max().item()
                     eb = (gb_f - gb_n).abs().max().item() / gb_n.abs().max().item()

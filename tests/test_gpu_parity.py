@@ -208,6 +208,62 @@ def test_symmetric_forward_matches_full_forward(sm3, monkeypatch, n, d, nq):
     assert np.abs(sym[1].cpu().numpy() - ref_lse).max() < 1e-4
 
 
+@pytest.mark.parametrize("world,n_local,d", [(2, 256, 128), (2, 384, 64), (3, 256, 256), (4, 384, 128), (8, 256, 128), (5, 128, 192)])
+def test_cross_rank_symmetric_forward_on_one_gpu(sm3, world, n_local, d):
+    """Mode 4 of the multi-rank step (every rank computes world/2 of its column blocks and ships the column sums of the
+    foreign ones) with this process playing all ranks on one device, production kernels throughout: each rank's K2 +
+    column-sum push into per-rank statistics / flag buffers, then each rank's loss kernel.  The assembled row statistics
+    must equal the full-matrix single-rank forward of the concatenated batch: odd and even world sizes, odd numbers of
+    row pairs per rank, every antipodal split."""
+    import ctypes as C
+    from skin_sm3_b200 import _lib
+    lib = _lib.lib()
+    T = 0.1
+    n_global = n_local * world
+    g = torch.Generator().manual_seed(41 + world * 7 + n_local)
+    p1 = torch.randn(n_global, d, generator=g)
+    p2 = p1 + 0.5 * torch.randn(n_global, d, generator=g)
+    z_all, _ = sm3.core.normalize_pair(p1.cuda(), p2.cuda(), torch.bfloat16)        # [2 n_global, d], global row order
+    ref_pos, ref_lse, ref_nsum = sm3.core.stats_fwd(z_all, z_all, n_global, 0, n_global, T, sm3.ALGO_TC)
+    epoch = 7
+    dev = z_all.device
+    stats = [torch.zeros(8 * n_global, dtype=torch.float32, device=dev) for _ in range(world)]
+    flags = [torch.zeros(128, dtype=torch.int32, device=dev) for _ in range(world)]
+    for f in flags:
+        f[:world] = epoch                                           # channel 0: every source's rows "have landed"
+    sp = (C.c_void_p * world)(*[t.data_ptr() for t in stats])
+    fp = (C.c_void_p * world)(*[t.data_ptr() for t in flags])
+    st = torch.cuda.current_stream().cuda_stream
+    rows_of = lambda r: torch.cat([torch.arange(r * n_local, (r + 1) * n_local),          # noqa: E731
+                                   n_global + torch.arange(r * n_local, (r + 1) * n_local)]).to(dev)
+    ws, pos, zl = [], [], []
+    for r in range(world):
+        nbytes = lib.sm3_debug_mr_workspace(n_local, world, r)
+        assert nbytes > 0
+        ws.append(torch.empty(nbytes, dtype=torch.uint8, device=dev))
+        pos.append(torch.full((2 * n_local,), float("nan"), device=dev))
+        zl.append(z_all[rows_of(r)].contiguous())
+        rc = lib.sm3_debug_mr_forward(zl[r].data_ptr(), z_all.data_ptr(), n_local, world, r, d, 1.0 / T, flags[r].data_ptr(),
+                                      sp, fp, epoch, pos[r].data_ptr(), ws[r].data_ptr(), nbytes, st)
+        assert rc == 0, _lib.last_error()
+    for r in range(world):
+        out = [torch.empty(2 * n_local, device=dev) for _ in range(3)]
+        loss = torch.zeros((), device=dev)
+        bws = torch.empty(4096, device=dev)
+        rc = lib.sm3_debug_mr_fold(ws[r].data_ptr(), n_local, world, r, 1.0 / T, pos[r].data_ptr(), stats[r].data_ptr(),
+                                   flags[r].data_ptr(), epoch, loss.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                   out[2].data_ptr(), bws.data_ptr(), st)
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        idx = rows_of(r)
+        assert torch.equal(pos[r], ref_pos[idx]) or (pos[r] - ref_pos[idx]).abs().max().item() < 1e-5, (world, r)
+        rel = ((out[0] - ref_nsum[idx]).abs() / ref_nsum[idx].abs()).max().item()
+        assert rel < 2e-5, (world, n_local, r, rel)
+        x = ref_lse[idx] - ref_pos[idx]
+        ref_loss = torch.nn.functional.softplus(x).mean().item()
+        assert abs(loss.item() - ref_loss) <= 2e-6 * abs(ref_loss), (world, r, loss.item(), ref_loss)
+
+
 @pytest.mark.parametrize("bwd_v,ns", [("1", "4"), ("2", "4"), ("2", "2"), ("3", "2"), ("4", "2")])
 def test_backward_forms_agree(sm3, monkeypatch, bwd_v, ns):
     """Both backward kernels and both S/H stage counts produce the same partial-gradient sums (bf16 H, fp32 accumulation:
