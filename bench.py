@@ -545,6 +545,11 @@ def comm_description(n, world):
     used += ", NVSwitch multicast stores)" if mc else ", unicast stores)"
     if os.environ.get("SM3_PEER_FUSED", "1") != "0" and (n // world) % 128 == 0:
         used += ", fused exchange: scatter+signal in the producer kernels, waits inside K2/K3"
+        from skin_sm3_b200.functional import _fused_mode
+        mode = _fused_mode()
+        used += {3: "; rows pushed from inside K2 (mode 3)",
+                 4: "; symmetric forward across ranks: W/2 of W column blocks per rank, column sums shipped to the row "
+                    "owners (mode 4)"}.get(mode, " (mode 2)")
     return used
 
 
@@ -637,13 +642,14 @@ def run_ours(args):
                 "sync_value": n / (e2e_sync_ms / args.steps * 1e-3), "sync_ms_per_step": e2e_sync_ms / args.steps,
                 "api": ("sm3_host_pipe_submit/wait (C ABI, pinned host buffers, 2-slot copy/compute pipeline); "
                         "sync_value = one synchronous sm3_infonce_host call per step") if world == 1 else E2E_MULTI_API},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 and "mode 4" in comm_used else 0)) * args.steps,
         "stages_ms": {k: round(v, 4) for k, v in stages.items()},
         "clocks": clk.summary(),
         "parity": parity,
     }
     tr = ncu_traffic()
-    t_bwd, t_fwd = stages.get("infonce_bwd"), stages.get("infonce_fwd")
+    t_bwd = stages.get("infonce_bwd")
+    t_fwd = stages.get("infonce_fwd") or stages.get("infonce_fwd_sym") or stages.get("infonce_fwd_push")
     if t_bwd:
         ach = flops_bwd / (t_bwd * 1e-3) / 1e12
         kname = "infonce_tc_bwd_kernel" if d > 128 else "infonce_tc_bwd2_kernel"
@@ -657,7 +663,9 @@ def run_ours(args):
         if t_fwd:
             achf = flops_fwd / (t_fwd * 1e-3) / 1e12
             sym, ex_fl = fwd_symmetric(sm3, n, d) if world == 1 else (False, flops_fwd)
-            r["fwd"] = {"kernel": ("infonce_tc_fwdsym_kernel (K2, upper-triangular tiles)" if sym else "infonce_tc_fwd2_kernel (K2)") +
+            r["fwd"] = {"kernel": ("infonce_tc_fwdsym_kernel (K2, upper-triangular tiles)" if sym else
+                                   "infonce_tc_fwdsym_mr_kernel (K2, W/2 of the W column blocks)" if "mode 4" in comm_used else
+                                   "infonce_tc_fwd2_kernel (K2)") +
                                   (", incl. in-kernel waits for the peers' rows" if world > 1 else ""),
                         "achieved": achf, "frac": achf / pk["tflops"], "launch_ms": t_fwd, "flops_per_launch": flops_fwd,
                         "executed_flops_per_launch": ex_fl,

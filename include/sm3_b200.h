@@ -302,7 +302,7 @@ int sm3_host_pipe_wait(sm3_host_pipe* pipe, int64_t ticket);
 int sm3_host_pipe_destroy(sm3_host_pipe* pipe);
 
 /* Peer mode of the pipeline (multi-rank jobs): the handle is created for this rank's n_local pairs of a job with n_global
- * pairs, and every submit runs sm3_infonce_step_peer (exchange mode 0, 2 or 3, see below) between the copies, with the
+ * pairs, and every submit runs sm3_infonce_step_peer (exchange mode 0, 2, 3 or 4, see below) between the copies, with the
  * symmetric buffers of the slot and the epoch the caller chose for that step (they must follow the same sequence on every
  * rank).  wait / destroy are the ordinary ones.  Gradients are those of sm3_infonce_step_peer (sum over ranks of the
  * per-rank mean losses). */

@@ -951,7 +951,7 @@ extern "C" int64_t sm3_host_pipe_submit_peer(sm3_host_pipe* hp, const void* p1_h
               "host_pipe_submit_peer: handle was not created for %d ranks", world);
   SM3_REQUIRE((dp1_host == nullptr) == (dp2_host == nullptr), SM3_ERR_SHAPE,
               "host_pipe_submit_peer: dp1_host/dp2_host must both be given or both NULL");
-  SM3_REQUIRE(mode == 0 || mode == 2 || mode == 3, SM3_ERR_SHAPE, "host_pipe_submit_peer: exchange mode must be 0, 2 or 3");
+  SM3_REQUIRE(mode == 0 || (mode >= 2 && mode <= 4), SM3_ERR_SHAPE, "host_pipe_submit_peer: exchange mode must be 0, 2, 3 or 4");
   int dev = -1;
   SM3_CHECK_CUDA(cudaGetDevice(&dev));
   SM3_REQUIRE(dev == hp->device, SM3_ERR_SHAPE, "host_pipe_submit_peer: handle belongs to device %d, current device is %d",
