@@ -7,11 +7,12 @@ T=${2:-I}${N}
 run() { # name, env...
   name=$1; shift
   env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29650 \
-      bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/${T}_bench_${name}.json 2> gpurun_out/${T}_bench_${name}.err
+      bench.py --gpus $N --steps 40 --warmup 8 > gpurun_out/${T}_bench_${name}.json 2> gpurun_out/${T}_bench_${name}.err
   echo "bench $name rc=$?"; tail -c 200 gpurun_out/${T}_bench_${name}.err
 }
-run sym SM3_PEER_SYM=1
 run nosym SM3_PEER_SYM=0
+run sym SM3_PEER_SYM=1
+run nosym_b SM3_PEER_SYM=0
 run sym_b SM3_PEER_SYM=1
 python - <<'PY'
 import json,glob
