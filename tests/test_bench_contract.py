@@ -78,3 +78,40 @@ def test_committed_bench_line_carries_the_contract_keys():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert not bad & set(d["clocks"]["reasons"])
+
+
+def test_round2_bench_line_carries_parity_and_consistent_roofline():
+    """The recorded round-2 B200 line (profiles/r02_bench_final.json): contract keys, a parity block measured on the
+    production path, the real reference as CPU baseline (marked estimated where it is), the dominant-kernel roofline
+    consistent with the stage time taken inside the production call, the forward's executed-vs-algorithmic FLOPs when the
+    symmetric kernel ran, and the next-row timings at a level the driver's record keeps."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity"):
+        assert k in d, k
+    n, dim = d["config"]["global_pairs"], d["config"]["dim"]
+    assert d["unit"] == "pairs/s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+    assert abs(d["value"] - n / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    m = 2 * n
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["flops_per_launch"] == 4.0 * m * m * dim
+    assert abs(r["achieved"] - r["flops_per_launch"] / (r["stages_ms"]["infonce_bwd"] * 1e-3) / 1e12) < 0.01 * r["achieved"]
+    assert abs(r["launch_ms"] - r["stages_ms"]["infonce_bwd"]) < 1e-3 and "production path" in r["stage_source"]
+    f = r["fwd"]
+    assert f["flops_per_launch"] == 2.0 * m * m * dim and 0 < f["executed_flops_per_launch"] <= f["flops_per_launch"]
+    if "fwdsym" in f["kernel"]:
+        assert f["executed_flops_per_launch"] < 0.55 * f["flops_per_launch"]
+    p = r["parity"]
+    assert p["ok"] is True and p["loss_relerr"] < 1e-4 and p["grad_relerr_rowblock"] < p["tolerance"] <= 2e-2 and p["rows_checked"] >= 256
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and c["estimated"] is True and c["scale_factor"] > 1
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 2 * n * dim * 2 and e["d2h_bytes_per_step"] == e["h2d_bytes_per_step"] + 4
+    assert 0 < e["value"] <= d["value"] * 1.05 and e["value"] != d["value"]
+    for key in ("cfg2", "cfg4_sweep", "hbm_kernels", "retrieval", "kmeans", "projector_tail", "small_shapes"):
+        assert key in r, key
+    c2 = r["cfg2"]
+    assert c2["parity"]["grad_relerr_all_rows"] < 2e-2 and c2["cpu_baseline"]["kind"] == "reference"
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert not bad & set(d["clocks"]["reasons"])
