@@ -8,6 +8,10 @@
 
 #include "common.cuh"
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace sm3 {
 
 static thread_local char g_err[512] = "";

@@ -1796,15 +1796,19 @@ infonce_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p)
       uint32_t h[16];
       const float4* ap = reinterpret_cast<const float4*>(p.acol + cb);
       if (!__any_sync(0xffffffffu, need)) {
+        // packed fp32 (FFMA2 / FADD2 / FMUL2 on register pairs): 13 issue slots per four logits instead of 19 -- the
+        // kernel is bound by its MMA chain, not by these warps, but it runs at the power cap
+        const uint64_t c2p = f2_pack(c2, c2), nc2p = f2_pack(-c2, -c2), aip = f2_pack(a_i, a_i);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 aj = kWait ? __ldcg(ap + i) : __ldg(ap + i);
-          const float e0 = ex2(fmaf(__uint_as_float(v[4 * i]), c2, -c2)) * (a_i + aj.x);
-          const float e1 = ex2(fmaf(__uint_as_float(v[4 * i + 1]), c2, -c2)) * (a_i + aj.y);
-          const float e2 = ex2(fmaf(__uint_as_float(v[4 * i + 2]), c2, -c2)) * (a_i + aj.z);
-          const float e3 = ex2(fmaf(__uint_as_float(v[4 * i + 3]), c2, -c2)) * (a_i + aj.w);
-          h[2 * i] = pack_bf16x2(e0, e1);
-          h[2 * i + 1] = pack_bf16x2(e2, e3);
+          const uint64_t e01 = f2_ex2(f2_fma(f2_pack_u(v[4 * i], v[4 * i + 1]), c2p, nc2p));
+          const uint64_t e23 = f2_ex2(f2_fma(f2_pack_u(v[4 * i + 2], v[4 * i + 3]), c2p, nc2p));
+          float h0, h1, h2, h3;
+          f2_unpack(f2_mul(e01, f2_add(aip, f2_pack(aj.x, aj.y))), h0, h1);
+          f2_unpack(f2_mul(e23, f2_add(aip, f2_pack(aj.z, aj.w))), h2, h3);
+          h[2 * i] = pack_bf16x2(h0, h1);
+          h[2 * i + 1] = pack_bf16x2(h2, h3);
         }
       } else {
         float hv[32];
@@ -2095,20 +2099,25 @@ infonce_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams p
         const float4* ap = reinterpret_cast<const float4*>(as_);
         uint32_t h[32];
         if (!__any_sync(0xffffffffu, need)) {
+          // packed fp32 (FFMA2 / FADD2 / FMUL2): x = s c - c, a_i + a_j and e * (a_i + a_j) on register pairs -- 13 issue
+          // slots per four logits instead of 19; the MUFU / FMA-pipe exponential split is unchanged
+          const uint64_t c2p = f2_pack(c2, c2), nc2p = f2_pack(-c2, -c2), aip = f2_pack(a_i, a_i);
+          const bool clamp = 2.0f * c2 > 125.0f;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 aj = ap[i];                     // broadcast LDS.128
             const uint32_t* v = i < 8 ? v0 : v1;
             const int o = 4 * (i & 7);
-            const float x0 = fmaf(__uint_as_float(v[o]), c2, -c2), x1 = fmaf(__uint_as_float(v[o + 1]), c2, -c2);
-            const float x2 = fmaf(__uint_as_float(v[o + 2]), c2, -c2), x3 = fmaf(__uint_as_float(v[o + 3]), c2, -c2);
-            // POLY of every 8 exponentials on the FMA pipes (i even: elements 0..3 of the group, i odd: 4..7)
-            const float e0 = ((i & 1) == 0 && 0 < POLY) || ((i & 1) == 1 && 4 < POLY) ? ex2_fma(x0) : ex2(x0);
-            const float e1 = ((i & 1) == 0 && 1 < POLY) || ((i & 1) == 1 && 5 < POLY) ? ex2_fma(x1) : ex2(x1);
-            const float e2 = ((i & 1) == 0 && 2 < POLY) || ((i & 1) == 1 && 6 < POLY) ? ex2_fma(x2) : ex2(x2);
-            const float e3 = ((i & 1) == 0 && 3 < POLY) || ((i & 1) == 1 && 7 < POLY) ? ex2_fma(x3) : ex2(x3);
-            h[2 * i] = pack_bf16x2(e0 * (a_i + aj.x), e1 * (a_i + aj.y));
-            h[2 * i + 1] = pack_bf16x2(e2 * (a_i + aj.z), e3 * (a_i + aj.w));
+            const uint64_t x01 = f2_fma(f2_pack_u(v[o], v[o + 1]), c2p, nc2p);
+            const uint64_t x23 = f2_fma(f2_pack_u(v[o + 2], v[o + 3]), c2p, nc2p);
+            // POLY of every 8 exponentials on the FMA pipes: 2 -> the first pair of every other group of four
+            const uint64_t e01 = ((i & 1) == 0 && POLY >= 2) ? f2_ex2_fma(x01, clamp) : f2_ex2(x01);
+            const uint64_t e23 = ((i & 1) == 0 && POLY >= 4) ? f2_ex2_fma(x23, clamp) : f2_ex2(x23);
+            float h0, h1, h2, h3;
+            f2_unpack(f2_mul(e01, f2_add(aip, f2_pack(aj.x, aj.y))), h0, h1);
+            f2_unpack(f2_mul(e23, f2_add(aip, f2_pack(aj.z, aj.w))), h2, h3);
+            h[2 * i] = pack_bf16x2(h0, h1);
+            h[2 * i + 1] = pack_bf16x2(h2, h3);
           }
         } else {
 #pragma unroll
