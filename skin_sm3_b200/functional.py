@@ -331,34 +331,72 @@ def l2_normalize(p: torch.Tensor, eps: float = _EPS, out_dtype: Optional[torch.d
     return _L2Normalize.apply(p, eps, out_dtype)
 
 
+_LOGITS_SLOTS = 8        # peer slots of the logits form: up to 4 terms between a forward and its backward (style 0 / 2)
+
+
+def _logits_peer_buffers(w: int, z_dtype, algo: int, n_global: int, d: int, device, group):
+    """PeerBuffers for ``cal_logits(group=...)`` (NVLink peer-memory exchange instead of NCCL all-gathers), or None.
+    SM3_LOGITS_COMM = auto | peer | nccl (auto: peer when symmetric memory can be set up)."""
+    comm = os.environ.get("SM3_LOGITS_COMM", "auto")
+    if w == 1 or comm == "nccl" or z_dtype != torch.bfloat16 or algo == ALGO_SIMT:
+        if comm == "peer" and w > 1:
+            raise RuntimeError("SM3_LOGITS_COMM=peer needs the bf16 tensor-core path")
+        return None
+    from . import peer
+    try:
+        return peer.get_peer_buffers(group, n_global, d, device, depth=_LOGITS_SLOTS)
+    except peer.PeerUnavailable:
+        if comm == "peer":
+            raise
+        return None
+
+
 class _InfoNCELogits(torch.autograd.Function):
-    """normalise -> (all-gather) -> K2 statistics;  backward = (all-gather of 3 floats/row) -> K3 -> normalise-bwd."""
+    """normalise -> exchange of the rows -> K2 statistics;  backward = exchange of 3 floats/row -> K3 -> normalise-bwd.
+    The exchange is the NVLink peer-memory scatter + cross-rank barrier (symmetric memory) where it can be set up, NCCL
+    all-gathers otherwise.  The peer slot of a term stays untouched until its backward has run: `_LOGITS_SLOTS` slots
+    rotate, enough for the four terms SimCLRSkinV3 keeps in flight between forward and backward."""
 
     @staticmethod
     def forward(ctx, p1, p2, temperature, z_dtype, algo, group):
         w, rank = _group_info(group)
         n_local = p1.shape[0]
         z, inv = core.normalize_pair(p1, p2, z_dtype)
-        z_cols = gather_global_order(z, group) if w > 1 else z
         n_global = n_local * w
+        pbuf = _logits_peer_buffers(w, z_dtype, algo, n_global, p1.shape[1], p1.device, group)
+        slot = -1
+        if w == 1:
+            z_cols = z
+        elif pbuf is not None:
+            slot = pbuf.next_slot()
+            z_cols = pbuf.scatter_z(slot, z, n_local)          # NVLink stores into every rank's z_cols[slot] + barrier
+        else:
+            z_cols = gather_global_order(z, group)
         pos, lse, nsum = core.stats_fwd(z, z_cols, n_local, rank * n_local, n_global, temperature, algo)
-        ctx.save_for_backward(z, inv, z_cols, nsum)
-        ctx.meta = (temperature, algo, group, w, rank, n_local, p1.dtype)
+        ctx.save_for_backward(z, inv, z_cols if pbuf is None else z.new_empty(0), nsum)
+        ctx.meta = (temperature, algo, group, w, rank, n_local, p1.dtype, pbuf, slot, pbuf.step if pbuf is not None else 0)
         return torch.stack((pos, lse), dim=1)
 
     @staticmethod
     def backward(ctx, g):
         z, inv, z_cols, nsum = ctx.saved_tensors
-        temperature, algo, group, w, rank, n_local, p_dtype = ctx.meta
+        temperature, algo, group, w, rank, n_local, p_dtype, pbuf, slot, issued = ctx.meta
         g = g.float()
         g_pos, g_lse = _contig(g[:, 0]), _contig(g[:, 1])
-        if w > 1:
-            packed = gather_global_order(torch.stack((g_pos, g_lse, nsum), dim=1), group)
-            gp_c, gl_c, ns_c = (_contig(packed[:, k]) for k in range(3))
+        if pbuf is not None:
+            if pbuf.step - issued >= pbuf.DEPTH:              # the slot has been handed to a later forward meanwhile
+                raise RuntimeError("cal_logits: more than %d terms between a forward and its backward" % pbuf.DEPTH)
+            stats = pbuf.scatter_stats(slot, g_pos, g_lse, nsum, n_local)      # (g_pos, g_lse, neg_sum) rows + barrier
+            ws, npart = core.stats_bwd_packed(z, pbuf.z[slot], n_local, rank * n_local, n_local * w, temperature, g_pos,
+                                              g_lse, nsum, stats, algo)
         else:
-            gp_c, gl_c, ns_c = g_pos, g_lse, nsum
-        ws, npart = core.stats_bwd(z, z_cols, n_local, rank * n_local, n_local * w, temperature, g_pos, g_lse, nsum,
-                                   gp_c, gl_c, ns_c, algo)
+            if w > 1:
+                packed = gather_global_order(torch.stack((g_pos, g_lse, nsum), dim=1), group)
+                gp_c, gl_c, ns_c = (_contig(packed[:, k]) for k in range(3))
+            else:
+                gp_c, gl_c, ns_c = g_pos, g_lse, nsum
+            ws, npart = core.stats_bwd(z, z_cols, n_local, rank * n_local, n_local * w, temperature, g_pos, g_lse, nsum,
+                                       gp_c, gl_c, ns_c, algo)
         dp1, dp2 = core.normalize_bwd(ws, npart, 1.0, z, inv, n_local, n_local, p_dtype)
         return dp1, dp2, None, None, None, None
 

@@ -29,7 +29,9 @@ class PeerUnavailable(RuntimeError):
 class PeerBuffers:
     DEPTH = 2
 
-    def __init__(self, group, n_global: int, d: int, device: torch.device):
+    def __init__(self, group, n_global: int, d: int, device: torch.device, depth: int = 0):
+        if depth:
+            self.DEPTH = int(depth)            # slots kept alive between a forward and its later backward (cal_logits)
         try:
             import torch.distributed._symmetric_memory as symm
         except Exception as e:  # pragma: no cover
@@ -140,11 +142,13 @@ class PeerBuffers:
         return self.st[slot]
 
 
-def get_peer_buffers(group, n_global: int, d: int, device: torch.device) -> PeerBuffers:
+def get_peer_buffers(group, n_global: int, d: int, device: torch.device, depth: int = 0) -> PeerBuffers:
+    """depth = 0: the two-slot buffers of the fused step; depth > 0: a separate pool whose slots stay untouched between a
+    term's forward and its backward (the logits form, where autograd runs the backward later)."""
     g = group if group is not None else dist.group.WORLD
-    key = (id(g), n_global, d, device.index)
+    key = (id(g), n_global, d, device.index, depth)
     pb = _CACHE.get(key)
     if pb is None:
-        pb = PeerBuffers(g, n_global, d, device)
+        pb = PeerBuffers(g, n_global, d, device, depth)
         _CACHE[key] = pb
     return pb

@@ -174,6 +174,28 @@ def main():
                     eb = (gb_f - gb_n).abs().max().item() / gb_n.abs().max().item()
                     assert ea <= 1e-2 and eb <= 1e-2, (which, "grads", n_local, step, ea, eb)
         results["fused"] = "ok"
+        # cal_logits(group=...) -- the drop-in module's form under SM3_GLOBAL_NEGATIVES=1 -- through the NVLink peer
+        # exchange: FOUR terms between forward and backward (SimCLRSkinV3's derm / clinic / cross / cross), two rounds so
+        # that the slots rotate, against the NCCL all-gather path on the same inputs
+        for rnd in range(3):
+            g = torch.Generator().manual_seed(700 + rnd + 50 * rank)
+            ps = [(torch.randn(256, 128, generator=g).bfloat16(), torch.randn(256, 128, generator=g).bfloat16())
+                  for _ in range(4)]
+            got = {}
+            for comm in ("nccl", "peer"):
+                os.environ["SM3_LOGITS_COMM"] = comm
+                leaves = [(a_.to(dev).requires_grad_(True), b_.to(dev).requires_grad_(True)) for a_, b_ in ps]
+                total = 0
+                for wgt, (a_, b_) in zip((1.0, 1.0, 0.5, 0.5), leaves):
+                    lg, lb = sm3.cal_logits(a_, b_, 0.1, precision="bf16", group=dist.group.WORLD)
+                    total = total + wgt * torch.nn.functional.cross_entropy(lg, lb)
+                total.backward()
+                got[comm] = (total.item(), [t.grad.double() for pr in leaves for t in pr])
+            os.environ.pop("SM3_LOGITS_COMM", None)
+            assert abs(got["peer"][0] - got["nccl"][0]) <= 1e-6 * abs(got["nccl"][0]), (rnd, got["peer"][0], got["nccl"][0])
+            for gp_, gn_ in zip(got["peer"][1], got["nccl"][1]):
+                assert (gp_ - gn_).abs().max().item() <= 1e-3 * gn_.abs().max().item(), ("cal_logits peer != nccl", rnd)
+        results["logits_peer"] = "ok"
         # peer mode of the pipelined host-buffer entry (sm3_host_pipe_submit_peer): several steps in flight, results
         # against the NCCL path on the same batches
         n_local, d, T = 512, 128, 0.1

@@ -21,4 +21,4 @@ def test_sharded_infonce_nccl(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = eval(out.read_text())
-    assert len(res) == 5 and res["fused"] == "ok" and res["kmeans"] == "ok" and res["pipe"] == "ok"
+    assert len(res) == 6 and res["fused"] == "ok" and res["kmeans"] == "ok" and res["pipe"] == "ok" and res["logits_peer"] == "ok"
