@@ -1045,14 +1045,20 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
         const uint32_t sph = (uint32_t)it & 1u;
         const bool do_col = J > 2 * R + 1;
         uint64_t col2[KS];                                       // packed column sums: columns 8 k + 2 t0 + {0, 1}
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb) {
+        // TMEM loads run one half tile ahead of the exponentials: vb(rb) is in flight during the first half of row block
+        // rb, and va of row block 1 (its S tile has been ready for a while: the MMA warp runs ahead) during the second
+        // half of row block 0 -- only the first load of a tile is exposed.
+        uint32_t va[4 * KS], vb[4 * KS];
+        auto begin_rb = [&](int rb) {
           mbar_wait(bar_sfull(rb), sph, bar_limit);
           tc_fence_after();
           if (warp == 2 && lane == 0) SM3_TR(3 + 2 * rb, it);
+          tmem_ld_16x256b(tmem + kColS + (uint32_t)rb * 128u + (uint32_t)(cg * CW) + lane_addr, va);   // rows t1, t1 + 8
+        };
+        begin_rb(0);
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
           const uint32_t taddr = tmem + kColS + (uint32_t)rb * 128u + (uint32_t)(cg * CW);
-          uint32_t va[4 * KS], vb[4 * KS];
-          tmem_ld_16x256b(taddr + lane_addr, va);                // rows t1, t1 + 8 of the quadrant
           tmem_ld_wait(va);
           tmem_ld_16x256b(taddr + lane_hi, vb);                  // rows t1 + 16, t1 + 24: in flight during the first half
           int Jp = 2 * R + rb + P;                               // the tile that holds these rows' positives
@@ -1066,6 +1072,7 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_sempty(rb));        // S stage free (the MMA warp runs a tile ahead anyway)
               if (warp == 2 && lane == 0) SM3_TR(4 + 2 * rb, it);
+              if (rb == 0) begin_rb(1);                          // va is dead: prefetch row block 1's first half
             }
             const uint32_t* v = hv == 0 ? va : vb;
             if (!special) {
@@ -1421,14 +1428,20 @@ infonce_tc_fwdsym_mr_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcPar
         const uint32_t sph = (uint32_t)it & 1u;
         const bool do_col = ps >= 0 || J > 2 * R + 1;
         uint64_t col2[KS];                                       // packed column sums: columns 8 k + 2 t0 + {0, 1}
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb) {
+        // TMEM loads run one half tile ahead of the exponentials: vb(rb) is in flight during the first half of row block
+        // rb, and va of row block 1 (its S tile has been ready for a while: the MMA warp runs ahead) during the second
+        // half of row block 0 -- only the first load of a tile is exposed.
+        uint32_t va[4 * KS], vb[4 * KS];
+        auto begin_rb = [&](int rb) {
           mbar_wait(bar_sfull(rb), sph, bar_limit);
           tc_fence_after();
           if (warp == 2 && lane == 0) SM3_TR(3 + 2 * rb, it);
+          tmem_ld_16x256b(tmem + kColS + (uint32_t)rb * 128u + (uint32_t)(cg * CW) + lane_addr, va);   // rows t1, t1 + 8
+        };
+        begin_rb(0);
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
           const uint32_t taddr = tmem + kColS + (uint32_t)rb * 128u + (uint32_t)(cg * CW);
-          uint32_t va[4 * KS], vb[4 * KS];
-          tmem_ld_16x256b(taddr + lane_addr, va);                // rows t1, t1 + 8 of the quadrant
           tmem_ld_wait(va);
           tmem_ld_16x256b(taddr + lane_hi, vb);                  // rows t1 + 16, t1 + 24: in flight during the first half
           int Jp = 2 * R + rb + P;                               // the tile that holds these rows' positives
@@ -1442,6 +1455,7 @@ infonce_tc_fwdsym_mr_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcPar
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_sempty(rb));        // S stage free (the MMA warp runs a tile ahead anyway)
               if (warp == 2 && lane == 0) SM3_TR(4 + 2 * rb, it);
+              if (rb == 0) begin_rb(1);                          // va is dead: prefetch row block 1's first half
             }
             const uint32_t* v = hv == 0 ? va : vb;
             if (!special) {
