@@ -11,6 +11,10 @@ Reference being replaced (paths relative to the reference checkout):
   * ``fused_infonce_multi``     the four style-0 terms of one step in one call  tools/backbone_train.py:101-121
   * ``sim_topk`` / ``knn_predict``  KNNOnlineEvaluator.predict                 src/models/evaluator.py:43-83
   * ``cluster_memory`` / ``spherical_kmeans``  DeepCluster memory-bank k-means tools/mlc_train.py:116-189
+  * ``tail_cal_logits``         projector tail Linear + BatchNorm1d(affine=False) + normalise + the above
+                                                                           src/models/simclr.py:25-26,61-62,293-294
+  * ``proto_heads`` / ``mlc_model_forward``  normalise + the eight prototype Linears of Model.forward
+                                                                           tools/mlc_train.py:58-89
   * ``HostInfoNCE`` / ``HostInfoNCEPipeline`` / ``GraphedInfoNCE``  host-buffer, pipelined and CUDA-graph front ends of
                                 the fused step (new capability; bench.py's ``e2e`` and small-shape numbers)
 

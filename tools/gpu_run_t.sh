@@ -2,7 +2,7 @@
 # Round-2 GPU run T (1 GPU): packed-math backward kernels -- parity tests, then cfg4 / cfg2 benches.
 mkdir -p gpurun_out
 T=${1:-T}
-timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=8 -k "tensor_core or backward_forms or cfg2_full or known_answers or fp16_inputs or golden" -p no:cacheprovider > gpurun_out/${T}_pytest.log 2>&1
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=8 -k "tensor_core or backward_forms or cfg2_full or known_answers or fp16_inputs or golden or symmetric" -p no:cacheprovider > gpurun_out/${T}_pytest.log 2>&1
 echo "pytest rc=$?"; tail -12 gpurun_out/${T}_pytest.log
 for i in 1 2; do
 timeout 600 python bench.py --steps 20 --warmup 5 --no-extras > gpurun_out/${T}_bench_$i.json 2>/dev/null
