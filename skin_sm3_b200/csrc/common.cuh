@@ -188,25 +188,35 @@ __device__ __forceinline__ float fold_row_partials(const float* __restrict__ par
                                                    int64_t i) {
   float s = 0.f;
   if (!(n_partials & kSymFlag)) {
-    for (int k = 0; k < n_partials; ++k) s += partial[(int64_t)k * rows + i];
-    return s;
+    float s1 = 0.f;                               // two chains: the loads of both are in flight together
+    int k = 0;
+    for (; k + 2 <= n_partials; k += 2) {
+      s += partial[(int64_t)k * rows + i];
+      s1 += partial[(int64_t)(k + 1) * rows + i];
+    }
+    if (k < n_partials) s += partial[(int64_t)k * rows + i];
+    return s + s1;
   }
   const int tpc = n_partials & (kSymFlag - 1);
   const int T = (int)(rows / 128), P = T / 2, R = (int)(i / 256);
   const long f = sym_flat_start(R, T, P);
   const int nseg = (int)((f + (T - 2 * R) - 1) / tpc - f / tpc) + 1;
-  for (int k = 0; k < nseg; ++k) s += partial[(int64_t)k * rows + i];
+  // one list of nseg + R addends (row-sum slabs of this row pair, then the column slabs of the earlier row pairs), eight
+  // independent chains: eight strided loads in flight per round, fixed association -> deterministic
   const float* col = partial + (int64_t)sym_maxseg(T, tpc) * rows + i;
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-  int r = 0;
-  for (; r + 4 <= R; r += 4) {
-    c0 += col[(int64_t)r * rows];
-    c1 += col[(int64_t)(r + 1) * rows];
-    c2 += col[(int64_t)(r + 2) * rows];
-    c3 += col[(int64_t)(r + 3) * rows];
+  const float* row = partial + i;
+  const int total = nseg + R;
+  auto term = [&](int j) { return j < nseg ? row[(int64_t)j * rows] : col[(int64_t)(j - nseg) * rows]; };
+  float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int j = 0;
+  for (; j + 8 <= total; j += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] += term(j + u);
   }
-  for (; r < R; ++r) c0 += col[(int64_t)r * rows];
-  return s + ((c0 + c1) + (c2 + c3));
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (j + u < total) c[u] += term(j + u);
+  return ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

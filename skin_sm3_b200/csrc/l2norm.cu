@@ -93,13 +93,16 @@ l2norm_bwd_small_kernel(const float* __restrict__ dz, int n_partials, int64_t pa
   const int64_t rows = rows_a + rows_b;
   const bool have = lane < D / kChunk;
   const int64_t row0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * R;
-  float gv[R][kChunk], zv[R][kChunk];
+  float gv[R][kChunk], zv[R][kChunk], g1[R][kChunk];
+  // the second partial slab (the common case: two column splits) is requested together with the first one and the rows
+  // of z: one memory round trip instead of two on the launch-bound sizes
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int64_t row = row0 + r;
     if (row < rows && have) {
       load8<float>(dz + row * D + lane * kChunk, gv[r]);
       load8<TZ>(z + row * D + lane * kChunk, zv[r]);
+      if (n_partials > 1) load8<float>(dz + partial_stride + row * D + lane * kChunk, g1[r]);
     } else {
 #pragma unroll
       for (int i = 0; i < kChunk; ++i) { gv[r][i] = 0.f; zv[r][i] = 0.f; }
@@ -109,7 +112,11 @@ l2norm_bwd_small_kernel(const float* __restrict__ dz, int n_partials, int64_t pa
   for (int r = 0; r < R; ++r) {
     const int64_t row = row0 + r;
     if (row < rows && have) {
-      for (int k = 1; k < n_partials; ++k) {
+      if (n_partials > 1) {
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) gv[r][i] += g1[r][i];
+      }
+      for (int k = 2; k < n_partials; ++k) {
         float t[kChunk];
         load8<float>(dz + k * partial_stride + row * D + lane * kChunk, t);
 #pragma unroll

@@ -172,6 +172,10 @@ l2norm_scatter_kernel(const TIn* __restrict__ pa, const TIn* __restrict__ pb, in
   last_block_signal(pf, &is_last);
 }
 
+// 128-thread CTAs: at the launch-bound sizes (8192 rows) that is 64 CTAs instead of 32 (64 threads: no better) -- the kernel is a chain of
+// dependent L2 round trips (fold, ticket, last-CTA fold), so more CTAs in flight is what shortens it
+constexpr int kLossThreads = 128;
+
 // CE on the sufficient statistics + its gradient + the backward exchange, one launch:
 //   neg_sum_i = sum_k partial[k][i] ; lse_i = inv_T + log(neg_sum_i) ; loss = scale * sum_i softplus(lse_i - pos_i)
 //   g_lse_i = scale * sigmoid(lse_i - pos_i) = -g_pos_i ; a_i = g_lse_i / neg_sum_i
@@ -180,7 +184,7 @@ l2norm_scatter_kernel(const TIn* __restrict__ pa, const TIn* __restrict__ pb, in
 // fixed order (deterministic), which then signals.  With pf.data.world == pf.flags.world == 0 nothing is published:
 // that is the single-GPU "finalize + loss" kernel (one multi-CTA launch instead of a finalize launch and a 1-CTA
 // reduction over all rows).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kLossThreads)
 loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, const float* __restrict__ pos, int n_local,
                           int pair_offset, int n_global, float inv_T, float scale, float* __restrict__ loss,
                           float* __restrict__ g_pos, float* __restrict__ g_lse, float* __restrict__ neg_sum,
@@ -242,7 +246,8 @@ loss_stats_scatter_kernel(const float* __restrict__ partial, int n_partials, con
   // ticket + signal; the CTA that draws the last ticket also folds the block sums
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (pf.data.world > 0 || pf.flags.world > 0) __threadfence_system();   // peers read what this CTA stored
+    else __threadfence();                                                  // single GPU: only the last CTA reads block_ws
     const unsigned t = atomicAdd(pf.counter, 1u);
     is_last = (t == gridDim.x - 1);
   }
@@ -338,10 +343,10 @@ int loss_stats_scatter_launch(const float* partial, int n_partials, const float*
                               int n_global, float inv_T, float scale, float* loss, float* g_pos, float* g_lse,
                               float* neg_sum, float* block_ws, const PeerFused& pf, cudaStream_t st, int accumulate,
                               float* a_local, const MrFold* mr) {
-  const unsigned grid = (unsigned)((2 * (int64_t)n_local + 255) / 256);
+  const unsigned grid = (unsigned)((2 * (int64_t)n_local + kLossThreads - 1) / kLossThreads);
   MrFold mf{};
   if (mr != nullptr) mf = *mr;
-  launch_k(loss_stats_scatter_kernel, dim3(grid), dim3(256), 0, st, partial, n_partials, pos, n_local, pair_offset, n_global,
+  launch_k(loss_stats_scatter_kernel, dim3(grid), dim3(kLossThreads), 0, st, partial, n_partials, pos, n_local, pair_offset, n_global,
            inv_T, scale, loss, g_pos, g_lse, neg_sum, block_ws, pf, accumulate, a_local, mf);
   SM3_CHECK_CUDA(cudaGetLastError());
   return SM3_OK;

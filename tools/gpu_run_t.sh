@@ -14,3 +14,7 @@ for f in sorted(glob.glob('gpurun_out/T_bench*.json')):
     d=json.loads(open(f).read().strip().splitlines()[-1]); r=d['roofline']
     print(f, round(d['ms_per_step'],4), d['stages_ms'], r['parity']['ok'], r['parity']['loss_relerr'], r['parity']['grad_relerr_rowblock'], (d.get('cuda_graph') or {}).get('ms_per_step'))
 PY
+CMD="python bench.py --workload cfg2 --steps 3 --warmup 3 --no-extras"
+$CMD > gpurun_out/${T}_plain_cfg2.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/${T}_launches_cfg2.csv $CMD > gpurun_out/${T}_ncu_launch2.log 2>&1
+python tools/ncu_summary.py launches gpurun_out/${T}_launches_cfg2.csv | head -9 | cut -c1-120
