@@ -12,8 +12,10 @@ run() { # name, env...
 }
 run nosym SM3_PEER_SYM=0
 run sym SM3_PEER_SYM=1
+if [ "$3" == "more" ]; then
 run nosym_b SM3_PEER_SYM=0
 run sym_b SM3_PEER_SYM=1
+fi
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/*_bench_*sym*.json')):
