@@ -8,6 +8,17 @@
 //              re-read as an MN-major B operand.  Row-local thanks to the symmetry of S (see sm3_b200.h).
 //   Nothing of size [M, M] is ever written; HBM traffic is ~ M*D*2 bytes per row-block pass (L2 resident).
 //
+// Kernels in this file:
+//   infonce_tc_fwd_kernel        forward, 128-row CTAs (small problems)
+//   infonce_tc_fwd2_kernel       forward, 256-row CTAs: every B tile feeds two S-MMAs (multi-rank row blocks; optional
+//                                owner-ordered tiles + in-kernel row push)
+//   infonce_tc_fwdsym_kernel     forward on ONE rank: S is symmetric, only the upper-triangular tiles are computed and a
+//                                tile's column sums stand in for the transposed tile (flat persistent work list)
+//   infonce_tc_fwdsym_mr_kernel  the same ACROSS ranks: W/2 of the W column blocks per rank (circulant assignment),
+//                                column sums of foreign blocks shipped to their owners (exchange mode 4)
+//   infonce_tc_bwd_kernel        backward, 64-column tiles (D > 128: TMEM is full)
+//   infonce_tc_bwd2_kernel       backward, 128-column tiles / tile-alternating groups (D <= 128)
+//
 // Replaces: matmul + mask/gather/cat + /T of src/models/simclr.py:296-320 (= :64-88, :140-164), the CE of
 // tools/backbone_train.py:531 and the autograd backward of both.
 //
