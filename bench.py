@@ -1077,6 +1077,16 @@ def retrieval_probe(sm3):
         rv, ri = (q @ bank.T).topk(k, dim=-1)
         out[name] = {"ours_us": round(ours, 1), "matmul_topk_us": round(ref, 1),
                      "index_agreement": float((i == ri).float().mean())}
+        saved = os.environ.get("SM3_TOPK_TILED")
+        try:        # the three forms side by side: 0 single pass, 1 tiled + threshold filter, 2 materialised + radix select
+            for form in ("0", "1", "2"):
+                os.environ["SM3_TOPK_TILED"] = form
+                out[name][f"form{form}_us"] = round(_ev_us(lambda: sm3.sim_topk(q, bank, k), reps=5), 1)
+        finally:
+            if saved is None:
+                os.environ.pop("SM3_TOPK_TILED", None)
+            else:
+                os.environ["SM3_TOPK_TILED"] = saved
     return out
 
 

@@ -207,6 +207,14 @@ size_t sm3_sim_topk_workspace_bytes(int64_t n_query, int64_t n_bank, int k);
 int sm3_sim_topk_ws(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype, int k,
                     int64_t exclude_self_offset, float* vals, int64_t* idx, void* workspace, size_t workspace_bytes,
                     void* stream);
+/* Third form: the similarities of up to ~256 MB worth of queries at a time are materialised in the workspace (fp32
+ * [chunk, n_bank]) by a register-tiled FP32 contraction over all SMs, then one CTA per query radix-selects the k-th
+ * largest key, collects the elements above it plus the lowest-index ties and sorts those k.  Same results.  Workspace:
+ * sm3_sim_topk_mat_workspace_bytes(), 16-byte aligned. */
+size_t sm3_sim_topk_mat_workspace_bytes(int64_t n_query, int64_t n_bank, int k);
+int sm3_sim_topk_mat(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype, int k,
+                     int64_t exclude_self_offset, float* vals, int64_t* idx, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * N3  prototype heads of the multi-label block    replaces tools/mlc_train.py:81-87 (Model.forward)

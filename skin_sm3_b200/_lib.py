@@ -58,6 +58,8 @@ SIGNATURES = {
     "sm3_sim_topk": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _i64, _vp, _vp, _vp]),
     "sm3_sim_topk_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "sm3_sim_topk_ws": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "sm3_sim_topk_mat_workspace_bytes": (_sz, [_i64, _i64, _i]),
+    "sm3_sim_topk_mat": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "sm3_proto_heads_supported": (_i, [_i, _i, _i]),
     "sm3_proto_heads_fwd": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "sm3_proto_heads_bwd": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -368,6 +368,239 @@ sim_topk_merge_kernel(const unsigned long long* __restrict__ lists, int splits, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Third form (sm3_sim_topk_mat): the similarities of a chunk of queries are MATERIALISED (fp32 [chunk, n_bank], at most
+// ~256 MB at a time -- what the reference does for the whole matrix) by a register-tiled FP32 contraction that uses every
+// SM whatever the query count (64 x 128 tiles, 8 x 4 outputs per thread), then ONE CTA PER QUERY selects the top k with a
+// 4-pass radix select on the order-preserving 32-bit keys (warp-aggregated histogram adds), collects the elements above
+// the threshold plus the lowest-index ties, and sorts those k.  Work per query is O(n_bank) with no per-tile sorting, and
+// the selection parallelises over queries, not over bank splits.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGQ = 64, kGB = 128, kGK = 32, kGT = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kGT)
+sim_gemm_kernel(const T* __restrict__ query, const T* __restrict__ bank, int64_t nq, int64_t n_bank, int D, int vec,
+                float* __restrict__ out) {
+  __shared__ __align__(16) float Qs[kGK * kGQ];
+  __shared__ __align__(16) float Bs[kGK * kGB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = lane, ty = warp;                       // 4 bank columns tx + 32 j | 8 queries 8 ty + i
+  const int64_t q0 = (int64_t)blockIdx.x * kGQ, b0 = (int64_t)blockIdx.y * kGB;
+  constexpr int V = VecIO<T>::N;
+  constexpr int NQV = kGQ * (kGK / V) / kGT, NBV = kGB * (kGK / V) / kGT;
+  float qreg[NQV][V], breg[NBV][V];
+  auto g_load = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NQV; ++i) {
+      const int v = tid + i * kGT;
+      const int r = v % kGQ, kv = v / kGQ;
+      if (q0 + r < nq && k0 + kv * V < D) VecIO<T>::load(query + (q0 + r) * D + k0 + kv * V, qreg[i]);
+      else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) qreg[i][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) {
+      const int v = tid + i * kGT;
+      const int r = v % kGB, kv = v / kGB;
+      if (b0 + r < n_bank && k0 + kv * V < D) VecIO<T>::load(bank + (b0 + r) * D + k0 + kv * V, breg[i]);
+      else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) breg[i][e] = 0.f;
+      }
+    }
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nchunk = (D + kGK - 1) / kGK;
+  if (vec) g_load(0);
+  for (int kc = 0; kc < nchunk; ++kc) {
+    const int k0 = kc * kGK;
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < NQV; ++i) {
+        const int v = tid + i * kGT;
+        const int r = v % kGQ, kv = v / kGQ;
+#pragma unroll
+        for (int e = 0; e < V; ++e) Qs[(kv * V + e) * kGQ + r] = qreg[i][e];
+      }
+#pragma unroll
+      for (int i = 0; i < NBV; ++i) {
+        const int v = tid + i * kGT;
+        const int r = v % kGB, kv = v / kGB;
+#pragma unroll
+        for (int e = 0; e < V; ++e) Bs[(kv * V + e) * kGB + r] = breg[i][e];
+      }
+    } else {
+      for (int v = tid; v < kGQ * kGK; v += kGT) {
+        const int r = v % kGQ, k = v / kGQ;
+        Qs[k * kGQ + r] = (q0 + r < nq && k0 + k < D) ? to_f32(query[(q0 + r) * D + k0 + k]) : 0.f;
+      }
+      for (int v = tid; v < kGB * kGK; v += kGT) {
+        const int r = v % kGB, k = v / kGB;
+        Bs[k * kGB + r] = (b0 + r < n_bank && k0 + k < D) ? to_f32(bank[(b0 + r) * D + k0 + k]) : 0.f;
+      }
+    }
+    __syncthreads();
+    if (vec && kc + 1 < nchunk) g_load(k0 + kGK);
+#pragma unroll 8
+    for (int k = 0; k < kGK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(Qs + k * kGQ + 8 * ty);
+      const float4 a1 = *reinterpret_cast<const float4*>(Qs + k * kGQ + 8 * ty + 4);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {Bs[k * kGB + tx], Bs[k * kGB + tx + 32], Bs[k * kGB + tx + 64], Bs[k * kGB + tx + 96]};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t q = q0 + 8 * ty + i;
+    if (q >= nq) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t col = b0 + tx + 32 * j;
+      if (col < n_bank) out[q * n_bank + col] = acc[i][j];
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned key32(float v) {
+  unsigned u = __float_as_uint(v);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+// one CTA per query: radix select of the k-th largest key, collection, sort.  sims: this chunk's [nq, n_bank] fp32.
+__global__ void __launch_bounds__(kTopkThreads)
+topk_radix_kernel(const float* __restrict__ sims, int64_t n_bank, int k, int K, int64_t q_first,
+                  int64_t exclude_self_offset, float* __restrict__ vals, int64_t* __restrict__ idx) {
+  __shared__ int hist[256];
+  __shared__ int wtot[8];
+  __shared__ unsigned s_prefix;
+  __shared__ int s_need, s_gt, s_eq, s_run, s_found;
+  __shared__ unsigned long long sel[kMaxK];
+  __shared__ unsigned tie_idx[kMaxK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t q = blockIdx.x;                                   // query within the chunk
+  const float* row = sims + q * n_bank;
+  const int64_t self = exclude_self_offset >= 0 ? exclude_self_offset + q_first + q : -1;
+  const int64_t n_round = (n_bank + kTopkThreads - 1) / kTopkThreads * kTopkThreads;
+  auto key_at = [&](int64_t i) -> unsigned { return (i < n_bank && i != self) ? key32(__ldg(row + i)) : 0u; };
+  if (tid == 0) { s_prefix = 0u; s_need = k; s_gt = 0; s_eq = 0; s_run = 0; }
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    if (tid == 0) s_found = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned himask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int64_t i = tid; i < n_round; i += kTopkThreads) {
+      const unsigned u = key_at(i);
+      const bool act = u != 0u && (u & himask) == (prefix & himask);
+      const unsigned bin = (u >> shift) & 255u;
+      const unsigned tag = act ? bin : (256u + (unsigned)lane);     // inactive lanes never group
+      const unsigned peers = __match_any_sync(0xffffffffu, tag);
+      if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    }
+    __syncthreads();
+    // suffix scan from the top bin: thread t looks at bin 255 - t
+    const int v = hist[255 - tid];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+    incl += off;
+    const int excl = incl - v;
+    const int need = s_need;
+    __syncthreads();
+    if (excl < need && need <= incl) {                              // exactly one bin holds the k-th largest
+      s_prefix = prefix | ((unsigned)(255 - tid) << shift);
+      s_need = need - excl;
+      s_found = 1;
+    }
+    __syncthreads();
+    if (!s_found) {                                                 // fewer than k valid elements: everything is taken
+      if (tid == 0) s_prefix = 0u;
+      __syncthreads();
+      break;
+    }
+  }
+  const unsigned ustar = s_prefix;
+  const int need = s_need;                                          // how many elements EQUAL to the threshold are taken
+  if (ustar == 0u) {                                                // fewer than k valid elements: take everything valid
+    for (int64_t i = tid; i < n_round; i += kTopkThreads) {
+      const unsigned u = key_at(i);
+      if (u != 0u) { const int s_ = atomicAdd(&s_gt, 1); if (s_ < kMaxK) sel[s_] = ((unsigned long long)u << 32) | (unsigned long long)(~(unsigned)i); }
+    }
+    __syncthreads();
+  } else {
+    for (int64_t i = tid; i < n_round; i += kTopkThreads) {
+      const unsigned u = key_at(i);
+      if (u > ustar) sel[atomicAdd(&s_gt, 1)] = ((unsigned long long)u << 32) | (unsigned long long)(~(unsigned)i);
+      else if (u == ustar) { const int e = atomicAdd(&s_eq, 1); if (e < kMaxK) tie_idx[e] = (unsigned)i; }
+    }
+    __syncthreads();
+    const int gt = s_gt, eq = s_eq;                                 // gt == k - need by construction
+    if (eq == need) {                                               // every tie is taken: no ordering needed
+      if (tid < need) sel[gt + tid] = ((unsigned long long)ustar << 32) | (unsigned long long)(~tie_idx[tid]);
+    } else {
+      // more ties than needed: the lowest bank indices win -> ordered scan over the row
+      for (int64_t base = 0; base < n_round && s_run < need; base += kTopkThreads) {
+        const bool f = key_at(base + tid) == ustar;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wtot[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_run;
+        for (int w = 0; w < warp; ++w) before += wtot[w];
+        const int pos = before + __popc(bal & ((1u << lane) - 1u));
+        if (f && pos < need) sel[gt + pos] = ((unsigned long long)ustar << 32) | (unsigned long long)(~(unsigned)(base + tid));
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += wtot[w]; s_run += t; }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+  const int have = min(k, ustar == 0u ? min(s_gt, kMaxK) : k);
+  for (int i = tid; i < K; i += kTopkThreads)
+    if (i >= have) sel[i] = 0ull;
+  bitonic_sort_desc(sel, K);
+  const int64_t qg = q_first + q;
+  for (int r = tid; r < k; r += kTopkThreads) {
+    const unsigned long long key = sel[r];
+    const bool ok = key != 0ull;
+    vals[qg * k + r] = ok ? key_value(key) : -INFINITY;
+    idx[qg * k + r] = ok ? (int64_t)(~(unsigned)(key & 0xFFFFFFFFull)) : -1;
+  }
+}
+
+struct Topk3Plan { int K; int64_t chunk; size_t ws; };
+Topk3Plan topk3_plan(int64_t n_query, int64_t n_bank, int k) {
+  Topk3Plan p{};
+  p.K = 8;
+  while (p.K < k) p.K <<= 1;
+  int64_t chunk = ((int64_t)256 << 20) / (n_bank * 4);
+  chunk = chunk / kGQ * kGQ;
+  if (chunk < kGQ) chunk = kGQ;
+  if (chunk > n_query) chunk = n_query;
+  p.chunk = chunk;
+  p.ws = (size_t)chunk * n_bank * sizeof(float);
+  return p;
+}
+
 struct Topk2Plan { int K, splits; int64_t rows_per_split; size_t smem, ws; };
 Topk2Plan topk2_plan(int64_t n_query, int64_t n_bank, int k) {
   Topk2Plan p{};
@@ -442,5 +675,40 @@ extern "C" int sm3_sim_topk_ws(const void* query, const void* bank, int64_t n_qu
   SM3_CHECK_CUDA(cudaGetLastError());
   sim_topk_merge_kernel<<<(unsigned)((n_query + 3) / 4), 128, 0, st>>>(lists, pl.splits, n_query, pl.K, k, vals, idx);
   SM3_CHECK_CUDA(cudaGetLastError());
+  return SM3_OK;
+}
+
+extern "C" size_t sm3_sim_topk_mat_workspace_bytes(int64_t n_query, int64_t n_bank, int k) {
+  if (n_query < 1 || n_bank < 1 || k < 1 || k > kMaxK) return 0;
+  return topk3_plan(n_query, n_bank, k).ws;
+}
+
+extern "C" int sm3_sim_topk_mat(const void* query, const void* bank, int64_t n_query, int64_t n_bank, int D, int dtype,
+                                int k, int64_t exclude_self_offset, float* vals, int64_t* idx, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SM3_REQUIRE(query && bank && vals && idx && workspace, SM3_ERR_SHAPE, "sim_topk_mat: null pointer");
+  SM3_REQUIRE(dtype_ok(dtype), SM3_ERR_DTYPE, "sim_topk_mat: bad dtype %d", dtype);
+  SM3_REQUIRE(n_query >= 1 && n_bank >= 1 && D >= 1, SM3_ERR_SHAPE, "sim_topk_mat: bad shape");
+  SM3_REQUIRE(n_bank < ((int64_t)1 << 31), SM3_ERR_SHAPE, "sim_topk_mat: bank too large");
+  SM3_REQUIRE(k >= 1 && k <= kMaxK && k <= n_bank, SM3_ERR_SHAPE, "sim_topk_mat: need 1 <= k <= min(%d, n_bank), got %d",
+              kMaxK, k);
+  const Topk3Plan pl = topk3_plan(n_query, n_bank, k);
+  SM3_REQUIRE(workspace_bytes >= pl.ws, SM3_ERR_WORKSPACE, "sim_topk_mat: workspace %zu < %zu", workspace_bytes, pl.ws);
+  SM3_REQUIRE((((uintptr_t)workspace) & 15u) == 0, SM3_ERR_SHAPE, "sim_topk_mat: workspace must be 16-byte aligned");
+  float* sims = (float*)workspace;
+  const size_t esz = (size_t)dtype_size(dtype);
+  for (int64_t q0 = 0; q0 < n_query; q0 += pl.chunk) {
+    const int64_t nq = n_query - q0 < pl.chunk ? n_query - q0 : pl.chunk;
+    const dim3 grid((unsigned)((nq + kGQ - 1) / kGQ), (unsigned)((n_bank + kGB - 1) / kGB));
+    const char* qptr = (const char*)query + (size_t)q0 * D * esz;
+    SM3_DISPATCH_DTYPE(dtype, T, {
+      const int vec = (D % VecIO<T>::N == 0) && ((((uintptr_t)bank) & 15u) == 0) && ((((uintptr_t)qptr) & 15u) == 0);
+      sim_gemm_kernel<T><<<grid, kGT, 0, st>>>((const T*)qptr, (const T*)bank, nq, n_bank, D, vec, sims);
+    });
+    SM3_CHECK_CUDA(cudaGetLastError());
+    topk_radix_kernel<<<(unsigned)nq, kTopkThreads, 0, st>>>(sims, n_bank, k, pl.K, q0, exclude_self_offset, vals, idx);
+    SM3_CHECK_CUDA(cudaGetLastError());
+  }
   return SM3_OK;
 }

@@ -932,7 +932,17 @@ def sim_topk(query: torch.Tensor, bank: torch.Tensor, k: int, exclude_self_offse
     vals = torch.empty((b, k), dtype=torch.float32, device=dev)
     idx = torch.empty((b, k), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        if os.environ.get("SM3_TOPK_TILED", "1") != "0":
+        # SM3_TOPK_TILED: 0 single pass | 1 tiled + threshold filter | 2 materialised + radix select | unset: 2 for k > 32
+        # (the per-split candidate merges of form 1 grow with k: 612 vs 349 us at k = 200), else 1 (a k = 5 search over
+        # 8192 x 8192 is 1.35 ms with form 1, 2.24 ms with form 2, whose matrix no longer fits L2)
+        form = os.environ.get("SM3_TOPK_TILED") or ("2" if int(k) > 32 else "1")
+        if form == "2":                             # materialised similarities + radix select per query
+            nbytes = int(lib().sm3_sim_topk_mat_workspace_bytes(b, bank.shape[0], int(k)))
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            check(lib().sm3_sim_topk_mat(ptr(query), ptr(bank), b, bank.shape[0], d, dtype_code(query), int(k),
+                                         int(exclude_self_offset), ptr(vals), ptr(idx), ptr(ws), ws.numel(),
+                                         stream_ptr()), "sm3_sim_topk_mat")
+        elif form != "0":
             nbytes = int(lib().sm3_sim_topk_workspace_bytes(b, bank.shape[0], int(k)))
             ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
             check(lib().sm3_sim_topk_ws(ptr(query), ptr(bank), b, bank.shape[0], d, dtype_code(query), int(k),

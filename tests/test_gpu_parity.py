@@ -855,9 +855,11 @@ def test_knn_topk_matches_reference_evaluator(sm3):
     assert (pred.cpu().numpy() == g["pred_labels"]).all()
 
 
+@pytest.mark.parametrize("form", ["1", "2"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("bq,nb,d,k", [(5, 7, 12, 3), (64, 1500, 128, 200), (257, 4096, 256, 50), (33, 1025, 64, 256)])
-def test_sim_topk_vs_oracle(sm3, dtype, bq, nb, d, k):
+def test_sim_topk_vs_oracle(sm3, monkeypatch, dtype, bq, nb, d, k, form):
+    monkeypatch.setenv("SM3_TOPK_TILED", form)      # 1: tiled + threshold filter, 2: materialised + radix select
     rng = np.random.default_rng(bq + nb)
     q = torch.from_numpy(rng.normal(size=(bq, d)).astype(np.float32)).to(dtype)
     bank = torch.from_numpy(rng.normal(size=(nb, d)).astype(np.float32)).to(dtype)
@@ -878,16 +880,24 @@ def test_sim_topk_vs_oracle(sm3, dtype, bq, nb, d, k):
 
 
 @pytest.mark.parametrize("bq,nb,d,k,self_off", [(512, 16384, 128, 200, -1), (1000, 3000, 96, 5, 0), (40, 70000, 64, 17, -1)])
-def test_sim_topk_tiled_equals_single_pass(sm3, monkeypatch, bq, nb, d, k, self_off):
+def test_sim_topk_forms_agree(sm3, monkeypatch, bq, nb, d, k, self_off):
     """The tiled, threshold-filtered search (bank split across CTAs + merge kernel) and the single-pass kernel return the
     same top-k set: same 64-bit keys, so any difference can only come from fp32 accumulation order of near-ties."""
     g = torch.Generator().manual_seed(bq + k)
     q = torch.randn(bq, d, generator=g).cuda()
     bank = torch.randn(nb, d, generator=g).cuda()
+    bank[7] = bank[3]                                                        # exact ties: lower index first in every form
+    monkeypatch.setenv("SM3_TOPK_TILED", "1")
     v1, i1 = sm3.sim_topk(q, bank, k, exclude_self_offset=self_off)
+    monkeypatch.setenv("SM3_TOPK_TILED", "2")
+    v2, i2 = sm3.sim_topk(q, bank, k, exclude_self_offset=self_off)
     monkeypatch.setenv("SM3_TOPK_TILED", "0")
     v0, i0 = sm3.sim_topk(q, bank, k, exclude_self_offset=self_off)
     monkeypatch.undo()
+    assert (i2 == i0).float().mean().item() > 0.999 and relerr(v2.cpu().numpy(), v0.cpu().numpy()) < 1e-5
+    assert (v2[:, :-1] >= v2[:, 1:]).all()
+    s2 = torch.sort(i2, dim=1).values
+    assert (s2[:, 1:] != s2[:, :-1]).all() and (i2 >= 0).all() and (i2 < nb).all()
     assert (v1[:, :-1] >= v1[:, 1:]).all()                                   # sorted descending
     assert (i1 >= 0).all() and (i1 < nb).all()
     if self_off >= 0:
@@ -904,6 +914,21 @@ def test_sim_topk_tiled_equals_single_pass(sm3, monkeypatch, bq, nb, d, k, self_
     rv, ri = sim.topk(k, dim=1)
     assert (ri == i1).float().mean().item() > 0.995
     assert relerr(v1.cpu().numpy(), rv.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("form", ["0", "1", "2"])
+def test_sim_topk_many_exact_ties_take_the_lowest_indices(sm3, monkeypatch, form):
+    """A bank of identical rows: every similarity ties, so the result must be indices 0 .. k-1 (1 .. k with the query's own
+    row excluded) -- the ordered tie scan of the radix-select form, the 64-bit keys of the other two."""
+    monkeypatch.setenv("SM3_TOPK_TILED", form)
+    row = torch.randn(1, 64, generator=torch.Generator().manual_seed(2))
+    bank = row.repeat(3000, 1).cuda()
+    q = row.repeat(9, 1).cuda()
+    v, i = sm3.sim_topk(q, bank, 17)
+    assert (i.cpu() == torch.arange(17)[None, :]).all()
+    v, i = sm3.sim_topk(bank[:9].contiguous(), bank, 17, exclude_self_offset=0)
+    exp = torch.stack([torch.tensor([j for j in range(18) if j != r][:17]) for r in range(9)])
+    assert (i.cpu() == exp).all()
 
 
 def test_in_batch_retrieval_top1_is_the_positive(sm3):
