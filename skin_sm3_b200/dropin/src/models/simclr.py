@@ -42,6 +42,17 @@ def _runtime():
     return os.environ.get("SM3_PRECISION", "auto"), group
 
 
+def _check_range(proj_dim, temperature):
+    """The fused kernels take D <= 256 and 1/T < 83 (include/sm3_b200.h); say so when the model is BUILT, not at the first
+    forward.  (The reference accepts any --proj-dim / --temperature; its configurations use 128 / 0.1.)"""
+    if int(proj_dim) > 256 or int(proj_dim) < 1:
+        raise ValueError(f"skin_sm3_b200 drop-in: proj_dim={proj_dim} is outside the fused kernels' range (1..256); "
+                         f"run with SM3_DROPIN=0 for the stock reference modules")
+    if not (float(temperature) > 0.0 and 1.0 / float(temperature) < 83.0):
+        raise ValueError(f"skin_sm3_b200 drop-in: temperature={temperature} is outside the fused kernels' range "
+                         f"(T > 0.012); run with SM3_DROPIN=0 for the stock reference modules")
+
+
 def _pair_logits(feats_a, feats_b, temperature):
     """(logits[2N,2], zeros[2N]) for the pairing rows(feats_a)[i] <-> rows(feats_b)[i]."""
     precision, group = _runtime()
@@ -84,6 +95,7 @@ class SimCLR(nn.Module):
 
     def __init__(self, arch, weights=None, proj_dim=128, temperature=0.5, return_feats=False):
         super().__init__()
+        _check_range(proj_dim, temperature)
         self.proj_dim = proj_dim
         self.temperature = temperature
         self.return_feats = return_feats
