@@ -113,17 +113,22 @@ def test_dropin_module_matches_reference_structure():
 def test_dropin_rejects_out_of_range_settings_at_construction():
     """D > 256 or 1/T >= 83 are outside the fused kernels' range: the drop-in says so when the model is built (CPU, no
     compute), pointing at SM3_DROPIN=0, instead of failing at the first forward."""
-    import importlib.util
+    import sys
     import pytest
-    path = os.path.join(ROOT, "skin_sm3_b200", "dropin", "src", "models", "simclr.py")
-    spec = importlib.util.spec_from_file_location("_sm3_shadow_simclr_range", path)
-    mod = importlib.util.module_from_spec(spec)
+    from oracle import vendor_ref
+    root = vendor_ref.ref_root()
+    if root is None:
+        pytest.skip("no reference checkout / vendored copy (src.models.resnet comes from it)")
+    sys.path.insert(0, root)
     try:
-        spec.loader.exec_module(mod)
-    except Exception as e:        # the shadow module needs the reference's resnet module next to it or the fallback
-        pytest.skip(f"shadow module not importable standalone: {e!r}")
-    with pytest.raises(ValueError, match="proj_dim"):
-        mod.SimCLR("resnet18", None, proj_dim=512)
-    with pytest.raises(ValueError, match="temperature"):
-        mod.SimCLR("resnet18", None, proj_dim=128, temperature=0.01)
-    mod.SimCLR("resnet18", None, proj_dim=128, temperature=0.1)
+        from skin_sm3_b200 import dropin
+        dropin.install()
+        import src.models.simclr as mine
+        assert mine.__file__.startswith(os.path.join(ROOT, "skin_sm3_b200"))
+        with pytest.raises(ValueError, match="proj_dim"):
+            mine.SimCLR("resnet18", None, proj_dim=512)
+        with pytest.raises(ValueError, match="temperature"):
+            mine.SimCLRSkinV32("resnet18", None, proj_dim=128, temperature=0.01)
+        mine.SimCLR("resnet18", None, proj_dim=128, temperature=0.1)
+    finally:
+        sys.path.remove(root)
