@@ -398,6 +398,12 @@ void sm3_debug_reload_env(void);
 int sm3_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* c, int n, int k, int variant,
                          void* stream);
 
+/* Host-only enumeration of the tiles the symmetric forward kernels visit (the kernels' own index functions; no GPU
+ * needed): per visited tile 5 ints (cta, row pair, GLOBAL column tile, column sums taken, slab row).  world == 1: the
+ * single-rank kernel over n_local pairs; world > 1: rank `rank` of exchange mode 4.  tpc_override > 0 forces the tiles per
+ * CTA.  Returns the number of records (only the first `cap` are written). */
+long long sm3_debug_sym_enumerate(int n_local, int world, int rank, int tpc_override, int* records, long long cap);
+
 /* debug / single-GPU test of mode 4 (symmetric forward across ranks): the caller plays every rank on one device.
  * _forward = rank `rank`'s K2 (flags_mine must hold `epoch` in channel 0 for all sources) + its column-sum push into the
  * per-rank statistics / flag buffers; _fold = that rank's loss kernel without publishing (neg_sum, gradients of the

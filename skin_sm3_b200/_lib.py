@@ -52,6 +52,7 @@ SIGNATURES = {
     "sm3_bce_workspace_bytes": (_sz, [_i64, _i]),
     "sm3_bce_logits": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp, _f, _vp, _sz, _vp]),
     "sm3_infonce_fwd_symmetric": (_i, [_i, _i, _vp]),
+    "sm3_debug_sym_enumerate": (C.c_longlong, [_i, _i, _i, _i, _vp, C.c_longlong]),
     "sm3_debug_mr_workspace": (_sz, [_i, _i, _i]),
     "sm3_debug_mr_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, C.c_uint, _vp, _vp, _sz, _vp]),
     "sm3_debug_mr_fold": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp, C.c_uint, _vp, _vp, _vp, _vp, _vp, _vp]),

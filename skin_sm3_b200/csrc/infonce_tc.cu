@@ -864,7 +864,7 @@ template <int DP> struct SymCfg {
   static constexpr uint32_t SMEM = FwdCfg<DP>::NSTAGE * FwdCfg<DP>::STAGE + 1024 /*align*/ + 256 /*barriers*/ +
                                    3072 /*xsum [3][2][128]*/ + 6144 /*cbuf [3][512]*/;
 };
-__device__ __forceinline__ void sym_decode(long f, int T, int P, int& R, int& off) {
+__host__ __device__ __forceinline__ void sym_decode(long f, int T, int P, int& R, int& off) {
   const int i = (int)(f / (T + 2));
   const int rem = (int)(f - (long)i * (T + 2));
   const int len_i = T - 2 * i;
@@ -1222,7 +1222,7 @@ infonce_tc_fwdsym_kernel(const __grid_constant__ CUtensorMap tmap_cols, TcParams
 // per-partner slabs (they are pushed to the owners by colsum_push_kernel).  Diagonal / positive masks only occur in the
 // own block, in local row / column indices.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mr_decode(const MrPlan& m, long f, int& R, int& off) {
+__host__ __device__ __forceinline__ void mr_decode(const MrPlan& m, long f, int& R, int& off) {
   int lo = 0, hi = m.P_l - 1;                       // largest R with mr_prefix(R) <= f
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -1232,7 +1232,7 @@ __device__ __forceinline__ void mr_decode(const MrPlan& m, long f, int& R, int& 
   off = (int)(f - mr_prefix(m, lo));
 }
 // t-th tile of row pair R: partner slot (-1 = own block) and the tile index in the owner's local tile order
-__device__ __forceinline__ void mr_tile(const MrPlan& m, int R, int t, int& ps, int& j_l) {
+__host__ __device__ __forceinline__ void mr_tile(const MrPlan& m, int R, int t, int& ps, int& j_l) {
   const int own = m.T_l - 2 * R;
   if (t < own) { ps = -1; j_l = 2 * R + t; return; }
   t -= own;
@@ -2732,6 +2732,66 @@ extern "C" int sm3_infonce_fwd_symmetric(int n_pairs, int D, long long* executed
   const SymPlan sp = tc_sym_plan(pb);
   if (executed_tiles) *executed_tiles = sp.on ? 2 * sp.W : (long long)((2L * n_pairs + 127) / 128) * ((2L * n_pairs + 127) / 128);
   return sp.on ? 1 : 0;
+}
+
+// Host-side enumeration of the work lists the symmetric kernels walk, with the kernels' own index functions (no GPU
+// needed): for every CTA piece of rank `rank`'s flat list, one record (cta, row pair R, global column tile, column sums
+// taken 0/1, slab row the column sums go to) per visited tile.  world == 1 enumerates the single-rank symmetric kernel
+// (n_local = all pairs).  Returns the number of records (<= cap written), or a negative error code.
+extern "C" long long sm3_debug_sym_enumerate(int n_local, int world, int rank, int tpc_override, int* records, long long cap) {
+  using namespace sm3;
+  SM3_REQUIRE(n_local >= 128 && n_local % 128 == 0 && world >= 1 && world <= 16 && rank >= 0 && rank < world && records,
+              SM3_ERR_SHAPE, "sym_enumerate: bad arguments");
+  long long n = 0;
+  auto put = [&](int cta, int R, int gtile, int docol, int slab) {
+    if (n < cap) { int* r = records + 5 * n; r[0] = cta; r[1] = R; r[2] = gtile; r[3] = docol; r[4] = slab; }
+    ++n;
+  };
+  if (world == 1) {
+    const int T = 2 * n_local / 128, P = T / 2;
+    const long W = (long)P * (P + 1);
+    const int sms = num_sms();
+    const int tpc = tpc_override > 0 ? tpc_override : (int)((W + sms - 1) / sms);
+    const int nctas = (int)((W + tpc - 1) / tpc);
+    for (int c = 0; c < nctas; ++c) {
+      const long f0 = (long)c * tpc, f1 = (f0 + tpc < W) ? f0 + tpc : W;
+      for (long f = f0; f < f1;) {
+        int R, off;
+        sym_decode(f, T, P, R, off);
+        const long left = f1 - f;
+        const int cnt = (int)((long)(T - 2 * R - off) < left ? (long)(T - 2 * R - off) : left);
+        const int kseg = c - (int)(sym_flat_start(R, T, P) / tpc);
+        SM3_REQUIRE(cnt > 0 && kseg >= 0 && kseg < sym_maxseg(T, tpc), SM3_ERR_SHAPE, "sym_enumerate: bad segment");
+        for (int t = 0; t < cnt; ++t) put(c, R, 2 * R + off + t, (2 * R + off + t) > 2 * R + 1, R);
+        f += cnt;
+      }
+    }
+    return n;
+  }
+  MrPlan m = infonce_tc_mr_plan(n_local, world, rank);
+  SM3_REQUIRE(m.on, SM3_ERR_SHAPE, "sym_enumerate: no plan");
+  if (tpc_override > 0) {
+    m.tpc = tpc_override;
+    m.nctas = (int)((m.flat + m.tpc - 1) / m.tpc);
+  }
+  for (int c = 0; c < m.nctas; ++c) {
+    const long f0 = (long)c * m.tpc, f1 = (f0 + m.tpc < m.flat) ? f0 + m.tpc : m.flat;
+    for (long f = f0; f < f1;) {
+      int R, off;
+      mr_decode(m, f, R, off);
+      const long left = f1 - f;
+      const int cnt = (int)((long)(mr_count(m, R) - off) < left ? (long)(mr_count(m, R) - off) : left);
+      SM3_REQUIRE(cnt > 0 && R >= 0 && R < m.P_l && off >= 0, SM3_ERR_SHAPE, "sym_enumerate: bad segment");
+      for (int t = 0; t < cnt; ++t) {
+        int ps, j_l;
+        mr_tile(m, R, off + t, ps, j_l);
+        const int owner = ps < 0 ? m.rank : mr_partner_rank(m, ps);
+        put(c, R, mr_global_tile(m, owner, j_l), (ps >= 0 || j_l > 2 * R + 1) ? 1 : 0, (ps < 0 ? 0 : (1 + ps) * m.P_l) + R);
+      }
+      f += cnt;
+    }
+  }
+  return n;
 }
 
 extern "C" void sm3_debug_reload_env(void) {
