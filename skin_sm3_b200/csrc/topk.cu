@@ -376,19 +376,24 @@ sim_topk_merge_kernel(const unsigned long long* __restrict__ lists, int splits, 
 // the threshold plus the lowest-index ties, and sorts those k.  Work per query is O(n_bank) with no per-tile sorting, and
 // the selection parallelises over queries, not over bank splits.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kGQ = 64, kGB = 128, kGK = 32, kGT = 256;
+constexpr int kGQ = 128, kGB = 128, kGK = 16, kGT = 256;
 
+// C[q, b] = sum_k Q[q, k] B[b, k] for a chunk of queries: 128 x 128 tile per CTA, 8 x 8 outputs per thread (rows
+// 4 ty .. + 3 and 64 + 4 ty .. + 3, columns 4 tx .. + 3 and 64 + 4 tx .. + 3: every shared-memory read is a conflict-free
+// LDS.128 and feeds 16 FMAs), operands staged k-major, the next k-chunk's global loads issued before the FMAs of the
+// current one.  fp32 accumulation in ascending k, like the other two forms (identical sums, identical top-k).
 template <typename T>
 __global__ void __launch_bounds__(kGT)
 sim_gemm_kernel(const T* __restrict__ query, const T* __restrict__ bank, int64_t nq, int64_t n_bank, int D, int vec,
                 float* __restrict__ out) {
   __shared__ __align__(16) float Qs[kGK * kGQ];
   __shared__ __align__(16) float Bs[kGK * kGB];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = lane, ty = warp;                       // 4 bank columns tx + 32 j | 8 queries 8 ty + i
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
   const int64_t q0 = (int64_t)blockIdx.x * kGQ, b0 = (int64_t)blockIdx.y * kGB;
   constexpr int V = VecIO<T>::N;
-  constexpr int NQV = kGQ * (kGK / V) / kGT, NBV = kGB * (kGK / V) / kGT;
+  constexpr int NQV = kGQ * kGK / V / kGT, NBV = kGB * kGK / V / kGT;       // 2 / 1 vectors per thread and operand
+  static_assert(NQV >= 1 && NBV >= 1, "tile / vector mismatch");
   float qreg[NQV][V], breg[NBV][V];
   auto g_load = [&](int k0) {
 #pragma unroll
@@ -412,11 +417,11 @@ sim_gemm_kernel(const T* __restrict__ query, const T* __restrict__ bank, int64_t
       }
     }
   };
-  float acc[8][4];
+  float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const int nchunk = (D + kGK - 1) / kGK;
   if (vec) g_load(0);
   for (int kc = 0; kc < nchunk; ++kc) {
@@ -448,27 +453,37 @@ sim_gemm_kernel(const T* __restrict__ query, const T* __restrict__ bank, int64_t
     }
     __syncthreads();
     if (vec && kc + 1 < nchunk) g_load(k0 + kGK);
-#pragma unroll 8
+#pragma unroll
     for (int k = 0; k < kGK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(Qs + k * kGQ + 8 * ty);
-      const float4 a1 = *reinterpret_cast<const float4*>(Qs + k * kGQ + 8 * ty + 4);
+      const float4 a0 = *reinterpret_cast<const float4*>(Qs + k * kGQ + 4 * ty);
+      const float4 a1 = *reinterpret_cast<const float4*>(Qs + k * kGQ + 64 + 4 * ty);
+      const float4 c0 = *reinterpret_cast<const float4*>(Bs + k * kGB + 4 * tx);
+      const float4 c1 = *reinterpret_cast<const float4*>(Bs + k * kGB + 64 + 4 * tx);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[4] = {Bs[k * kGB + tx], Bs[k * kGB + tx + 32], Bs[k * kGB + tx + 64], Bs[k * kGB + tx + 96]};
+      const float b[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
+  const bool vec_out = (n_bank % 4 == 0);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int64_t q = q0 + 8 * ty + i;
+    const int64_t q = q0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
     if (q >= nq) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t col = b0 + tx + 32 * j;
-      if (col < n_bank) out[q * n_bank + col] = acc[i][j];
+    for (int h = 0; h < 2; ++h) {
+      const int64_t col = b0 + 64 * h + 4 * tx;
+      float* dst = out + q * n_bank + col;
+      if (vec_out && col + 3 < n_bank) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col + e < n_bank) dst[e] = acc[i][4 * h + e];
+      }
     }
   }
 }
@@ -505,9 +520,14 @@ topk_radix_kernel(const float* __restrict__ sims, int64_t n_bank, int k, int K, 
       const unsigned u = key_at(i);
       const bool act = u != 0u && (u & himask) == (prefix & himask);
       const unsigned bin = (u >> shift) & 255u;
-      const unsigned tag = act ? bin : (256u + (unsigned)lane);     // inactive lanes never group
-      const unsigned peers = __match_any_sync(0xffffffffu, tag);
-      if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      if (shift == 24) {
+        // top digit (sign + high exponent bits): a handful of bins take everything -> one add per warp and bin
+        const unsigned tag = act ? bin : (256u + (unsigned)lane);   // inactive lanes never group
+        const unsigned peers = __match_any_sync(0xffffffffu, tag);
+        if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      } else if (act) {
+        atomicAdd(&hist[bin], 1);                                   // lower digits are spread: plain shared-memory adds
+      }
     }
     __syncthreads();
     // suffix scan from the top bin: thread t looks at bin 255 - t

@@ -932,10 +932,10 @@ def sim_topk(query: torch.Tensor, bank: torch.Tensor, k: int, exclude_self_offse
     vals = torch.empty((b, k), dtype=torch.float32, device=dev)
     idx = torch.empty((b, k), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        # SM3_TOPK_TILED: 0 single pass | 1 tiled + threshold filter | 2 materialised + radix select | unset: 2 for k > 32
-        # (the per-split candidate merges of form 1 grow with k: 612 vs 349 us at k = 200), else 1 (a k = 5 search over
-        # 8192 x 8192 is 1.35 ms with form 1, 2.24 ms with form 2, whose matrix no longer fits L2)
-        form = os.environ.get("SM3_TOPK_TILED") or ("2" if int(k) > 32 else "1")
+        # SM3_TOPK_TILED: 0 single pass | 1 tiled + threshold filter | 2 materialised + radix select | unset: 2 unless the
+        # bank is tiny (one CTA per query only pays off with >= ~1000 bank rows to scan).  Measured on B200, us: 512 x 16384 x
+        # 128, k = 200: 1582 / 628 / 176 (library 250); 8192 x 8192 x 128, k = 5: 6860 / 1341 / 934 (library 1280).
+        form = os.environ.get("SM3_TOPK_TILED") or ("2" if bank.shape[0] >= 1024 else "1")
         if form == "2":                             # materialised similarities + radix select per query
             nbytes = int(lib().sm3_sim_topk_mat_workspace_bytes(b, bank.shape[0], int(k)))
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
