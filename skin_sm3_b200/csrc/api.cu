@@ -429,6 +429,12 @@ PeerPlan plan_peer(int n_local, int n_global, int D) {
     const size_t f3 = infonce_tc_workspace(fullp, 0);
     if (h.ws_b_bytes < f3) h.ws_b_bytes = f3;
   }
+  if (n_local % 128 == 0 && n_global > n_local && n_global % n_local == 0 && n_global / n_local <= 16) {
+    // mode 4: the symmetric forward across ranks keeps its row / column slabs here.  Sized for EVERY rank (the plan differs
+    // slightly between the two antipodal classes), so that whether mode 4 applies never depends on the rank.
+    const size_t f4 = infonce_tc_mr_workspace_any(n_local, n_global / n_local);
+    if (h.ws_b_bytes < f4) h.ws_b_bytes = f4;
+  }
   h.ws_b = take(h.ws_b_bytes);
   h.total = o;
   return h;
@@ -543,7 +549,7 @@ extern "C" int sm3_infonce_step_peer(const void* p1, const void* p2, int n_local
     //      sends the column sums of the foreign blocks to their owners (see MrPlan, common.cuh).  Falls back to mode 2
     //      when the plan does not apply (n_local %% 128, workspace). ----
     const MrPlan mp = infonce_tc_mr_plan(n_local, world, rank);
-    if (!mp.on || infonce_tc_mr_workspace(mp) > h.ws_b_bytes) overlap = 2;
+    if (!mp.on || infonce_tc_mr_workspace_any(n_local, world) > h.ws_b_bytes) overlap = 2;   // rank-independent decision
   }
   if (overlap == 4) {
     SM3_REQUIRE(aligned16(p1) && aligned16(p2), SM3_ERR_SHAPE, "infonce_step_peer: fused mode needs 16-byte aligned rows");

@@ -384,6 +384,7 @@ int colsum_push_launch(const float* partner_slabs, const MrPlan& plan, int n_loc
                        const PeerPtrs& flags, unsigned* ticket, unsigned epoch, cudaStream_t st);
 MrPlan infonce_tc_mr_plan(int n_local, int world, int rank);
 size_t infonce_tc_mr_workspace(const MrPlan& m);
+size_t infonce_tc_mr_workspace_any(int n_local, int world);   // max over the ranks' plans (0 when mode 4 does not apply)
 int infonce_tc_fwd_mr(const InfoNceProblem& pb, const MrPlan& m, float* pos, void* ws, size_t ws_bytes, cudaStream_t st);
 // byte offset of the a_j array (padded to a multiple of 64 columns + 64) inside the tcgen05 backward workspace
 size_t infonce_tc_acol_offset(const InfoNceProblem& pb);

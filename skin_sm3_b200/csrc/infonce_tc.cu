@@ -2642,6 +2642,16 @@ MrPlan infonce_tc_mr_plan(int n_local, int world, int rank) {
 size_t infonce_tc_mr_workspace(const MrPlan& m) {
   return (size_t)(m.maxseg + (1 + m.np) * m.P_l) * (size_t)m.T_l * 128 * sizeof(float) + 256;
 }
+size_t infonce_tc_mr_workspace_any(int n_local, int world) {
+  size_t w = 0;
+  for (int r = 0; r < world; ++r) {
+    const MrPlan m = infonce_tc_mr_plan(n_local, world, r);
+    if (!m.on) return 0;
+    const size_t b = infonce_tc_mr_workspace(m);
+    w = b > w ? b : w;
+  }
+  return w;
+}
 namespace {
 template <int DP>
 int launch_fwdsym_mr(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {
