@@ -72,3 +72,15 @@ def test_cross_rank_lists_cover_the_global_matrix_once(world, n_local, tpc):
     # the circulant assignment is balanced: every rank computes about half of its row block's tiles
     assert max(work) <= 1.15 * min(work) + T_l, work
     assert sum(work) <= 0.5 * (T_g // 2) * T_g + world * T_l
+
+
+@pytest.mark.parametrize("world,n_local,d", [(2, 16384, 256), (2, 16384, 64), (4, 8192, 256), (8, 4096, 256), (8, 256, 64),
+                                             (3, 384, 128), (16, 128, 64)])
+def test_peer_step_scratch_covers_every_ranks_symmetric_workspace(world, n_local, d):
+    """Whether exchange mode 4 applies must not depend on the rank (a rank that fell back to mode 2 alone would leave its
+    partners waiting for column sums): the peer step's scratch is sized for the largest per-rank plan."""
+    lib = _lib.lib()
+    total = lib.sm3_infonce_step_peer_scratch_bytes(n_local, n_local * world, d)
+    need = [lib.sm3_debug_mr_workspace(n_local, world, r) for r in range(world)]
+    assert min(need) > 0 and total >= max(need), (total, need)
+    assert max(need) - min(need) <= 0.2 * max(need)                 # the two antipodal classes differ by a few slabs at most
